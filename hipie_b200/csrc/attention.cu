@@ -1,0 +1,400 @@
+// Fused multi-head attention (flash-style online softmax; the (T x T) score matrix never exists
+// in HBM) with the ViTDet decomposed relative-position bias and an optional additive key bias.
+//
+// Reference semantics: softmax((q*scale) k^T + rel_h[q, kh] + rel_w[q, kw]) v
+//   (/root/reference/projects/HIPIE/hipie/backbone/vit.py:67-83, backbone/utils.py:96-125),
+// nn.MultiheadAttention of the decoders (deformable_transformer_dino.py:432-438) and BERT
+// self-attention with a padding mask (key_bias).
+//
+// Round-1 implementation: warp-level mma.sync (m16n8k16 bf16, fp32 accumulate) with cp.async
+// double-buffered K/V tiles.  Operands are bf16 hi/lo planes; prec==3 evaluates
+// S = Qh.Kh + Qh.Kl + Ql.Kh and O += Ph.Vh + Ph.Vl + Pl.Vh so the result is fp32-class.
+// (The tcgen05/TMEM port of this kernel is the next step; see DESIGN.md.)
+#include "common.cuh"
+
+namespace hipie {
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct AttnParams {
+    const __nv_bfloat16 *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo;
+    int64_t q_bs, q_ts, q_hs, k_bs, k_ts, k_hs, v_bs, v_ts, v_hs;
+    const float *rel_h, *rel_w;
+    int kh, kw;
+    const float* key_bias;
+    float* out_f32;
+    __nv_bfloat16 *out_hi, *out_lo;
+    int64_t o_bs, o_ts;
+    int B, H, Tq, Tk;
+    float scale;
+};
+
+constexpr int ATT_BM = 64;   // query rows per CTA (4 warps x 16)
+constexpr int ATT_BN = 64;   // keys per tile
+
+template <int HD, int PREC>
+__global__ void __launch_bounds__(128)
+attention_kernel(const AttnParams p) {
+    constexpr int ROWB = HD * 2 + 16;             // padded smem row (bytes), odd number of 16B units
+    constexpr int PLANE = ATT_BN * ROWB;          // one K or V plane of a tile
+    constexpr int NPL = PREC == 3 ? 4 : 2;        // Khi,(Klo),Vhi,(Vlo)
+    constexpr int STAGE = NPL * PLANE;
+    constexpr int KSTEPS = HD / 16;
+    constexpr int DTILES = HD / 8;
+    constexpr int CHUNKS = HD / 8;                // 16B chunks per row
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * ATT_BM;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+
+    const __nv_bfloat16* qh_g = p.q_hi + (int64_t)b * p.q_bs + (int64_t)h * p.q_hs;
+    const __nv_bfloat16* ql_g = PREC == 3 ? p.q_lo + (int64_t)b * p.q_bs + (int64_t)h * p.q_hs : nullptr;
+    const __nv_bfloat16* kv_g[4];
+    int64_t kv_ts[4];
+    kv_g[0] = p.k_hi + (int64_t)b * p.k_bs + (int64_t)h * p.k_hs; kv_ts[0] = p.k_ts;
+    if (PREC == 3) {
+        kv_g[1] = p.k_lo + (int64_t)b * p.k_bs + (int64_t)h * p.k_hs; kv_ts[1] = p.k_ts;
+        kv_g[2] = p.v_hi + (int64_t)b * p.v_bs + (int64_t)h * p.v_hs; kv_ts[2] = p.v_ts;
+        kv_g[3] = p.v_lo + (int64_t)b * p.v_bs + (int64_t)h * p.v_hs; kv_ts[3] = p.v_ts;
+    } else {
+        kv_g[1] = p.v_hi + (int64_t)b * p.v_bs + (int64_t)h * p.v_hs; kv_ts[1] = p.v_ts;
+        kv_g[2] = kv_g[3] = nullptr; kv_ts[2] = kv_ts[3] = 0;
+    }
+    constexpr int VPL = PREC == 3 ? 2 : 1;  // index of the first V plane
+
+    auto load_tile = [&](int stage, int kv0) {
+        const uint32_t sb = smem_base + stage * STAGE;
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
+            for (int i = threadIdx.x; i < ATT_BN * CHUNKS; i += 128) {
+                const int r = i / CHUNKS, c = i - r * CHUNKS;
+                const int key = kv0 + r;
+                const bool ok = key < p.Tk;
+                const __nv_bfloat16* src = kv_g[pl] + (int64_t)(ok ? key : 0) * kv_ts[pl] + c * 8;
+                cp_async16(sb + pl * PLANE + r * ROWB + c * 16, src, ok ? 16 : 0);
+            }
+        }
+    };
+
+    // ---- stage Q (hi, lo) through the second stage buffer, pull A fragments into registers ----
+    {
+        const uint32_t sb = smem_base + STAGE;
+        for (int pl = 0; pl < (PREC == 3 ? 2 : 1); ++pl) {
+            const __nv_bfloat16* g = pl == 0 ? qh_g : ql_g;
+            for (int i = threadIdx.x; i < ATT_BM * CHUNKS; i += 128) {
+                const int r = i / CHUNKS, c = i - r * CHUNKS;
+                const int q = q0 + r;
+                const bool ok = q < p.Tq;
+                cp_async16(sb + pl * PLANE + r * ROWB + c * 16, g + (int64_t)(ok ? q : 0) * p.q_ts + c * 8, ok ? 16 : 0);
+            }
+        }
+        cp_async_commit();
+    }
+    load_tile(0, 0);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    uint32_t qa_hi[KSTEPS][4], qa_lo[PREC == 3 ? KSTEPS : 1][4];
+    {
+        const uint32_t sb = smem_base + STAGE;
+        const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int cb = (lane >> 4) * 16;  // bytes
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+            ldsm_x4(sb + r * ROWB + kk * 32 + cb, qa_hi[kk][0], qa_hi[kk][1], qa_hi[kk][2], qa_hi[kk][3]);
+            if (PREC == 3)
+                ldsm_x4(sb + PLANE + r * ROWB + kk * 32 + cb, qa_lo[kk][0], qa_lo[kk][1], qa_lo[kk][2], qa_lo[kk][3]);
+        }
+    }
+    __syncthreads();
+
+    float o[DTILES][4];
+#pragma unroll
+    for (int j = 0; j < DTILES; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    const int qrow[2] = {q0 + warp * 16 + (lane >> 2), q0 + warp * 16 + (lane >> 2) + 8};
+    const bool has_rel = p.rel_h != nullptr;
+    const float* relh_r[2] = {nullptr, nullptr};
+    const float* relw_r[2] = {nullptr, nullptr};
+    if (has_rel) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int qq = min(qrow[i], p.Tq - 1);
+            relh_r[i] = p.rel_h + (((int64_t)b * p.H + h) * p.Tq + qq) * p.kh;
+            relw_r[i] = p.rel_w + (((int64_t)b * p.H + h) * p.Tq + qq) * p.kw;
+        }
+    }
+    const float* kb = p.key_bias ? p.key_bias + (int64_t)b * p.Tk : nullptr;
+    constexpr float LOG2E = 1.4426950408889634f;
+
+    const int ntiles = (p.Tk + ATT_BN - 1) / ATT_BN;
+    for (int t = 0; t < ntiles; ++t) {
+        const int kv0 = t * ATT_BN;
+        if (t + 1 < ntiles) load_tile((t + 1) & 1, kv0 + ATT_BN);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const uint32_t sb = smem_base + (t & 1) * STAGE;
+
+        // ---- S = Q K^T ----
+        float s[ATT_BN / 8][4];
+#pragma unroll
+        for (int j = 0; j < ATT_BN / 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        {
+            const int key_l = (lane & 7) + (lane >> 4) * 8;
+            const int cb = ((lane >> 3) & 1) * 16;
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+#pragma unroll
+                for (int j = 0; j < ATT_BN / 8; j += 2) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4(sb + (j * 8 + key_l) * ROWB + kk * 32 + cb, b0, b1, b2, b3);
+                    mma_bf16(s[j], qa_hi[kk], b0, b1);
+                    mma_bf16(s[j + 1], qa_hi[kk], b2, b3);
+                    if (PREC == 3) {
+                        mma_bf16(s[j], qa_lo[kk], b0, b1);
+                        mma_bf16(s[j + 1], qa_lo[kk], b2, b3);
+                        uint32_t c0, c1, c2, c3;
+                        ldsm_x4(sb + PLANE + (j * 8 + key_l) * ROWB + kk * 32 + cb, c0, c1, c2, c3);
+                        mma_bf16(s[j], qa_hi[kk], c0, c1);
+                        mma_bf16(s[j + 1], qa_hi[kk], c2, c3);
+                    }
+                }
+            }
+        }
+        // ---- scale + bias + mask, online softmax ----
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < ATT_BN / 8; ++j) {
+            const int key = kv0 + j * 8 + (lane & 3) * 2;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int kk = key + e;
+                const bool ok = kk < p.Tk;
+                float add0 = 0.f, add1 = 0.f;
+                if (ok) {
+                    if (has_rel) {
+                        const int khi = kk / p.kw, kwi = kk - khi * p.kw;
+                        add0 = __ldg(relh_r[0] + khi) + __ldg(relw_r[0] + kwi);
+                        add1 = __ldg(relh_r[1] + khi) + __ldg(relw_r[1] + kwi);
+                    }
+                    if (kb) { const float kbv = __ldg(kb + kk); add0 += kbv; add1 += kbv; }
+                }
+                s[j][e] = ok ? s[j][e] * p.scale + add0 : -INFINITY;
+                s[j][2 + e] = ok ? s[j][2 + e] * p.scale + add1 : -INFINITY;
+                mx[0] = fmaxf(mx[0], s[j][e]);
+                mx[1] = fmaxf(mx[1], s[j][2 + e]);
+            }
+        }
+        float corr[2], msafe[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+            mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+            const float mnew = fmaxf(m_run[i], mx[i]);
+            msafe[i] = mnew == -INFINITY ? 0.f : mnew;
+            corr[i] = exp2f((m_run[i] - msafe[i]) * LOG2E);  // m_run = -inf -> 0
+            m_run[i] = mnew;
+            l_run[i] *= corr[i];
+        }
+#pragma unroll
+        for (int j = 0; j < DTILES; ++j) {
+            o[j][0] *= corr[0]; o[j][1] *= corr[0];
+            o[j][2] *= corr[1]; o[j][3] *= corr[1];
+        }
+        uint32_t pa_hi[ATT_BN / 16][4], pa_lo[PREC == 3 ? ATT_BN / 16 : 1][4];
+#pragma unroll
+        for (int j = 0; j < ATT_BN / 8; ++j) {
+            const float p0 = exp2f((s[j][0] - msafe[0]) * LOG2E), p1 = exp2f((s[j][1] - msafe[0]) * LOG2E);
+            const float p2 = exp2f((s[j][2] - msafe[1]) * LOG2E), p3 = exp2f((s[j][3] - msafe[1]) * LOG2E);
+            l_run[0] += p0 + p1;
+            l_run[1] += p2 + p3;
+            const int kk = j >> 1, half = (j & 1) * 2;
+            if (PREC == 3) {
+                split2(p0, p1, pa_hi[kk][half], pa_lo[kk][half]);
+                split2(p2, p3, pa_hi[kk][half + 1], pa_lo[kk][half + 1]);
+            } else {
+                pa_hi[kk][half] = pack_bf16x2(p0, p1);
+                pa_hi[kk][half + 1] = pack_bf16x2(p2, p3);
+            }
+        }
+        // ---- O += P V ----
+        {
+            const int key_l = (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int cb = (lane >> 4) * 16;
+#pragma unroll
+            for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+#pragma unroll
+                for (int j = 0; j < DTILES; j += 2) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4_t(sb + VPL * PLANE + (kk * 16 + key_l) * ROWB + j * 16 + cb, b0, b1, b2, b3);
+                    mma_bf16(o[j], pa_hi[kk], b0, b1);
+                    mma_bf16(o[j + 1], pa_hi[kk], b2, b3);
+                    if (PREC == 3) {
+                        mma_bf16(o[j], pa_lo[kk], b0, b1);
+                        mma_bf16(o[j + 1], pa_lo[kk], b2, b3);
+                        uint32_t c0, c1, c2, c3;
+                        ldsm_x4_t(sb + (VPL + 1) * PLANE + (kk * 16 + key_l) * ROWB + j * 16 + cb, c0, c1, c2, c3);
+                        mma_bf16(o[j], pa_hi[kk], c0, c1);
+                        mma_bf16(o[j + 1], pa_hi[kk], c2, c3);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // everyone done with this stage before it is refilled
+    }
+    cp_async_wait<0>();
+
+    // ---- finalise ----
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        l_run[i] += __shfl_xor_sync(0xffffffffu, l_run[i], 1);
+        l_run[i] += __shfl_xor_sync(0xffffffffu, l_run[i], 2);
+    }
+    const float inv[2] = {l_run[0] > 0.f ? 1.f / l_run[0] : 0.f, l_run[1] > 0.f ? 1.f / l_run[1] : 0.f};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        if (qrow[i] >= p.Tq) continue;
+        const int64_t base = (int64_t)b * p.o_bs + (int64_t)qrow[i] * p.o_ts + (int64_t)h * HD + (lane & 3) * 2;
+#pragma unroll
+        for (int j = 0; j < DTILES; ++j) {
+            const float a = o[j][2 * i] * inv[i], c = o[j][2 * i + 1] * inv[i];
+            if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + base + j * 8) = make_float2(a, c);
+            if (p.out_hi) {
+                uint32_t hi, lo;
+                split2(a, c, hi, lo);
+                *reinterpret_cast<uint32_t*>(p.out_hi + base + j * 8) = hi;
+                if (p.out_lo) *reinterpret_cast<uint32_t*>(p.out_lo + base + j * 8) = lo;
+            }
+        }
+    }
+}
+
+// rel[b,h,q,j] = sum_c q[b,q,h,c] * Rt[coord(q)][c][j]   (Rt pre-transposed: (qsize, hd, ksize))
+// one warp per (b, h, q); lanes over j.
+__global__ void __launch_bounds__(256)
+relpos_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __restrict__ q_lo, int64_t q_bs,
+              int64_t q_ts, int64_t q_hs, const float* __restrict__ Rt, int axis, int qh, int qw, int ksize,
+              float* __restrict__ rel, int B, int H, int hd) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int T = qh * qw;
+    if (w >= (int64_t)B * H * T) return;
+    const int q = (int)(w % T);
+    const int h = (int)((w / T) % H);
+    const int b = (int)(w / ((int64_t)T * H));
+    const int coord = axis == 0 ? q / qw : q % qw;
+    const __nv_bfloat16* qp = q_hi + (int64_t)b * q_bs + (int64_t)q * q_ts + (int64_t)h * q_hs;
+    const __nv_bfloat16* ql = q_lo ? q_lo + (int64_t)b * q_bs + (int64_t)q * q_ts + (int64_t)h * q_hs : nullptr;
+    // lane c holds q[c], q[c+32], q[c+64], q[c+96]
+    float qv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = lane + 32 * i;
+        qv[i] = c < hd ? __bfloat162float(qp[c]) + (ql ? __bfloat162float(ql[c]) : 0.f) : 0.f;
+    }
+    const float* Rb = Rt + (int64_t)coord * hd * ksize;
+    for (int j0 = 0; j0 < ksize; j0 += 32) {
+        const int j = j0 + lane;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int cmax = min(32, hd - 32 * i);
+            for (int cc = 0; cc < cmax; ++cc) {
+                const float qc = __shfl_sync(0xffffffffu, qv[i], cc);
+                if (j < ksize) acc += qc * __ldg(Rb + (int64_t)(32 * i + cc) * ksize + j);
+            }
+        }
+        if (j < ksize) rel[w * ksize + j] = acc;
+    }
+}
+
+template <int HD, int PREC>
+static int launch_attn(const AttnParams& p, cudaStream_t st) {
+    constexpr int ROWB = HD * 2 + 16;
+    constexpr int SMEM = 2 * (PREC == 3 ? 4 : 2) * ATT_BN * ROWB;
+    static bool attr = false;
+    if (!attr) {
+        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<HD, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr = true;
+    }
+    dim3 grid((p.Tq + ATT_BM - 1) / ATT_BM, p.H, p.B);
+    attention_kernel<HD, PREC><<<grid, 128, SMEM, st>>>(p);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+}  // namespace hipie
+
+using namespace hipie;
+
+extern "C" int hipie_attention(const hipie_attn_args* a, void* stream) {
+    HIPIE_CHECK_ARG(a, "hipie_attention: null args");
+    HIPIE_CHECK_ARG(a->q_hi && a->k_hi && a->v_hi, "hipie_attention: q/k/v hi planes required");
+    HIPIE_CHECK_ARG(a->prec == 1 || (a->prec == 3 && a->q_lo && a->k_lo && a->v_lo), "hipie_attention: prec/lo planes mismatch");
+    HIPIE_CHECK_ARG(a->out_f32 || a->out_hi, "hipie_attention: no output requested");
+    HIPIE_CHECK_ARG(a->B > 0 && a->H > 0 && a->Tq > 0 && a->Tk > 0, "hipie_attention: bad sizes");
+    HIPIE_CHECK_ARG((a->rel_h == nullptr) == (a->rel_w == nullptr), "hipie_attention: rel_h and rel_w go together");
+    HIPIE_CHECK_ARG(!a->rel_h || (a->kh > 0 && a->kw > 0 && a->kh * a->kw == a->Tk), "hipie_attention: kh*kw must equal Tk");
+    HIPIE_CHECK_ARG(a->q_ts % 8 == 0 && a->k_ts % 8 == 0 && a->v_ts % 8 == 0 && a->q_hs % 8 == 0 && a->k_hs % 8 == 0 &&
+                        a->v_hs % 8 == 0 && a->q_bs % 8 == 0 && a->k_bs % 8 == 0 && a->v_bs % 8 == 0,
+                    "hipie_attention: strides must be multiples of 8 elements (16 bytes)");
+    AttnParams p;
+    p.q_hi = (const __nv_bfloat16*)a->q_hi; p.q_lo = (const __nv_bfloat16*)a->q_lo;
+    p.k_hi = (const __nv_bfloat16*)a->k_hi; p.k_lo = (const __nv_bfloat16*)a->k_lo;
+    p.v_hi = (const __nv_bfloat16*)a->v_hi; p.v_lo = (const __nv_bfloat16*)a->v_lo;
+    p.q_bs = a->q_bs; p.q_ts = a->q_ts; p.q_hs = a->q_hs;
+    p.k_bs = a->k_bs; p.k_ts = a->k_ts; p.k_hs = a->k_hs;
+    p.v_bs = a->v_bs; p.v_ts = a->v_ts; p.v_hs = a->v_hs;
+    p.rel_h = a->rel_h; p.rel_w = a->rel_w; p.kh = a->kh; p.kw = a->kw;
+    p.key_bias = a->key_bias;
+    p.out_f32 = a->out_f32; p.out_hi = (__nv_bfloat16*)a->out_hi; p.out_lo = (__nv_bfloat16*)a->out_lo;
+    p.o_bs = a->o_bs; p.o_ts = a->o_ts;
+    p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk; p.scale = a->scale;
+    cudaStream_t st = (cudaStream_t)stream;
+#define HIPIE_ATT(HDV)                                                              \
+    if (a->hd == HDV) return a->prec == 3 ? launch_attn<HDV, 3>(p, st) : launch_attn<HDV, 1>(p, st)
+    HIPIE_ATT(32);
+    HIPIE_ATT(64);
+    HIPIE_ATT(80);
+#undef HIPIE_ATT
+    set_error("hipie_attention: unsupported head dim %d (supported: 32, 64, 80)", a->hd);
+    return HIPIE_EUNSUPPORTED;
+}
+
+extern "C" int hipie_relpos_bias(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int64_t q_hs,
+                                 const float* table_t, int axis, int qh, int qw, int ksize, float* rel, int B, int H,
+                                 int hd, void* stream) {
+    HIPIE_CHECK_ARG(q_hi && table_t && rel, "hipie_relpos_bias: null pointer");
+    HIPIE_CHECK_ARG(hd <= 128 && (axis == 0 || axis == 1), "hipie_relpos_bias: hd <= 128, axis in {0,1}");
+    const int64_t warps = (int64_t)B * H * qh * qw;
+    if (warps == 0) return HIPIE_OK;
+    relpos_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)q_hi, (const __nv_bfloat16*)q_lo, q_bs, q_ts, q_hs, table_t, axis, qh, qw, ksize, rel, B, H, hd);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}

@@ -1,0 +1,96 @@
+// Shared host/device helpers for the hipie_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/hipie_b200.h"
+
+namespace hipie {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launch_count;
+
+inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+#define HIPIE_CHECK_ARG(cond, ...)                \
+    do {                                          \
+        if (!(cond)) {                            \
+            ::hipie::set_error(__VA_ARGS__);      \
+            return HIPIE_EINVAL;                  \
+        }                                         \
+    } while (0)
+
+#define HIPIE_CHECK_CUDA(expr)                                                              \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ::hipie::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                               __FILE__, __LINE__);                                         \
+            return HIPIE_ECUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+#define HIPIE_CHECK_LAUNCH()                                                                \
+    do {                                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                \
+        if (_e != cudaSuccess) {                                                            \
+            ::hipie::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),  \
+                               __FILE__, __LINE__);                                         \
+            return HIPIE_ECUDA;                                                             \
+        }                                                                                   \
+        ::hipie::count_launch();                                                            \
+    } while (0)
+
+static inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ---- device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float bf16_round(float x) {
+    return __bfloat162float(__float2bfloat16_rn(x));
+}
+
+// hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+    __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+    __nv_bfloat162 h(ah, bh), l(al, bl);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace hipie

@@ -1,0 +1,437 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:
+//   C[b] = epilogue( alpha * A[b] . W[b]^T )      A: (M,K) bf16 K-major,  W: (N,K) bf16 K-major
+//
+// This one kernel carries every dense contraction of the hot path: the ViT-H qkv / proj / fc1 /
+// fc2 linears (/root/reference/projects/HIPIE/hipie/backbone/vit.py:67-83,212-230), the DETR /
+// MaskDINO / BERT linears, convolutions lowered to GEMM, and the MaskDINO mask-embed contraction
+// einsum("bqc,bchw->bqhw") (.../maskdino/transformer_decoder/maskdino_decoder.py:520-529) with the
+// sigmoid-threshold fused as a bit-packed output.
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles of A / W into a 4-stage 128B/64B-swizzled
+//               shared-memory ring, completion on mbarriers (expect_tx)
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a
+//               double-buffered fp32 accumulator in tensor memory; tcgen05.commit releases the
+//               smem stage / publishes the accumulator
+//   warps 2-5   epilogue: tcgen05.ld the accumulator (32 lanes x 32 columns per warp), transpose
+//               through padded smem so global stores are row-contiguous, fused bias / activation /
+//               layer-scale / residual / fp32 + bf16-split + bit-packed outputs
+//
+// Precision: operands are bf16 "split" planes.  prec==1 uses hi only; prec==3 computes
+// Ahi.Whi + Ahi.Wlo + Alo.Whi in the same fp32 TMEM accumulator (error ~2^-16 relative, i.e.
+// fp32-class results from the bf16 tensor pipe), loading 4 tiles per 3 MMAs per k-block.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <mutex>
+#include <unordered_map>
+#include <string.h>
+
+namespace hipie {
+using namespace ptx;
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_STAGES = 4;
+constexpr int EPI_LD = 36;  // padded row length (floats) of the epilogue transpose buffer
+
+struct GemmParams {
+    const float* bias;
+    const float* colscale;
+    const float* residual;
+    int64_t ldr, r_bstride;
+    float* c_f32;
+    __nv_bfloat16* c_hi;
+    __nv_bfloat16* c_lo;
+    int64_t ldc, c_bstride;
+    uint32_t* c_bits;
+    float bits_threshold;
+    int M, N, K, batch;
+    int act;
+    float alpha;
+    int transposed;  // 1: C stored as [N, ldc] (column-major output), lanes = rows
+    int tiles_m, tiles_n;
+    const int* row_map;
+};
+
+template <int PREC, int BN>
+struct GemmCfg {
+    static constexpr int BK = PREC == 3 ? 32 : 64;          // elements; BK*2 bytes == swizzle span
+    static constexpr int SWZ = BK * 2;
+    static constexpr int A_TILE = GEMM_BM * BK * 2;          // bytes
+    static constexpr int W_TILE = BN * BK * 2;
+    static constexpr int NPLANES = PREC == 3 ? 2 : 1;
+    static constexpr int STAGE = NPLANES * (A_TILE + W_TILE);
+    static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+    static constexpr int SMEM = GEMM_STAGES * STAGE + EPI_BYTES + 256 + 1024;
+    static constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : (2 * BN >= 128 ? 128 : 64));
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == HIPIE_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == HIPIE_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    if (act == HIPIE_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    return v;
+}
+
+template <int PREC, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+               const GemmParams p) {
+    using Cfg = GemmCfg<PREC, BN>;
+    constexpr int BK = Cfg::BK;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    float* epi = reinterpret_cast<float*>(smem + GEMM_STAGES * Cfg::STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * Cfg::STAGE + Cfg::EPI_BYTES);
+    uint64_t* full_bar = bars;                     // [STAGES]
+    uint64_t* empty_bar = bars + GEMM_STAGES;      // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * GEMM_STAGES;  // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_kb = (p.K + BK - 1) / BK;
+    const int tiles_per_batch = p.tiles_m * p.tiles_n;
+    const int total_tiles = tiles_per_batch * p.batch;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_a_hi);
+        prefetch_tmap(&tm_w_hi);
+        if (PREC == 3) {
+            prefetch_tmap(&tm_a_lo);
+            prefetch_tmap(&tm_w_lo);
+        }
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < GEMM_STAGES; ++i) {
+                mbar_init(&full_bar[i], 1);
+                mbar_init(&empty_bar[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&tfull_bar[i], 1);
+                mbar_init(&tempty_bar[i], 4);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int b = t / tiles_per_batch;
+                const int r = t - b * tiles_per_batch;
+                const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+                const int m0 = mt * GEMM_BM, n0 = nt * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = stage_base + s * Cfg::STAGE;
+                    mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
+                    const int k0 = kb * BK;
+                    tma_load_3d(st, &tm_a_hi, &full_bar[s], k0, m0, b);
+                    tma_load_3d(st + Cfg::A_TILE, &tm_w_hi, &full_bar[s], k0, n0, b);
+                    if (PREC == 3) {
+                        tma_load_3d(st + Cfg::A_TILE + Cfg::W_TILE, &tm_a_lo, &full_bar[s], k0, m0, b);
+                        tma_load_3d(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tm_w_lo, &full_bar[s], k0, n0, b);
+                    }
+                    if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+        int s = 0;
+        uint32_t ph = 0;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st = smem_u32(stage_base + s * Cfg::STAGE);
+                    const uint64_t a_hi = make_kmajor_desc<Cfg::SWZ>(st);
+                    const uint64_t w_hi = make_kmajor_desc<Cfg::SWZ>(st + Cfg::A_TILE);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in addr>>4 units
+                        umma_f16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    if (PREC == 3) {
+                        const uint64_t a_lo = make_kmajor_desc<Cfg::SWZ>(st + Cfg::A_TILE + Cfg::W_TILE);
+                        const uint64_t w_lo = make_kmajor_desc<Cfg::SWZ>(st + 2 * Cfg::A_TILE + Cfg::W_TILE);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, w_hi + 2 * k, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);                       // smem stage free when MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator ready
+                }
+                __syncwarp();
+                if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        float* my_epi = epi + (warp - 2) * 32 * EPI_LD;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int b = t / tiles_per_batch;
+            const int r = t - b * tiles_per_batch;
+            const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+            const int m0 = mt * GEMM_BM + quarter * 32, n0 = nt * BN;
+            mbar_wait(&tfull_bar[acc], acc_ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+            const float* res_b = p.residual ? p.residual + (int64_t)b * p.r_bstride : nullptr;
+            float* cf_b = p.c_f32 ? p.c_f32 + (int64_t)b * p.c_bstride : nullptr;
+            __nv_bfloat16* chi_b = p.c_hi ? p.c_hi + (int64_t)b * p.c_bstride : nullptr;
+            __nv_bfloat16* clo_b = p.c_lo ? p.c_lo + (int64_t)b * p.c_bstride : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int nbase = n0 + c * 32;
+                if (nbase >= p.N) break;  // warp-uniform
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, v);
+                tmem_ld_wait();
+                if (p.transposed) {
+                    // lanes = 32 consecutive rows (m); register j = column nbase + j
+                    const int row = m0 + lane;
+                    const bool rok = row < p.M;
+                    uint32_t bitsword = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = nbase + j;
+                        if (col < p.N) {
+                            float x = __uint_as_float(v[j]) * p.alpha;
+                            if (p.bias) x += __ldg(p.bias + col);
+                            x = act_apply(x, p.act);
+                            if (p.colscale) x *= __ldg(p.colscale + col);
+                            const int64_t off = (int64_t)col * p.ldc + row;
+                            if (res_b && rok) x += res_b[(int64_t)col * p.ldr + row];
+                            if (rok) {
+                                if (cf_b) cf_b[off] = x;
+                                if (chi_b) {
+                                    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                                    chi_b[off] = h;
+                                    if (clo_b) clo_b[off] = __float2bfloat16_rn(x - __bfloat162float(h));
+                                }
+                            }
+                            if (p.c_bits) {
+                                const uint32_t word = __ballot_sync(0xffffffffu, rok && x > p.bits_threshold);
+                                if (lane == j) bitsword = word;
+                            }
+                        }
+                    }
+                    if (p.c_bits) {
+                        const int col = nbase + lane;
+                        // bits packed along M: word index = row / 32 (M tile rows are 32-aligned)
+                        if (col < p.N && m0 < p.M) {
+                            const int64_t words_per_col = (p.M + 31) / 32;
+                            p.c_bits[((int64_t)b * p.N + col) * words_per_col + (m0 >> 5)] = bitsword;
+                        }
+                    }
+                } else {
+                    // transpose through smem: thread (row) writes 32 columns, then lanes = columns
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<uint4*>(my_epi + lane * EPI_LD + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    __syncwarp();
+                    const int col = nbase + lane;
+                    const bool cok = col < p.N;
+                    const float bias = (p.bias && cok) ? __ldg(p.bias + col) : 0.f;
+                    const float cs = (p.colscale && cok) ? __ldg(p.colscale + col) : 1.f;
+                    const int rmax = min(32, p.M - m0);
+#pragma unroll 4
+                    for (int rr = 0; rr < rmax; ++rr) {
+                        float x = my_epi[rr * EPI_LD + lane] * p.alpha + bias;
+                        x = act_apply(x, p.act) * cs;
+                        int64_t row = m0 + rr;
+                        if (p.row_map) row = p.row_map[(int64_t)b * p.M + row];
+                        if (cok && row >= 0) {
+                            if (res_b) x += res_b[row * p.ldr + col];
+                            const int64_t off = row * p.ldc + col;
+                            if (cf_b) cf_b[off] = x;
+                            if (chi_b) {
+                                const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                                chi_b[off] = h;
+                                if (clo_b) clo_b[off] = __float2bfloat16_rn(x - __bfloat162float(h));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor-map construction (driver entry point fetched through the runtime) + launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    });
+    return fn;
+}
+
+struct TmapKey {
+    const void* ptr;
+    int64_t rows, cols, ld, bstride;
+    int batch, box_rows, box_cols;
+    bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+        uint64_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+
+// bf16 matrix (batch, rows, cols) with row stride ld and batch stride bstride (elements);
+// box = (box_cols along K, box_rows, 1); swizzle span == box_cols*2 bytes.
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int batch,
+                   int64_t bstride, int box_rows, int box_cols) {
+    static std::mutex mu;
+    static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    TmapKey key;
+    memset(&key, 0, sizeof(key));
+    key.ptr = ptr; key.rows = rows; key.cols = cols; key.ld = ld; key.bstride = bstride;
+    key.batch = batch; key.box_rows = box_rows; key.box_cols = box_cols;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return HIPIE_OK; }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return HIPIE_ECUDA; }
+    HIPIE_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map base %p not 16B aligned", ptr);
+    HIPIE_CHECK_ARG((ld * 2) % 16 == 0, "row stride %lld elements is not a multiple of 8", (long long)ld);
+    HIPIE_CHECK_ARG(batch == 1 || (bstride * 2) % 16 == 0, "batch stride must be a multiple of 8 elements");
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? bstride : rows * ld) * 2};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMapSwizzle swz = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                             : (box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld cols=%lld ld=%lld batch=%d", (int)r, ptr,
+                  (long long)rows, (long long)cols, (long long)ld, batch);
+        return HIPIE_ECUDA;
+    }
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (cache.size() > 4096) cache.clear();
+        cache.emplace(key, *out);
+    }
+    return HIPIE_OK;
+}
+
+template <int PREC, int BN>
+static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
+    using Cfg = GemmCfg<PREC, BN>;
+    CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+    int rc;
+    if ((rc = make_tmap_bf16(&ta_hi, a->a_hi, a->M, a->K, a->lda, a->batch, a->a_bstride, GEMM_BM, Cfg::BK))) return rc;
+    if ((rc = make_tmap_bf16(&tw_hi, a->w_hi, a->N, a->K, a->ldw, a->batch, a->w_bstride, BN, Cfg::BK))) return rc;
+    if (PREC == 3) {
+        if ((rc = make_tmap_bf16(&ta_lo, a->a_lo, a->M, a->K, a->lda, a->batch, a->a_bstride, GEMM_BM, Cfg::BK))) return rc;
+        if ((rc = make_tmap_bf16(&tw_lo, a->w_lo, a->N, a->K, a->ldw, a->batch, a->w_bstride, BN, Cfg::BK))) return rc;
+    } else {
+        ta_lo = ta_hi;
+        tw_lo = tw_hi;
+    }
+    GemmParams p;
+    p.bias = a->bias; p.colscale = a->colscale; p.residual = a->residual;
+    p.ldr = a->ldr; p.r_bstride = a->r_bstride;
+    p.c_f32 = a->c_f32; p.c_hi = (__nv_bfloat16*)a->c_hi; p.c_lo = (__nv_bfloat16*)a->c_lo;
+    p.ldc = a->ldc; p.c_bstride = a->c_bstride;
+    p.c_bits = a->c_bits; p.bits_threshold = a->bits_threshold;
+    p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
+    p.act = a->act; p.alpha = a->alpha;
+    p.transposed = a->transposed;
+    p.row_map = a->c_row_map;
+    p.tiles_m = (a->M + GEMM_BM - 1) / GEMM_BM;
+    p.tiles_n = (a->N + BN - 1) / BN;
+    const int64_t total = (int64_t)p.tiles_m * p.tiles_n * a->batch;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PREC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_set = true;
+    }
+    const int grid = (int)(total < num_sms() ? total : num_sms());
+    gemm_tc_kernel<PREC, BN><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+}  // namespace hipie
+
+using namespace hipie;
+
+extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
+    HIPIE_CHECK_ARG(a != nullptr, "hipie_gemm: null args");
+    HIPIE_CHECK_ARG(a->a_hi && a->w_hi, "hipie_gemm: a_hi / w_hi required");
+    HIPIE_CHECK_ARG(a->prec == 1 || a->prec == 3, "hipie_gemm: prec must be 1 or 3 (got %d)", a->prec);
+    HIPIE_CHECK_ARG(a->prec == 1 || (a->a_lo && a->w_lo), "hipie_gemm: prec 3 needs a_lo and w_lo");
+    HIPIE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "hipie_gemm: bad sizes M=%d N=%d K=%d batch=%d",
+                    a->M, a->N, a->K, a->batch);
+    HIPIE_CHECK_ARG(a->K % 8 == 0, "hipie_gemm: K (%d) must be a multiple of 8", a->K);
+    HIPIE_CHECK_ARG(a->c_f32 || a->c_hi || a->c_bits, "hipie_gemm: no output requested");
+    HIPIE_CHECK_ARG(!a->c_bits || a->transposed, "hipie_gemm: bit-packed output requires transposed=1");
+    HIPIE_CHECK_ARG(!a->c_lo || a->c_hi, "hipie_gemm: c_lo requires c_hi");
+    HIPIE_CHECK_ARG(!a->c_row_map || !a->transposed, "hipie_gemm: c_row_map is not supported with transposed=1");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->N <= 64) return a->prec == 3 ? launch_gemm<3, 64>(a, st) : launch_gemm<1, 64>(a, st);
+    if (a->N <= 128) return a->prec == 3 ? launch_gemm<3, 128>(a, st) : launch_gemm<1, 128>(a, st);
+    return a->prec == 3 ? launch_gemm<3, 256>(a, st) : launch_gemm<1, 256>(a, st);
+}

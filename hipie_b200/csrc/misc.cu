@@ -1,0 +1,367 @@
+// Memory-bound helper kernels of the hot path: bf16 splitting, patch extraction, NHWC im2col,
+// pixel shuffle for the 2x2 transposed convolutions, 2x2 max-pool, masked row softmax for the
+// VL-fusion scores, and the fused CondInst dynamic mask head.
+#include "common.cuh"
+
+namespace hipie {
+
+// ---- fp32 -> bf16 hi/lo, optional second addend ---------------------------------------------
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ sum_f32,
+             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(a)[i];
+        if (b) {
+            const float4 w = reinterpret_cast<const float4*>(b)[i];
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        if (sum_f32) reinterpret_cast<float4*>(sum_f32)[i] = v;
+        if (hi) {
+            uint2 h, l;
+            split2(v.x, v.y, h.x, l.x);
+            split2(v.z, v.w, h.y, l.y);
+            reinterpret_cast<uint2*>(hi)[i] = h;
+            if (lo) reinterpret_cast<uint2*>(lo)[i] = l;
+        }
+    }
+}
+
+// ---- patch extraction (PatchEmbed conv k=16,s=16 as a GEMM; utils.py:160-186) fused with the
+//      pixel normalisation (hipie_img.py:880-898).  img (B,3,H,W) raw fp32; rows (B*hp*wp, 3*P*P)
+//      in (c, py, px) column order == conv weight.view(out, -1).
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                int B, int H, int W, int P, float m0, float m1, float m2, float s0, float s1, float s2) {
+    const int hp = H / P, wp = W / P;
+    const int K = 3 * P * P;
+    const int64_t total = (int64_t)B * hp * wp * K / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i * 4;
+        const int col = (int)(e % K);
+        const int64_t row = e / K;
+        const int px = col % P, py = (col / P) % P, c = col / (P * P);
+        const int tx = (int)(row % wp), ty = (int)((row / wp) % hp), b = (int)(row / ((int64_t)wp * hp));
+        const float4 v = *reinterpret_cast<const float4*>(img + (((int64_t)b * 3 + c) * H + ty * P + py) * W + tx * P + px);
+        const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+        const float istd = 1.f / (c == 0 ? s0 : (c == 1 ? s1 : s2));
+        uint2 h, l;
+        split2((v.x - mean) * istd, (v.y - mean) * istd, h.x, l.x);
+        split2((v.z - mean) * istd, (v.w - mean) * istd, h.y, l.y);
+        *reinterpret_cast<uint2*>(hi + e) = h;
+        if (lo) *reinterpret_cast<uint2*>(lo + e) = l;
+    }
+}
+
+// ---- NHWC im2col for k x k convs (pad, stride): rows (B*Ho*Wo, k*k*C), column order (ky,kx,c)
+__global__ void __launch_bounds__(256)
+im2col_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                   int B, int H, int W, int C, int ksz, int stride, int pad, int Ho, int Wo) {
+    const int K = ksz * ksz * C;
+    const int64_t total = (int64_t)B * Ho * Wo * K / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i * 4;
+        const int col = (int)(e % K);
+        const int64_t row = e / K;
+        const int c = col % C, kx = (col / C) % ksz, ky = col / (C * ksz);
+        const int ox = (int)(row % Wo), oy = (int)((row / Wo) % Ho), b = (int)(row / ((int64_t)Wo * Ho));
+        const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+            v = *reinterpret_cast<const float4*>(x + (((int64_t)b * H + iy) * W + ix) * C + c);
+        uint2 h, l;
+        split2(v.x, v.y, h.x, l.x);
+        split2(v.z, v.w, h.y, l.y);
+        *reinterpret_cast<uint2*>(hi + e) = h;
+        if (lo) *reinterpret_cast<uint2*>(lo + e) = l;
+    }
+}
+
+// ---- ConvTranspose2d(k=2,s=2) epilogue: GEMM output rows (B*H*W, 4*C) with column order
+//      (dy, dx, c) -> NHWC (B, 2H, 2W, C); optional bf16 split output.
+__global__ void __launch_bounds__(256)
+pixel_shuffle2_kernel(const float* __restrict__ g, float* __restrict__ y, __nv_bfloat16* __restrict__ hi,
+                      __nv_bfloat16* __restrict__ lo, int B, int H, int W, int C) {
+    const int64_t total = (int64_t)B * H * W * 4 * C / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i * 4;
+        const int c = (int)(e % C);
+        const int q = (int)((e / C) % 4);
+        const int64_t row = e / (4 * (int64_t)C);
+        const int x = (int)(row % W), yy = (int)((row / W) % H), b = (int)(row / ((int64_t)W * H));
+        const int dy = q >> 1, dx = q & 1;
+        const float4 v = *reinterpret_cast<const float4*>(g + e);
+        const int64_t o = ((((int64_t)b * 2 * H + 2 * yy + dy) * 2 * W) + 2 * x + dx) * C + c;
+        if (y) *reinterpret_cast<float4*>(y + o) = v;
+        if (hi) {
+            uint2 h, l;
+            split2(v.x, v.y, h.x, l.x);
+            split2(v.z, v.w, h.y, l.y);
+            *reinterpret_cast<uint2*>(hi + o) = h;
+            if (lo) *reinterpret_cast<uint2*>(lo + o) = l;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ hi,
+                     __nv_bfloat16* __restrict__ lo, int B, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2;
+    const int64_t total = (int64_t)B * Ho * Wo * C / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i * 4;
+        const int c = (int)(e % C);
+        const int64_t row = e / C;
+        const int ox = (int)(row % Wo), oy = (int)((row / Wo) % Ho), b = (int)(row / ((int64_t)Wo * Ho));
+        const float* p = x + (((int64_t)b * H + 2 * oy) * W + 2 * ox) * C + c;
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        const float4 bb = *reinterpret_cast<const float4*>(p + C);
+        const float4 cc = *reinterpret_cast<const float4*>(p + (int64_t)W * C);
+        const float4 d = *reinterpret_cast<const float4*>(p + (int64_t)W * C + C);
+        float4 v;
+        v.x = fmaxf(fmaxf(a.x, bb.x), fmaxf(cc.x, d.x));
+        v.y = fmaxf(fmaxf(a.y, bb.y), fmaxf(cc.y, d.y));
+        v.z = fmaxf(fmaxf(a.z, bb.z), fmaxf(cc.z, d.z));
+        v.w = fmaxf(fmaxf(a.w, bb.w), fmaxf(cc.w, d.w));
+        if (y) *reinterpret_cast<float4*>(y + e) = v;
+        if (hi) {
+            uint2 h, l;
+            split2(v.x, v.y, h.x, l.x);
+            split2(v.z, v.w, h.y, l.y);
+            *reinterpret_cast<uint2*>(hi + e) = h;
+            if (lo) *reinterpret_cast<uint2*>(lo + e) = l;
+        }
+    }
+}
+
+// ---- masked row softmax (BiMultiHeadAttention, fuse_helper.py:79-109) --------------------------
+// x (rows, n) fp32 -> p = softmax(clamp(x - (sub_rowmax ? rowmax : 0), +-clampv) + colbias[b, :])
+// written as bf16 hi/lo (operand of the following P.V GEMM).  One block per row.
+__global__ void __launch_bounds__(256)
+row_softmax_kernel(const float* __restrict__ x, const float* __restrict__ colbias, int64_t rows_per_batch,
+                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ p_f32,
+                   int n, float clampv, int sub_rowmax) {
+    __shared__ float red[8];
+    __shared__ float bc;
+    const int64_t row = blockIdx.x;
+    const float* xr = x + row * n;
+    const float* cb = colbias ? colbias + (row / rows_per_batch) * n : nullptr;
+    auto block_reduce = [&](float v, bool is_max) {
+        v = is_max ? warp_max(v) : warp_sum(v);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float r = red[0];
+            for (int i = 1; i < 8; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
+            bc = r;
+        }
+        __syncthreads();
+        const float r = bc;
+        __syncthreads();
+        return r;
+    };
+    float pre = 0.f;
+    if (sub_rowmax) {
+        float m = -INFINITY;
+        for (int c = threadIdx.x; c < n; c += 256) m = fmaxf(m, fminf(fmaxf(xr[c], -clampv), clampv));
+        pre = block_reduce(m, true);
+    }
+    auto val = [&](int c) {
+        float v = fminf(fmaxf(xr[c], -clampv), clampv);
+        if (sub_rowmax) v = fminf(fmaxf(v - pre, -clampv), clampv);
+        if (cb) v += cb[c];
+        return v;
+    };
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < n; c += 256) m = fmaxf(m, val(c));
+    m = block_reduce(m, true);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < n; c += 256) s += expf(val(c) - m);
+    s = block_reduce(s, false);
+    const float inv = 1.f / s;
+    for (int c = threadIdx.x; c < n; c += 256) {
+        const float pv = expf(val(c) - m) * inv;
+        if (p_f32) p_f32[row * n + c] = pv;
+        if (hi) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(pv);
+            hi[row * n + c] = h;
+            if (lo) lo[row * n + c] = __float2bfloat16_rn(pv - __bfloat162float(h));
+        }
+    }
+}
+
+// ---- CondInst dynamic mask head, fused (ddetrs_dn.py:1390-1502, 1806-1870) --------------------
+// feats (B, Hf*Wf, 8) NHWC fp32; params (B, Q, 169) = [w0 (8x10) | w1 (8x8) | w2 (1x8) | b0 8 | b1 8 | b2 1];
+// ref_px (B, Q, 2) reference point in pixels.  Per (b, q): 3-layer 1x1 MLP over
+// [ref - (grid*stride + stride/2), feats] at stride-8 resolution, then aligned_bilinear(x2):
+//   out[2i+a, 2j+b] with a,b in {0,1}: replicate-pad / align_corners arithmetic reduces to
+//   out[Y, X] = lerp of coarse[(Y-1)/2 ...] — evaluated exactly as the reference's pad+interpolate+pad.
+// One block per (q-chunk, b): coarse logits staged in shared memory (Hf*Wf <= 160*160).
+__global__ void __launch_bounds__(256)
+condinst_kernel(const float* __restrict__ feats, const float* __restrict__ params, const float* __restrict__ ref_px,
+                float* __restrict__ out, int B, int Q, int Hf, int Wf, int stride) {
+    extern __shared__ float coarse[];  // Hf*Wf
+    const int q = blockIdx.x, b = blockIdx.y;
+    __shared__ float prm[169];
+    __shared__ float ref[2];
+    for (int i = threadIdx.x; i < 169; i += blockDim.x) prm[i] = params[((int64_t)b * Q + q) * 169 + i];
+    if (threadIdx.x < 2) ref[threadIdx.x] = ref_px[((int64_t)b * Q + q) * 2 + threadIdx.x];
+    __syncthreads();
+    const float* w0 = prm;          // [8][10]
+    const float* w1 = prm + 80;     // [8][8]
+    const float* w2 = prm + 144;    // [8]
+    const float* b0 = prm + 152;
+    const float* b1 = prm + 160;
+    const float b2 = prm[168];
+    const int HW = Hf * Wf;
+    const float* fb = feats + (int64_t)b * HW * 8;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        const int y = i / Wf, x = i - y * Wf;
+        float in[10];
+        in[0] = ref[0] - (float)(x * stride + stride / 2);
+        in[1] = ref[1] - (float)(y * stride + stride / 2);
+        const float4 f0 = *reinterpret_cast<const float4*>(fb + (int64_t)i * 8);
+        const float4 f1 = *reinterpret_cast<const float4*>(fb + (int64_t)i * 8 + 4);
+        in[2] = f0.x; in[3] = f0.y; in[4] = f0.z; in[5] = f0.w;
+        in[6] = f1.x; in[7] = f1.y; in[8] = f1.z; in[9] = f1.w;
+        float h0[8], h1[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            float a = b0[o];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) a += w0[o * 10 + k] * in[k];
+            h0[o] = fmaxf(a, 0.f);
+        }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            float a = b1[o];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a += w1[o * 8 + k] * h0[k];
+            h1[o] = fmaxf(a, 0.f);
+        }
+        float a = b2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a += w2[k] * h1[k];
+        coarse[i] = a;
+    }
+    __syncthreads();
+    // aligned_bilinear(factor 2): pad right/bottom by replicate -> (Hf+1, Wf+1); interpolate with
+    // align_corners=True to (2Hf+1, 2Wf+1): sample position = Y/2 exactly; pad left/top by 1
+    // (replicate) and crop to (2Hf, 2Wf): out[Y, X] = up[max(Y-1,0), max(X-1,0)].
+    const int Ho = 2 * Hf, Wo = 2 * Wf;
+    float* ob = out + ((int64_t)b * Q + q) * Ho * Wo;
+    for (int i = threadIdx.x; i < Ho * Wo; i += blockDim.x) {
+        const int Y = i / Wo, X = i - Y * Wo;
+        const int uy = max(Y - 1, 0), ux = max(X - 1, 0);
+        const int y0 = uy >> 1, x0 = ux >> 1;
+        const float fy = (uy & 1) ? 0.5f : 0.f, fx = (ux & 1) ? 0.5f : 0.f;
+        const int y1 = min(y0 + 1, Hf - 1 + 1), x1 = min(x0 + 1, Wf - 1 + 1);
+        auto at = [&](int yy, int xx) { return coarse[min(yy, Hf - 1) * Wf + min(xx, Wf - 1)]; };
+        const float v00 = at(y0, x0), v01 = at(y0, x1), v10 = at(y1, x0), v11 = at(y1, x1);
+        const float top = v00 + (v01 - v00) * fx, bot = v10 + (v11 - v10) * fx;
+        ob[i] = top + (bot - top) * fy;
+    }
+}
+
+static inline int grid_for(int64_t n, int threads = 256) {
+    int64_t b = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace hipie
+
+using namespace hipie;
+
+extern "C" int hipie_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+    HIPIE_CHECK_ARG(x && hi, "hipie_split_bf16: null pointer");
+    HIPIE_CHECK_ARG(n % 4 == 0, "hipie_split_bf16: n must be a multiple of 4");
+    if (n == 0) return HIPIE_OK;
+    split_kernel<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(x, nullptr, nullptr, (__nv_bfloat16*)hi,
+                                                                   (__nv_bfloat16*)lo, n / 4);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+extern "C" int hipie_add_split(const float* a, const float* b, float* sum_f32, void* hi, void* lo, int64_t n,
+                               void* stream) {
+    HIPIE_CHECK_ARG(a && (sum_f32 || hi), "hipie_add_split: null pointer");
+    HIPIE_CHECK_ARG(n % 4 == 0, "hipie_add_split: n must be a multiple of 4");
+    if (n == 0) return HIPIE_OK;
+    split_kernel<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(a, b, sum_f32, (__nv_bfloat16*)hi,
+                                                                   (__nv_bfloat16*)lo, n / 4);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+extern "C" int hipie_patchify(const float* img, void* hi, void* lo, int B, int H, int W, int P, const float* mean3,
+                              const float* std3, void* stream) {
+    HIPIE_CHECK_ARG(img && hi && mean3 && std3, "hipie_patchify: null pointer");
+    HIPIE_CHECK_ARG(P % 4 == 0 && H % P == 0 && W % P == 0, "hipie_patchify: H, W must be multiples of P, P of 4");
+    const int64_t total = (int64_t)B * (H / P) * (W / P) * 3 * P * P / 4;
+    patchify_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, B, H,
+                                                                      W, P, mean3[0], mean3[1], mean3[2], std3[0],
+                                                                      std3[1], std3[2]);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+extern "C" int hipie_im2col_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int C, int ksz, int stride,
+                                 int pad, void* stream) {
+    HIPIE_CHECK_ARG(x && hi, "hipie_im2col_nhwc: null pointer");
+    HIPIE_CHECK_ARG(C % 4 == 0, "hipie_im2col_nhwc: C must be a multiple of 4");
+    const int Ho = (H + 2 * pad - ksz) / stride + 1, Wo = (W + 2 * pad - ksz) / stride + 1;
+    const int64_t total = (int64_t)B * Ho * Wo * ksz * ksz * C / 4;
+    im2col_nhwc_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, B,
+                                                                         H, W, C, ksz, stride, pad, Ho, Wo);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+extern "C" int hipie_pixel_shuffle2(const float* g, float* y, void* hi, void* lo, int B, int H, int W, int C,
+                                    void* stream) {
+    HIPIE_CHECK_ARG(g && (y || hi), "hipie_pixel_shuffle2: null pointer");
+    HIPIE_CHECK_ARG(C % 4 == 0, "hipie_pixel_shuffle2: C must be a multiple of 4");
+    const int64_t total = (int64_t)B * H * W * C;
+    pixel_shuffle2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(g, y, (__nv_bfloat16*)hi,
+                                                                            (__nv_bfloat16*)lo, B, H, W, C);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+extern "C" int hipie_maxpool2_nhwc(const float* x, float* y, void* hi, void* lo, int B, int H, int W, int C,
+                                   void* stream) {
+    HIPIE_CHECK_ARG(x && (y || hi), "hipie_maxpool2_nhwc: null pointer");
+    HIPIE_CHECK_ARG(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "hipie_maxpool2_nhwc: bad sizes");
+    const int64_t total = (int64_t)B * (H / 2) * (W / 2) * C / 4;
+    maxpool2_nhwc_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, y, (__nv_bfloat16*)hi,
+                                                                           (__nv_bfloat16*)lo, B, H, W, C);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+extern "C" int hipie_row_softmax(const float* x, const float* colbias, int64_t rows, int64_t rows_per_batch, int n,
+                                 float clampv, int sub_rowmax, void* hi, void* lo, float* p_f32, void* stream) {
+    HIPIE_CHECK_ARG(x && (hi || p_f32), "hipie_row_softmax: null pointer");
+    HIPIE_CHECK_ARG(rows >= 0 && n > 0 && rows_per_batch > 0, "hipie_row_softmax: bad sizes");
+    if (rows == 0) return HIPIE_OK;
+    row_softmax_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, colbias, rows_per_batch, (__nv_bfloat16*)hi,
+                                                                        (__nv_bfloat16*)lo, p_f32, n, clampv, sub_rowmax);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+extern "C" int hipie_condinst_masks(const float* feats, const float* params, const float* ref_px, float* out, int B,
+                                    int Q, int Hf, int Wf, int stride, void* stream) {
+    HIPIE_CHECK_ARG(feats && params && ref_px && out, "hipie_condinst_masks: null pointer");
+    HIPIE_CHECK_ARG(B > 0 && Q > 0 && Hf > 0 && Wf > 0 && (int64_t)Hf * Wf * 4 <= 200 * 1024,
+                    "hipie_condinst_masks: bad sizes B=%d Q=%d Hf=%d Wf=%d", B, Q, Hf, Wf);
+    const int smem = Hf * Wf * (int)sizeof(float);
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(condinst_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set = smem;
+    }
+    condinst_kernel<<<dim3(Q, B), 256, smem, (cudaStream_t)stream>>>(feats, params, ref_px, out, B, Q, Hf, Wf, stride);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}

@@ -1,0 +1,307 @@
+// Multi-scale deformable attention forward for sm_100a.
+//
+// Semantics follow the reference operator `ms_deform_attn_forward`
+// (/root/reference/projects/HIPIE/hipie/models/deformable_detr/ops/src/cuda/ms_deform_attn_cuda.cu:20-78,
+//  ms_deform_im2col_cuda.cuh:33-84,237-299) == ms_deform_attn_core_pytorch
+// (.../ops/functions/ms_deform_attn_func.py:43-63): pixel = loc * size - 0.5, bilinear with zero
+// padding, weighted sum over L levels x P points.  The design is new:
+//
+//  * fast path (fp32 math, D == 32, L == 4, P == 4, M % 4 == 0 — every HIPIE call site): one warp
+//    owns (query, 4 heads); 8 lanes x float4 cover the 32 channels of a head, so every bilinear
+//    tap is one fully used 128-byte line (64 B with a bf16 value map) and the per-(query, head)
+//    locations / weights are loaded once, coalesced, and broadcast with shuffles instead of being
+//    re-read by each channel lane.  All 64 taps of a head are independent loads in flight.
+//  * optionally fused front half of MSDeformAttn.forward (softmax over L*P, reference-point +
+//    offset arithmetic; .../ops/modules/ms_deform_attn.py:97-109) so the (N,Lq,M,L,P,2) location
+//    tensor never exists in HBM, and the output can be emitted directly as the bf16 hi/lo split
+//    consumed by the output_proj GEMM.
+//  * generic path (any D/L/P, fp32 or fp64): one thread per output scalar; used by the
+//    reference's own test shapes (ops/test.py: D=2, fp64).
+#include "common.cuh"
+
+namespace hipie {
+
+// ------------------------------------------------------------------------------------------
+// generic path
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void msda_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
+                                    const int64_t* __restrict__ lstart, const T* __restrict__ loc,
+                                    const T* __restrict__ attw, T* __restrict__ out, int N, int S,
+                                    int M, int D, int L, int Lq, int P) {
+    const int64_t total = (int64_t)N * Lq * M * D;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int d = (int)(idx % D);
+        const int m = (int)((idx / D) % M);
+        const int64_t bq = idx / ((int64_t)D * M);  // b * Lq + q
+        const int b = (int)(bq / Lq);
+        const T* lp = loc + (bq * M + m) * (int64_t)L * P * 2;
+        const T* wp = attw + (bq * M + m) * (int64_t)L * P;
+        T acc = 0;
+        for (int l = 0; l < L; ++l) {
+            const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+            const T* vbase = value + ((int64_t)b * S + lstart[l]) * M * D + (int64_t)m * D + d;
+            const int64_t pix = (int64_t)M * D;
+            for (int p = 0; p < P; ++p) {
+                const T x = lp[(l * P + p) * 2] * W - (T)0.5;
+                const T y = lp[(l * P + p) * 2 + 1] * H - (T)0.5;
+                const T w = wp[l * P + p];
+                if (y > -1 && x > -1 && y < H && x < W) {
+                    const int y0 = (int)floor(y), x0 = (int)floor(x);
+                    const T ly = y - y0, lx = x - x0, hy = 1 - ly, hx = 1 - lx;
+                    T v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+                    if (y0 >= 0 && x0 >= 0) v1 = vbase[((int64_t)y0 * W + x0) * pix];
+                    if (y0 >= 0 && x0 + 1 <= W - 1) v2 = vbase[((int64_t)y0 * W + x0 + 1) * pix];
+                    if (y0 + 1 <= H - 1 && x0 >= 0) v3 = vbase[((int64_t)(y0 + 1) * W + x0) * pix];
+                    if (y0 + 1 <= H - 1 && x0 + 1 <= W - 1)
+                        v4 = vbase[((int64_t)(y0 + 1) * W + x0 + 1) * pix];
+                    const T val = hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
+                    acc += w * val;
+                }
+            }
+        }
+        out[idx] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fast path
+// ------------------------------------------------------------------------------------------
+template <bool BF16V>
+struct ValLoad;
+template <>
+struct ValLoad<false> {
+    static __device__ __forceinline__ float4 ld(const void* base, int64_t elem_off) {
+        return ldg_nc_f4(reinterpret_cast<const float*>(base) + elem_off);
+    }
+};
+template <>
+struct ValLoad<true> {
+    static __device__ __forceinline__ float4 ld(const void* base, int64_t elem_off) {
+        uint2 r;
+        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + elem_off;
+        asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        float4 o;
+        o.x = __uint_as_float(r.x << 16);
+        o.y = __uint_as_float(r.x & 0xffff0000u);
+        o.z = __uint_as_float(r.y << 16);
+        o.w = __uint_as_float(r.y & 0xffff0000u);
+        return o;
+    }
+};
+
+// FUSED: offs_logits rows are [M*L*P*2 offsets | M*L*P logits]; REFDIM in {2,4}.
+// otherwise loc/attw are the reference operator's tensors.
+template <bool BF16V, bool FUSED, int REFDIM, bool SPLIT_OUT>
+__global__ void __launch_bounds__(256)
+msda_fast_kernel(const void* __restrict__ value, const int64_t* __restrict__ shapes,
+                 const int64_t* __restrict__ lstart, const float* __restrict__ loc,
+                 const float* __restrict__ attw, const float* __restrict__ refp,
+                 float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                 __nv_bfloat16* __restrict__ out_lo, int N, int S, int M, int Lq) {
+    constexpr int D = 32, L = 4, P = 4;
+    const int lane = threadIdx.x & 31;
+    const int hgroups = M >> 2;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwork = (int64_t)N * Lq * hgroups;
+    if (warp_global >= nwork) return;
+    // consecutive warps -> consecutive head groups of the same query, then next query
+    const int hg = (int)(warp_global % hgroups);
+    const int64_t bq = warp_global / hgroups;
+    const int b = (int)(bq / Lq);
+    const int hsub = lane >> 3, dsub = lane & 7;
+    const int m = hg * 4 + hsub;
+
+    int Hl[L], Wl[L];
+    int64_t st[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        Hl[l] = (int)__ldg(shapes + 2 * l);
+        Wl[l] = (int)__ldg(shapes + 2 * l + 1);
+        st[l] = __ldg(lstart + l);
+    }
+
+    // this lane owns points p0 = 2*dsub, p0+1 of head m (both on level dsub >> 1)
+    float x0p, y0p, x1p, y1p, w0p, w1p;
+    {
+        const int lown = dsub >> 1;
+        int Hown = Hl[0], Wown = Wl[0];
+#pragma unroll
+        for (int l = 1; l < L; ++l)
+            if (lown == l) { Hown = Hl[l]; Wown = Wl[l]; }
+        const float Wf = (float)Wown, Hf = (float)Hown;
+        float4 o;
+        float2 lg;
+        if (FUSED) {
+            const float* row = loc + bq * (int64_t)(M * L * P * 3);
+            o = *reinterpret_cast<const float4*>(row + (hg * 4) * (L * P * 2) + lane * 4);
+            lg = *reinterpret_cast<const float2*>(row + M * L * P * 2 + (hg * 4) * (L * P) + lane * 2);
+            // softmax over the 16 logits of this head (8 lanes x 2)
+            float mx = fmaxf(lg.x, lg.y);
+#pragma unroll
+            for (int s = 1; s < 8; s <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+            float e0 = expf(lg.x - mx), e1 = expf(lg.y - mx);
+            float sum = e0 + e1;
+#pragma unroll
+            for (int s = 1; s < 8; s <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+            const float inv = 1.0f / sum;
+            w0p = e0 * inv;
+            w1p = e1 * inv;
+            const float* rp = refp + (bq * L + lown) * REFDIM;
+            float lx0, ly0, lx1, ly1;
+            if (REFDIM == 2) {
+                const float rx = rp[0], ry = rp[1];
+                lx0 = rx + o.x / Wf; ly0 = ry + o.y / Hf;
+                lx1 = rx + o.z / Wf; ly1 = ry + o.w / Hf;
+            } else {
+                const float rx = rp[0], ry = rp[1], rw = rp[2], rh = rp[3];
+                lx0 = rx + o.x / (float)P * rw * 0.5f; ly0 = ry + o.y / (float)P * rh * 0.5f;
+                lx1 = rx + o.z / (float)P * rw * 0.5f; ly1 = ry + o.w / (float)P * rh * 0.5f;
+            }
+            x0p = lx0 * Wf - 0.5f; y0p = ly0 * Hf - 0.5f;
+            x1p = lx1 * Wf - 0.5f; y1p = ly1 * Hf - 0.5f;
+        } else {
+            const float* lrow = loc + (bq * M + hg * 4) * (int64_t)(L * P * 2);
+            const float* wrow = attw + (bq * M + hg * 4) * (int64_t)(L * P);
+            o = *reinterpret_cast<const float4*>(lrow + lane * 4);
+            lg = *reinterpret_cast<const float2*>(wrow + lane * 2);
+            w0p = lg.x; w1p = lg.y;
+            x0p = o.x * Wf - 0.5f; y0p = o.y * Hf - 0.5f;
+            x1p = o.z * Wf - 0.5f; y1p = o.w * Hf - 0.5f;
+        }
+    }
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t pixstride = (int64_t)M * D;
+    const int64_t vb = (int64_t)b * S * pixstride + (int64_t)m * D + dsub * 4;
+    const int src_base = lane & 24;
+
+#pragma unroll
+    for (int p = 0; p < L * P; ++p) {
+        const int l = p >> 2;
+        const int src = src_base | (p >> 1);
+        const float x = __shfl_sync(0xffffffffu, (p & 1) ? x1p : x0p, src);
+        const float y = __shfl_sync(0xffffffffu, (p & 1) ? y1p : y0p, src);
+        const float w = __shfl_sync(0xffffffffu, (p & 1) ? w1p : w0p, src);
+        const int H = Hl[l], W = Wl[l];
+        if (y > -1.f && x > -1.f && y < (float)H && x < (float)W) {
+            const float yf = floorf(y), xf = floorf(x);
+            const int yi = (int)yf, xi = (int)xf;
+            const float ly = y - yf, lx = x - xf, hy = 1.f - ly, hx = 1.f - lx;
+            const int64_t base = vb + (st[l] + (int64_t)yi * W + xi) * pixstride;
+            const bool t = yi >= 0, btm = yi + 1 <= H - 1, lft = xi >= 0, rgt = xi + 1 <= W - 1;
+            float4 v1 = make_float4(0, 0, 0, 0), v2 = v1, v3 = v1, v4 = v1;
+            if (t && lft) v1 = ValLoad<BF16V>::ld(value, base);
+            if (t && rgt) v2 = ValLoad<BF16V>::ld(value, base + pixstride);
+            if (btm && lft) v3 = ValLoad<BF16V>::ld(value, base + (int64_t)W * pixstride);
+            if (btm && rgt) v4 = ValLoad<BF16V>::ld(value, base + (int64_t)(W + 1) * pixstride);
+            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+            acc.x += w * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x);
+            acc.y += w * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y);
+            acc.z += w * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z);
+            acc.w += w * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w);
+        }
+    }
+
+    const int64_t o = bq * (int64_t)(M * D) + m * D + dsub * 4;
+    if (SPLIT_OUT) {
+        uint2 hi, lo;
+        split2(acc.x, acc.y, hi.x, lo.x);
+        split2(acc.z, acc.w, hi.y, lo.y);
+        *reinterpret_cast<uint2*>(out_hi + o) = hi;
+        if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = lo;
+        if (out) *reinterpret_cast<float4*>(out + o) = acc;
+    } else {
+        *reinterpret_cast<float4*>(out + o) = acc;
+    }
+}
+
+template <bool BF16V, bool FUSED, int REFDIM, bool SPLIT>
+static int launch_fast(const void* value, const int64_t* shapes, const int64_t* lstart,
+                       const float* loc, const float* attw, const float* refp, float* out,
+                       void* out_hi, void* out_lo, int N, int S, int M, int Lq, cudaStream_t st) {
+    const int64_t warps = (int64_t)N * Lq * (M / 4);
+    const int64_t blocks = (warps + 7) / 8;
+    if (blocks == 0) return HIPIE_OK;
+    msda_fast_kernel<BF16V, FUSED, REFDIM, SPLIT><<<(unsigned)blocks, 256, 0, st>>>(
+        value, shapes, lstart, loc, attw, refp, out, (__nv_bfloat16*)out_hi,
+        (__nv_bfloat16*)out_lo, N, S, M, Lq);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+}  // namespace hipie
+
+using namespace hipie;
+
+extern "C" int hipie_msda_forward(const void* value, const int64_t* spatial_shapes,
+                                  const int64_t* level_start_index, const void* sampling_loc,
+                                  const void* attn_weight, void* out, int N, int S, int M, int D,
+                                  int L, int Lq, int P, int dtype, int value_dtype, void* stream) {
+    HIPIE_CHECK_ARG(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out,
+                    "hipie_msda_forward: null pointer argument");
+    HIPIE_CHECK_ARG(N >= 0 && S > 0 && M > 0 && D > 0 && L > 0 && Lq >= 0 && P > 0,
+                    "hipie_msda_forward: bad sizes N=%d S=%d M=%d D=%d L=%d Lq=%d P=%d", N, S, M, D, L, Lq, P);
+    HIPIE_CHECK_ARG(dtype == HIPIE_F32 || dtype == HIPIE_F64, "hipie_msda_forward: dtype must be f32/f64");
+    HIPIE_CHECK_ARG(value_dtype == dtype || (value_dtype == HIPIE_BF16 && dtype == HIPIE_F32),
+                    "hipie_msda_forward: value_dtype %d incompatible with dtype %d", value_dtype, dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((int64_t)N * Lq == 0) return HIPIE_OK;
+    const bool fast = dtype == HIPIE_F32 && D == 32 && L == 4 && P == 4 && (M % 4) == 0 &&
+                      (((uintptr_t)value | (uintptr_t)sampling_loc | (uintptr_t)attn_weight | (uintptr_t)out) & 15) == 0;
+    if (fast) {
+        if (value_dtype == HIPIE_BF16)
+            return launch_fast<true, false, 2, false>(value, spatial_shapes, level_start_index,
+                                                      (const float*)sampling_loc, (const float*)attn_weight,
+                                                      nullptr, (float*)out, nullptr, nullptr, N, S, M, Lq, st);
+        return launch_fast<false, false, 2, false>(value, spatial_shapes, level_start_index,
+                                                   (const float*)sampling_loc, (const float*)attn_weight,
+                                                   nullptr, (float*)out, nullptr, nullptr, N, S, M, Lq, st);
+    }
+    HIPIE_CHECK_ARG(value_dtype == dtype, "hipie_msda_forward: bf16 value map needs the D=32,L=4,P=4 fast path");
+    const int64_t total = (int64_t)N * Lq * M * D;
+    const int threads = 256;
+    int64_t blocks = (total + threads - 1) / threads;
+    const int64_t cap = (int64_t)num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    if (dtype == HIPIE_F32)
+        msda_generic_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(
+            (const float*)value, spatial_shapes, level_start_index, (const float*)sampling_loc,
+            (const float*)attn_weight, (float*)out, N, S, M, D, L, Lq, P);
+    else
+        msda_generic_kernel<double><<<(unsigned)blocks, threads, 0, st>>>(
+            (const double*)value, spatial_shapes, level_start_index, (const double*)sampling_loc,
+            (const double*)attn_weight, (double*)out, N, S, M, D, L, Lq, P);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+extern "C" int hipie_msda_fused_forward(const void* value, const int64_t* spatial_shapes,
+                                        const int64_t* level_start_index, const float* offs_logits,
+                                        const float* reference_points, int ref_dim, void* out, int N,
+                                        int S, int M, int D, int L, int Lq, int P, int value_dtype,
+                                        int out_split_bf16, void* out_lo, void* stream) {
+    HIPIE_CHECK_ARG(value && spatial_shapes && level_start_index && offs_logits && reference_points && out,
+                    "hipie_msda_fused_forward: null pointer argument");
+    HIPIE_CHECK_ARG(D == 32 && L == 4 && P == 4 && M > 0 && (M % 4) == 0,
+                    "hipie_msda_fused_forward: only D=32, L=4, P=4, M%%4==0 (got D=%d L=%d P=%d M=%d)", D, L, P, M);
+    HIPIE_CHECK_ARG(ref_dim == 2 || ref_dim == 4, "hipie_msda_fused_forward: ref_dim must be 2 or 4");
+    HIPIE_CHECK_ARG(value_dtype == HIPIE_F32 || value_dtype == HIPIE_BF16, "bad value_dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((int64_t)N * Lq == 0) return HIPIE_OK;
+    float* of = out_split_bf16 ? nullptr : (float*)out;
+    void* ohi = out_split_bf16 ? out : nullptr;
+#define HIPIE_MSDA_GO(BV, RD, SP)                                                                   \
+    return launch_fast<BV, true, RD, SP>(value, spatial_shapes, level_start_index, offs_logits,    \
+                                         nullptr, reference_points, of, ohi, out_lo, N, S, M, Lq, st)
+    const bool bv = value_dtype == HIPIE_BF16;
+    if (bv) {
+        if (ref_dim == 2) { if (out_split_bf16) HIPIE_MSDA_GO(true, 2, true); else HIPIE_MSDA_GO(true, 2, false); }
+        else { if (out_split_bf16) HIPIE_MSDA_GO(true, 4, true); else HIPIE_MSDA_GO(true, 4, false); }
+    } else {
+        if (ref_dim == 2) { if (out_split_bf16) HIPIE_MSDA_GO(false, 2, true); else HIPIE_MSDA_GO(false, 2, false); }
+        else { if (out_split_bf16) HIPIE_MSDA_GO(false, 4, true); else HIPIE_MSDA_GO(false, 4, false); }
+    }
+#undef HIPIE_MSDA_GO
+}

@@ -1,0 +1,336 @@
+"""Python wrappers of the C-ABI hot-path operators (include/hipie_b200.h).
+
+torch is used for device memory and streams only: every function takes CUDA tensors, passes raw
+pointers to libhipie_b200.so on the current stream and returns freshly allocated outputs.  Nothing in
+here computes on the CPU or through ATen; a missing library or a CPU tensor raises.
+"""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+# operand precision of the tensor-core paths: 3 = bf16x3 split (fp32-class results, parity mode),
+# 1 = plain bf16 (fast mode).
+PREC = 3
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3
+
+
+def set_precision(prec: int):
+    global PREC
+    assert prec in (1, 3)
+    PREC = prec
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("hipie_b200 ops take CUDA tensors only (no CPU fallback)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class BF2:
+    """bf16 hi/lo planes of an fp32 tensor (lo is None in plain-bf16 mode)."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo=None):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def view(self, *s):
+        return BF2(self.hi.view(*s), None if self.lo is None else self.lo.view(*s))
+
+    def __getitem__(self, idx):
+        return BF2(self.hi[idx], None if self.lo is None else self.lo[idx])
+
+    def float(self):
+        f = self.hi.float()
+        return f if self.lo is None else f + self.lo.float()
+
+
+def _empty_bf2(shape, device, need_lo=None):
+    need_lo = (PREC == 3) if need_lo is None else need_lo
+    hi = torch.empty(shape, dtype=torch.bfloat16, device=device)
+    lo = torch.empty(shape, dtype=torch.bfloat16, device=device) if need_lo else None
+    return BF2(hi, lo)
+
+
+def split(x: torch.Tensor) -> BF2:
+    x = x.contiguous()
+    assert x.dtype == torch.float32
+    out = _empty_bf2(x.shape, x.device)
+    _lib.check(_lib.load().hipie_split_bf16(_p(x), _p(out.hi), _p(out.lo), x.numel(), _stream()), "split_bf16")
+    return out
+
+
+def split_weight(w: torch.Tensor) -> BF2:
+    """Weights always carry both planes so the precision mode can be switched at run time."""
+    w = w.contiguous().float()
+    out = _empty_bf2(w.shape, w.device, need_lo=True)
+    _lib.check(_lib.load().hipie_split_bf16(_p(w), _p(out.hi), _p(out.lo), w.numel(), _stream()), "split_bf16")
+    return out
+
+
+def add_split(a, b=None, want_f32=False, want_split=True):
+    a = a.contiguous()
+    if b is not None:
+        b = b.contiguous()
+        assert a.shape == b.shape
+    s = torch.empty_like(a) if want_f32 else None
+    o = _empty_bf2(a.shape, a.device) if want_split else None
+    _lib.check(_lib.load().hipie_add_split(_p(a), _p(b), _p(s), _p(o.hi) if o else None, _p(o.lo) if o else None,
+                                           a.numel(), _stream()), "add_split")
+    return s, o
+
+
+def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, alpha=1.0, want_f32=True,
+         want_split=False, out_f32=None, transposed=False, row_map=None, out_rows=None, bits_threshold=None,
+         M=None, N=None, K=None, batch=1, lda=None, ldw=None, a_bstride=0, w_bstride=0, ldc=None, c_bstride=0,
+         ldr=None, r_bstride=0, prec=None):
+    """C = act(alpha * A.W^T + bias) * colscale + residual.
+
+    A: (.., M, K) planes, W: (N, K) planes.  Default: 2-D row-major operands.  Strided / batched views
+    are described with the explicit M/N/K/ld*/bstride arguments (elements).
+    Returns (c_f32 or None, c_split or None, c_bits or None).
+    """
+    lib = _lib.load()
+    prec = PREC if prec is None else prec
+    if prec == 3 and (a.lo is None or w.lo is None):
+        raise RuntimeError("gemm: prec=3 needs lo planes")
+    dev = a.hi.device
+    if M is None:
+        assert a.hi.dim() == 2 and w.hi.dim() == 2
+        M, K = a.hi.shape
+        N = w.hi.shape[0]
+        assert w.hi.shape[1] == K
+        lda = a.hi.stride(0)
+        ldw = w.hi.stride(0)
+    rows_out = out_rows if out_rows is not None else M
+    if transposed:
+        shape = (batch, N, rows_out) if batch > 1 else (N, rows_out)
+        ldc_ = rows_out if ldc is None else ldc
+        cb = N * rows_out if (batch > 1 and c_bstride == 0) else c_bstride
+    else:
+        shape = (batch, rows_out, N) if batch > 1 else (rows_out, N)
+        ldc_ = N if ldc is None else ldc
+        cb = rows_out * N if (batch > 1 and c_bstride == 0) else c_bstride
+    c_f32 = out_f32 if out_f32 is not None else (torch.empty(shape, dtype=torch.float32, device=dev) if want_f32 else None)
+    c_split = _empty_bf2(shape, dev) if want_split else None
+    c_bits = None
+    if bits_threshold is not None:
+        assert transposed
+        c_bits = torch.zeros((batch, N, (M + 31) // 32), dtype=torch.int32, device=dev)
+    if residual is not None and ldr is None:
+        ldr = residual.stride(-2) if not transposed else residual.stride(-2)
+    args = _lib.GemmArgs(
+        a_hi=a.hi.data_ptr(), a_lo=a.lo.data_ptr() if (a.lo is not None and prec == 3) else None, lda=lda, a_bstride=a_bstride,
+        w_hi=w.hi.data_ptr(), w_lo=w.lo.data_ptr() if (w.lo is not None and prec == 3) else None, ldw=ldw, w_bstride=w_bstride,
+        bias=bias.data_ptr() if bias is not None else None,
+        colscale=colscale.data_ptr() if colscale is not None else None,
+        residual=residual.data_ptr() if residual is not None else None,
+        ldr=ldr or 0, r_bstride=r_bstride,
+        c_f32=c_f32.data_ptr() if c_f32 is not None else None,
+        c_hi=c_split.hi.data_ptr() if c_split is not None else None,
+        c_lo=c_split.lo.data_ptr() if (c_split is not None and c_split.lo is not None) else None,
+        ldc=ldc_, c_bstride=cb,
+        c_bits=c_bits.data_ptr() if c_bits is not None else None,
+        bits_threshold=float(bits_threshold) if bits_threshold is not None else 0.0,
+        M=M, N=N, K=K, batch=batch, act=act, prec=prec, alpha=float(alpha), transposed=1 if transposed else 0,
+        c_row_map=row_map.data_ptr() if row_map is not None else None)
+    _lib.check(lib.hipie_gemm(ctypes.byref(args), _stream()), "gemm")
+    return c_f32, c_split, c_bits
+
+
+def linear(x: BF2, w: BF2, bias=None, **kw):
+    """x: (..., K) planes -> (..., N); convenience over gemm for contiguous inputs."""
+    lead = x.hi.shape[:-1]
+    x2 = x.view(-1, x.hi.shape[-1])
+    f, s, _ = gemm(x2, w, bias=bias, **kw)
+    N = w.hi.shape[0]
+    if f is not None:
+        f = f.view(*lead, N)
+    if s is not None:
+        s = s.view(*lead, N)
+    return f, s
+
+
+def layernorm(x, gamma, beta, eps, add=None, want_f32=False, want_split=True, want_sum=False, row_map=None,
+              out_rows=None, out_split: Optional[BF2] = None):
+    x = x.contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if add is not None:
+        add = add.contiguous()
+    oshape = x.shape if out_rows is None else (out_rows, C)
+    y = torch.empty(oshape, dtype=torch.float32, device=x.device) if want_f32 else None
+    s = out_split if out_split is not None else (_empty_bf2(oshape, x.device) if want_split else None)
+    ssum = torch.empty_like(x) if (want_sum and add is not None) else None
+    _lib.check(_lib.load().hipie_layernorm(_p(x), _p(add), _p(gamma), _p(beta), float(eps), _p(ssum), _p(y),
+                                           _p(s.hi) if s else None, _p(s.lo) if (s and s.lo is not None) else None,
+                                           rows, C, _p(row_map), _stream()), "layernorm")
+    return y, s, ssum
+
+
+_gn_ws = {}
+
+
+def groupnorm_nhwc(x, gamma, beta, eps=1e-5, groups=32, relu=False, post_add=None, want_f32=True, want_split=False,
+                   out_f32=None, y_bstride=None, add_bstride=None):
+    """x: (N, HW, C) fp32 contiguous."""
+    N, HW, C = x.shape
+    dev = x.device
+    ws = _gn_ws.get((dev, N * groups))
+    if ws is None:
+        ws = torch.empty(2 * N * groups, dtype=torch.float64, device=dev)
+        _gn_ws[(dev, N * groups)] = ws
+    y = out_f32 if out_f32 is not None else (torch.empty_like(x) if want_f32 else None)
+    s = _empty_bf2(x.shape, dev) if want_split else None
+    yb = HW * C if y_bstride is None else y_bstride
+    ab = HW * C if add_bstride is None else add_bstride
+    _lib.check(_lib.load().hipie_groupnorm_nhwc(_p(x), _p(gamma), _p(beta), float(eps), _p(post_add), _p(y),
+                                                _p(s.hi) if s else None, _p(s.lo) if (s and s.lo is not None) else None,
+                                                _p(ws), N, HW, C, groups, 1 if relu else 0, HW * C, yb, ab, _stream()),
+               "groupnorm_nhwc")
+    return y, s
+
+
+def patchify(img, mean, std, P=16) -> BF2:
+    B, _, H, W = img.shape
+    img = img.contiguous()
+    rows = B * (H // P) * (W // P)
+    out = _empty_bf2((rows, 3 * P * P), img.device)
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _lib.check(_lib.load().hipie_patchify(_p(img), _p(out.hi), _p(out.lo), B, H, W, P,
+                                          ctypes.cast(m, ctypes.c_void_p), ctypes.cast(s, ctypes.c_void_p), _stream()),
+               "patchify")
+    return out
+
+
+def im2col_nhwc(x, ksz=3, stride=1, pad=1) -> BF2:
+    B, H, W, C = x.shape
+    x = x.contiguous()
+    Ho = (H + 2 * pad - ksz) // stride + 1
+    Wo = (W + 2 * pad - ksz) // stride + 1
+    out = _empty_bf2((B * Ho * Wo, ksz * ksz * C), x.device)
+    _lib.check(_lib.load().hipie_im2col_nhwc(_p(x), _p(out.hi), _p(out.lo), B, H, W, C, ksz, stride, pad, _stream()),
+               "im2col_nhwc")
+    return out, Ho, Wo
+
+
+def pixel_shuffle2(g, B, H, W, C, want_f32=True, want_split=False):
+    g = g.contiguous()
+    y = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float32, device=g.device) if want_f32 else None
+    s = _empty_bf2((B, 2 * H, 2 * W, C), g.device) if want_split else None
+    _lib.check(_lib.load().hipie_pixel_shuffle2(_p(g), _p(y), _p(s.hi) if s else None,
+                                                _p(s.lo) if (s and s.lo is not None) else None, B, H, W, C, _stream()),
+               "pixel_shuffle2")
+    return y, s
+
+
+def maxpool2_nhwc(x, want_f32=True, want_split=False):
+    B, H, W, C = x.shape
+    x = x.contiguous()
+    y = torch.empty((B, H // 2, W // 2, C), dtype=torch.float32, device=x.device) if want_f32 else None
+    s = _empty_bf2((B, H // 2, W // 2, C), x.device) if want_split else None
+    _lib.check(_lib.load().hipie_maxpool2_nhwc(_p(x), _p(y), _p(s.hi) if s else None,
+                                               _p(s.lo) if (s and s.lo is not None) else None, B, H, W, C, _stream()),
+               "maxpool2_nhwc")
+    return y, s
+
+
+def row_softmax(x, colbias=None, rows_per_batch=None, clampv=50000.0, sub_rowmax=False, want_split=True, want_f32=False):
+    n = x.shape[-1]
+    rows = x.numel() // n
+    x = x.contiguous()
+    s = _empty_bf2(x.shape, x.device) if want_split else None
+    pf = torch.empty_like(x) if want_f32 else None
+    _lib.check(_lib.load().hipie_row_softmax(_p(x), _p(colbias), rows, rows_per_batch or rows, n, float(clampv),
+                                             1 if sub_rowmax else 0, _p(s.hi) if s else None,
+                                             _p(s.lo) if (s and s.lo is not None) else None, _p(pf), _stream()), "row_softmax")
+    return pf, s
+
+
+def attention(q: BF2, k: BF2, v: BF2, B, H, Tq, Tk, hd, q_strides, k_strides, v_strides, scale, rel_h=None, rel_w=None,
+              kh=0, kw=0, key_bias=None, want_f32=False, want_split=True, prec=None):
+    """q/k/v: planes with explicit (batch, token, head) element strides; output (B, Tq, H*hd)."""
+    prec = PREC if prec is None else prec
+    dev = q.hi.device
+    o = torch.empty((B, Tq, H * hd), dtype=torch.float32, device=dev) if want_f32 else None
+    s = _empty_bf2((B, Tq, H * hd), dev) if want_split else None
+    lo = lambda t: t.lo.data_ptr() if (t.lo is not None and prec == 3) else None
+    args = _lib.AttnArgs(
+        q_hi=q.hi.data_ptr(), q_lo=lo(q), k_hi=k.hi.data_ptr(), k_lo=lo(k), v_hi=v.hi.data_ptr(), v_lo=lo(v),
+        q_bs=q_strides[0], q_ts=q_strides[1], q_hs=q_strides[2],
+        k_bs=k_strides[0], k_ts=k_strides[1], k_hs=k_strides[2],
+        v_bs=v_strides[0], v_ts=v_strides[1], v_hs=v_strides[2],
+        rel_h=rel_h.data_ptr() if rel_h is not None else None, rel_w=rel_w.data_ptr() if rel_w is not None else None,
+        kh=kh, kw=kw, key_bias=key_bias.data_ptr() if key_bias is not None else None,
+        out_f32=o.data_ptr() if o is not None else None, out_hi=s.hi.data_ptr() if s else None,
+        out_lo=s.lo.data_ptr() if (s and s.lo is not None) else None, o_bs=Tq * H * hd, o_ts=H * hd,
+        B=B, H=H, Tq=Tq, Tk=Tk, hd=hd, scale=float(scale), prec=prec)
+    _lib.check(_lib.load().hipie_attention(ctypes.byref(args), _stream()), "attention")
+    return o, s
+
+
+def relpos_bias(q: BF2, q_strides, table_t, axis, qh, qw, B, H, hd):
+    """table_t: (qsize, hd, ksize) fp32.  Returns (B, H, qh*qw, ksize) fp32."""
+    ksize = table_t.shape[-1]
+    rel = torch.empty((B, H, qh * qw, ksize), dtype=torch.float32, device=table_t.device)
+    _lib.check(_lib.load().hipie_relpos_bias(_p(q.hi), _p(q.lo), q_strides[0], q_strides[1], q_strides[2], _p(table_t),
+                                             axis, qh, qw, ksize, _p(rel), B, H, hd, _stream()), "relpos_bias")
+    return rel
+
+
+def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    """Drop-in core op (reference signature minus im2col_step): fp32/fp64 tensors on CUDA."""
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    dt = {torch.float32: 0, torch.float64: 1}[sampling_locations.dtype]
+    vdt = 2 if value.dtype == torch.bfloat16 else dt
+    out = torch.empty((N, Lq, M * D), dtype=sampling_locations.dtype, device=value.device)
+    _lib.check(_lib.load().hipie_msda_forward(_p(value.contiguous()), _p(spatial_shapes.contiguous()),
+                                              _p(level_start_index.contiguous()), _p(sampling_locations.contiguous()),
+                                              _p(attention_weights.contiguous()), _p(out), N, S, M, D, L, Lq, P, dt, vdt,
+                                              _stream()), "msda_forward")
+    return out
+
+
+def msda_fused(value, spatial_shapes, level_start_index, offs_logits, reference_points, M=8, D=32, L=4, P=4,
+               want_split=True):
+    """value (N,S,M*D) fp32|bf16; offs_logits (N,Lq,M*L*P*3) fp32; reference_points (N,Lq,L,2|4) fp32."""
+    N, S = value.shape[0], value.shape[1]
+    Lq = offs_logits.shape[1]
+    ref_dim = reference_points.shape[-1]
+    vdt = 2 if value.dtype == torch.bfloat16 else 0
+    dev = value.device
+    if want_split:
+        s = _empty_bf2((N, Lq, M * D), dev)
+        out, out_lo = s.hi, s.lo
+    else:
+        s = None
+        out, out_lo = torch.empty((N, Lq, M * D), dtype=torch.float32, device=dev), None
+    _lib.check(_lib.load().hipie_msda_fused_forward(_p(value), _p(spatial_shapes), _p(level_start_index),
+                                                    _p(offs_logits.contiguous()), _p(reference_points.contiguous()), ref_dim,
+                                                    _p(out), N, S, M, D, L, Lq, P, vdt, 1 if want_split else 0, _p(out_lo),
+                                                    _stream()), "msda_fused_forward")
+    return s if want_split else out
+
+
+def condinst_masks(feats_nhwc, params, ref_px, Hf, Wf, stride=8):
+    B, Q = params.shape[0], params.shape[1]
+    out = torch.empty((B, Q, 2 * Hf, 2 * Wf), dtype=torch.float32, device=params.device)
+    _lib.check(_lib.load().hipie_condinst_masks(_p(feats_nhwc.contiguous()), _p(params.contiguous()), _p(ref_px.contiguous()),
+                                                _p(out), B, Q, Hf, Wf, stride, _stream()), "condinst_masks")
+    return out

@@ -1,0 +1,199 @@
+/*
+ * hipie_b200 — C-ABI of the B200-native HIPIE inference hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a
+ * CUDA stream (passed as void*; NULL = legacy default stream), never
+ * allocates, never synchronises, and returns 0 on success or a negative
+ * HIPIE_E* code.  hipie_last_error() returns a static, human-readable string
+ * for the calling thread's last failure.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference,
+ * H: = projects/HIPIE/hipie/):
+ *   hipie_msda_forward      <- ms_deform_attn_forward, pybind module
+ *                              `MultiScaleDeformableAttention`
+ *                              (H:models/deformable_detr/ops/src/vision.cpp:13-16,
+ *                               ms_deform_attn.h:21-40,
+ *                               cuda/ms_deform_attn_cuda.cu:20-78); the twin copy under
+ *                              H:models/maskdino/pixel_decoder/ops/src/ is the same function.
+ *   hipie_gemm_*            <- torch.nn.functional.linear call sites of the ViT / DETR /
+ *                              BERT blocks (H:backbone/vit.py:67-83,212-230; timm Mlp) and
+ *                              einsum("bqc,bchw->bqhw") of
+ *                              H:models/maskdino/transformer_decoder/maskdino_decoder.py:520-529
+ *   hipie_attention_*       <- Attention.forward + add_decomposed_rel_pos
+ *                              (H:backbone/vit.py:67-83, H:backbone/utils.py:96-125),
+ *                              nn.MultiheadAttention of the decoders, BiMultiHeadAttention
+ *                              (H:models/deformable_detr/fuse_helper.py:54-139)
+ *   hipie_layernorm_* / hipie_groupnorm_* <- nn.LayerNorm / nn.GroupNorm call sites
+ *   hipie_condinst_*        <- dynamic_mask_with_coords (H:models/ddetrs_dn.py:1411-1502)
+ *
+ * dtype codes: 0 = float32, 1 = float64 (msda generic path only), 2 = bfloat16.
+ */
+#ifndef HIPIE_B200_H_
+#define HIPIE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HIPIE_OK 0
+#define HIPIE_EINVAL (-1)   /* bad argument (shape, dtype, alignment, null pointer) */
+#define HIPIE_ECUDA (-2)    /* a CUDA runtime / driver call failed */
+#define HIPIE_EUNSUPPORTED (-3)
+
+#define HIPIE_F32 0
+#define HIPIE_F64 1
+#define HIPIE_BF16 2
+
+/* epilogue activation codes for hipie_gemm */
+#define HIPIE_ACT_NONE 0
+#define HIPIE_ACT_RELU 1
+#define HIPIE_ACT_GELU 2      /* exact erf GELU (timm Mlp / nn.GELU default) */
+#define HIPIE_ACT_SIGMOID 3
+
+const char* hipie_last_error(void);
+int hipie_abi_version(void);
+/* Number of kernel launches issued through this library by the calling process. */
+int64_t hipie_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-scale deformable attention, forward.
+ *   value             (N, S, M, D)        dtype, contiguous, device
+ *   spatial_shapes    (L, 2) int64 (H_l, W_l), device
+ *   level_start_index (L,)   int64, device
+ *   sampling_loc      (N, Lq, M, L, P, 2) dtype, (x, y) normalised to [0,1], device
+ *   attn_weight       (N, Lq, M, L, P)    dtype, device
+ *   out               (N, Lq, M*D)        dtype, device; fully overwritten
+ * dtype: HIPIE_F32 (fast path when D == 32, generic otherwise) or HIPIE_F64 (generic).
+ * value_dtype: dtype of `value` storage; HIPIE_BF16 allowed only with dtype == HIPIE_F32
+ *              (fast mode: bf16 value map, fp32 locations/weights/accumulation/output).
+ * ------------------------------------------------------------------------------------------ */
+int hipie_msda_forward(const void* value, const int64_t* spatial_shapes,
+                       const int64_t* level_start_index, const void* sampling_loc,
+                       const void* attn_weight, void* out, int N, int S, int M, int D, int L,
+                       int Lq, int P, int dtype, int value_dtype, void* stream);
+
+/* Fused front half of MSDeformAttn.forward (H:.../ops/modules/ms_deform_attn.py:97-109):
+ * takes the raw `sampling_offsets` / `attention_weights` linear outputs packed as one
+ * (N*Lq, M*L*P*3) fp32 matrix [offsets (M,L,P,2) | logits (M,L*P)], the reference points
+ * (N, Lq, L, 2|4), does softmax over L*P, builds the sampling locations and runs the core op. */
+int hipie_msda_fused_forward(const void* value, const int64_t* spatial_shapes,
+                             const int64_t* level_start_index, const float* offs_logits,
+                             const float* reference_points, int ref_dim, void* out, int N, int S,
+                             int M, int D, int L, int Lq, int P, int value_dtype,
+                             int out_split_bf16, void* out_lo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * tcgen05 GEMM:  C[M,N] = act( A[M,K] . W[N,K]^T + bias[N] ) * colscale[N] + residual[M,N]
+ * A and W are bf16 "split" operands: a_hi/a_lo and w_hi/w_lo (lo may be NULL when prec == 1).
+ *   prec == 1 : C = Ahi.Whi                      (plain bf16, fp32 accumulate)
+ *   prec == 3 : C = Ahi.Whi + Ahi.Wlo + Alo.Whi  (bf16x3 split, ~fp32 accuracy)
+ * Row strides (in elements) lda / ldw / ldc allow strided sub-matrices; K % 8 == 0,
+ * all base pointers 16-byte aligned.  Outputs (any subset, NULL to skip):
+ *   c_f32 (fp32), c_hi / c_lo (bf16 split of the fp32 result, for feeding the next GEMM),
+ *   c_bits: 1 bit per element (result > threshold), row-major, N padded to 32 — used by the
+ *           mask-embed contraction fused with sigmoid+threshold.
+ * batch: number of independent problems; *_bstride are element strides between them.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hipie_gemm_args {
+    const void* a_hi; const void* a_lo; int64_t lda; int64_t a_bstride;
+    const void* w_hi; const void* w_lo; int64_t ldw; int64_t w_bstride;
+    const float* bias;        /* [N] or NULL */
+    const float* colscale;    /* [N] or NULL (layer-scale gamma) */
+    const float* residual;    /* [M, ldr] fp32 or NULL */
+    int64_t ldr; int64_t r_bstride;
+    float* c_f32; void* c_hi; void* c_lo; int64_t ldc; int64_t c_bstride;
+    uint32_t* c_bits; float bits_threshold;
+    int M, N, K, batch;
+    int act;                  /* HIPIE_ACT_* */
+    int prec;                 /* 1 or 3 */
+    float alpha;              /* scales the accumulator before bias (1.0f default) */
+    int transposed;           /* 1: C (and residual, c_hi/lo) addressed as [col * ld + row]; required for c_bits,
+                                 which is then packed along M: bits[b][col][row/32] */
+    const int32_t* c_row_map; /* optional (non-transposed only): GEMM row r is stored to / takes its residual
+                                 from row c_row_map[r]; negative entries are skipped (window un-partition) */
+} hipie_gemm_args;
+
+int hipie_gemm(const hipie_gemm_args* args, void* stream);
+
+/* fp32 -> bf16 hi (+ lo = bf16(x - hi)) split of a contiguous array of n elements. */
+int hipie_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
+
+/* LayerNorm over the last dim C of x[rows, C] (fp32 in).  Outputs: y_f32 and/or bf16 split
+ * (y_hi, y_lo).  Optional `add` tensor is added to x before normalisation and the sum is
+ * written to sum_out (residual stream), matching post-LN layers: y = LN(x + add). */
+int hipie_layernorm(const float* x, const float* add, const float* gamma, const float* beta,
+                    float eps, float* sum_out, float* y_f32, void* y_hi, void* y_lo,
+                    int64_t rows, int C, const int32_t* out_row_map, void* stream);
+
+/* GroupNorm(G) over NHWC fp32 (N, HW, C) with per-sample strides, optional fused ReLU and a
+ * tensor added after the normalisation; stats_ws: 2*N*G doubles of scratch. */
+int hipie_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float eps,
+                         const float* post_add, float* y_f32, void* y_hi, void* y_lo, double* stats_ws,
+                         int N, int HW, int C, int G, int relu, int64_t x_bstride, int64_t y_bstride,
+                         int64_t add_bstride, void* stream);
+
+/* out = a + b (b may be NULL) as fp32 and/or bf16 split. */
+int hipie_add_split(const float* a, const float* b, float* sum_f32, void* hi, void* lo, int64_t n,
+                    void* stream);
+/* PatchEmbed im2col fused with (x - mean) / std: img (B,3,H,W) -> rows (B*(H/P)*(W/P), 3*P*P). */
+int hipie_patchify(const float* img, void* hi, void* lo, int B, int H, int W, int P,
+                   const float* mean3_host, const float* std3_host, void* stream);
+/* NHWC im2col for k x k convolutions: rows (B*Ho*Wo, k*k*C), column order (ky, kx, c). */
+int hipie_im2col_nhwc(const float* x, void* hi, void* lo, int B, int H, int W, int C, int ksz,
+                      int stride, int pad, void* stream);
+/* ConvTranspose2d(k=2,s=2) pixel shuffle: (B*H*W, 4*C) [dy,dx,c] -> NHWC (B,2H,2W,C). */
+int hipie_pixel_shuffle2(const float* g, float* y, void* hi, void* lo, int B, int H, int W, int C,
+                         void* stream);
+int hipie_maxpool2_nhwc(const float* x, float* y, void* hi, void* lo, int B, int H, int W, int C,
+                        void* stream);
+/* p = softmax(clamp(x [- rowmax], +-clampv) + colbias[row / rows_per_batch, :]) over the last dim. */
+int hipie_row_softmax(const float* x, const float* colbias, int64_t rows, int64_t rows_per_batch,
+                      int n, float clampv, int sub_rowmax, void* hi, void* lo, float* p_f32,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-head attention with optional decomposed relative-position bias
+ * (H:backbone/utils.py:96-125) and optional additive key mask.
+ *   q, k, v : bf16 split planes (hi, lo), logical shape (B, T, H, hd) with element strides
+ *             given explicitly so the packed qkv GEMM output can be consumed in place.
+ *   rel_h   : (B, H, Tq, kh) fp32 or NULL ; rel_w : (B, H, Tq, kw) fp32 or NULL ; Tk = kh*kw
+ *   key_bias: (B, Tk) fp32 additive (0 / -inf style) or NULL
+ *   out     : (B, Tq, H*hd) fp32 and/or bf16 split.
+ * scale is applied to q.k^T before the bias (reference: (q*scale) @ k^T + rel).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hipie_attn_args {
+    const void* q_hi; const void* q_lo; const void* k_hi; const void* k_lo;
+    const void* v_hi; const void* v_lo;
+    int64_t q_bs, q_ts, q_hs;   /* element strides: batch, token, head (q) */
+    int64_t k_bs, k_ts, k_hs;
+    int64_t v_bs, v_ts, v_hs;
+    const float* rel_h; const float* rel_w; int kh, kw;
+    const float* key_bias;
+    float* out_f32; void* out_hi; void* out_lo; int64_t o_bs, o_ts;
+    int B, H, Tq, Tk, hd;
+    float scale;
+    int prec;
+} hipie_attn_args;
+
+int hipie_attention(const hipie_attn_args* args, void* stream);
+
+/* rel[b,h,q,j] = sum_c q[b,q,h,c] * table[idx(q,j), c] for the decomposed rel-pos bias.
+ * axis 0: height (idx from q // qw), axis 1: width (q % qw).  table: (2*max(q,k)-1, hd) fp32,
+ * table_t: get_rel_pos output (H:backbone/utils.py:63-93) pre-transposed to (qsize, hd, ksize) fp32.
+ * q is read as hi (+ lo) bf16 planes. */
+int hipie_relpos_bias(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int64_t q_hs,
+                      const float* table_t, int axis, int qh, int qw, int ksize, float* rel,
+                      int B, int H, int hd, void* stream);
+
+/* CondInst dynamic mask head, fused (H:models/ddetrs_dn.py:1390-1502,1806-1870):
+ *   feats  (B, Hf*Wf, 8) NHWC fp32, params (B, Q, 169) fp32, ref_px (B, Q, 2) fp32 (pixels)
+ *   out    (B, Q, 2*Hf, 2*Wf) fp32 mask logits after aligned_bilinear(x2). */
+int hipie_condinst_masks(const float* feats, const float* params, const float* ref_px, float* out,
+                         int B, int Q, int Hf, int Wf, int stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIPIE_B200_H_ */

@@ -1,0 +1,380 @@
+"""GPU: every CUDA kernel of libhipie_b200.so, called through the C-ABI (hipie_b200.ops -> ctypes), against
+fp64 / fp32 PyTorch restatements of the same op and the CPU oracle.  Tolerances are written per test."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    from hipie_b200 import ops as o
+    o.set_precision(3)
+    return o
+
+
+def _split_ref(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def test_split(ops, cuda):
+    x = torch.randn(4, 1000, device=cuda) * 3
+    s = ops.split(x)
+    hi, lo = _split_ref(x)
+    assert torch.equal(s.hi, hi) and torch.equal(s.lo, lo)
+    assert (s.float() - x).abs().max() <= x.abs().max() * 2 ** -16
+
+
+# ------------------------------------------------------------------------------------------ MSDA
+def _msda_inputs(N, Lq, shapes, M, D, P, dev, dtype=torch.float32, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    shapes_t = torch.as_tensor(shapes, dtype=torch.long)
+    S = int(shapes_t.prod(1).sum())
+    L = len(shapes)
+    value = torch.randn(N, S, M, D, generator=g, dtype=dtype)
+    loc = (torch.rand(N, Lq, M, L, P, 2, generator=g, dtype=dtype) * 1.2 - 0.1)
+    w = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g, dtype=dtype), -1).view(N, Lq, M, L, P)
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    return value, shapes_t, lsi, loc, w
+
+
+def test_msda_reference_test_py_fixtures(ops, cuda, golden_dir):
+    """The reference's own ops/test.py cases (seed 3; fp64 allclose default, fp32 rtol 1e-2 atol 1e-3)."""
+    cases = torch.load(os.path.join(golden_dir, "msda_core.pt"))
+    for name, c in cases.items():
+        shapes = c["shapes"]
+        lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+        out = ops.msda_forward(c["value"].to(cuda), shapes.to(cuda), lsi.to(cuda), c["loc"].to(cuda), c["w"].to(cuda)).cpu()
+        if c["value"].dtype == torch.float64:
+            assert torch.allclose(out, c["out"]), name
+        else:
+            assert torch.allclose(out, c["out"], rtol=1e-2, atol=1e-3), name
+            assert (out - c["out"]).abs().max() < 2e-5, name
+
+
+@pytest.mark.parametrize("Lq", [1, 33, 910])
+def test_msda_fast_vs_oracle(ops, cuda, Lq):
+    from hipie_oracle.msda import ms_deform_attn_core
+    shapes = [(32, 32), (16, 16), (8, 8), (4, 4)]
+    value, shapes_t, lsi, loc, w = _msda_inputs(2, Lq, shapes, 8, 32, 4, cuda, seed=Lq)
+    ref = ms_deform_attn_core(value.double(), shapes_t, loc.double(), w.double()).float()
+    out = ops.msda_forward(value.to(cuda), shapes_t.to(cuda), lsi.to(cuda), loc.to(cuda), w.to(cuda)).cpu()
+    assert (out - ref).abs().max() < 1e-5
+    # bf16 value map (fast mode): error bounded by bf16 rounding of value
+    outb = ops.msda_forward(value.to(cuda).bfloat16(), shapes_t.to(cuda), lsi.to(cuda), loc.to(cuda), w.to(cuda)).cpu()
+    assert (outb - ref).abs().max() < 2e-2
+
+
+def test_msda_empty_queries(ops, cuda):
+    value, shapes_t, lsi, loc, w = _msda_inputs(1, 0, [(4, 4), (2, 2), (2, 2), (1, 1)], 8, 32, 4, cuda)
+    out = ops.msda_forward(value.to(cuda), shapes_t.to(cuda), lsi.to(cuda), loc.to(cuda), w.to(cuda))
+    assert out.shape == (1, 0, 256)
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_msda_fused_front_half(ops, cuda, ref_dim):
+    """softmax + location arithmetic of MSDeformAttn.forward (ms_deform_attn.py:97-109) fused with the core."""
+    from hipie_oracle.msda import ms_deform_attn_core
+    shapes = [(24, 20), (12, 10), (6, 5), (3, 3)]
+    g = torch.Generator().manual_seed(3)
+    shapes_t = torch.as_tensor(shapes)
+    S = int(shapes_t.prod(1).sum())
+    N, Lq, M, L, P = 2, 77, 8, 4, 4
+    value = torch.randn(N, S, M * 32, generator=g)
+    offs = torch.randn(N, Lq, M, L, P, 2, generator=g) * 2
+    logits = torch.randn(N, Lq, M, L * P, generator=g)
+    if ref_dim == 2:
+        refp = torch.rand(N, Lq, L, 2, generator=g)
+        norm = torch.stack([shapes_t[:, 1], shapes_t[:, 0]], -1).float()
+        loc = refp[:, :, None, :, None, :] + offs / norm[None, None, None, :, None, :]
+    else:
+        refp = torch.rand(N, Lq, L, 4, generator=g)
+        loc = refp[:, :, None, :, None, :2] + offs / P * refp[:, :, None, :, None, 2:] * 0.5
+    w = torch.softmax(logits, -1).view(N, Lq, M, L, P)
+    ref = ms_deform_attn_core(value.view(N, S, M, 32).double(), shapes_t, loc.double(), w.double()).float()
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    packed = torch.cat([offs.reshape(N, Lq, -1), logits.reshape(N, Lq, -1)], -1).to(cuda)
+    out = ops.msda_fused(value.to(cuda), shapes_t.to(cuda), lsi.to(cuda), packed, refp.to(cuda), want_split=False).cpu()
+    assert (out - ref).abs().max() < 2e-5
+    s = ops.msda_fused(value.to(cuda), shapes_t.to(cuda), lsi.to(cuda), packed, refp.to(cuda), want_split=True)
+    assert (s.float().cpu() - ref).abs().max() < 2e-4
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def _gemm_ref(a, w, bias=None, act=0, colscale=None, residual=None, alpha=1.0):
+    c = (a.double() @ w.double().transpose(-1, -2)) * alpha
+    if bias is not None:
+        c = c + bias.double()
+    if act == 1:
+        c = torch.relu(c)
+    elif act == 2:
+        c = F.gelu(c)
+    elif act == 3:
+        c = torch.sigmoid(c)
+    if colscale is not None:
+        c = c * colscale.double()
+    if residual is not None:
+        c = c + residual.double()
+    return c
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (300, 256, 256), (4096, 1280, 768), (910, 384, 256),
+                                   (77, 4, 256), (130, 100, 40), (1000, 3840, 1280)])
+@pytest.mark.parametrize("prec", [3, 1])
+def test_gemm_plain(ops, cuda, M, N, K, prec):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, device=cuda, generator=g)
+    w = torch.randn(N, K, device=cuda, generator=g) * 0.05
+    A, W = ops.split(a), ops.split_weight(w)
+    c, _, _ = ops.gemm(A, W, prec=prec)
+    if prec == 3:
+        ref = _gemm_ref(a, w)
+        tol = 3e-5 * math.sqrt(K) * 0.05 * 4 + 1e-5
+    else:
+        ref = _gemm_ref(A.hi.float(), W.hi.float())   # exact-input reference: only accumulation order differs
+        tol = 1e-4 * math.sqrt(K) * 0.05 + 1e-5
+    err = (c.double() - ref).abs().max().item()
+    assert err < tol, f"max err {err} (tol {tol})"
+
+
+def test_gemm_epilogues(ops, cuda):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    M, N, K = 517, 640, 256
+    a = torch.randn(M, K, device=cuda, generator=g)
+    w = torch.randn(N, K, device=cuda, generator=g) * 0.06
+    bias = torch.randn(N, device=cuda, generator=g)
+    cs = torch.rand(N, device=cuda, generator=g)
+    res = torch.randn(M, N, device=cuda, generator=g)
+    A, W = ops.split(a), ops.split_weight(w)
+    for act in (0, 1, 2, 3):
+        c, s, _ = ops.gemm(A, W, bias=bias, act=act, colscale=cs, residual=res, alpha=0.5, want_split=True)
+        ref = _gemm_ref(a, w, bias, act, cs, res, 0.5)
+        assert (c.double() - ref).abs().max() < 2e-4, act
+        assert (s.float().double() - ref).abs().max() < 2e-3
+        hi, lo = _split_ref(c)
+        assert torch.equal(s.hi, hi) and torch.equal(s.lo, lo)
+    # in-place residual update (x = x + f(x) pattern)
+    x = res.clone()
+    ops.gemm(A, W, bias=bias, residual=x, out_f32=x)
+    assert (x.double() - _gemm_ref(a, w, bias, residual=res)).abs().max() < 2e-4
+
+
+def test_gemm_row_map(ops, cuda):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    M, N, K = 300, 128, 64
+    a = torch.randn(M, K, device=cuda, generator=g)
+    w = torch.randn(N, K, device=cuda, generator=g) * 0.1
+    perm = torch.randperm(M, device=cuda, generator=g).int()
+    perm[::7] = -1
+    out = torch.full((M, N), 7.0, device=cuda)
+    resid = out.clone()
+    ops.gemm(ops.split(a), ops.split_weight(w), row_map=perm, residual=resid, out_f32=out)
+    ref = _gemm_ref(a, w)
+    for r in range(0, M, 13):
+        d = int(perm[r])
+        if d >= 0:
+            assert (out[d].double() - (ref[r] + 7.0)).abs().max() < 1e-4
+    untouched = torch.ones(M, dtype=torch.bool, device=cuda)
+    untouched[perm[perm >= 0].long()] = False
+    assert torch.all(out[untouched] == 7.0)
+
+
+def test_gemm_batched_transposed_bits(ops, cuda):
+    """The mask-embed contraction layout: out[b, q, hw] = sum_c F[b, hw, c] E[b, q, c], + bit-packed threshold."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B, HW, Q, C = 3, 1000, 300, 256
+    Fm = torch.randn(B, HW, C, device=cuda, generator=g)
+    E = torch.randn(B, Q, C, device=cuda, generator=g) * 0.1
+    A, W = ops.split(Fm), ops.split(E)
+    c, _, bits = ops.gemm(A, W, M=HW, N=Q, K=C, batch=B, lda=C, ldw=C, a_bstride=HW * C, w_bstride=Q * C,
+                          transposed=True, bits_threshold=0.0)
+    ref = torch.einsum("bqc,bhc->bqh", E.double(), Fm.double())
+    assert c.shape == (B, Q, HW)
+    assert (c.double() - ref).abs().max() < 2e-4
+    words = (HW + 31) // 32
+    got = bits.view(B, Q, words)
+    pad = words * 32 - HW
+    pred = F.pad((c > 0.0), (0, pad)).view(B, Q, words, 32).long()
+    want = (pred << torch.arange(32, device=cuda)).sum(-1)
+    want = torch.where(want >= 2 ** 31, want - 2 ** 32, want).int()
+    assert torch.equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("C", [256, 768, 1280, 2048, 100])
+def test_layernorm(ops, cuda, C):
+    x = torch.randn(333, C, device=cuda) * 2 + 0.5
+    add = torch.randn(333, C, device=cuda)
+    gm = torch.randn(C, device=cuda)
+    bt = torch.randn(C, device=cuda)
+    y, s, ssum = ops.layernorm(x, gm, bt, 1e-6, add=add, want_f32=True, want_split=True, want_sum=True)
+    ref = F.layer_norm((x + add).double(), (C,), gm.double(), bt.double(), 1e-6)
+    assert (y.double() - ref).abs().max() < 2e-5
+    assert torch.equal(ssum, x + add)
+    assert (s.float().double() - ref).abs().max() < 1e-3
+    y2, _, _ = ops.layernorm(x, gm, bt, 1e-5, want_f32=True, want_split=False)
+    assert (y2.double() - F.layer_norm(x.double(), (C,), gm.double(), bt.double(), 1e-5)).abs().max() < 2e-5
+
+
+def test_layernorm_row_map(ops, cuda):
+    x = torch.randn(50, 256, device=cuda)
+    gm, bt = torch.ones(256, device=cuda), torch.zeros(256, device=cuda)
+    rmap = (torch.arange(50, device=cuda) * 2 + 1).int()
+    out = ops.BF2(torch.zeros(120, 256, dtype=torch.bfloat16, device=cuda), torch.zeros(120, 256, dtype=torch.bfloat16, device=cuda))
+    ops.layernorm(x, gm, bt, 1e-6, row_map=rmap, out_split=out)
+    ref = F.layer_norm(x, (256,))
+    assert (out.float()[1:100:2] - ref).abs().max() < 1e-3
+    assert out.float()[0::2].abs().max() == 0
+
+
+@pytest.mark.parametrize("HW", [64, 1000])
+def test_groupnorm_nhwc(ops, cuda, HW):
+    x = torch.randn(3, HW, 256, device=cuda) * 3 + 1
+    gm, bt = torch.randn(256, device=cuda), torch.randn(256, device=cuda)
+    add = torch.randn(3, HW, 256, device=cuda)
+    y, s = ops.groupnorm_nhwc(x, gm, bt, relu=True, post_add=add, want_split=True)
+    ref = F.relu(F.group_norm(x.double().transpose(1, 2), 32, gm.double(), bt.double(), 1e-5)).transpose(1, 2) + add.double()
+    assert (y.double() - ref).abs().max() < 5e-5
+    assert (s.float().double() - ref).abs().max() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ data movement
+def test_patchify_matches_conv(ops, cuda):
+    img = torch.rand(2, 3, 64, 96, device=cuda) * 255
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    w = torch.randn(40, 3, 16, 16, device=cuda) * 0.05
+    rows = ops.patchify(img, mean, std)
+    c, _, _ = ops.gemm(rows, ops.split_weight(w.view(40, -1)))
+    xn = (img - torch.tensor(mean, device=cuda).view(1, 3, 1, 1)) / torch.tensor(std, device=cuda).view(1, 3, 1, 1)
+    ref = F.conv2d(xn.double(), w.double(), stride=16).permute(0, 2, 3, 1).reshape(-1, 40)
+    assert (c.double() - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_im2col_conv3x3(ops, cuda, stride):
+    x = torch.randn(2, 10, 12, 16, device=cuda)
+    w = torch.randn(24, 16, 3, 3, device=cuda) * 0.1
+    cols, Ho, Wo = ops.im2col_nhwc(x, 3, stride, 1)
+    wk = w.permute(0, 2, 3, 1).reshape(24, -1).contiguous()       # (ky, kx, c) column order
+    c, _, _ = ops.gemm(cols, ops.split_weight(wk))
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), stride=stride, padding=1).permute(0, 2, 3, 1).reshape(-1, 24)
+    assert (Ho, Wo) == (ref.shape[0] // 2 // ((12 + 2 - 3) // stride + 1), (12 + 2 - 3) // stride + 1)
+    assert (c.double() - ref).abs().max() < 1e-4
+
+
+def test_convtranspose2x2_as_gemm(ops, cuda):
+    B, H, W, Ci, Co = 2, 6, 5, 32, 16
+    x = torch.randn(B, H, W, Ci, device=cuda)
+    wt = torch.randn(Ci, Co, 2, 2, device=cuda) * 0.1
+    bias = torch.randn(Co, device=cuda)
+    wk = wt.permute(2, 3, 1, 0).reshape(4 * Co, Ci).contiguous()   # rows (dy, dx, co)
+    g, _, _ = ops.gemm(ops.split(x.view(-1, Ci)), ops.split_weight(wk), bias=bias.repeat(4))
+    y, _ = ops.pixel_shuffle2(g, B, H, W, Co)
+    ref = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), wt.double(), bias.double(), stride=2).permute(0, 2, 3, 1)
+    assert (y.double() - ref).abs().max() < 1e-4
+
+
+def test_maxpool(ops, cuda):
+    x = torch.randn(2, 8, 6, 16, device=cuda)
+    y, _ = ops.maxpool2_nhwc(x)
+    ref = F.max_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    assert torch.equal(y, ref)
+
+
+def test_row_softmax(ops, cuda):
+    x = torch.randn(2 * 5, 77, device=cuda) * 4
+    cb = torch.zeros(2, 77, device=cuda)
+    cb[1, 50:] = -9e15
+    cb[cb == 0] = 1.0
+    p, s = ops.row_softmax(x, colbias=cb, rows_per_batch=5, want_f32=True)
+    ref = torch.softmax(x.double().clamp(-5e4, 5e4).view(2, 5, 77) + cb.double()[:, None], -1).view(10, 77)
+    assert (p.double() - ref).abs().max() < 1e-6
+    p2, _ = ops.row_softmax(x, sub_rowmax=True, want_f32=True, want_split=False)
+    xr = x.double()
+    ref2 = torch.softmax((xr - xr.max(-1, keepdim=True)[0]).clamp(-5e4, 5e4), -1)
+    assert (p2.double() - ref2).abs().max() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, scale, rel_h=None, rel_w=None, kh=0, kw=0, key_bias=None):
+    # q,k,v: (B,H,T,hd) double
+    s = (q * scale) @ k.transpose(-1, -2)
+    if rel_h is not None:
+        B, H, Tq, _ = q.shape
+        s = (s.view(B, H, Tq, kh, kw) + rel_h.double()[..., :, None] + rel_w.double()[..., None, :]).view(B, H, Tq, kh * kw)
+    if key_bias is not None:
+        s = s + key_bias.double()[:, None, None, :]
+    return torch.softmax(s, -1) @ v
+
+
+@pytest.mark.parametrize("hd,H", [(80, 4), (64, 3), (32, 8)])
+@pytest.mark.parametrize("Tq,Tk", [(196, 196), (64, 64), (100, 300), (910, 910)])
+@pytest.mark.parametrize("prec", [3, 1])
+def test_attention(ops, cuda, hd, H, Tq, Tk, prec):
+    g = torch.Generator(device="cuda").manual_seed(hd + Tq)
+    B = 2
+    qkv = torch.randn(B, max(Tq, Tk), 3, H, hd, device=cuda, generator=g)
+    S = ops.split(qkv)
+    q, k, v = S[:, :Tq, 0], S[:, :Tk, 1], S[:, :Tk, 2]
+    ts, bs = 3 * H * hd, max(Tq, Tk) * 3 * H * hd
+    kb = None
+    if Tk == 300:
+        kb = torch.zeros(B, Tk, device=cuda)
+        kb[1, 250:] = -1e9
+    o, _ = ops.attention(ops.BF2(q.hi, q.lo), ops.BF2(k.hi, k.lo), ops.BF2(v.hi, v.lo), B, H, Tq, Tk, hd,
+                         (bs, ts, hd), (bs, ts, hd), (bs, ts, hd), hd ** -0.5, key_bias=kb, want_f32=True,
+                         want_split=False, prec=prec)
+    if prec == 3:
+        qq, kk, vv = (qkv[:, :Tq, 0], qkv[:, :Tk, 1], qkv[:, :Tk, 2])
+    else:
+        qq, kk, vv = (S.hi[:, :Tq, 0].float(), S.hi[:, :Tk, 1].float(), S.hi[:, :Tk, 2].float())
+    ref = _attn_ref(qq.permute(0, 2, 1, 3).double(), kk.permute(0, 2, 1, 3).double(), vv.permute(0, 2, 1, 3).double(),
+                    hd ** -0.5, key_bias=kb).permute(0, 2, 1, 3).reshape(B, Tq, H * hd)
+    err = (o.double() - ref).abs().max().item()
+    assert err < (2e-5 if prec == 3 else 2e-2), err
+
+
+def test_attention_decomposed_relpos(ops, cuda):
+    """rel-pos tables built by relpos_bias + fused attention == Attention.forward with add_decomposed_rel_pos."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, H, hd, gh, gw = 2, 4, 80, 14, 14
+    T = gh * gw
+    qkv = torch.randn(B, T, 3, H, hd, device=cuda, generator=g)
+    Rh = torch.randn(gh, gh, hd, device=cuda, generator=g) * 0.2     # get_rel_pos output (q, k, c)
+    Rw = torch.randn(gw, gw, hd, device=cuda, generator=g) * 0.2
+    S = ops.split(qkv)
+    ts, bs = 3 * H * hd, T * 3 * H * hd
+    qs = ops.BF2(S.hi[:, :, 0], S.lo[:, :, 0])
+    rel_h = ops.relpos_bias(qs, (bs, ts, hd), Rh.permute(0, 2, 1).contiguous(), 0, gh, gw, B, H, hd)
+    rel_w = ops.relpos_bias(qs, (bs, ts, hd), Rw.permute(0, 2, 1).contiguous(), 1, gh, gw, B, H, hd)
+    q = qkv[:, :, 0].permute(0, 2, 1, 3).double()
+    rq = q.reshape(B, H, gh, gw, hd)
+    ref_h = torch.einsum("bnhwc,hkc->bnhwk", rq, Rh.double()).reshape(B, H, T, gh)
+    ref_w = torch.einsum("bnhwc,wkc->bnhwk", rq, Rw.double()).reshape(B, H, T, gw)
+    assert (rel_h.double() - ref_h).abs().max() < 1e-4
+    assert (rel_w.double() - ref_w).abs().max() < 1e-4
+    o, _ = ops.attention(qs, ops.BF2(S.hi[:, :, 1], S.lo[:, :, 1]), ops.BF2(S.hi[:, :, 2], S.lo[:, :, 2]), B, H, T, T, hd,
+                         (bs, ts, hd), (bs, ts, hd), (bs, ts, hd), hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=gh, kw=gw,
+                         want_f32=True, want_split=False)
+    ref = _attn_ref(q, qkv[:, :, 1].permute(0, 2, 1, 3).double(), qkv[:, :, 2].permute(0, 2, 1, 3).double(), hd ** -0.5,
+                    ref_h, ref_w, gh, gw).permute(0, 2, 1, 3).reshape(B, T, H * hd)
+    assert (o.double() - ref).abs().max() < 3e-5
+
+
+# ------------------------------------------------------------------------------------------ CondInst
+def test_condinst_fused(ops, cuda):
+    from hipie_oracle.condinst import dynamic_mask_with_coords
+    g = torch.Generator().manual_seed(2)
+    B, Q, Hf, Wf = 2, 9, 12, 10
+    feats = torch.randn(B, 8, Hf, Wf, generator=g)
+    params = torch.randn(B, Q, 169, generator=g) * 0.3
+    ref_px = torch.rand(B, Q, 2, generator=g) * 80
+    ref = dynamic_mask_with_coords(feats, ref_px, params, stride=8)       # (B, Q, 2Hf, 2Wf)
+    out = ops.condinst_masks(feats.permute(0, 2, 3, 1).contiguous().to(cuda), params.to(cuda), ref_px.to(cuda), Hf, Wf).cpu()
+    assert (out - ref).abs().max() < 2e-3 * ref.abs().max()
