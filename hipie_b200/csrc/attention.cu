@@ -149,6 +149,17 @@ attention_kernel(const AttnParams p) {
         }
     }
     const float* kb = p.key_bias ? p.key_bias + (int64_t)b * p.Tk : nullptr;
+    // one KV tile == one key row of the grid (kw == 64): rel_w terms are tile-invariant -> registers
+    const bool hoist = has_rel && p.kw == ATT_BN;
+    float rw[ATT_BN / 8][4];
+    if (hoist) {
+#pragma unroll
+        for (int j = 0; j < ATT_BN / 8; ++j) {
+            const float2 a = *reinterpret_cast<const float2*>(relw_r[0] + j * 8 + (lane & 3) * 2);
+            const float2 c = *reinterpret_cast<const float2*>(relw_r[1] + j * 8 + (lane & 3) * 2);
+            rw[j][0] = a.x; rw[j][1] = a.y; rw[j][2] = c.x; rw[j][3] = c.y;
+        }
+    }
     constexpr float LOG2E = 1.4426950408889634f;
 
     const int ntiles = (p.Tk + ATT_BN - 1) / ATT_BN;
@@ -188,6 +199,8 @@ attention_kernel(const AttnParams p) {
         }
         // ---- scale + bias + mask, online softmax ----
         float mx[2] = {-INFINITY, -INFINITY};
+        float rh0 = 0.f, rh1 = 0.f;
+        if (hoist) { rh0 = __ldg(relh_r[0] + t); rh1 = __ldg(relh_r[1] + t); }
 #pragma unroll
         for (int j = 0; j < ATT_BN / 8; ++j) {
             const int key = kv0 + j * 8 + (lane & 3) * 2;
@@ -197,7 +210,10 @@ attention_kernel(const AttnParams p) {
                 const bool ok = kk < p.Tk;
                 float add0 = 0.f, add1 = 0.f;
                 if (ok) {
-                    if (has_rel) {
+                    if (hoist) {
+                        add0 = rh0 + rw[j][e];
+                        add1 = rh1 + rw[j][2 + e];
+                    } else if (has_rel) {
                         const int khi = kk / p.kw, kwi = kk - khi * p.kw;
                         add0 = __ldg(relh_r[0] + khi) + __ldg(relw_r[0] + kwi);
                         add1 = __ldg(relh_r[1] + khi) + __ldg(relw_r[1] + kwi);

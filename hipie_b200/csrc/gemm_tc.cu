@@ -7,13 +7,13 @@
 // einsum("bqc,bchw->bqhw") (.../maskdino/transformer_decoder/maskdino_decoder.py:520-529) with the
 // sigmoid-threshold fused as a bit-packed output.
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles of A / W into a 4-stage 128B/64B-swizzled
 //               shared-memory ring, completion on mbarriers (expect_tx)
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a
 //               double-buffered fp32 accumulator in tensor memory; tcgen05.commit releases the
 //               smem stage / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld the accumulator (32 lanes x 32 columns per warp), transpose
+//   warps 2-9   epilogue: tcgen05.ld the accumulator (32 lanes x 32 columns per warp), transpose
 //               through padded smem so global stores are row-contiguous, fused bias / activation /
 //               layer-scale / residual / fp32 + bf16-split + bit-packed outputs
 //
@@ -30,9 +30,9 @@ namespace hipie {
 using namespace ptx;
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int GEMM_STAGES = 4;
-constexpr int EPI_LD = 36;  // padded row length (floats) of the epilogue transpose buffer
+constexpr int EPI_LD = 20;  // padded row length (floats) of the epilogue transpose buffer (16 cols + 4)
 
 struct GemmParams {
     const float* bias;
@@ -61,7 +61,7 @@ struct GemmCfg {
     static constexpr int W_TILE = BN * BK * 2;
     static constexpr int NPLANES = PREC == 3 ? 2 : 1;
     static constexpr int STAGE = NPLANES * (A_TILE + W_TILE);
-    static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+    static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4;
     static constexpr int SMEM = GEMM_STAGES * STAGE + EPI_BYTES + 256 + 1024;
     static constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : (2 * BN >= 128 ? 128 : 64));
 };
@@ -71,6 +71,158 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == HIPIE_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
     if (act == HIPIE_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
     return v;
+}
+
+
+template <int ACT>
+__device__ __forceinline__ float act_apply_t(float v) {
+    if (ACT == HIPIE_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == HIPIE_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    if (ACT == HIPIE_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    return v;
+}
+
+// Row-major epilogue for one warp: `nch` chunks of 32 columns starting at chunk c0.  The accumulator rows
+// (one per lane) are transposed through padded smem; afterwards lanes 0-7 cover one row with float4s, so a
+// warp stores four fully coalesced 128-byte row segments per instruction.
+template <int ACT>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, float* my_epi, int b, int m0,
+                                              int n0, int col_begin, int col_end, int lane) {
+    const float* res_b = p.residual ? p.residual + (int64_t)b * p.r_bstride : nullptr;
+    float* cf_b = p.c_f32 ? p.c_f32 + (int64_t)b * p.c_bstride : nullptr;
+    __nv_bfloat16* chi_b = p.c_hi ? p.c_hi + (int64_t)b * p.c_bstride : nullptr;
+    __nv_bfloat16* clo_b = p.c_lo ? p.c_lo + (int64_t)b * p.c_bstride : nullptr;
+    const int rsub = lane >> 2, c4 = (lane & 3) * 4;   // 8 rows x 16 columns per warp instruction
+    const bool vec_ok = ((p.ldc & 3) == 0) && (!res_b || (p.ldr & 3) == 0);
+    const int rmax = min(32, p.M - m0);
+#pragma unroll 1
+    for (int cb = col_begin; cb < col_end; cb += 16) {
+        const int nbase = n0 + cb;
+        if (nbase >= p.N) break;  // warp-uniform
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + cb, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<uint4*>(my_epi + lane * EPI_LD + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const int col = nbase + c4;
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f);
+        const bool full4 = col + 3 < p.N;
+        if (p.bias) {
+            if (full4) bias = *reinterpret_cast<const float4*>(p.bias + col);
+            else {
+                if (col < p.N) bias.x = p.bias[col];
+                if (col + 1 < p.N) bias.y = p.bias[col + 1];
+                if (col + 2 < p.N) bias.z = p.bias[col + 2];
+            }
+        }
+        if (p.colscale) {
+            if (full4) cs = *reinterpret_cast<const float4*>(p.colscale + col);
+            else {
+                if (col < p.N) cs.x = p.colscale[col];
+                if (col + 1 < p.N) cs.y = p.colscale[col + 1];
+                if (col + 2 < p.N) cs.z = p.colscale[col + 2];
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + rsub;
+            if (rr >= rmax || col >= p.N) continue;
+            float4 x = *reinterpret_cast<const float4*>(my_epi + rr * EPI_LD + c4);
+            x.x = act_apply_t<ACT>(x.x * p.alpha + bias.x) * cs.x;
+            x.y = act_apply_t<ACT>(x.y * p.alpha + bias.y) * cs.y;
+            x.z = act_apply_t<ACT>(x.z * p.alpha + bias.z) * cs.z;
+            x.w = act_apply_t<ACT>(x.w * p.alpha + bias.w) * cs.w;
+            int64_t row = m0 + rr;
+            if (p.row_map) {
+                row = p.row_map[(int64_t)b * p.M + row];
+                if (row < 0) continue;
+            }
+            const int64_t off = row * p.ldc + col;
+            if (full4 && vec_ok) {
+                if (res_b) {
+                    const float4 rv = *reinterpret_cast<const float4*>(res_b + row * p.ldr + col);
+                    x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
+                }
+                if (cf_b) *reinterpret_cast<float4*>(cf_b + off) = x;
+                if (chi_b) {
+                    uint2 hi, lo;
+                    split2(x.x, x.y, hi.x, lo.x);
+                    split2(x.z, x.w, hi.y, lo.y);
+                    *reinterpret_cast<uint2*>(chi_b + off) = hi;
+                    if (clo_b) *reinterpret_cast<uint2*>(clo_b + off) = lo;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (col + e < p.N) {
+                        float xv = e == 0 ? x.x : (e == 1 ? x.y : (e == 2 ? x.z : x.w));
+                        if (res_b) xv += res_b[row * p.ldr + col + e];
+                        if (cf_b) cf_b[off + e] = xv;
+                        if (chi_b) {
+                            const __nv_bfloat16 h = __float2bfloat16_rn(xv);
+                            chi_b[off + e] = h;
+                            if (clo_b) clo_b[off + e] = __float2bfloat16_rn(xv - __bfloat162float(h));
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Transposed epilogue (C stored [col * ldc + row]): lanes hold 32 consecutive rows, so each register j is a
+// coalesced 128-byte store along M; optional bit-packed (x > threshold) output packed along M.
+__device__ __forceinline__ void epilogue_transposed(const GemmParams& p, uint32_t taddr, int b, int m0, int n0,
+                                                    int col_begin, int col_end, int lane) {
+    const float* res_b = p.residual ? p.residual + (int64_t)b * p.r_bstride : nullptr;
+    float* cf_b = p.c_f32 ? p.c_f32 + (int64_t)b * p.c_bstride : nullptr;
+    __nv_bfloat16* chi_b = p.c_hi ? p.c_hi + (int64_t)b * p.c_bstride : nullptr;
+    __nv_bfloat16* clo_b = p.c_lo ? p.c_lo + (int64_t)b * p.c_bstride : nullptr;
+    const int row = m0 + lane;
+    const bool rok = row < p.M;
+#pragma unroll 1
+    for (int cb = col_begin; cb < col_end; cb += 32) {
+        const int nbase = n0 + cb;
+        if (nbase >= p.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + cb, v);
+        tmem_ld_wait();
+        uint32_t bitsword = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = nbase + j;
+            if (col < p.N) {
+                float x = __uint_as_float(v[j]) * p.alpha;
+                if (p.bias) x += __ldg(p.bias + col);
+                x = act_apply(x, p.act);
+                if (p.colscale) x *= __ldg(p.colscale + col);
+                const int64_t off = (int64_t)col * p.ldc + row;
+                if (res_b && rok) x += res_b[(int64_t)col * p.ldr + row];
+                if (rok) {
+                    if (cf_b) cf_b[off] = x;
+                    if (chi_b) {
+                        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                        chi_b[off] = h;
+                        if (clo_b) clo_b[off] = __float2bfloat16_rn(x - __bfloat162float(h));
+                    }
+                }
+                if (p.c_bits) {
+                    const uint32_t word = __ballot_sync(0xffffffffu, rok && x > p.bits_threshold);
+                    if (lane == j) bitsword = word;
+                }
+            }
+        }
+        if (p.c_bits) {
+            const int col = nbase + lane;
+            if (col < p.N && m0 < p.M) {
+                const int64_t words_per_col = (p.M + 31) / 32;
+                p.c_bits[((int64_t)b * p.N + col) * words_per_col + (m0 >> 5)] = bitsword;
+            }
+        }
+    }
 }
 
 template <int PREC, int BN>
@@ -113,7 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&tfull_bar[i], 1);
-                mbar_init(&tempty_bar[i], 4);
+                mbar_init(&tempty_bar[i], 8);
             }
             fence_barrier_init();
         }
@@ -191,9 +343,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        float* my_epi = epi + (warp - 2) * 32 * EPI_LD;
+        // ===================== epilogue (warps 2..9) =====================
+        // warp w may only touch TMEM lanes [32*(w%4), +32); two warps share a lane quarter and split
+        // the BN columns between them.
+        const int quarter = warp & 3;
+        const int ew = warp - 2;                 // 0..7
+        const int chalf = ew >> 2;               // which half of the column chunks
+        float* my_epi = epi + ew * 32 * EPI_LD;
+        constexpr int COLS_PER = BN >= 64 ? BN / 2 : BN;     // columns per warp of a lane-quarter pair
+        const bool active = BN >= 64 || chalf == 0;
+        const int cbeg = chalf * COLS_PER, cend = cbeg + COLS_PER;
         int acc = 0;
         uint32_t acc_ph = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -204,84 +363,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-            const float* res_b = p.residual ? p.residual + (int64_t)b * p.r_bstride : nullptr;
-            float* cf_b = p.c_f32 ? p.c_f32 + (int64_t)b * p.c_bstride : nullptr;
-            __nv_bfloat16* chi_b = p.c_hi ? p.c_hi + (int64_t)b * p.c_bstride : nullptr;
-            __nv_bfloat16* clo_b = p.c_lo ? p.c_lo + (int64_t)b * p.c_bstride : nullptr;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int nbase = n0 + c * 32;
-                if (nbase >= p.N) break;  // warp-uniform
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(taddr + c * 32, v);
-                tmem_ld_wait();
-                if (p.transposed) {
-                    // lanes = 32 consecutive rows (m); register j = column nbase + j
-                    const int row = m0 + lane;
-                    const bool rok = row < p.M;
-                    uint32_t bitsword = 0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = nbase + j;
-                        if (col < p.N) {
-                            float x = __uint_as_float(v[j]) * p.alpha;
-                            if (p.bias) x += __ldg(p.bias + col);
-                            x = act_apply(x, p.act);
-                            if (p.colscale) x *= __ldg(p.colscale + col);
-                            const int64_t off = (int64_t)col * p.ldc + row;
-                            if (res_b && rok) x += res_b[(int64_t)col * p.ldr + row];
-                            if (rok) {
-                                if (cf_b) cf_b[off] = x;
-                                if (chi_b) {
-                                    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-                                    chi_b[off] = h;
-                                    if (clo_b) clo_b[off] = __float2bfloat16_rn(x - __bfloat162float(h));
-                                }
-                            }
-                            if (p.c_bits) {
-                                const uint32_t word = __ballot_sync(0xffffffffu, rok && x > p.bits_threshold);
-                                if (lane == j) bitsword = word;
-                            }
-                        }
+            if (active) {
+                if (p.transposed)
+                    epilogue_transposed(p, taddr, b, m0, n0, cbeg, cend, lane);
+                else
+                    switch (p.act) {
+                        case HIPIE_ACT_RELU: epilogue_rows<HIPIE_ACT_RELU>(p, taddr, my_epi, b, m0, n0, cbeg, cend, lane); break;
+                        case HIPIE_ACT_GELU: epilogue_rows<HIPIE_ACT_GELU>(p, taddr, my_epi, b, m0, n0, cbeg, cend, lane); break;
+                        case HIPIE_ACT_SIGMOID: epilogue_rows<HIPIE_ACT_SIGMOID>(p, taddr, my_epi, b, m0, n0, cbeg, cend, lane); break;
+                        default: epilogue_rows<HIPIE_ACT_NONE>(p, taddr, my_epi, b, m0, n0, cbeg, cend, lane); break;
                     }
-                    if (p.c_bits) {
-                        const int col = nbase + lane;
-                        // bits packed along M: word index = row / 32 (M tile rows are 32-aligned)
-                        if (col < p.N && m0 < p.M) {
-                            const int64_t words_per_col = (p.M + 31) / 32;
-                            p.c_bits[((int64_t)b * p.N + col) * words_per_col + (m0 >> 5)] = bitsword;
-                        }
-                    }
-                } else {
-                    // transpose through smem: thread (row) writes 32 columns, then lanes = columns
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<uint4*>(my_epi + lane * EPI_LD + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    __syncwarp();
-                    const int col = nbase + lane;
-                    const bool cok = col < p.N;
-                    const float bias = (p.bias && cok) ? __ldg(p.bias + col) : 0.f;
-                    const float cs = (p.colscale && cok) ? __ldg(p.colscale + col) : 1.f;
-                    const int rmax = min(32, p.M - m0);
-#pragma unroll 4
-                    for (int rr = 0; rr < rmax; ++rr) {
-                        float x = my_epi[rr * EPI_LD + lane] * p.alpha + bias;
-                        x = act_apply(x, p.act) * cs;
-                        int64_t row = m0 + rr;
-                        if (p.row_map) row = p.row_map[(int64_t)b * p.M + row];
-                        if (cok && row >= 0) {
-                            if (res_b) x += res_b[row * p.ldr + col];
-                            const int64_t off = row * p.ldc + col;
-                            if (cf_b) cf_b[off] = x;
-                            if (chi_b) {
-                                const __nv_bfloat16 h = __float2bfloat16_rn(x);
-                                chi_b[off] = h;
-                                if (clo_b) clo_b[off] = __float2bfloat16_rn(x - __bfloat162float(h));
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
             }
             // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
             tc_fence_before();

@@ -239,6 +239,7 @@ extern "C" int hipie_msda_forward(const void* value, const int64_t* spatial_shap
                                   const int64_t* level_start_index, const void* sampling_loc,
                                   const void* attn_weight, void* out, int N, int S, int M, int D,
                                   int L, int Lq, int P, int dtype, int value_dtype, void* stream) {
+    if (N >= 0 && Lq >= 0 && (int64_t)N * Lq == 0) return HIPIE_OK;   // empty batch / no queries
     HIPIE_CHECK_ARG(value && spatial_shapes && level_start_index && sampling_loc && attn_weight && out,
                     "hipie_msda_forward: null pointer argument");
     HIPIE_CHECK_ARG(N >= 0 && S > 0 && M > 0 && D > 0 && L > 0 && Lq >= 0 && P > 0,
