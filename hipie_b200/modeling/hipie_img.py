@@ -1,0 +1,315 @@
+"""HIPIE_IMG meta-architecture on the B200 engine — drop-in for the reference's
+`META_ARCH_REGISTRY.get("HIPIE_IMG")(cfg)` (/root/reference/projects/HIPIE/hipie/hipie_img.py:45-420):
+same constructor argument (a cfg node), same `forward(batched_inputs, do_postprocess=True)` contract, same
+state_dict key names (modeling/params.py), same output dictionaries.
+
+The forward path has no CPU fallback: the CUDA extension must be built and a CUDA device present.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..structures import Boxes, ImageList, Instances
+from . import params as P
+from .engine import Engine, inverse_sigmoid
+
+
+def box_cxcywh_to_xyxy(x):
+    x_c, y_c, w, h = x.unbind(-1)
+    return torch.stack([(x_c - 0.5 * w), (y_c - 0.5 * h), (x_c + 0.5 * w), (y_c + 0.5 * h)], dim=-1)
+
+
+def hp_from_cfg(cfg):
+    """Translate the detectron2-style cfg (config.py: add_hipie_config + the MaskDINO yaml) into engine hyper-parameters."""
+    m = cfg.MODEL
+    hp = dict(hidden_dim=m.DDETRS.HIDDEN_DIM, enc_layers=m.DDETRS.ENC_LAYERS, dec_layers=m.DDETRS.DEC_LAYERS,
+              dim_ff=m.DDETRS.DIM_FEEDFORWARD, num_queries=m.DDETRS.TWO_STAGE_NUM_PROPOSALS,
+              num_bg=m.DDETRS.TWO_STAGE_NUM_BG_PROPOSALS, vl_hidden=m.DDETRS.VL_HIDDEN_DIM, lang_dim=m.LANGUAGE_BACKBONE.LANG_DIM,
+              max_query_len=m.LANGUAGE_BACKBONE.MAX_QUERY_LEN, max_pool=bool(cfg.TEST.MAX_POOL),
+              bg_cls_agnostic=bool(cfg.TEST.BG_CLS_AGNOSTIC),
+              bert=dict(vocab=30522, hidden=768, layers=12, heads=12, inter=3072, max_pos=512))
+    if m.BACKBONE.NAME == "D2ViT":
+        dims = {"ViT-Base": (768, 12, 12), "ViT-Large": (1024, 24, 16), "ViT-huge": (1280, 32, 16)}[m.VIT.NAME]
+        hp["backbone"] = "vit"
+        hp["vit"] = dict(embed_dim=dims[0], depth=dims[1], num_heads=dims[2], window_size=14,
+                         window_block_indexes=(0, 1, 3, 4, 6, 7, 9, 10), img_size=1024, patch_size=16, pretrain_img_size=224)
+    else:
+        hp["backbone"] = "r50"
+    md = getattr(cfg, "_maskdino_cfg", None)
+    if md is not None:
+        hp.update(md_queries=md.MODEL.MaskDINO.NUM_OBJECT_QUERIES, md_dec_layers=md.MODEL.MaskDINO.DEC_LAYERS,
+                  md_enc_layers=md.MODEL.SEM_SEG_HEAD.TRANSFORMER_ENC_LAYERS, md_dim_ff=md.MODEL.MaskDINO.DIM_FEEDFORWARD)
+    else:
+        hp.update(md_queries=300, md_dec_layers=9, md_enc_layers=6, md_dim_ff=2048)
+    return hp
+
+
+class HIPIE_IMG(nn.Module):
+    """Unified open-vocabulary detection / segmentation / grounding model, inference only."""
+
+    def __init__(self, cfg=None, hp=None, state_dict=None, device=None):
+        super().__init__()
+        if hp is None:
+            hp = hp_from_cfg(cfg)
+        self.cfg = cfg
+        self.hp = hp
+        self.device_ = torch.device(device or (cfg.MODEL.DEVICE if cfg is not None else "cuda"))
+        if self.device_.type != "cuda":
+            raise RuntimeError("hipie_b200.HIPIE_IMG runs on a CUDA (sm_100a) device only; there is no CPU path")
+        self.demo_only = False
+        self.num_bg, self.num_fg = hp.get("num_bg", 10), hp.get("num_queries", 900)
+        self.mask_stride, self.mask_thres = 4, 0.5
+        self.pano_temp, self.object_mask_threshold, self.overlap_threshold = 0.06, 0.25, 0.8
+        self.max_pool, self.bg_cls_agnostic, self.use_bg_for_pano = hp.get("max_pool", False), hp.get("bg_cls_agnostic", False), False
+        self._sd = OrderedDict()
+        self.engine = None
+        if state_dict is None:
+            state_dict = P.random_state_dict(hp, seed=0)
+        self.load_state_dict(state_dict)
+
+    @property
+    def device(self):
+        return self.device_
+
+    # ---- checkpoint interface (reference key names)
+    def state_dict(self, *a, **k):
+        return OrderedDict(self._sd)
+
+    def load_state_dict(self, sd, strict=True):
+        spec = P.build_spec(self.hp)
+        new = OrderedDict()
+        for k, v in sd.items():
+            c = P.canonical_name(k, self.hp)
+            if c in spec.shapes:
+                if tuple(v.shape) != spec.shapes[c]:
+                    raise RuntimeError(f"size mismatch for {c}: {tuple(v.shape)} vs {spec.shapes[c]}")
+                new.setdefault(c, v.detach().float().cpu())
+        missing = [k for k in spec.shapes if k not in new]
+        if strict and missing:
+            raise RuntimeError(f"missing keys in state_dict: {missing[:8]} ... ({len(missing)})")
+        self._sd = new
+        self.engine = Engine(new, self.hp, self.device_)
+        return missing
+
+    # ---- stages
+    def preprocess_image(self, batched_inputs):
+        """hipie_img.py:880-898 + util/misc.py:288-316: the (x-mean)/std normalisation is fused into the patch kernel for the
+        ViT path, so this only pads raw pixels; padded pixels must equal `mean` so that they normalise to 0."""
+        imgs = [x["image"].to(self.device_, non_blocking=True).float() for x in batched_inputs]
+        sizes = [tuple(i.shape[-2:]) for i in imgs]
+        div = 32 if self.hp["backbone"] == "vit" else 0
+        H, Wd = max(s[0] for s in sizes), max(s[1] for s in sizes)
+        if div > 1:
+            H, Wd = (H + div - 1) // div * div, (Wd + div - 1) // div * div
+        mean = torch.tensor([123.675, 116.280, 103.530], device=self.device_).view(3, 1, 1)
+        if all(s == (H, Wd) for s in sizes):
+            tensor = torch.stack(imgs)
+        else:
+            tensor = mean.expand(3, H, Wd).unsqueeze(0).repeat(len(imgs), 1, 1, 1).contiguous()
+            for i, im in enumerate(imgs):
+                tensor[i, :, :im.shape[1], :im.shape[2]] = im
+        mask = torch.ones(len(imgs), H, Wd, dtype=torch.bool, device=self.device_)
+        for i, s in enumerate(sizes):
+            mask[i, :s[0], :s[1]] = False
+        return tensor, mask, sizes
+
+    @torch.no_grad()
+    def coco_inference(self, tensor, pad_mask, image_sizes, lang, task="detection", forced=None):
+        """DDETRSegmUniDN.coco_inference (H/models/ddetrs_dn.py:801-978)."""
+        forced = forced or {}
+        eng, hp = self.engine, self.hp
+        B = tensor.shape[0]
+        if hp["backbone"] != "vit":
+            raise RuntimeError("the B200 engine implements the ViT backbones; the R50 configuration (#1) is CPU plumbing only")
+        feats = eng.vit(tensor)
+        if task == "grounding":
+            lm = lang["masks"].float()
+            lang_feat_pool = ((lang["hidden"] * lm.unsqueeze(-1)).sum(1) / lm.sum(-1, keepdim=True)).unsqueeze(1)   # pre-fusion (:809-811)
+        di = eng.detr_inputs(feats, pad_mask, B)
+        tr = eng.detr_transformer(di, lang, B, forced_topk=forced.get("topk_fg"))
+        md = eng.maskdino(feats, B, forced_topk=forced.get("topk_md"))
+        nd = hp.get("dec_layers", 6)
+        lvl = nd - 1
+        hs, hs_s = tr["hs"][lvl]
+        Q = hs.shape[1]
+        lang_for_cls = lang_feat_pool if task == "grounding" else tr["lang_hidden"]
+        out = {}
+        out["pred_logits"] = eng.vl_align(f"detr.detr.class_embed.{lvl}", hs_s.view(B * Q, 256), lang_for_cls, B, Q)
+        out["pred_boxes"] = tr["refs"][lvl]          # == sigmoid(bbox_embed[lvl](hs[lvl]) + inverse_sigmoid(refs[lvl-1])) (:900-920)
+        wi, bi = eng.W.lin(f"detr.detr.iou_head.{lvl}")
+        out["pred_boxious"] = ops.gemm(hs_s.view(B * Q, 256), wi, bias=bi)[0].view(B, Q, 1)
+        masks, mh_feats, params, ref_px = eng.condinst(tr["memory"], tr, di, image_sizes, B)
+        out["pred_masks"] = masks.unsqueeze(2)
+        nqm = md["pred_logits_emb"].shape[1]
+        ncls = hp.get("md_dec_layers", 9) + 2
+        out["pred_logits_maskdino"] = eng.vl_align(f"detr.mask_dino_cls_embed.{ncls - 1}", md["pred_logits_emb_s"], lang_for_cls, B, nqm)
+        out["pred_masks_maskdino"] = md["pred_masks"]
+        out["pred_boxes_maskdino"] = md["pred_boxes"]
+        out["aux"] = dict(enc_scores=tr["enc_scores"], topk=tr["topk"], md_enc_scores=md["enc_scores"], md_topk=md["topk"],
+                          memory=tr["memory"], hs=[h[0] for h in tr["hs"]], refs=tr["refs"], mask_head_feats=mh_feats,
+                          lang_hidden_fused=tr["lang_hidden"], feats={k: v[0] for k, v in feats.items()},
+                          mask_bits=md["mask_bits"])
+        return out
+
+    # ---- post-processing (hipie_img.py:537-766, 473-535, 870-878, 1025-1052); device-side torch glue for now ("next" tier)
+    @staticmethod
+    def convert_grounding_to_od_logits(logits, num_classes, positive_map, is_thing, mode=None, max_pool=False):
+        scores = torch.zeros(logits.shape[0], logits.shape[1], num_classes, device=logits.device)
+        for label_j in positive_map:
+            idx = torch.as_tensor(positive_map[label_j], dtype=torch.long, device=logits.device)
+            if max_pool:
+                scores[:, :, label_j - 1] = logits[:, :, idx].max(-1)[0]
+            else:
+                scores[:, :, label_j - 1] = logits[:, :, idx].mean(-1)
+            if mode == "FG" and (not is_thing.get(label_j, True)):
+                scores[:, :, label_j - 1] = -9999.0
+            elif mode == "BG" and is_thing.get(label_j, True):
+                scores[:, :, label_j - 1] = -9999.0
+        return scores
+
+    def semantic_inference(self, mask_cls, mask_pred):
+        return torch.einsum("qc,qhw->chw", mask_cls, mask_pred.sigmoid())
+
+    def panoptic_inference(self, mask_cls, mask_pred, is_thing):
+        scores, labels = mask_cls.max(-1)
+        mask_pred = mask_pred.sigmoid()
+        keep = scores > self.object_mask_threshold
+        cur_scores, cur_classes, cur_masks = scores[keep], labels[keep], mask_pred[keep]
+        cur_prob_masks = cur_scores.view(-1, 1, 1) * cur_masks
+        h, w = cur_masks.shape[-2:]
+        panoptic_seg = torch.zeros((h, w), dtype=torch.int32, device=cur_masks.device)
+        segments_info = []
+        current_segment_id = 0
+        if cur_masks.shape[0] == 0:
+            return panoptic_seg, segments_info
+        cur_mask_ids = cur_prob_masks.argmax(0)
+        K = cur_classes.shape[0]
+        ids = torch.arange(K, device=cur_masks.device).view(K, 1, 1)
+        own = cur_mask_ids.unsqueeze(0) == ids
+        mask_area = own.flatten(1).sum(1)
+        original_area = (cur_masks >= 0.5).flatten(1).sum(1)
+        inter = (own & (cur_masks >= 0.5))
+        inter_area = inter.flatten(1).sum(1)
+        mask_area_c, original_area_c, inter_area_c, classes_c = mask_area.tolist(), original_area.tolist(), inter_area.tolist(), cur_classes.tolist()
+        stuff_memory_list = {}
+        for k in range(K):
+            pred_class = classes_c[k]
+            isthing = is_thing.get(int(pred_class + 1), True)
+            if mask_area_c[k] > 0 and original_area_c[k] > 0 and inter_area_c[k] > 0:
+                if mask_area_c[k] / original_area_c[k] < self.overlap_threshold:
+                    continue
+                if not isthing:
+                    if int(pred_class) in stuff_memory_list:
+                        panoptic_seg[inter[k]] = stuff_memory_list[int(pred_class)]
+                        continue
+                    stuff_memory_list[int(pred_class)] = current_segment_id + 1
+                current_segment_id += 1
+                panoptic_seg[inter[k]] = current_segment_id
+                segments_info.append({"id": current_segment_id, "isthing": bool(isthing), "category_id": int(pred_class)})
+        return panoptic_seg, segments_info
+
+    @torch.no_grad()
+    def inference(self, out, image_sizes, positive_map, num_classes, task, is_thing, sizes):
+        import torchvision.ops as tvops
+        max_num_inst = 100 if task == "detection" else 1
+        fg = self.num_bg
+        box_cls, box_pred = out["pred_logits"][:, fg:], out["pred_boxes"][:, fg:]
+        mask_pred, iou_pred = out["pred_masks"][:, fg:], out["pred_boxious"][:, fg:]
+        box_cls_bg = out["pred_logits_maskdino"]
+        mask_pred_bg = out["pred_masks_maskdino"].unsqueeze(2)
+        results = []
+        for i in range(len(image_sizes)):
+            image_size = image_sizes[i]
+            has_thing = any(is_thing[i].values())
+            logits_per_image = self.convert_grounding_to_od_logits(box_cls[i].unsqueeze(0), num_classes, positive_map, is_thing[i],
+                                                                   mode="FG" if has_thing else None, max_pool=self.max_pool)[0]
+            prob = torch.sqrt(logits_per_image.sigmoid() * iou_pred[i].sigmoid())
+            nms_scores, idxs = torch.max(prob, 1)
+            keep_indices = tvops.batched_nms(box_cxcywh_to_xyxy(box_pred[i]), nms_scores, idxs, 0.7)
+            prob = prob[keep_indices]
+            num_inst = min(max_num_inst, prob.numel())
+            box_k, mask_k = box_pred[i][keep_indices], mask_pred[i][keep_indices]
+            topk_values, topk_indexes = torch.topk(prob.view(-1), num_inst, dim=0)
+            topk_boxes = torch.div(topk_indexes, logits_per_image.shape[1], rounding_mode="floor")
+            labels = topk_indexes % logits_per_image.shape[1]
+            box_k, mask_i = box_k[topk_boxes], mask_k[topk_boxes]
+            result = Instances(image_size)
+            result.pred_boxes = Boxes(box_cxcywh_to_xyxy(box_k))
+            result.pred_boxes.scale(scale_x=image_size[1], scale_y=image_size[0])
+            N, C, H, Wd = mask_i.shape
+            m = F.interpolate(mask_i, size=(H * self.mask_stride, Wd * self.mask_stride), mode="bilinear", align_corners=False)
+            result.pred_masks = (m.sigmoid() > self.mask_thres)[:, :, :image_size[0], :image_size[1]]
+            result.scores = topk_values
+            result.pred_classes = labels
+            sem = None
+            pano = (None, None)
+            if task == "detection":
+                mode = None if (self.use_bg_for_pano or self.bg_cls_agnostic) else "BG"
+                logits_bg = self.convert_grounding_to_od_logits(box_cls_bg[i].unsqueeze(0), num_classes, positive_map, is_thing[i],
+                                                                mode=mode, max_pool=self.max_pool)[0]
+                logits_all = torch.cat([logits_per_image[keep_indices], logits_bg], dim=0)
+                mask_all = torch.cat([mask_pred[i][keep_indices], mask_pred_bg[i]], dim=0)
+                N, C, H, Wd = mask_all.shape
+                logits_all = F.softmax(logits_all.sigmoid() / self.pano_temp, dim=-1)
+                mask_all = F.interpolate(mask_all, size=(H * self.mask_stride, Wd * self.mask_stride), mode="bilinear", align_corners=False)
+                mask_all = mask_all[:, :, :image_size[0], :image_size[1]]
+                mask_up = F.interpolate(mask_all, size=sizes[i], mode="bilinear", align_corners=False)[:, 0]
+                sem = self.semantic_inference(logits_all, mask_up)
+                pano = self.panoptic_inference(logits_all, mask_up, is_thing[i])
+            results.append(dict(instances=result, panoptic_seg=pano, sem_seg=sem))
+        return results
+
+    @staticmethod
+    def segmentation_postprocess(results, output_height, output_width):
+        """H/models/ddetrs.py:1029-1076"""
+        sx, sy = output_width / results.image_size[1], output_height / results.image_size[0]
+        out = Instances((output_height, output_width))
+        boxes = Boxes(results.pred_boxes.tensor.clone())
+        boxes.scale(sx, sy)
+        boxes.clip((output_height, output_width))
+        keep = boxes.nonempty()
+        out.pred_boxes = Boxes(boxes.tensor[keep])
+        masks = F.interpolate(results.pred_masks.float(), size=(output_height, output_width), mode="nearest")[:, 0].to(torch.uint8)
+        out.pred_masks = masks[keep]
+        out.scores = results.scores[keep]
+        out.pred_classes = results.pred_classes[keep]
+        return out
+
+    def forward_text(self, input_ids, attention_mask):
+        return self.engine.forward_text(input_ids.to(self.device_), attention_mask.to(self.device_))
+
+    @torch.no_grad()
+    def forward(self, batched_inputs, do_postprocess=True, forced=None, return_raw=False):
+        """batched_inputs: list[dict] with image (3,H,W) 0..255, height, width, task, is_thing, positive_map_label_to_token and
+        either `expressions` (str; needs a tokenizer attached via `self.tokenizer`) or pre-tokenised `input_ids`/`attention_mask`."""
+        task_list = [x["task"] for x in batched_inputs]
+        assert len(set(task_list)) == 1
+        task = task_list[0]
+        if task not in ("detection", "grounding"):
+            raise ValueError("task must be detection or grounding")
+        tensor, pad_mask, image_sizes = self.preprocess_image(batched_inputs)
+        positive_map = {1: [0]} if task == "grounding" else batched_inputs[0]["positive_map_label_to_token"]
+        num_classes = len(positive_map)
+        if "input_ids" in batched_inputs[0]:
+            ids = torch.stack([x["input_ids"] for x in batched_inputs])
+            am = torch.stack([x["attention_mask"] for x in batched_inputs])
+        else:
+            tok = getattr(self, "tokenizer", None)
+            if tok is None:
+                raise RuntimeError("no tokenizer attached (projects/HIPIE/bert-base-uncased is not available offline); "
+                                   "pass pre-tokenised input_ids / attention_mask")
+            enc = tok.batch_encode_plus([x["expressions"] for x in batched_inputs], max_length=self.hp["max_query_len"],
+                                        padding="max_length", return_tensors="pt", truncation=True)
+            ids, am = enc.input_ids, enc.attention_mask
+        lang = self.forward_text(ids, am)
+        out = self.coco_inference(tensor, pad_mask, image_sizes, lang, task=task, forced=forced)
+        is_thing = [x["is_thing"] for x in batched_inputs]
+        sizes = [(x.get("height", s[0]), x.get("width", s[1])) for x, s in zip(batched_inputs, image_sizes)]
+        results = self.inference(out, image_sizes, positive_map, num_classes, task, is_thing, sizes)
+        if do_postprocess:
+            for r, x, s in zip(results, batched_inputs, image_sizes):
+                r["instances"] = self.segmentation_postprocess(r["instances"], x.get("height", s[0]), x.get("width", s[1]))
+        return (results, out) if return_raw else results

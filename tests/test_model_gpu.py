@@ -1,0 +1,128 @@
+"""GPU: whole-model parity of the B200 engine against the CPU oracle on the tiny ViT configuration
+(same code paths as ViT-H: windowed + global blocks with rel-pos interpolation, 4 levels, VL fusion, two-stage
+top-k, bg queries, MaskDINO branch, CondInst), same seeded weights and inputs.
+
+The discontinuous selections (top-k proposals, NMS) are compared as sets on their scores and then pinned to the
+oracle's indices for the tensor comparisons (SURVEY.md §7 "hard parts").  Tolerances (bf16x3 parity mode):
+north-star says 1e-3 abs on mask logits; the random-weight CondInst logits are O(50..1000) (relative pixel
+coordinates times unit-variance dynamic weights), so those are checked at 1e-3 relative to the max logit and
+the MaskDINO mask logits (O(1)) at 1e-3 absolute.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup(cuda):
+    from hipie_oracle import hparams, synth
+    from hipie_oracle.model import HipieOracle
+    from hipie_b200 import ops
+    from hipie_b200.modeling.hipie_img import HIPIE_IMG
+    torch.manual_seed(0)
+    hp = hparams.get("vit_tiny")
+    oracle = HipieOracle(hp).eval()
+    synth.perturb_(oracle)
+    inputs, ids, am = synth.make_batch(2, 256, 256, 5, hp["max_query_len"])
+    with torch.no_grad():
+        res_o, out_o = oracle(inputs, ids, am)
+    ops.set_precision(3)
+    model = HIPIE_IMG(hp=hp, state_dict=oracle.state_dict(), device="cuda:0")
+    for x, i, a in zip(inputs, ids, am):
+        x["input_ids"], x["attention_mask"] = i, a
+    forced = {"topk_fg": out_o["aux"]["topk"].to(cuda), "topk_md": out_o["md"]["topk"].to(cuda)}
+    res_g, out_g = model(inputs, forced=forced, return_raw=True)
+    res_u, out_u = model(inputs, return_raw=True)
+    return dict(oracle=oracle, model=model, res_o=res_o, out_o=out_o, res_g=res_g, out_g=out_g, out_u=out_u, inputs=inputs)
+
+
+def _err(a, b):
+    return (a.detach().float().cpu() - b.detach().float().cpu()).abs().max().item()
+
+
+def test_backbone_features(setup):
+    o, g = setup["out_o"]["features"], setup["out_g"]["aux"]["feats"]
+    for k in ("res3", "res4", "res5"):
+        ref = o[k].permute(0, 2, 3, 1)
+        e = _err(g[k], ref)
+        assert e < 1e-3 * max(1.0, ref.abs().max().item()), (k, e)
+
+
+def test_text_and_fusion(setup):
+    e = _err(setup["out_g"]["aux"]["lang_hidden_fused"], setup["out_o"]["lang_hidden_fused"])
+    assert e < 1e-3, e
+    e = _err(setup["out_g"]["aux"]["memory"], setup["out_o"]["memory"])
+    assert e < 1e-3, e
+
+
+def test_proposal_scores_and_topk_sets(setup):
+    so, sg = setup["out_o"]["aux"]["enc_scores"], setup["out_u"]["aux"]["enc_scores"].cpu()
+    assert (so - sg).abs().max() < 1e-3
+    to, tg = setup["out_o"]["aux"]["topk"], setup["out_u"]["aux"]["topk"].cpu()
+    for b in range(to.shape[0]):
+        same = len(set(to[b].tolist()) & set(tg[b].tolist())) / to.shape[1]
+        assert same >= 0.95, same       # near-ties at the cut-off may swap
+    so, sg = setup["out_o"]["md"]["enc_scores"], setup["out_u"]["aux"]["md_enc_scores"].cpu()
+    assert (so - sg).abs().max() < 1e-3
+
+
+def test_decoder_states_boxes_logits(setup):
+    o, g = setup["out_o"], setup["out_g"]
+    for l in range(o["hs"].shape[0]):
+        assert _err(g["aux"]["hs"][l], o["hs"][l]) < 2e-3, l
+        assert _err(g["aux"]["refs"][l], o["inter_references"][l]) < 1e-4, l
+    assert _err(g["pred_boxes"], o["pred_boxes"]) < 1e-4
+    assert _err(g["pred_logits"], o["pred_logits"]) < 2e-3
+    assert _err(g["pred_boxious"], o["pred_boxious"]) < 2e-3
+    assert _err(g["pred_logits_maskdino"], o["pred_logits_maskdino"]) < 2e-3
+    assert _err(g["pred_boxes_maskdino"], o["pred_boxes_maskdino"]) < 1e-4
+
+
+def test_mask_logits(setup):
+    o, g = setup["out_o"], setup["out_g"]
+    e = _err(g["pred_masks_maskdino"], o["pred_masks_maskdino"])
+    assert e < 1e-3, e                                           # north-star: 1e-3 abs on mask logits
+    ref = o["pred_masks"]
+    e = _err(g["pred_masks"], ref)
+    assert e < 1e-3 * ref.abs().max().item(), (e, ref.abs().max().item())
+    # fused sigmoid>0.5 bit-packed output of the mask-embed GEMM == sign of the logits
+    bits = g["aux"]["mask_bits"].cpu()
+    lg = g["pred_masks_maskdino"].cpu().flatten(2)
+    B, Q, HW = lg.shape
+    want = (lg > 0).view(B, Q, HW // 32, 32).long()
+    want = (want << torch.arange(32)).sum(-1)
+    want = torch.where(want >= 2 ** 31, want - 2 ** 32, want).int()
+    assert torch.equal(bits.view(B, Q, HW // 32), want)
+
+
+def test_final_outputs_identical_classes(setup):
+    """identical argmax class assignments (pred_classes, sem_seg argmax, panoptic categories) with pinned selections"""
+    for ro, rg in zip(setup["res_o"], setup["res_g"]):
+        io, ig = ro["instances_post"], rg["instances"]
+        assert torch.equal(io["pred_classes"], ig.pred_classes.cpu())
+        assert (io["scores"] - ig.scores.cpu()).abs().max() < 1e-4
+        assert (io["pred_boxes"] - ig.pred_boxes.tensor.cpu()).abs().max() < 1e-2
+        agree = (io["pred_masks"] == ig.pred_masks.cpu()).float().mean()
+        assert agree > 0.9999, agree
+        so, sg = ro["sem_seg"], rg["sem_seg"].cpu()
+        assert (so.argmax(0) == sg.argmax(0)).float().mean() > 0.9995
+        assert (so - sg).abs().max() < 1e-3 * max(1.0, so.abs().max().item())
+        po, pg = ro["panoptic_seg"], rg["panoptic_seg"]
+        assert [s["category_id"] for s in po[1]] == [s["category_id"] for s in pg[1]]
+        assert (po[0] == pg[0].cpu()).float().mean() > 0.9995
+
+
+def test_fast_mode_runs_and_is_close(setup):
+    """plain-bf16 mode (prec 1 + bf16 value map): same pipeline, looser agreement — reported, not a parity claim."""
+    from hipie_b200 import ops
+    model = setup["model"]
+    ops.set_precision(1)
+    try:
+        forced = {"topk_fg": setup["out_o"]["aux"]["topk"].cuda(), "topk_md": setup["out_o"]["md"]["topk"].cuda()}
+        _, out = model(setup["inputs"], forced=forced, return_raw=True)
+    finally:
+        ops.set_precision(3)
+    ref = setup["out_o"]["pred_masks_maskdino"]
+    rel = _err(out["pred_masks_maskdino"], ref) / ref.abs().max().item()
+    assert rel < 0.25, rel
