@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the HIPIE inference hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+  python bench.py --gpus N --steps K --warmup W           # product arm (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ... # reference arm: the CPU oracle of the same path, rank 0 only
+
+Workload = BASELINE.json configs[1]: ViT-H, 8 x 1024x1024 synthetic images per GPU, 80-class COCO-style vocabulary
+(Lt = 512), task "detection", random-init weights of that architecture, synthetic token ids.
+A step = one pass of the hot path (preprocess -> ViT-H -> BERT -> VL fusion -> deformable encoder/decoder -> MaskDINO
+pixel decoder/decoder + mask-embed contraction -> CondInst masks) over the per-GPU batch with
+inputs resident in HBM.  `e2e` times the public API call (HIPIE_IMG.forward incl. post-processing, rows a20-a23) from
+pinned host images, H2D and D2H inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec at 1024x1024, ViT-H HIPIE inference hot path (synthetic batch)"
+PER_GPU_BATCH = 8
+IMG = 1024
+NUM_CLASSES = 80
+VIT_H_FLOPS_PER_IMG = 7.41e12      # SURVEY §8d / BASELINE.md §3 (patch-embed + 32 blocks + FPN @1024^2)
+
+
+def vit_h_hp():
+    bert = dict(vocab=30522, hidden=768, layers=12, heads=12, inter=3072, max_pos=512)
+    return dict(backbone="vit",
+                vit=dict(embed_dim=1280, depth=32, num_heads=16, window_size=14, window_block_indexes=(0, 1, 3, 4, 6, 7, 9, 10),
+                         img_size=1024, patch_size=16, pretrain_img_size=224),
+                hidden_dim=256, enc_layers=6, dec_layers=6, dim_ff=2048, num_queries=900, num_bg=10, vl_hidden=2048, lang_dim=768,
+                md_queries=300, md_dec_layers=9, md_enc_layers=6, md_dim_ff=2048, bert=bert, max_query_len=512)
+
+
+def synth_text(num_classes, max_len, seed=0):
+    """[CLS] + per-class 1-3 random word-piece ids joined by '.' (1012) + [SEP], zero padded."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    ids, pos_map = [101], {}
+    for c in range(1, num_classes + 1):
+        n = int(torch.randint(1, 4, (1,), generator=g))
+        toks = torch.randint(1996, 30000, (n,), generator=g).tolist()
+        pos_map[c] = list(range(len(ids), len(ids) + n))
+        ids += toks + [1012]
+    ids.append(102)
+    assert len(ids) <= max_len
+    input_ids = torch.zeros(max_len, dtype=torch.long)
+    input_ids[:len(ids)] = torch.tensor(ids)
+    attn = torch.zeros(max_len, dtype=torch.long)
+    attn[:len(ids)] = 1
+    n_thing = -(-num_classes * 6 // 10)
+    return input_ids, attn, pos_map, {c: c <= n_thing for c in range(1, num_classes + 1)}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        mx = max(float(s[1]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples if len(s) >= 7)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------ CPU oracle arm
+def cpu_oracle_seconds_per_image(verbose=False):
+    """Times the CPU oracle (oracle/, the restatement of the reference eval forward; the unmodified reference cannot
+    run on CPU: its MSDeformAttn op throws and detectron2/fvcore/timm are absent — DESIGN.md) on ONE 1024^2 image.
+    Bounded sample: the 32-block ViT-H is timed on 1 windowed + 1 global block and scaled to 8 + 24 blocks; everything
+    else on the path (patch embed, FPN, BERT, VL fusion, deformable encoder/decoder, MaskDINO, CondInst) runs in full."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from hipie_oracle import hparams, synth
+    from hipie_oracle.model import HipieOracle
+    torch.set_num_threads(os.cpu_count())
+    hp = hparams.get("vit_h")
+    hp["vit"] = dict(hp["vit"], depth=2, window_block_indexes=(0,))       # block 0 windowed, block 1 global
+    torch.manual_seed(0)
+    model = HipieOracle(hp).eval()
+    synth.perturb_(model)
+    inputs, ids, am = synth.make_batch(1, IMG, IMG, NUM_CLASSES, hp["max_query_len"])
+    vit = model.detr.detr.backbone[0].backbone
+    times = {"win": 0.0, "glob": 0.0}
+    import types
+
+    def timed_block(blk, kind):
+        orig = blk.forward
+
+        def fwd(self, x):
+            t0 = time.perf_counter()
+            y = orig(x)
+            times[kind] += time.perf_counter() - t0
+            return y
+        blk.forward = types.MethodType(fwd, blk)
+    for i, blk in enumerate(vit.blocks):
+        timed_block(blk, "win" if i < 1 else "glob")
+    with torch.no_grad():
+        tensor, mask, sizes = model.preprocess([x["image"] for x in inputs])
+        t0 = time.perf_counter()
+        lang = model.forward_text(ids, am)
+        out = model.coco_inference(tensor, mask, sizes, lang, task="detection")
+        total = time.perf_counter() - t0
+    rest = total - times["win"] - times["glob"]
+    full = rest + times["win"] * 8 + times["glob"] * 24
+    if verbose:
+        print(f"[cpu oracle] measured {total:.1f}s: window blk {times['win']:.2f}s, global blk {times['glob']:.2f}s, rest {rest:.1f}s"
+              f" -> scaled {full:.1f}s/img", file=sys.stderr)
+    return full, total, "1 image 1024^2: ViT-H timed on 1 windowed + 1 global block and scaled to 8 + 24, rest of the path " \
+                        "(BERT, VL fusion, deformable enc/dec, MaskDINO, CondInst) run once in full"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    secs = []
+    sample = ""
+    t_start = time.perf_counter()
+    warm = min(args.warmup, 1)           # one untimed sample warms the allocator / thread pool
+    done = 0
+    for i in range(warm + args.steps):
+        full, measured, sample = cpu_oracle_seconds_per_image(verbose=True)
+        if i >= warm:
+            secs.append(full)
+            done += 1
+        if secs and time.perf_counter() - t_start > args.ref_budget_s:
+            break                        # keep the whole reference run within a few minutes
+    spi = sorted(secs)[len(secs) // 2]
+    val = 1.0 / spi
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": spi * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: ViT-H, 1024x1024 synthetic, 80-class vocab (Lt=512), CPU oracle of the reference path",
+                       "note": f"each step is a bounded sample (see cpu_baseline.sample); {done} timed samples (median) within a "
+                               f"{args.ref_budget_s:.0f}s wall-clock budget, {warm} warm-up sample"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ product arm
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    from hipie_b200 import _lib, ops
+    from hipie_b200.modeling import params as P
+    from hipie_b200.modeling.hipie_img import HIPIE_IMG
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (product arm) needs a CUDA device: there is no CPU fallback for the hot path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    prec = 1 if args.precision == "bf16" else 3
+    ops.set_precision(prec)
+    hp = vit_h_hp()
+    model = HIPIE_IMG(hp=hp, state_dict=P.random_state_dict(hp, seed=0), device=str(dev))
+    model.engine.bf16_value_map = prec == 1
+    B = PER_GPU_BATCH
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_imgs = [(torch.rand(3, IMG, IMG, generator=g) * 255.0).pin_memory() for _ in range(B)]
+    ids, am, pos_map, is_thing = synth_text(NUM_CLASSES, hp["max_query_len"])
+    dev_imgs = torch.stack(host_imgs).to(dev)
+    ids_d, am_d = ids.unsqueeze(0).repeat(B, 1).to(dev), am.unsqueeze(0).repeat(B, 1).to(dev)
+    pad_mask = torch.zeros(B, IMG, IMG, dtype=torch.bool, device=dev)
+    sizes = [(IMG, IMG)] * B
+
+    def hot_step():
+        lang = model.forward_text(ids_d, am_d)
+        out = model.coco_inference(dev_imgs, pad_mask, sizes, lang, task="detection")
+        if world > 1:     # the only collective of the data-parallel path: all-gather of the fixed-shape logits / boxes
+            for k in ("pred_logits", "pred_boxes", "pred_logits_maskdino"):
+                t = out[k].contiguous()
+                gathered = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
+                dist.all_gather_into_tensor(gathered, t)
+        return out
+
+    def e2e_step():
+        batched = [dict(image=im, height=IMG, width=IMG, task="detection", is_thing=is_thing, positive_map_label_to_token=pos_map,
+                        input_ids=ids, attention_mask=am) for im in host_imgs]
+        res = model(batched)
+        host = []
+        for r in res:
+            inst = r["instances"]
+            host.append((inst.pred_boxes.tensor.cpu(), inst.scores.cpu(), inst.pred_classes.cpu(), r["panoptic_seg"][0].cpu(),
+                         r["sem_seg"].argmax(0).to(torch.uint8).cpu()))
+        return host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            hot_step()
+        barrier()
+        launches0 = _lib.launch_count()
+        with ClockSampler(local) as clk:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(args.steps):
+                hot_step()
+            e.record()
+            barrier()
+        ms = s.elapsed_time(e)
+        launches = _lib.launch_count() - launches0
+        # per-kernel live event timing (separate, identical steps so the events do not perturb the headline number)
+        ops.profiler.start()
+        prof_steps = max(1, min(2, args.steps))
+        for _ in range(prof_steps):
+            hot_step()
+        prof = ops.profiler.stop()
+        # end-to-end through the public API with host buffers
+        e2e_iters = max(1, min(args.steps, 3))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_iters):
+            host = e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_iters
+    t_ms = torch.tensor([ms, e2e_s * 1000.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t_ms[0]), float(t_ms[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    imgs_total = world * B * args.steps
+    value = imgs_total / (ms_max / 1000.0)
+    h2d = B * 3 * IMG * IMG * 4 + 2 * B * hp["max_query_len"] * 8
+    d2h = sum(sum(t.numel() * t.element_size() for t in h) for h in host)
+    # dominant kernel of the step
+    tot_prof = sum(v["ms"] for v in prof.values()) or 1.0
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    kernels = {}
+    for tag, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        per = v["ms"] / v["launches"]
+        entry = {"share_of_timed_kernels": v["ms"] / tot_prof, "launches_per_step": v["launches"] / prof_steps, "avg_ms": per}
+        if v["work"] > 0:
+            rate = v["work"] / v["launches"] / (per / 1000.0)
+            if tag.startswith("msda") or tag.startswith("condinst"):
+                entry.update(bound="hbm", achieved=rate / 1e9, unit="GB/s", frac=rate / 1e9 / pk["hbm"])
+            else:
+                entry.update(bound="tensor", achieved=rate / 1e12, unit="TFLOP/s", frac=rate / 1e12 / pk["tf_sustained"])
+        kernels[tag] = entry
+    tk = kernels[top[0]]
+    roofline = {"kernel": top[0], "bound": tk.get("bound", "tensor"), "achieved": tk.get("achieved"), "peak": pk["hbm"] if tk.get("bound") == "hbm" else pk["tf_sustained"],
+                "unit": tk.get("unit"), "frac": tk.get("frac"), "traffic": None, "peak_source": pk["src"] + " (sustained figure: kernel timed inside a long step)",
+                "vit_h_forward_tensor_frac": (VIT_H_FLOPS_PER_IMG * B * world * args.steps / (ms_max / 1000.0)) / 1e12 / (pk["tf_sustained"] * world),
+                "kernels": kernels}
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            full, measured, sample = cpu_oracle_seconds_per_image(verbose=True)
+            cpu = {"value": 1.0 / full, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample,
+                   "seconds_per_image_scaled": full, "seconds_measured": measured}
+        except Exception as ex:  # the CPU leg must never take the GPU number down with it
+            cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (split-bf16 tensor-core operands, fp32 accumulate; fp32-class results)" if prec == 3 else "bf16",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: ViT-H, batch 8 x 1024x1024 synthetic per GPU, 80-class COCO-style vocab (Lt=512), task detection",
+                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world} (image sharding, all-gather of logits)",
+                       "value_scope": "SURVEY 8a rows a1-a19: preprocess, ViT-H, BERT, VL fusion, deformable enc/dec, MaskDINO + mask-embed, CondInst masks",
+                       "e2e_scope": "HIPIE_IMG.forward (public API) incl. post-processing rows a20-a23, pinned-host images in, results out",
+                       "l2": "per-step working set (>= 1 GB activations per block) exceeds the 126 MB L2; no explicit flush",
+                       "precision_mode": args.precision},
+            "clocks": clk.summary(),
+            "e2e": {"value": world * B / (e2e_ms_max / 1000.0), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"],
+                    help="bf16x3 = parity-grade split precision (default, the headline); bf16 = fast mode")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0, help="wall-clock budget of the --impl reference run")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,6 +28,52 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _Profiler:
+    """Optional CUDA-event timing of individual kernel launches on the launching stream (used by bench.py for the
+    live roofline numbers).  Disabled by default: no events, no overhead."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []      # (tag, work, start_event, end_event)
+
+    def start(self):
+        self.records = []
+        self.enabled = True
+
+    def stop(self):
+        self.enabled = False
+        torch.cuda.synchronize()
+        out = {}
+        for tag, work, s, e in self.records:
+            d = out.setdefault(tag, {"ms": 0.0, "launches": 0, "work": 0.0})
+            d["ms"] += s.elapsed_time(e)
+            d["launches"] += 1
+            d["work"] += work
+        self.records = []
+        return out
+
+
+profiler = _Profiler()
+
+
+class _timed:
+    def __init__(self, tag, work=0.0):
+        self.tag, self.work = tag, work
+
+    def __enter__(self):
+        if profiler.enabled:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if profiler.enabled:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            profiler.records.append((self.tag, self.work, self.s, e))
+        return False
+
+
 def _p(t: Optional[torch.Tensor]):
     if t is None:
         return None
@@ -148,7 +194,8 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
         bits_threshold=float(bits_threshold) if bits_threshold is not None else 0.0,
         M=M, N=N, K=K, batch=batch, act=act, prec=prec, alpha=float(alpha), transposed=1 if transposed else 0,
         c_row_map=row_map.data_ptr() if row_map is not None else None)
-    _lib.check(lib.hipie_gemm(ctypes.byref(args), _stream()), "gemm")
+    with _timed(f"gemm_tc[p{prec}]" + (":mask_embed" if c_bits is not None else ""), 2.0 * M * N * K * batch):
+        _lib.check(lib.hipie_gemm(ctypes.byref(args), _stream()), "gemm")
     return c_f32, c_split, c_bits
 
 
@@ -280,7 +327,8 @@ def attention(q: BF2, k: BF2, v: BF2, B, H, Tq, Tk, hd, q_strides, k_strides, v_
         out_f32=o.data_ptr() if o is not None else None, out_hi=s.hi.data_ptr() if s else None,
         out_lo=s.lo.data_ptr() if (s and s.lo is not None) else None, o_bs=Tq * H * hd, o_ts=H * hd,
         B=B, H=H, Tq=Tq, Tk=Tk, hd=hd, scale=float(scale), prec=prec)
-    _lib.check(_lib.load().hipie_attention(ctypes.byref(args), _stream()), "attention")
+    with _timed(f"attention[p{prec}]" + (":global" if Tq >= 1024 else ":small"), 4.0 * B * H * Tq * Tk * hd):
+        _lib.check(_lib.load().hipie_attention(ctypes.byref(args), _stream()), "attention")
     return o, s
 
 
@@ -288,8 +336,9 @@ def relpos_bias(q: BF2, q_strides, table_t, axis, qh, qw, B, H, hd):
     """table_t: (qsize, hd, ksize) fp32.  Returns (B, H, qh*qw, ksize) fp32."""
     ksize = table_t.shape[-1]
     rel = torch.empty((B, H, qh * qw, ksize), dtype=torch.float32, device=table_t.device)
-    _lib.check(_lib.load().hipie_relpos_bias(_p(q.hi), _p(q.lo), q_strides[0], q_strides[1], q_strides[2], _p(table_t),
-                                             axis, qh, qw, ksize, _p(rel), B, H, hd, _stream()), "relpos_bias")
+    with _timed("relpos_bias"):
+        _lib.check(_lib.load().hipie_relpos_bias(_p(q.hi), _p(q.lo), q_strides[0], q_strides[1], q_strides[2], _p(table_t),
+                                                 axis, qh, qw, ksize, _p(rel), B, H, hd, _stream()), "relpos_bias")
     return rel
 
 
@@ -321,16 +370,21 @@ def msda_fused(value, spatial_shapes, level_start_index, offs_logits, reference_
     else:
         s = None
         out, out_lo = torch.empty((N, Lq, M * D), dtype=torch.float32, device=dev), None
-    _lib.check(_lib.load().hipie_msda_fused_forward(_p(value), _p(spatial_shapes), _p(level_start_index),
-                                                    _p(offs_logits.contiguous()), _p(reference_points.contiguous()), ref_dim,
-                                                    _p(out), N, S, M, D, L, Lq, P, vdt, 1 if want_split else 0, _p(out_lo),
-                                                    _stream()), "msda_fused_forward")
+    fv = 2 if vdt == 2 else 4
+    # algorithmic bytes: value map + offsets/logits (3 floats per sample) + output
+    alg = float(N) * (S * M * D * fv + Lq * M * L * P * 3 * 4 + Lq * M * D * 4)
+    with _timed("msda_fused" + (":enc" if Lq == S else ":dec"), alg):
+        _lib.check(_lib.load().hipie_msda_fused_forward(_p(value), _p(spatial_shapes), _p(level_start_index),
+                                                        _p(offs_logits.contiguous()), _p(reference_points.contiguous()), ref_dim,
+                                                        _p(out), N, S, M, D, L, Lq, P, vdt, 1 if want_split else 0, _p(out_lo),
+                                                        _stream()), "msda_fused_forward")
     return s if want_split else out
 
 
 def condinst_masks(feats_nhwc, params, ref_px, Hf, Wf, stride=8):
     B, Q = params.shape[0], params.shape[1]
     out = torch.empty((B, Q, 2 * Hf, 2 * Wf), dtype=torch.float32, device=params.device)
-    _lib.check(_lib.load().hipie_condinst_masks(_p(feats_nhwc.contiguous()), _p(params.contiguous()), _p(ref_px.contiguous()),
-                                                _p(out), B, Q, Hf, Wf, stride, _stream()), "condinst_masks")
+    with _timed("condinst", float(out.numel()) * 4):
+        _lib.check(_lib.load().hipie_condinst_masks(_p(feats_nhwc.contiguous()), _p(params.contiguous()), _p(ref_px.contiguous()),
+                                                    _p(out), B, Q, Hf, Wf, stride, _stream()), "condinst_masks")
     return out
