@@ -64,6 +64,8 @@ SYMBOLS = {
     "hipie_attention": (c_int, [ctypes.POINTER(AttnArgs), c_void_p]),
     "hipie_relpos_bias": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
                                   c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "hipie_relpos_bias_tc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
+                                     c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hipie_condinst_masks": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
 }
 

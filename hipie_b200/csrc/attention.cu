@@ -349,6 +349,103 @@ relpos_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __res
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Decomposed rel-pos tables on tensor cores.  Queries that share a grid coordinate (same row for the
+// height axis, same column for the width axis) share the (ksize x hd) table R[coord], so
+//   rel[b,h,q,:] = q[b,q,h,:] . R[coord(q)]^T
+// is a (G x hd) x (hd x ksize) GEMM per (b, h, coord) group of G queries.  One CTA = one (coord, b, h)
+// group; R[coord] (bf16 hi/lo, K-major) is staged in shared memory, each warp computes m16 slabs with
+// mma.sync in bf16x3 (fp32-class) and stores fp32.
+// ------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128)
+relpos_mma_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __restrict__ q_lo, int64_t q_bs,
+                  int64_t q_ts, int64_t q_hs, const __nv_bfloat16* __restrict__ R_hi,
+                  const __nv_bfloat16* __restrict__ R_lo, int axis, int qh, int qw, int ksize, int kpad,
+                  float* __restrict__ rel, int B, int H) {
+    constexpr int ROWB = HD * 2 + 16;
+    constexpr int KSTEPS = HD / 16;
+    constexpr int CHUNKS = HD / 8;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int coord = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int G = axis == 0 ? qw : qh;                       // queries sharing this coordinate
+    const int T = qh * qw;
+    // stage R[coord] (kpad rows x HD), rows >= ksize zero-filled
+    for (int pl = 0; pl < 2; ++pl) {
+        const __nv_bfloat16* src = (pl == 0 ? R_hi : R_lo) + (int64_t)coord * ksize * HD;
+        for (int i = threadIdx.x; i < kpad * CHUNKS; i += 128) {
+            const int r = i / CHUNKS, c = i - r * CHUNKS;
+            const bool ok = r < ksize;
+            cp_async16(sb + pl * kpad * ROWB + r * ROWB + c * 16, src + (int64_t)(ok ? r : 0) * HD + c * 8, ok ? 16 : 0);
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int nslabs = (G + 15) / 16;
+    for (int slab = warp; slab < nslabs; slab += 4) {
+        // A fragments straight from global: rows = members g of the group
+        const int g0 = slab * 16 + (lane >> 2), g1 = g0 + 8;
+        auto tok = [&](int g) { return axis == 0 ? coord * qw + g : g * qw + coord; };
+        const bool ok0 = g0 < G, ok1 = g1 < G;
+        const int64_t base0 = (int64_t)b * q_bs + (int64_t)tok(ok0 ? g0 : 0) * q_ts + (int64_t)h * q_hs + (lane & 3) * 2;
+        const int64_t base1 = (int64_t)b * q_bs + (int64_t)tok(ok1 ? g1 : 0) * q_ts + (int64_t)h * q_hs + (lane & 3) * 2;
+        uint32_t ah[KSTEPS][4], al[KSTEPS][4];
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+            ah[kk][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q_hi + base0 + kk * 16) : 0u;
+            ah[kk][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q_hi + base1 + kk * 16) : 0u;
+            ah[kk][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q_hi + base0 + kk * 16 + 8) : 0u;
+            ah[kk][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q_hi + base1 + kk * 16 + 8) : 0u;
+            if (q_lo) {
+                al[kk][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q_lo + base0 + kk * 16) : 0u;
+                al[kk][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q_lo + base1 + kk * 16) : 0u;
+                al[kk][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q_lo + base0 + kk * 16 + 8) : 0u;
+                al[kk][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q_lo + base1 + kk * 16 + 8) : 0u;
+            }
+        }
+        const int key_l = (lane & 7) + (lane >> 4) * 8;
+        const int cb = ((lane >> 3) & 1) * 16;
+        for (int j = 0; j < kpad / 8; j += 2) {
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(sb + (j * 8 + key_l) * ROWB + kk * 32 + cb, b0, b1, b2, b3);
+                mma_bf16(c0, ah[kk], b0, b1);
+                mma_bf16(c1, ah[kk], b2, b3);
+                if (q_lo) {
+                    mma_bf16(c0, al[kk], b0, b1);
+                    mma_bf16(c1, al[kk], b2, b3);
+                }
+                uint32_t d0, d1, d2, d3;
+                ldsm_x4(sb + kpad * ROWB + (j * 8 + key_l) * ROWB + kk * 32 + cb, d0, d1, d2, d3);
+                mma_bf16(c0, ah[kk], d0, d1);
+                mma_bf16(c1, ah[kk], d2, d3);
+            }
+            const int col = j * 8 + (lane & 3) * 2;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const float* c = half == 0 ? c0 : c1;
+                const int cc = col + half * 8;
+                if (ok0) {
+                    float* o = rel + ((((int64_t)b * H + h) * T) + tok(g0)) * ksize + cc;
+                    if (cc < ksize) o[0] = c[0];
+                    if (cc + 1 < ksize) o[1] = c[1];
+                }
+                if (ok1) {
+                    float* o = rel + ((((int64_t)b * H + h) * T) + tok(g1)) * ksize + cc;
+                    if (cc < ksize) o[0] = c[2];
+                    if (cc + 1 < ksize) o[1] = c[3];
+                }
+            }
+        }
+    }
+}
+
 template <int HD, int PREC>
 static int launch_attn(const AttnParams& p, cudaStream_t st) {
     constexpr int ROWB = HD * 2 + 16;
@@ -413,4 +510,38 @@ extern "C" int hipie_relpos_bias(const void* q_hi, const void* q_lo, int64_t q_b
         (const __nv_bfloat16*)q_hi, (const __nv_bfloat16*)q_lo, q_bs, q_ts, q_hs, table_t, axis, qh, qw, ksize, rel, B, H, hd);
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
+}
+
+
+// table given as bf16 hi/lo planes of get_rel_pos output, (qsize, ksize, hd) K-major (no transpose needed)
+extern "C" int hipie_relpos_bias_tc(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int64_t q_hs,
+                                    const void* table_hi, const void* table_lo, int axis, int qh, int qw, int ksize,
+                                    float* rel, int B, int H, int hd, void* stream) {
+    HIPIE_CHECK_ARG(q_hi && table_hi && table_lo && rel, "hipie_relpos_bias_tc: null pointer");
+    HIPIE_CHECK_ARG(axis == 0 || axis == 1, "hipie_relpos_bias_tc: axis in {0,1}");
+    HIPIE_CHECK_ARG(q_ts % 2 == 0 && q_hs % 2 == 0 && q_bs % 2 == 0, "hipie_relpos_bias_tc: strides must be even");
+    if ((int64_t)B * H * qh * qw == 0) return HIPIE_OK;
+    const int kpad = (ksize + 15) / 16 * 16;
+    dim3 grid(axis == 0 ? qh : qw, H, B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define HIPIE_RP(HDV)                                                                                           \
+    if (hd == HDV) {                                                                                            \
+        const int smem = 2 * kpad * (HDV * 2 + 16);                                                             \
+        static int smem_set = 0;                                                                                \
+        if (smem > smem_set) {                                                                                  \
+            HIPIE_CHECK_CUDA(cudaFuncSetAttribute(relpos_mma_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            smem_set = smem;                                                                                    \
+        }                                                                                                       \
+        relpos_mma_kernel<HDV><<<grid, 128, smem, st>>>((const __nv_bfloat16*)q_hi, (const __nv_bfloat16*)q_lo, q_bs, q_ts, \
+                                                         q_hs, (const __nv_bfloat16*)table_hi,                  \
+                                                         (const __nv_bfloat16*)table_lo, axis, qh, qw, ksize, kpad, rel, B, H); \
+        HIPIE_CHECK_LAUNCH();                                                                                   \
+        return HIPIE_OK;                                                                                        \
+    }
+    HIPIE_RP(32)
+    HIPIE_RP(64)
+    HIPIE_RP(80)
+#undef HIPIE_RP
+    set_error("hipie_relpos_bias_tc: unsupported head dim %d", hd);
+    return HIPIE_EUNSUPPORTED;
 }

@@ -206,10 +206,10 @@ class Engine:
             q = BF2(qkv.hi[:, 0:E], None if qkv.lo is None else qkv.lo[:, 0:E])
             k = BF2(qkv.hi[:, E:2 * E], None if qkv.lo is None else qkv.lo[:, E:2 * E])
             vv = BF2(qkv.hi[:, 2 * E:], None if qkv.lo is None else qkv.lo[:, 2 * E:])
-            Rh = W.cached(("relh", i, qh), lambda: _get_rel_pos_table(qh, qh, W[blk + ".attn.rel_pos_h"]).permute(0, 2, 1).contiguous())
-            Rw = W.cached(("relw", i, qw), lambda: _get_rel_pos_table(qw, qw, W[blk + ".attn.rel_pos_w"]).permute(0, 2, 1).contiguous())
-            rel_h = ops.relpos_bias(q, st, Rh, 0, qh, qw, Bq, nh, hd)
-            rel_w = ops.relpos_bias(q, st, Rw, 1, qh, qw, Bq, nh, hd)
+            Rh = W.cached(("relh", i, qh), lambda: ops.split_weight(_get_rel_pos_table(qh, qh, W[blk + ".attn.rel_pos_h"])))
+            Rw = W.cached(("relw", i, qw), lambda: ops.split_weight(_get_rel_pos_table(qw, qw, W[blk + ".attn.rel_pos_w"])))
+            rel_h = ops.relpos_bias_tc(q, st, Rh, 0, qh, qw, Bq, nh, hd)
+            rel_w = ops.relpos_bias_tc(q, st, Rw, 1, qh, qw, Bq, nh, hd)
             _, ao = ops.attention(q, k, vv, Bq, nh, Tq, Tq, hd, st, st, st, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=qh, kw=qw)
             ao = ao.view(Bq * Tq, E)
             if windowed:

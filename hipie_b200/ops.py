@@ -342,6 +342,17 @@ def relpos_bias(q: BF2, q_strides, table_t, axis, qh, qw, B, H, hd):
     return rel
 
 
+def relpos_bias_tc(q: BF2, q_strides, table: BF2, axis, qh, qw, B, H, hd):
+    """table: BF2 (qsize, ksize, hd) planes (split_weight of get_rel_pos output).  Returns (B, H, qh*qw, ksize) fp32."""
+    ksize = table.hi.shape[1]
+    rel = torch.empty((B, H, qh * qw, ksize), dtype=torch.float32, device=q.hi.device)
+    with _timed("relpos_bias_tc"):
+        _lib.check(_lib.load().hipie_relpos_bias_tc(_p(q.hi), _p(q.lo) if PREC == 3 else None, q_strides[0], q_strides[1], q_strides[2],
+                                                    _p(table.hi), _p(table.lo), axis, qh, qw, ksize, _p(rel), B, H, hd, _stream()),
+                   "relpos_bias_tc")
+    return rel
+
+
 def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
     """Drop-in core op (reference signature minus im2col_step): fp32/fp64 tensors on CUDA."""
     N, S, M, D = value.shape

@@ -187,6 +187,12 @@ int hipie_relpos_bias(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t 
                       const float* table_t, int axis, int qh, int qw, int ksize, float* rel,
                       int B, int H, int hd, void* stream);
 
+/* Tensor-core variant: table as bf16 hi/lo planes of the (qsize, ksize, hd) get_rel_pos output (K-major, no
+ * transpose); one CTA per (coordinate, head, batch) group, mma.sync bf16x3. */
+int hipie_relpos_bias_tc(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int64_t q_hs,
+                         const void* table_hi, const void* table_lo, int axis, int qh, int qw, int ksize,
+                         float* rel, int B, int H, int hd, void* stream);
+
 /* CondInst dynamic mask head, fused (H:models/ddetrs_dn.py:1390-1502,1806-1870):
  *   feats  (B, Hf*Wf, 8) NHWC fp32, params (B, Q, 169) fp32, ref_px (B, Q, 2) fp32 (pixels)
  *   out    (B, Q, 2*Hf, 2*Wf) fp32 mask logits after aligned_bilinear(x2). */

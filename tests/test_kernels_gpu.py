@@ -359,12 +359,36 @@ def test_attention_decomposed_relpos(ops, cuda):
     ref_w = torch.einsum("bnhwc,wkc->bnhwk", rq, Rw.double()).reshape(B, H, T, gw)
     assert (rel_h.double() - ref_h).abs().max() < 1e-4
     assert (rel_w.double() - ref_w).abs().max() < 1e-4
+    # tensor-core variant (the one the engine uses)
+    th = ops.relpos_bias_tc(qs, (bs, ts, hd), ops.split_weight(Rh), 0, gh, gw, B, H, hd)
+    tw = ops.relpos_bias_tc(qs, (bs, ts, hd), ops.split_weight(Rw), 1, gh, gw, B, H, hd)
+    assert (th.double() - ref_h).abs().max() < 1e-4
+    assert (tw.double() - ref_w).abs().max() < 1e-4
     o, _ = ops.attention(qs, ops.BF2(S.hi[:, :, 1], S.lo[:, :, 1]), ops.BF2(S.hi[:, :, 2], S.lo[:, :, 2]), B, H, T, T, hd,
                          (bs, ts, hd), (bs, ts, hd), (bs, ts, hd), hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=gh, kw=gw,
                          want_f32=True, want_split=False)
     ref = _attn_ref(q, qkv[:, :, 1].permute(0, 2, 1, 3).double(), qkv[:, :, 2].permute(0, 2, 1, 3).double(), hd ** -0.5,
                     ref_h, ref_w, gh, gw).permute(0, 2, 1, 3).reshape(B, T, H * hd)
     assert (o.double() - ref).abs().max() < 3e-5
+
+
+def test_relpos_tc_global_grid(ops, cuda):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, H, hd, gh, gw = 1, 2, 80, 64, 64
+    T = gh * gw
+    qkv = torch.randn(B, T, 3, H, hd, device=cuda, generator=g)
+    Rh = torch.randn(gh, gh, hd, device=cuda, generator=g) * 0.2
+    Rw = torch.randn(gw, gw, hd, device=cuda, generator=g) * 0.2
+    S = ops.split(qkv)
+    ts, bs = 3 * H * hd, T * 3 * H * hd
+    qs = ops.BF2(S.hi[:, :, 0], S.lo[:, :, 0])
+    th = ops.relpos_bias_tc(qs, (bs, ts, hd), ops.split_weight(Rh), 0, gh, gw, B, H, hd)
+    tw = ops.relpos_bias_tc(qs, (bs, ts, hd), ops.split_weight(Rw), 1, gh, gw, B, H, hd)
+    rq = qkv[:, :, 0].permute(0, 2, 1, 3).double().reshape(B, H, gh, gw, hd)
+    ref_h = torch.einsum("bnhwc,hkc->bnhwk", rq, Rh.double()).reshape(B, H, T, gh)
+    ref_w = torch.einsum("bnhwc,wkc->bnhwk", rq, Rw.double()).reshape(B, H, T, gw)
+    assert (th.double() - ref_h).abs().max() < 2e-4
+    assert (tw.double() - ref_w).abs().max() < 2e-4
 
 
 # ------------------------------------------------------------------------------------------ CondInst
