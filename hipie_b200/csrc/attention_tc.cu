@@ -1,0 +1,409 @@
+// tcgen05 flash attention for the ViT-H global blocks (hd = 80, T % 128 == 0), sm_100a.
+//
+//   softmax((q*scale) k^T + rel_h[q, kh] + rel_w[q, kw]) v      (/root/reference/projects/HIPIE/hipie/backbone/vit.py:67-83,
+//                                                                 backbone/utils.py:96-125)
+//
+// One CTA = 128 query rows of one (batch, head).  192 threads:
+//   warp 0      TMA producer: Q once, then K tiles (64 keys x 80) and V^T tiles (80 x 64 keys) into double-buffered,
+//               hardware-swizzled shared memory (head dim 80 = one 128B-swizzled 64-wide box + one 32B-swizzled
+//               16-wide box per operand)
+//   warp 1      MMA issuer: S_j = Q K_j^T (M=128, N=64, K=80) into one of two TMEM score buffers, and
+//               O += P_j V_j (M=128, N=80, K=64) into the TMEM output accumulator; QK of tile j+1 is issued before
+//               PV of tile j so the tensor pipe works while the softmax warps process tile j
+//   warps 2-5   softmax: thread = query row; tcgen05.ld the score row, scale + rel-pos bias (rel_w row hoisted in
+//               registers, one rel_h scalar per tile because a 64-key tile is one key row of the 64-wide grid),
+//               online softmax with lazy rescaling of the TMEM accumulator, P written as bf16 (hi, lo) straight into
+//               the 128B-swizzled K-major layout the PV MMA reads; epilogue divides by the row sum and stores
+// Precision: PREC==3 evaluates Qh.Kh + Qh.Kl + Ql.Kh and Ph.Vh + Ph.Vl + Pl.Vh (bf16x3, fp32-class); PREC==1 plain bf16.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace hipie {
+using namespace ptx;
+
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int batch,
+                   int64_t bstride, int box_rows, int box_cols);
+
+constexpr int FA_BM = 128, FA_BN = 64, FA_HD = 80;
+
+struct FaMaps {
+    CUtensorMap q64[2], q16[2], k64[2], k16[2], vt[2];   // [hi, lo]
+};
+
+struct FaParams {
+    const float *rel_h, *rel_w;   // (B,H,T,kh), (B,H,T,64) or null
+    int kh;
+    float* out_f32;
+    __nv_bfloat16 *out_hi, *out_lo;
+    int64_t o_bs, o_ts;
+    int B, H, T;
+    int q_col0, k_col0;           // column of head 0 inside the q / k tensor-map rows
+    float scale_log2e;
+};
+
+template <int PREC>
+struct FaSmem {
+    static constexpr int NPL = PREC == 3 ? 2 : 1;
+    static constexpr int Q64 = FA_BM * 128, Q16 = FA_BM * 32;
+    static constexpr int K64 = FA_BN * 128, K16 = FA_BN * 32;
+    static constexpr int VT = FA_HD * 128;
+    static constexpr int P = FA_BM * 128;
+    static constexpr int Q_BYTES = NPL * (Q64 + Q16);
+    static constexpr int K_STAGE = NPL * (K64 + K16);
+    static constexpr int V_STAGE = NPL * VT;
+    static constexpr int P_BYTES = NPL * P;
+    static constexpr int OFF_K = Q_BYTES;
+    static constexpr int OFF_V = OFF_K + 2 * K_STAGE;
+    static constexpr int OFF_P = OFF_V + 2 * V_STAGE;
+    static constexpr int OFF_BAR = OFF_P + P_BYTES;
+    static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+};
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int PREC>
+__global__ void __launch_bounds__(192, 1)
+attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
+    using SM = FaSmem<PREC>;
+    constexpr int NPL = SM::NPL;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    uint64_t* q_full = bars;            // [1]
+    uint64_t* k_full = bars + 1;        // [2]
+    uint64_t* k_empty = bars + 3;       // [2]
+    uint64_t* v_full = bars + 5;        // [2]
+    uint64_t* v_empty = bars + 7;       // [2]
+    uint64_t* s_full = bars + 9;        // [2]
+    uint64_t* s_empty = bars + 11;      // [2]
+    uint64_t* p_full = bars + 13;       // [1]
+    uint64_t* pv_done = bars + 14;      // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+    const int ntiles = p.T / FA_BN;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < NPL; ++i) {
+            prefetch_tmap(&maps.q64[i]); prefetch_tmap(&maps.q16[i]);
+            prefetch_tmap(&maps.k64[i]); prefetch_tmap(&maps.k16[i]);
+            prefetch_tmap(&maps.vt[i]);
+        }
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(q_full, 1);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+                mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+                mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+            }
+            mbar_init(p_full, 4);
+            mbar_init(pv_done, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_S = tmem_base;            // 2 x 64 columns
+    const uint32_t tmem_O = tmem_base + 128;      // 80 columns
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, SM::Q_BYTES);
+            for (int pl = 0; pl < NPL; ++pl) {
+                tma_load_3d(smem + pl * (SM::Q64 + SM::Q16), &maps.q64[pl], q_full, p.q_col0 + h * FA_HD, q0, b);
+                tma_load_3d(smem + pl * (SM::Q64 + SM::Q16) + SM::Q64, &maps.q16[pl], q_full, p.q_col0 + h * FA_HD + 64, q0, b);
+            }
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                mbar_wait(&k_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&k_full[s], SM::K_STAGE);
+                uint8_t* kb = smem + SM::OFF_K + s * SM::K_STAGE;
+                for (int pl = 0; pl < NPL; ++pl) {
+                    tma_load_3d(kb + pl * (SM::K64 + SM::K16), &maps.k64[pl], &k_full[s], p.k_col0 + h * FA_HD, j * FA_BN, b);
+                    tma_load_3d(kb + pl * (SM::K64 + SM::K16) + SM::K64, &maps.k16[pl], &k_full[s], p.k_col0 + h * FA_HD + 64, j * FA_BN, b);
+                }
+                mbar_wait(&v_empty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&v_full[s], SM::V_STAGE);
+                uint8_t* vb = smem + SM::OFF_V + s * SM::V_STAGE;
+                for (int pl = 0; pl < NPL; ++pl)
+                    tma_load_3d(vb + pl * SM::VT, &maps.vt[pl], &v_full[s], b * p.T + j * FA_BN, h * FA_HD, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BM, FA_BN);
+        constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BM, FA_HD);
+        const uint32_t sq = smem_u32(smem);
+        auto desc32 = [](uint32_t addr) {  // K-major, 32B swizzle, one K=16 step; 8-row atoms every 256 B
+            return make_kmajor_desc<32>(addr);
+        };
+        auto issue_pv = [&](int j) {
+            const int s = j & 1;
+            mbar_wait(p_full, j & 1);
+            mbar_wait(&v_full[s], (j >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t pb = smem_u32(smem + SM::OFF_P), vb = smem_u32(smem + SM::OFF_V + s * SM::V_STAGE);
+                const uint64_t p_hi = make_kmajor_desc<128>(pb), v_hi = make_kmajor_desc<128>(vb);
+                uint32_t accum = j > 0;
+#pragma unroll
+                for (int k = 0; k < FA_BN / 16; ++k) { umma_f16(tmem_O, p_hi + 2 * k, v_hi + 2 * k, idesc_pv, accum); accum = 1; }
+                if (PREC == 3) {
+                    const uint64_t p_lo = make_kmajor_desc<128>(pb + SM::P), v_lo = make_kmajor_desc<128>(vb + SM::VT);
+#pragma unroll
+                    for (int k = 0; k < FA_BN / 16; ++k) umma_f16(tmem_O, p_hi + 2 * k, v_lo + 2 * k, idesc_pv, 1);
+#pragma unroll
+                    for (int k = 0; k < FA_BN / 16; ++k) umma_f16(tmem_O, p_lo + 2 * k, v_hi + 2 * k, idesc_pv, 1);
+                }
+                umma_commit(pv_done);
+                umma_commit(&v_empty[s]);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j & 1;
+            const uint32_t ph = (j >> 1) & 1;
+            mbar_wait(&k_full[s], ph);
+            mbar_wait(&s_empty[s], ph ^ 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t kb = smem_u32(smem + SM::OFF_K + s * SM::K_STAGE);
+                const uint32_t d = tmem_S + s * FA_BN;
+                const uint64_t q64h = make_kmajor_desc<128>(sq), q16h = desc32(sq + SM::Q64);
+                const uint64_t k64h = make_kmajor_desc<128>(kb), k16h = desc32(kb + SM::K64);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(d, q64h + 2 * k, k64h + 2 * k, idesc_qk, k > 0);
+                umma_f16(d, q16h, k16h, idesc_qk, 1);
+                if (PREC == 3) {
+                    const uint64_t q64l = make_kmajor_desc<128>(sq + SM::Q64 + SM::Q16), q16l = desc32(sq + 2 * SM::Q64 + SM::Q16);
+                    const uint64_t k64l = make_kmajor_desc<128>(kb + SM::K64 + SM::K16), k16l = desc32(kb + 2 * SM::K64 + SM::K16);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(d, q64h + 2 * k, k64l + 2 * k, idesc_qk, 1);
+                    umma_f16(d, q16h, k16l, idesc_qk, 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(d, q64l + 2 * k, k64h + 2 * k, idesc_qk, 1);
+                    umma_f16(d, q16l, k16h, idesc_qk, 1);
+                }
+                umma_commit(&s_full[s]);
+                umma_commit(&k_empty[s]);
+            }
+            __syncwarp();
+            if (j >= 1) issue_pv(j - 1);
+        }
+        issue_pv(ntiles - 1);
+    } else {
+        // ===================== softmax / epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;            // row of the Q tile == TMEM lane
+        const int qrow = q0 + r;
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        const bool has_rel = p.rel_h != nullptr;
+        float rw[FA_BN];
+        const float* relh_row = nullptr;
+        if (has_rel) {
+            const int64_t rowi = ((int64_t)b * p.H + h) * p.T + qrow;
+            const float* rwp = p.rel_w + rowi * FA_BN;
+#pragma unroll
+            for (int i = 0; i < FA_BN; i += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(rwp + i);
+                rw[i] = v.x * 1.4426950408889634f; rw[i + 1] = v.y * 1.4426950408889634f;
+                rw[i + 2] = v.z * 1.4426950408889634f; rw[i + 3] = v.w * 1.4426950408889634f;
+            }
+            relh_row = p.rel_h + rowi * p.kh;
+        }
+        float m = -INFINITY, l = 0.f;
+        uint8_t* p_hi = smem + SM::OFF_P;
+        uint8_t* p_lo = smem + SM::OFF_P + SM::P;
+        const int sw = r & 7;
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j & 1;
+            mbar_wait(&s_full[s], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t sv[FA_BN];
+            {
+                uint32_t t0[32], t1[32];
+                tmem_ld_32x32b_x32(tmem_S + lane_off + s * FA_BN, t0);
+                tmem_ld_32x32b_x32(tmem_S + lane_off + s * FA_BN + 32, t1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { sv[i] = t0[i]; sv[32 + i] = t1[i]; }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);   // score buffer may be overwritten by QK(j+2)
+            const float rh = has_rel ? __ldg(relh_row + j) * 1.4426950408889634f : 0.f;
+            float tmax = -INFINITY;
+            float t[FA_BN];
+#pragma unroll
+            for (int i = 0; i < FA_BN; ++i) {
+                t[i] = __uint_as_float(sv[i]) * p.scale_log2e + rh + (has_rel ? rw[i] : 0.f);
+                tmax = fmaxf(tmax, t[i]);
+            }
+            // lazy rescale: keep the running reference max unless the tile exceeds it by more than 2^8
+            float corr = 1.f;
+            const bool need = tmax > m + 8.f;
+            if (need) {
+                corr = exp2f(m - tmax);   // m == -inf -> 0
+                m = tmax;
+                l *= corr;
+            }
+            float rowsum = 0.f;
+#pragma unroll
+            for (int i = 0; i < FA_BN; ++i) {
+                t[i] = exp2f(t[i] - m);
+                rowsum += t[i];
+            }
+            l += rowsum;
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);      // PV(j-1) retired: P smem free, O up to date
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+                    for (int c = 0; c < FA_HD; c += 16) {
+                        uint32_t o[16];
+                        tmem_ld_32x32b_x16(tmem_O + lane_off + c, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                        tmem_st_32x32b_x16(tmem_O + lane_off + c, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            // P -> swizzled K-major smem tile [128 rows x 64 keys] (128-byte rows, 16-byte chunk index XOR row%8)
+#pragma unroll
+            for (int c = 0; c < FA_BN / 8; ++c) {
+                uint4 hi, lo;
+                if (PREC == 3) {
+                    split2(t[c * 8 + 0], t[c * 8 + 1], hi.x, lo.x);
+                    split2(t[c * 8 + 2], t[c * 8 + 3], hi.y, lo.y);
+                    split2(t[c * 8 + 4], t[c * 8 + 5], hi.z, lo.z);
+                    split2(t[c * 8 + 6], t[c * 8 + 7], hi.w, lo.w);
+                } else {
+                    hi.x = pack_bf16x2(t[c * 8 + 0], t[c * 8 + 1]); hi.y = pack_bf16x2(t[c * 8 + 2], t[c * 8 + 3]);
+                    hi.z = pack_bf16x2(t[c * 8 + 4], t[c * 8 + 5]); hi.w = pack_bf16x2(t[c * 8 + 6], t[c * 8 + 7]);
+                }
+                const int off = r * 128 + ((c ^ sw) << 4);
+                *reinterpret_cast<uint4*>(p_hi + off) = hi;
+                if (PREC == 3) *reinterpret_cast<uint4*>(p_lo + off) = lo;
+            }
+            fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        // ---- epilogue: O / l ----
+        mbar_wait(pv_done, (ntiles - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.f / l;
+        const int64_t obase = (int64_t)b * p.o_bs + (int64_t)qrow * p.o_ts + (int64_t)h * FA_HD;
+#pragma unroll
+        for (int c = 0; c < FA_HD; c += 16) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tmem_O + lane_off + c, o);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(o[i]) * inv;
+            if (p.out_f32) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(p.out_f32 + obase + c + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+            }
+            if (p.out_hi) {
+                uint4 h0, h1, l0, l1;
+                split2(f[0], f[1], h0.x, l0.x); split2(f[2], f[3], h0.y, l0.y);
+                split2(f[4], f[5], h0.z, l0.z); split2(f[6], f[7], h0.w, l0.w);
+                split2(f[8], f[9], h1.x, l1.x); split2(f[10], f[11], h1.y, l1.y);
+                split2(f[12], f[13], h1.z, l1.z); split2(f[14], f[15], h1.w, l1.w);
+                *reinterpret_cast<uint4*>(p.out_hi + obase + c) = h0;
+                *reinterpret_cast<uint4*>(p.out_hi + obase + c + 8) = h1;
+                if (p.out_lo) {
+                    *reinterpret_cast<uint4*>(p.out_lo + obase + c) = l0;
+                    *reinterpret_cast<uint4*>(p.out_lo + obase + c + 8) = l1;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+template <int PREC>
+static int launch_fa(const FaMaps& maps, const FaParams& p, cudaStream_t st) {
+    using SM = FaSmem<PREC>;
+    static bool attr = false;
+    if (!attr) {
+        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+        attr = true;
+    }
+    dim3 grid(p.T / FA_BM, p.H, p.B);
+    attn_tc_kernel<PREC><<<grid, 192, SM::TOTAL, st>>>(maps, p);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+}  // namespace hipie
+
+using namespace hipie;
+
+// q / k: bf16 planes viewed as (B, T, row_width) with token stride q_ts / k_ts and batch stride q_bs / k_bs (elements);
+// head h occupies columns [q_col0 + 80 h, +80).  vt: V transposed, (H*80 rows, B*T columns) planes with row stride vt_ld.
+extern "C" int hipie_attention_tc(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
+                                  const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
+                                  const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
+                                  int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
+                                  int H, int T, int hd, float scale, int prec, void* stream) {
+    HIPIE_CHECK_ARG(q_hi && k_hi && vt_hi, "hipie_attention_tc: q/k/vt hi planes required");
+    HIPIE_CHECK_ARG(prec == 1 || (prec == 3 && q_lo && k_lo && vt_lo), "hipie_attention_tc: prec/lo planes mismatch");
+    HIPIE_CHECK_ARG(hd == FA_HD, "hipie_attention_tc: head dim must be 80 (got %d)", hd);
+    HIPIE_CHECK_ARG(T > 0 && T % FA_BM == 0, "hipie_attention_tc: T (%d) must be a multiple of 128", T);
+    HIPIE_CHECK_ARG((rel_h == nullptr) == (rel_w == nullptr), "hipie_attention_tc: rel_h and rel_w go together");
+    HIPIE_CHECK_ARG(!rel_h || (kw == FA_BN && kh * kw == T), "hipie_attention_tc: rel-pos needs kw == 64 and kh*kw == T");
+    HIPIE_CHECK_ARG(out_f32 || out_hi, "hipie_attention_tc: no output requested");
+    FaMaps maps;
+    int rc;
+    const void* qp[2] = {q_hi, q_lo};
+    const void* kp[2] = {k_hi, k_lo};
+    const void* vp[2] = {vt_hi, vt_lo};
+    for (int pl = 0; pl < (prec == 3 ? 2 : 1); ++pl) {
+        if ((rc = make_tmap_bf16(&maps.q64[pl], qp[pl], T, q_width, q_ts, B, q_bs, FA_BM, 64))) return rc;
+        if ((rc = make_tmap_bf16(&maps.q16[pl], qp[pl], T, q_width, q_ts, B, q_bs, FA_BM, 16))) return rc;
+        if ((rc = make_tmap_bf16(&maps.k64[pl], kp[pl], T, k_width, k_ts, B, k_bs, FA_BN, 64))) return rc;
+        if ((rc = make_tmap_bf16(&maps.k16[pl], kp[pl], T, k_width, k_ts, B, k_bs, FA_BN, 16))) return rc;
+        if ((rc = make_tmap_bf16(&maps.vt[pl], vp[pl], (int64_t)H * FA_HD, (int64_t)B * T, vt_ld, 1, 0, FA_HD, 64))) return rc;
+    }
+    if (prec == 1) {
+        maps.q64[1] = maps.q64[0]; maps.q16[1] = maps.q16[0]; maps.k64[1] = maps.k64[0]; maps.k16[1] = maps.k16[0];
+        maps.vt[1] = maps.vt[0];
+    }
+    FaParams p;
+    p.rel_h = rel_h; p.rel_w = rel_w; p.kh = kh;
+    p.out_f32 = out_f32; p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo;
+    p.o_bs = o_bs; p.o_ts = o_ts; p.B = B; p.H = H; p.T = T; p.q_col0 = q_col0; p.k_col0 = k_col0;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    cudaStream_t st = (cudaStream_t)stream;
+    return prec == 3 ? launch_fa<3>(maps, p, st) : launch_fa<1>(maps, p, st);
+}

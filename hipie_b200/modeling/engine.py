@@ -145,6 +145,7 @@ class Engine:
         self._maps = {}
         self._bufs = {}
         self.bf16_value_map = False     # fast mode: MSDeformAttn value map stored as bf16
+        self.use_tc_attention = True    # tcgen05 flash attention for the global ViT blocks
 
     # ------------------------------------------------------------ helpers
     def _window_maps(self, B, gh, gw, ws):
@@ -201,16 +202,33 @@ class Engine:
             else:
                 _, xn, _ = ops.layernorm(x, W[blk + ".norm1.weight"], W[blk + ".norm1.bias"], 1e-6)
                 Bq, Tq, qh, qw = B, T, gh, gw
-            _, qkv, _ = ops.gemm(xn, wqkv, bias=bqkv, want_f32=False, want_split=True)
             st = (Tq * 3 * E, 3 * E, hd)
-            q = BF2(qkv.hi[:, 0:E], None if qkv.lo is None else qkv.lo[:, 0:E])
-            k = BF2(qkv.hi[:, E:2 * E], None if qkv.lo is None else qkv.lo[:, E:2 * E])
-            vv = BF2(qkv.hi[:, 2 * E:], None if qkv.lo is None else qkv.lo[:, 2 * E:])
+            use_tc = (not windowed) and self.use_tc_attention and hd == 80 and Tq % 128 == 0 and qw == 64
+            if use_tc:
+                # q,k as one GEMM (N = 2E); V emitted transposed (E, B*T) so it is the K-major B operand of P.V
+                wqk, bqk, wv, bv = W.cached(("qk_v", blk), lambda: (ops.split_weight(W[blk + ".attn.qkv.weight"][:2 * E]),
+                                                                     W[blk + ".attn.qkv.bias"][:2 * E].contiguous(),
+                                                                     ops.split_weight(W[blk + ".attn.qkv.weight"][2 * E:]),
+                                                                     W[blk + ".attn.qkv.bias"][2 * E:].contiguous()))
+                _, qk, _ = ops.gemm(xn, wqk, bias=bqk, want_f32=False, want_split=True)              # (B*T, 2E)
+                _, vt, _ = ops.gemm(xn, wv, bias=bv, want_f32=False, want_split=True, transposed=True)  # (E, B*T)
+                q = BF2(qk.hi[:, 0:E], None if qk.lo is None else qk.lo[:, 0:E])
+                k = BF2(qk.hi[:, E:], None if qk.lo is None else qk.lo[:, E:])
+                st = (Tq * 2 * E, 2 * E, hd)
+            else:
+                _, qkv, _ = ops.gemm(xn, wqkv, bias=bqkv, want_f32=False, want_split=True)
+                q = BF2(qkv.hi[:, 0:E], None if qkv.lo is None else qkv.lo[:, 0:E])
+                k = BF2(qkv.hi[:, E:2 * E], None if qkv.lo is None else qkv.lo[:, E:2 * E])
+                vv = BF2(qkv.hi[:, 2 * E:], None if qkv.lo is None else qkv.lo[:, 2 * E:])
             Rh = W.cached(("relh", i, qh), lambda: ops.split_weight(_get_rel_pos_table(qh, qh, W[blk + ".attn.rel_pos_h"])))
             Rw = W.cached(("relw", i, qw), lambda: ops.split_weight(_get_rel_pos_table(qw, qw, W[blk + ".attn.rel_pos_w"])))
             rel_h = ops.relpos_bias_tc(q, st, Rh, 0, qh, qw, Bq, nh, hd)
             rel_w = ops.relpos_bias_tc(q, st, Rw, 1, qh, qw, Bq, nh, hd)
-            _, ao = ops.attention(q, k, vv, Bq, nh, Tq, Tq, hd, st, st, st, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=qh, kw=qw)
+            if use_tc:
+                _, ao = ops.attention_tc(q, k, vt, Bq, nh, Tq, hd, st[0], st[1], st[0], st[1], hd ** -0.5, rel_h=rel_h, rel_w=rel_w,
+                                         kh=qh, kw=qw)
+            else:
+                _, ao = ops.attention(q, k, vv, Bq, nh, Tq, Tq, hd, st, st, st, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=qh, kw=qw)
             ao = ao.view(Bq * Tq, E)
             if windowed:
                 ops.gemm(ao, wproj, bias=bproj, residual=x, out_f32=x, row_map=win2tok, out_rows=B * T)

@@ -332,6 +332,23 @@ def attention(q: BF2, k: BF2, v: BF2, B, H, Tq, Tk, hd, q_strides, k_strides, v_
     return o, s
 
 
+def attention_tc(q: BF2, k: BF2, vt: BF2, B, H, T, hd, q_bs, q_ts, k_bs, k_ts, scale, rel_h=None, rel_w=None, kh=0, kw=0,
+                 want_f32=False, want_split=True, prec=None):
+    """tcgen05 flash attention.  q, k: plane views whose row (token) holds all heads contiguously (head h at columns
+    [80h, 80h+80) of the view); vt: BF2 (H*hd, B*T) = V transposed.  Output (B, T, H*hd)."""
+    prec = PREC if prec is None else prec
+    dev = q.hi.device
+    o = torch.empty((B, T, H * hd), dtype=torch.float32, device=dev) if want_f32 else None
+    s = _empty_bf2((B, T, H * hd), dev) if want_split else None
+    lo = lambda t: _p(t.lo) if (t.lo is not None and prec == 3) else None
+    with _timed(f"attention_tc[p{prec}]", 4.0 * B * H * T * T * hd):
+        _lib.check(_lib.load().hipie_attention_tc(
+            _p(q.hi), lo(q), q_bs, q_ts, 0, H * hd, _p(k.hi), lo(k), k_bs, k_ts, 0, H * hd, _p(vt.hi), lo(vt), vt.hi.stride(0),
+            _p(rel_h), _p(rel_w), kh, kw, _p(o), _p(s.hi) if s else None, _p(s.lo) if (s and s.lo is not None) else None,
+            T * H * hd, H * hd, B, H, T, hd, float(scale), prec, _stream()), "attention_tc")
+    return o, s
+
+
 def relpos_bias(q: BF2, q_strides, table_t, axis, qh, qw, B, H, hd):
     """table_t: (qsize, hd, ksize) fp32.  Returns (B, H, qh*qw, ksize) fp32."""
     ksize = table_t.shape[-1]

@@ -179,6 +179,16 @@ typedef struct hipie_attn_args {
 
 int hipie_attention(const hipie_attn_args* args, void* stream);
 
+/* tcgen05 flash attention for the ViT-H global blocks: hd == 80, T % 128 == 0, optional decomposed rel-pos bias
+ * with kw == 64.  q / k are bf16 planes viewed as (B, T, width) rows (token stride *_ts, batch stride *_bs, head h at
+ * columns [*_col0 + 80 h, +80)); vt is V transposed: (H*80, B*T) planes, row stride vt_ld (the qkv GEMM emits it with
+ * transposed=1).  Output (B, T, H*80) fp32 and/or bf16 split. */
+int hipie_attention_tc(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
+                       const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
+                       const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
+                       int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
+                       int H, int T, int hd, float scale, int prec, void* stream);
+
 /* rel[b,h,q,j] = sum_c q[b,q,h,c] * table[idx(q,j), c] for the decomposed rel-pos bias.
  * axis 0: height (idx from q // qw), axis 1: width (q % qw).  table: (2*max(q,k)-1, hd) fp32,
  * table_t: get_rel_pos output (H:backbone/utils.py:63-93) pre-transposed to (qsize, hd, ksize) fp32.

@@ -372,6 +372,34 @@ def test_attention_decomposed_relpos(ops, cuda):
     assert (o.double() - ref).abs().max() < 3e-5
 
 
+@pytest.mark.parametrize("prec", [3, 1])
+@pytest.mark.parametrize("with_rel", [True, False])
+def test_attention_tcgen05(ops, cuda, prec, with_rel):
+    """tcgen05/TMEM flash attention (global ViT-H blocks) vs fp64 softmax attention; V supplied transposed."""
+    g = torch.Generator(device="cuda").manual_seed(21 + prec)
+    B, H, hd, gh, gw = 2, 3, 80, 4, 64          # T = 256 tokens: 2 query tiles x 4 key tiles
+    T, E = gh * gw, H * hd
+    qk = torch.randn(B * T, 2 * E, device=cuda, generator=g)
+    v = torch.randn(B * T, E, device=cuda, generator=g)
+    S, Vs = ops.split(qk), ops.split(v.t().contiguous())          # vt: (E, B*T)
+    q = ops.BF2(S.hi[:, :E], S.lo[:, :E])
+    k = ops.BF2(S.hi[:, E:], S.lo[:, E:])
+    rel_h = rel_w = None
+    if with_rel:
+        rel_h = torch.randn(B, H, T, gh, device=cuda, generator=g)
+        rel_w = torch.randn(B, H, T, gw, device=cuda, generator=g)
+    o, _ = ops.attention_tc(q, k, Vs, B, H, T, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, rel_h=rel_h, rel_w=rel_w,
+                            kh=gh, kw=gw, want_f32=True, want_split=False, prec=prec)
+    if prec == 3:
+        qq, kk, vv = qk[:, :E], qk[:, E:], v
+    else:
+        qq, kk, vv = S.hi[:, :E].float(), S.hi[:, E:].float(), Vs.hi.float().t()
+    sh = lambda x: x.reshape(B, T, H, hd).permute(0, 2, 1, 3).double()
+    ref = _attn_ref(sh(qq), sh(kk), sh(vv), hd ** -0.5, rel_h, rel_w, gh, gw).permute(0, 2, 1, 3).reshape(B, T, E)
+    err = (o.double() - ref).abs().max().item()
+    assert err < (3e-5 if prec == 3 else 3e-2), err
+
+
 def test_relpos_tc_global_grid(ops, cuda):
     g = torch.Generator(device="cuda").manual_seed(11)
     B, H, hd, gh, gw = 1, 2, 80, 64, 64
