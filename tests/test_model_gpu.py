@@ -126,3 +126,34 @@ def test_fast_mode_runs_and_is_close(setup):
     ref = setup["out_o"]["pred_masks_maskdino"]
     rel = _err(out["pred_masks_maskdino"], ref) / ref.abs().max().item()
     assert rel < 0.25, rel
+
+
+def test_wide_image_uses_tcgen05_attention(cuda):
+    """128 x 1024 input -> 8 x 64 token grid: the global blocks take the tcgen05 flash-attention path (kw == 64, T % 128 == 0,
+    V emitted transposed by the GEMM); rel-pos tables are interpolated 127 -> 15 along the height axis."""
+    from hipie_oracle import hparams, synth
+    from hipie_oracle.model import HipieOracle
+    from hipie_b200 import ops
+    from hipie_b200.modeling.hipie_img import HIPIE_IMG
+    torch.manual_seed(1)
+    hp = hparams.get("vit_tiny")
+    hp["vit"] = dict(hp["vit"], img_size=1024, depth=3, window_block_indexes=(0,))
+    oracle = HipieOracle(hp).eval()
+    synth.perturb_(oracle, seed=3)
+    inputs, ids, am = synth.make_batch(1, 128, 1024, 4, hp["max_query_len"], seed=5)
+    with torch.no_grad():
+        _, out_o = oracle(inputs, ids, am)
+    ops.set_precision(3)
+    model = HIPIE_IMG(hp=hp, state_dict=oracle.state_dict(), device="cuda:0")
+    for x, i, a in zip(inputs, ids, am):
+        x["input_ids"], x["attention_mask"] = i, a
+    forced = {"topk_fg": out_o["aux"]["topk"].to(cuda), "topk_md": out_o["md"]["topk"].to(cuda)}
+    ops.profiler.start()
+    _, out_g = model(inputs, forced=forced, return_raw=True)
+    prof = ops.profiler.stop()
+    assert any(k.startswith("attention_tc") for k in prof), list(prof)
+    for k in ("res3", "res4", "res5"):
+        ref = out_o["features"][k].permute(0, 2, 3, 1)
+        assert _err(out_g["aux"]["feats"][k], ref) < 1e-3 * max(1.0, ref.abs().max().item()), k
+    assert _err(out_g["pred_masks_maskdino"], out_o["pred_masks_maskdino"]) < 1e-3
+    assert _err(out_g["pred_logits"], out_o["pred_logits"]) < 2e-3
