@@ -3,14 +3,14 @@
 //   softmax((q*scale) k^T + rel_h[q, kh] + rel_w[q, kw]) v      (/root/reference/projects/HIPIE/hipie/backbone/vit.py:67-83,
 //                                                                 backbone/utils.py:96-125)
 //
-// One CTA = 128 query rows of one (batch, head).  192 threads:
+// One CTA = 128 query rows of one (batch, head).  320 threads:
 //   warp 0      TMA producer: Q once, then K tiles (64 keys x 80) and V^T tiles (80 x 64 keys) into double-buffered,
 //               hardware-swizzled shared memory (head dim 80 = one 128B-swizzled 64-wide box + one 32B-swizzled
 //               16-wide box per operand)
 //   warp 1      MMA issuer: S_j = Q K_j^T (M=128, N=64, K=80) into one of two TMEM score buffers, and
 //               O += P_j V_j (M=128, N=80, K=64) into the TMEM output accumulator; QK of tile j+1 is issued before
 //               PV of tile j so the tensor pipe works while the softmax warps process tile j
-//   warps 2-5   softmax: thread = query row; tcgen05.ld the score row, scale + rel-pos bias (rel_w row hoisted in
+//   warps 2-9   softmax: two warps per TMEM lane quarter, each owning half of the tile's key columns; thread = query row; tcgen05.ld the score row, scale + rel-pos bias (rel_w row hoisted in
 //               registers, one rel_h scalar per tile because a 64-key tile is one key row of the 64-wide grid),
 //               online softmax with lazy rescaling of the TMEM accumulator, P written as bf16 (hi, lo) straight into
 //               the 128B-swizzled K-major layout the PV MMA reads; epilogue divides by the row sum and stores
@@ -56,7 +56,7 @@ struct FaSmem {
     static constexpr int OFF_V = OFF_K + 2 * K_STAGE;
     static constexpr int OFF_P = OFF_V + 2 * V_STAGE;
     static constexpr int OFF_BAR = OFF_P + P_BYTES;
-    static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+    static constexpr int TOTAL = OFF_BAR + 256 + 3 * 2 * FA_BM * 4 + 1024;
 };
 
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -69,7 +69,7 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int PREC>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     using SM = FaSmem<PREC>;
     constexpr int NPL = SM::NPL;
@@ -86,6 +86,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     uint64_t* p_full = bars + 13;       // [1]
     uint64_t* pv_done = bars + 14;      // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+    float* xchg = reinterpret_cast<float*>(smem + SM::OFF_BAR + 256);   // [3][2][128] max / row-sum exchange
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
@@ -104,9 +105,9 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
                 mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-                mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+                mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
             }
-            mbar_init(p_full, 4);
+            mbar_init(p_full, 8);
             mbar_init(pv_done, 1);
             fence_barrier_init();
         }
@@ -210,22 +211,26 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         }
         issue_pv(ntiles - 1);
     } else {
-        // ===================== softmax / epilogue (warps 2..5) =====================
+        // ===================== softmax / epilogue (warps 2..9) =====================
+        // two warps per TMEM lane quarter: `half` selects which 32 of the tile's 64 key columns (and which part of
+        // the 80 output columns) this thread owns; the pair only exchanges the tile maximum (and the row sum at the end)
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int r = quarter * 32 + lane;            // row of the Q tile == TMEM lane
         const int qrow = q0 + r;
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         const bool has_rel = p.rel_h != nullptr;
-        float rw[FA_BN];
+        constexpr int HC = FA_BN / 2;                 // 32 columns per thread
+        constexpr float LOG2E = 1.4426950408889634f;
+        float rw[HC];
         const float* relh_row = nullptr;
         if (has_rel) {
             const int64_t rowi = ((int64_t)b * p.H + h) * p.T + qrow;
-            const float* rwp = p.rel_w + rowi * FA_BN;
+            const float* rwp = p.rel_w + rowi * FA_BN + half * HC;
 #pragma unroll
-            for (int i = 0; i < FA_BN; i += 4) {
+            for (int i = 0; i < HC; i += 4) {
                 const float4 v = *reinterpret_cast<const float4*>(rwp + i);
-                rw[i] = v.x * 1.4426950408889634f; rw[i + 1] = v.y * 1.4426950408889634f;
-                rw[i + 2] = v.z * 1.4426950408889634f; rw[i + 3] = v.w * 1.4426950408889634f;
+                rw[i] = v.x * LOG2E; rw[i + 1] = v.y * LOG2E; rw[i + 2] = v.z * LOG2E; rw[i + 3] = v.w * LOG2E;
             }
             relh_row = p.rel_h + rowi * p.kh;
         }
@@ -233,30 +238,29 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         uint8_t* p_hi = smem + SM::OFF_P;
         uint8_t* p_lo = smem + SM::OFF_P + SM::P;
         const int sw = r & 7;
+        const int o_c0 = half == 0 ? 0 : 48, o_c1 = half == 0 ? 48 : FA_HD;   // output columns owned (x16 granules)
         for (int j = 0; j < ntiles; ++j) {
             const int s = j & 1;
             mbar_wait(&s_full[s], (j >> 1) & 1);
             tc_fence_after();
-            uint32_t sv[FA_BN];
-            {
-                uint32_t t0[32], t1[32];
-                tmem_ld_32x32b_x32(tmem_S + lane_off + s * FA_BN, t0);
-                tmem_ld_32x32b_x32(tmem_S + lane_off + s * FA_BN + 32, t1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { sv[i] = t0[i]; sv[32 + i] = t1[i]; }
-            }
+            uint32_t sv[HC];
+            tmem_ld_32x32b_x32(tmem_S + lane_off + s * FA_BN + half * HC, sv);
+            tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[s]);   // score buffer may be overwritten by QK(j+2)
-            const float rh = has_rel ? __ldg(relh_row + j) * 1.4426950408889634f : 0.f;
+            const float rh = has_rel ? __ldg(relh_row + j) * LOG2E : 0.f;
             float tmax = -INFINITY;
-            float t[FA_BN];
+            float t[HC];
 #pragma unroll
-            for (int i = 0; i < FA_BN; ++i) {
+            for (int i = 0; i < HC; ++i) {
                 t[i] = __uint_as_float(sv[i]) * p.scale_log2e + rh + (has_rel ? rw[i] : 0.f);
                 tmax = fmaxf(tmax, t[i]);
             }
+            // exchange the tile max with the partner warp (same rows, other column half)
+            xchg[(s * 2 + half) * FA_BM + r] = tmax;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            tmax = fmaxf(tmax, xchg[(s * 2 + (half ^ 1)) * FA_BM + r]);
             // lazy rescale: keep the running reference max unless the tile exceeds it by more than 2^8
             float corr = 1.f;
             const bool need = tmax > m + 8.f;
@@ -267,7 +271,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             }
             float rowsum = 0.f;
 #pragma unroll
-            for (int i = 0; i < FA_BN; ++i) {
+            for (int i = 0; i < HC; ++i) {
                 t[i] = exp2f(t[i] - m);
                 rowsum += t[i];
             }
@@ -276,8 +280,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 mbar_wait(pv_done, (j - 1) & 1);      // PV(j-1) retired: P smem free, O up to date
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, need)) {
-#pragma unroll
-                    for (int c = 0; c < FA_HD; c += 16) {
+                    for (int c = o_c0; c < o_c1; c += 16) {
                         uint32_t o[16];
                         tmem_ld_32x32b_x16(tmem_O + lane_off + c, o);
                         tmem_ld_wait();
@@ -290,16 +293,17 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             }
             // P -> swizzled K-major smem tile [128 rows x 64 keys] (128-byte rows, 16-byte chunk index XOR row%8)
 #pragma unroll
-            for (int c = 0; c < FA_BN / 8; ++c) {
+            for (int cc = 0; cc < HC / 8; ++cc) {
+                const int c = half * (HC / 8) + cc;
                 uint4 hi, lo;
                 if (PREC == 3) {
-                    split2(t[c * 8 + 0], t[c * 8 + 1], hi.x, lo.x);
-                    split2(t[c * 8 + 2], t[c * 8 + 3], hi.y, lo.y);
-                    split2(t[c * 8 + 4], t[c * 8 + 5], hi.z, lo.z);
-                    split2(t[c * 8 + 6], t[c * 8 + 7], hi.w, lo.w);
+                    split2(t[cc * 8 + 0], t[cc * 8 + 1], hi.x, lo.x);
+                    split2(t[cc * 8 + 2], t[cc * 8 + 3], hi.y, lo.y);
+                    split2(t[cc * 8 + 4], t[cc * 8 + 5], hi.z, lo.z);
+                    split2(t[cc * 8 + 6], t[cc * 8 + 7], hi.w, lo.w);
                 } else {
-                    hi.x = pack_bf16x2(t[c * 8 + 0], t[c * 8 + 1]); hi.y = pack_bf16x2(t[c * 8 + 2], t[c * 8 + 3]);
-                    hi.z = pack_bf16x2(t[c * 8 + 4], t[c * 8 + 5]); hi.w = pack_bf16x2(t[c * 8 + 6], t[c * 8 + 7]);
+                    hi.x = pack_bf16x2(t[cc * 8 + 0], t[cc * 8 + 1]); hi.y = pack_bf16x2(t[cc * 8 + 2], t[cc * 8 + 3]);
+                    hi.z = pack_bf16x2(t[cc * 8 + 4], t[cc * 8 + 5]); hi.w = pack_bf16x2(t[cc * 8 + 6], t[cc * 8 + 7]);
                 }
                 const int off = r * 128 + ((c ^ sw) << 4);
                 *reinterpret_cast<uint4*>(p_hi + off) = hi;
@@ -310,13 +314,15 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
         }
-        // ---- epilogue: O / l ----
+        // ---- epilogue: O / l (row sum = both halves) ----
+        xchg[(2 * 2 + half) * FA_BM + r] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        l += xchg[(2 * 2 + (half ^ 1)) * FA_BM + r];
         mbar_wait(pv_done, (ntiles - 1) & 1);
         tc_fence_after();
         const float inv = 1.f / l;
         const int64_t obase = (int64_t)b * p.o_bs + (int64_t)qrow * p.o_ts + (int64_t)h * FA_HD;
-#pragma unroll
-        for (int c = 0; c < FA_HD; c += 16) {
+        for (int c = o_c0; c < o_c1; c += 16) {
             uint32_t o[16];
             tmem_ld_32x32b_x16(tmem_O + lane_off + c, o);
             tmem_ld_wait();
@@ -360,7 +366,7 @@ static int launch_fa(const FaMaps& maps, const FaParams& p, cudaStream_t st) {
         attr = true;
     }
     dim3 grid(p.T / FA_BM, p.H, p.B);
-    attn_tc_kernel<PREC><<<grid, 192, SM::TOTAL, st>>>(maps, p);
+    attn_tc_kernel<PREC><<<grid, 320, SM::TOTAL, st>>>(maps, p);
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
 }

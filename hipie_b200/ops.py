@@ -34,6 +34,7 @@ class _Profiler:
 
     def __init__(self):
         self.enabled = False
+        self.shapes = False    # include GEMM shapes in the tags
         self.records = []      # (tag, work, start_event, end_event)
 
     def start(self):
@@ -194,7 +195,10 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
         bits_threshold=float(bits_threshold) if bits_threshold is not None else 0.0,
         M=M, N=N, K=K, batch=batch, act=act, prec=prec, alpha=float(alpha), transposed=1 if transposed else 0,
         c_row_map=row_map.data_ptr() if row_map is not None else None)
-    with _timed(f"gemm_tc[p{prec}]" + (":mask_embed" if c_bits is not None else ""), 2.0 * M * N * K * batch):
+    tag = f"gemm_tc[p{prec}]" + (":mask_embed" if c_bits is not None else "")
+    if profiler.enabled and profiler.shapes:
+        tag += f" {M}x{N}x{K}" + (f"x{batch}" if batch > 1 else "") + ("T" if transposed else "")
+    with _timed(tag, 2.0 * M * N * K * batch):
         _lib.check(lib.hipie_gemm(ctypes.byref(args), _stream()), "gemm")
     return c_f32, c_split, c_bits
 
