@@ -233,7 +233,7 @@ attention_kernel(const AttnParams p) {
             mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
             const float mnew = fmaxf(m_run[i], mx[i]);
             msafe[i] = mnew == -INFINITY ? 0.f : mnew;
-            corr[i] = exp2f((m_run[i] - msafe[i]) * LOG2E);  // m_run = -inf -> 0
+            corr[i] = ex2_approx((m_run[i] - msafe[i]) * LOG2E);  // m_run = -inf -> 0
             m_run[i] = mnew;
             l_run[i] *= corr[i];
         }
@@ -245,8 +245,8 @@ attention_kernel(const AttnParams p) {
         uint32_t pa_hi[ATT_BN / 16][4], pa_lo[PREC == 3 ? ATT_BN / 16 : 1][4];
 #pragma unroll
         for (int j = 0; j < ATT_BN / 8; ++j) {
-            const float p0 = exp2f((s[j][0] - msafe[0]) * LOG2E), p1 = exp2f((s[j][1] - msafe[0]) * LOG2E);
-            const float p2 = exp2f((s[j][2] - msafe[1]) * LOG2E), p3 = exp2f((s[j][3] - msafe[1]) * LOG2E);
+            const float p0 = ex2_approx((s[j][0] - msafe[0]) * LOG2E), p1 = ex2_approx((s[j][1] - msafe[0]) * LOG2E);
+            const float p2 = ex2_approx((s[j][2] - msafe[1]) * LOG2E), p3 = ex2_approx((s[j][3] - msafe[1]) * LOG2E);
             l_run[0] += p0 + p1;
             l_run[1] += p2 + p3;
             const int kk = j >> 1, half = (j & 1) * 2;

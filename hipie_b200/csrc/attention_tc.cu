@@ -234,13 +234,16 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             }
             relh_row = p.rel_h + rowi * p.kh;
         }
-        float m = -INFINITY, l = 0.f;
+        float m = -INFINITY, l = 0.f;          // m: running reference max of (scaled logit + rel_w) + rel_h, log2 domain
         uint8_t* p_hi = smem + SM::OFF_P;
         uint8_t* p_lo = smem + SM::OFF_P + SM::P;
         const int sw = r & 7;
         const int o_c0 = half == 0 ? 0 : 48, o_c1 = half == 0 ? 48 : FA_HD;   // output columns owned (x16 granules)
+        float rh_next = has_rel ? __ldg(relh_row) * LOG2E : 0.f;
         for (int j = 0; j < ntiles; ++j) {
             const int s = j & 1;
+            const float rh = rh_next;
+            if (has_rel && j + 1 < ntiles) rh_next = __ldg(relh_row + j + 1) * LOG2E;   // prefetch: latency hidden by this tile
             mbar_wait(&s_full[s], (j >> 1) & 1);
             tc_fence_after();
             uint32_t sv[HC];
@@ -249,14 +252,15 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[s]);   // score buffer may be overwritten by QK(j+2)
-            const float rh = has_rel ? __ldg(relh_row + j) * LOG2E : 0.f;
+            // t_i = s_i*scale*log2e + rel_w_i (+ rel_h added to the max / exponent offset, it is uniform over the tile)
             float tmax = -INFINITY;
             float t[HC];
 #pragma unroll
             for (int i = 0; i < HC; ++i) {
-                t[i] = __uint_as_float(sv[i]) * p.scale_log2e + rh + (has_rel ? rw[i] : 0.f);
+                t[i] = fmaf(__uint_as_float(sv[i]), p.scale_log2e, has_rel ? rw[i] : 0.f);
                 tmax = fmaxf(tmax, t[i]);
             }
+            tmax += rh;
             // exchange the tile max with the partner warp (same rows, other column half)
             xchg[(s * 2 + half) * FA_BM + r] = tmax;
             asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
@@ -265,14 +269,15 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             float corr = 1.f;
             const bool need = tmax > m + 8.f;
             if (need) {
-                corr = exp2f(m - tmax);   // m == -inf -> 0
+                corr = ex2_approx(m - tmax);   // m == -inf -> 0
                 m = tmax;
                 l *= corr;
             }
+            const float off = m - rh;
             float rowsum = 0.f;
 #pragma unroll
             for (int i = 0; i < HC; ++i) {
-                t[i] = exp2f(t[i] - m);
+                t[i] = ex2_approx(t[i] - off);
                 rowsum += t[i];
             }
             l += rowsum;

@@ -72,14 +72,20 @@ __device__ __forceinline__ float bf16_round(float x) {
     return __bfloat162float(__float2bfloat16_rn(x));
 }
 
-// hi = bf16(x), lo = bf16(x - hi)
+// hi = bf16(x), lo = bf16(x - hi) for a pair of floats; packed conversions (one F2FP per pair, ALU pipe)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-    __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-    __nv_bfloat162 h(ah, bh), l(al, bl);
-    hi = *reinterpret_cast<uint32_t*>(&h);
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const uint32_t hu = *reinterpret_cast<uint32_t*>(&h);
+    const float ha = __uint_as_float(hu << 16), hb = __uint_as_float(hu & 0xffff0000u);
+    __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+    hi = hu;
     lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -1,0 +1,50 @@
+"""Launches each hot kernel once at a realistic shape (for ncu captures; not a benchmark)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hipie_b200 import ops
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+prec = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dev = torch.device("cuda:0")
+ops.set_precision(prec)
+torch.manual_seed(0)
+if which in ("all", "attn"):
+    B, H, hd, T = 2, 16, 80, 4096
+    E = H * hd
+    qk = torch.randn(B * T, 2 * E, device=dev)
+    v = torch.randn(E, B * T, device=dev)
+    S, Vs = ops.split(qk), ops.split(v)
+    q, k = ops.BF2(S.hi[:, :E], S.lo[:, :E]), ops.BF2(S.hi[:, E:], S.lo[:, E:])
+    rel_h = torch.randn(B, H, T, 64, device=dev)
+    rel_w = torch.randn(B, H, T, 64, device=dev)
+    for _ in range(2):
+        ops.attention_tc(q, k, Vs, B, H, T, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=64, kw=64)
+if which in ("all", "gemm"):
+    a = torch.randn(32768, 1280, device=dev)
+    w = torch.randn(5120, 1280, device=dev) * 0.02
+    A, W = ops.split(a), ops.split_weight(w)
+    for _ in range(2):
+        ops.gemm(A, W, act=ops.ACT_GELU, want_f32=False, want_split=True)
+if which in ("all", "msda"):
+    B = 8
+    shapes = torch.tensor([(128, 128), (64, 64), (32, 32), (16, 16)], device=dev)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    Sx = int(shapes.prod(1).sum())
+    value = torch.randn(B, Sx, 256, device=dev)
+    packed = torch.cat([torch.randn(B, Sx, 256, device=dev) * 2.0, torch.randn(B, Sx, 128, device=dev)], -1)
+    refs = []
+    for (h, w_) in shapes.tolist():
+        ys, xs = torch.meshgrid(torch.linspace(0.5, h - 0.5, h, device=dev) / h, torch.linspace(0.5, w_ - 0.5, w_, device=dev) / w_, indexing="ij")
+        refs.append(torch.stack([xs.reshape(-1), ys.reshape(-1)], -1))
+    refp = torch.cat(refs, 0)[None, :, None, :].repeat(B, 1, 4, 1).contiguous()
+    for _ in range(2):
+        ops.msda_fused(value, shapes, lsi, packed, refp)
+if which in ("all", "maskembed"):
+    B, HW, Q, C = 8, 65536, 300, 256
+    Fm = ops.split(torch.randn(B * HW, C, device=dev))
+    Em = ops.split(torch.randn(B * Q, C, device=dev) * 0.1)
+    for _ in range(2):
+        ops.gemm(Fm, Em, M=HW, N=Q, K=C, batch=B, lda=C, ldw=C, a_bstride=HW * C, w_bstride=Q * C, transposed=True, bits_threshold=0.0)
+torch.cuda.synchronize()
+print("done", which)
