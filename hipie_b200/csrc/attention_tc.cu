@@ -55,7 +55,7 @@ struct FaSmem {
     static constexpr int OFF_K = Q_BYTES;
     static constexpr int OFF_V = OFF_K + 2 * K_STAGE;
     static constexpr int OFF_P = OFF_V + 2 * V_STAGE;
-    static constexpr int OFF_BAR = OFF_P + P_BYTES;
+    static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;    // P is double buffered
     static constexpr int TOTAL = OFF_BAR + 256 + 3 * 2 * FA_BM * 4 + 1024;
 };
 
@@ -83,9 +83,9 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     uint64_t* v_empty = bars + 7;       // [2]
     uint64_t* s_full = bars + 9;        // [2]
     uint64_t* s_empty = bars + 11;      // [2]
-    uint64_t* p_full = bars + 13;       // [1]
-    uint64_t* pv_done = bars + 14;      // [1]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* p_full = bars + 13;       // [2]
+    uint64_t* pv_done = bars + 15;      // [2]  PV(j) commits to pv_done[j & 1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
     float* xchg = reinterpret_cast<float*>(smem + SM::OFF_BAR + 256);   // [3][2][128] max / row-sum exchange
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,8 +107,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
                 mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
             }
-            mbar_init(p_full, 8);
-            mbar_init(pv_done, 1);
+            for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], 8); mbar_init(&pv_done[i], 1); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -157,11 +156,11 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         };
         auto issue_pv = [&](int j) {
             const int s = j & 1;
-            mbar_wait(p_full, j & 1);
+            mbar_wait(&p_full[s], (j >> 1) & 1);
             mbar_wait(&v_full[s], (j >> 1) & 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t pb = smem_u32(smem + SM::OFF_P), vb = smem_u32(smem + SM::OFF_V + s * SM::V_STAGE);
+                const uint32_t pb = smem_u32(smem + SM::OFF_P + s * SM::P_BYTES), vb = smem_u32(smem + SM::OFF_V + s * SM::V_STAGE);
                 const uint64_t p_hi = make_kmajor_desc<128>(pb), v_hi = make_kmajor_desc<128>(vb);
                 uint32_t accum = j > 0;
 #pragma unroll
@@ -173,7 +172,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
 #pragma unroll
                     for (int k = 0; k < FA_BN / 16; ++k) umma_f16(tmem_O, p_lo + 2 * k, v_hi + 2 * k, idesc_pv, 1);
                 }
-                umma_commit(pv_done);
+                umma_commit(&pv_done[s]);
                 umma_commit(&v_empty[s]);
             }
             __syncwarp();
@@ -235,8 +234,6 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             relh_row = p.rel_h + rowi * p.kh;
         }
         float m = -INFINITY, l = 0.f;          // m: running reference max of (scaled logit + rel_w) + rel_h, log2 domain
-        uint8_t* p_hi = smem + SM::OFF_P;
-        uint8_t* p_lo = smem + SM::OFF_P + SM::P;
         const int sw = r & 7;
         const int o_c0 = half == 0 ? 0 : 48, o_c1 = half == 0 ? 48 : FA_HD;   // output columns owned (x16 granules)
         float rh_next = has_rel ? __ldg(relh_row) * LOG2E : 0.f;
@@ -281,10 +278,11 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 rowsum += t[i];
             }
             l += rowsum;
-            if (j > 0) {
-                mbar_wait(pv_done, (j - 1) & 1);      // PV(j-1) retired: P smem free, O up to date
+            if (j > 0 && __any_sync(0xffffffffu, need)) {
+                // O must reflect PV(j-1) before it is rescaled (rare once the running max has settled)
+                mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, need)) {
+                {
                     for (int c = o_c0; c < o_c1; c += 16) {
                         uint32_t o[16];
                         tmem_ld_32x32b_x16(tmem_O + lane_off + c, o);
@@ -296,6 +294,10 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                     tmem_st_wait();
                 }
             }
+            // P buffer s is free once PV(j-2) has retired
+            mbar_wait(&pv_done[s], ((j >> 1) & 1) ^ 1);
+            uint8_t* p_hi = smem + SM::OFF_P + s * SM::P_BYTES;
+            uint8_t* p_lo = p_hi + SM::P;
             // P -> swizzled K-major smem tile [128 rows x 64 keys] (128-byte rows, 16-byte chunk index XOR row%8)
 #pragma unroll
             for (int cc = 0; cc < HC / 8; ++cc) {
@@ -317,13 +319,13 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
+            if (lane == 0) mbar_arrive(&p_full[s]);
         }
         // ---- epilogue: O / l (row sum = both halves) ----
         xchg[(2 * 2 + half) * FA_BM + r] = l;
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
         l += xchg[(2 * 2 + (half ^ 1)) * FA_BM + r];
-        mbar_wait(pv_done, (ntiles - 1) & 1);
+        mbar_wait(&pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
         tc_fence_after();
         const float inv = 1.f / l;
         const int64_t obase = (int64_t)b * p.o_bs + (int64_t)qrow * p.o_ts + (int64_t)h * FA_HD;
