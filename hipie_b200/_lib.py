@@ -65,6 +65,9 @@ SYMBOLS = {
     "hipie_attention_tc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                    c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                    c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
+    "hipie_attention_tc_traced": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                                          c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     "hipie_relpos_bias": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
                                   c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hipie_relpos_bias_tc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,

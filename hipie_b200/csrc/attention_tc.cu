@@ -39,6 +39,7 @@ struct FaParams {
     int B, H, T;
     int q_col0, k_col0;           // column of head 0 inside the q / k tensor-map rows
     float scale_log2e;
+    long long* trace;             // debug: per-tile clock64 timestamps of CTA (0,0,0) or null
 };
 
 template <int PREC>
@@ -156,9 +157,13 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         };
         auto issue_pv = [&](int j) {
             const int s = j & 1;
+            const bool trm = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j < 32;
+            if (trm) p.trace[j * 16 + 10] = clock64();
             mbar_wait(&p_full[s], (j >> 1) & 1);
+            if (trm) p.trace[j * 16 + 11] = clock64();
             mbar_wait(&v_full[s], (j >> 1) & 1);
             tc_fence_after();
+            if (trm) p.trace[j * 16 + 12] = clock64();
             if (lane == 0) {
                 const uint32_t pb = smem_u32(smem + SM::OFF_P + s * SM::P_BYTES), vb = smem_u32(smem + SM::OFF_V + s * SM::V_STAGE);
                 const uint64_t p_hi = make_kmajor_desc<128>(pb), v_hi = make_kmajor_desc<128>(vb);
@@ -175,15 +180,19 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 umma_commit(&pv_done[s]);
                 umma_commit(&v_empty[s]);
             }
+            if (trm) p.trace[j * 16 + 13] = clock64();
             __syncwarp();
         };
         mbar_wait(q_full, 0);
         for (int j = 0; j < ntiles; ++j) {
             const int s = j & 1;
             const uint32_t ph = (j >> 1) & 1;
+            const bool trq = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j < 32;
+            if (trq) p.trace[j * 16 + 7] = clock64();
             mbar_wait(&k_full[s], ph);
             mbar_wait(&s_empty[s], ph ^ 1);
             tc_fence_after();
+            if (trq) p.trace[j * 16 + 8] = clock64();
             if (lane == 0) {
                 const uint32_t kb = smem_u32(smem + SM::OFF_K + s * SM::K_STAGE);
                 const uint32_t d = tmem_S + s * FA_BN;
@@ -205,6 +214,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 umma_commit(&s_full[s]);
                 umma_commit(&k_empty[s]);
             }
+            if (trq) p.trace[j * 16 + 9] = clock64();
             __syncwarp();
             if (j >= 1) issue_pv(j - 1);
         }
@@ -241,14 +251,18 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             const int s = j & 1;
             const float rh = rh_next;
             if (has_rel && j + 1 < ntiles) rh_next = __ldg(relh_row + j + 1) * LOG2E;   // prefetch: latency hidden by this tile
+            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0 && j < 32;
+            if (tr) p.trace[j * 16 + 0] = clock64();
             mbar_wait(&s_full[s], (j >> 1) & 1);
             tc_fence_after();
+            if (tr) p.trace[j * 16 + 1] = clock64();
             uint32_t sv[HC];
             tmem_ld_32x32b_x32(tmem_S + lane_off + s * FA_BN + half * HC, sv);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[s]);   // score buffer may be overwritten by QK(j+2)
+            if (tr) p.trace[j * 16 + 2] = clock64();
             // t_i = s_i*scale*log2e + rel_w_i (+ rel_h added to the max / exponent offset, it is uniform over the tile)
             float tmax = -INFINITY;
             float t[HC];
@@ -262,6 +276,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             xchg[(s * 2 + half) * FA_BM + r] = tmax;
             asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
             tmax = fmaxf(tmax, xchg[(s * 2 + (half ^ 1)) * FA_BM + r]);
+            if (tr) p.trace[j * 16 + 3] = clock64();
             // lazy rescale: keep the running reference max unless the tile exceeds it by more than 2^8
             float corr = 1.f;
             const bool need = tmax > m + 8.f;
@@ -278,6 +293,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 rowsum += t[i];
             }
             l += rowsum;
+            if (tr) p.trace[j * 16 + 4] = clock64() + (long long)(rowsum == 12345.f);
             if (j > 0 && __any_sync(0xffffffffu, need)) {
                 // O must reflect PV(j-1) before it is rescaled (rare once the running max has settled)
                 mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
@@ -296,6 +312,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             }
             // P buffer s is free once PV(j-2) has retired
             mbar_wait(&pv_done[s], ((j >> 1) & 1) ^ 1);
+            if (tr) p.trace[j * 16 + 5] = clock64();
             uint8_t* p_hi = smem + SM::OFF_P + s * SM::P_BYTES;
             uint8_t* p_lo = p_hi + SM::P;
             // P -> swizzled K-major smem tile [128 rows x 64 keys] (128-byte rows, 16-byte chunk index XOR row%8)
@@ -320,6 +337,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[s]);
+            if (tr) p.trace[j * 16 + 6] = clock64();
         }
         // ---- epilogue: O / l (row sum = both halves) ----
         xchg[(2 * 2 + half) * FA_BM + r] = l;
@@ -382,6 +400,10 @@ static int launch_fa(const FaMaps& maps, const FaParams& p, cudaStream_t st) {
 
 using namespace hipie;
 
+extern "C" int hipie_attention_tc_traced(const void*, const void*, int64_t, int64_t, int, int, const void*, const void*, int64_t, int64_t, int,
+                                         int, const void*, const void*, int64_t, const float*, const float*, int, int, float*, void*, void*,
+                                         int64_t, int64_t, int, int, int, int, float, int, long long*, void*);
+
 // q / k: bf16 planes viewed as (B, T, row_width) with token stride q_ts / k_ts and batch stride q_bs / k_bs (elements);
 // head h occupies columns [q_col0 + 80 h, +80).  vt: V transposed, (H*80 rows, B*T columns) planes with row stride vt_ld.
 extern "C" int hipie_attention_tc(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
@@ -389,6 +411,15 @@ extern "C" int hipie_attention_tc(const void* q_hi, const void* q_lo, int64_t q_
                                   const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
                                   int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
                                   int H, int T, int hd, float scale, int prec, void* stream) {
+    return hipie_attention_tc_traced(q_hi, q_lo, q_bs, q_ts, q_col0, q_width, k_hi, k_lo, k_bs, k_ts, k_col0, k_width, vt_hi, vt_lo, vt_ld, rel_h,
+                                     rel_w, kh, kw, out_f32, out_hi, out_lo, o_bs, o_ts, B, H, T, hd, scale, prec, nullptr, stream);
+}
+
+extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
+                                         const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
+                                         const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
+                                         int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
+                                         int H, int T, int hd, float scale, int prec, long long* trace, void* stream) {
     HIPIE_CHECK_ARG(q_hi && k_hi && vt_hi, "hipie_attention_tc: q/k/vt hi planes required");
     HIPIE_CHECK_ARG(prec == 1 || (prec == 3 && q_lo && k_lo && vt_lo), "hipie_attention_tc: prec/lo planes mismatch");
     HIPIE_CHECK_ARG(hd == FA_HD, "hipie_attention_tc: head dim must be 80 (got %d)", hd);
@@ -417,6 +448,7 @@ extern "C" int hipie_attention_tc(const void* q_hi, const void* q_lo, int64_t q_
     p.out_f32 = out_f32; p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo;
     p.o_bs = o_bs; p.o_ts = o_ts; p.B = B; p.H = H; p.T = T; p.q_col0 = q_col0; p.k_col0 = k_col0;
     p.scale_log2e = scale * 1.4426950408889634f;
+    p.trace = trace;
     cudaStream_t st = (cudaStream_t)stream;
     return prec == 3 ? launch_fa<3>(maps, p, st) : launch_fa<1>(maps, p, st);
 }

@@ -189,6 +189,13 @@ int hipie_attention_tc(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t
                        int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
                        int H, int T, int hd, float scale, int prec, void* stream);
 
+/* Same, with an optional device buffer (32 tiles x 16 slots of clock64 stamps of CTA (0,0,0)) for pipeline debugging. */
+int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
+                              const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
+                              const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
+                              int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
+                              int H, int T, int hd, float scale, int prec, long long* trace, void* stream);
+
 /* rel[b,h,q,j] = sum_c q[b,q,h,c] * table[idx(q,j), c] for the decomposed rel-pos bias.
  * axis 0: height (idx from q // qw), axis 1: width (q % qw).  table: (2*max(q,k)-1, hd) fp32,
  * table_t: get_rel_pos output (H:backbone/utils.py:63-93) pre-transposed to (qsize, hd, ksize) fp32.

@@ -1,0 +1,30 @@
+import os, sys, ctypes
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hipie_b200 import ops, _lib
+prec = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+ops.set_precision(prec)
+dev = torch.device("cuda:0")
+B, H, hd, T = 2, 16, 80, 4096
+E = H * hd
+qk = torch.randn(B * T, 2 * E, device=dev); v = torch.randn(E, B * T, device=dev)
+S, Vs = ops.split(qk), ops.split(v)
+rel_h = torch.randn(B, H, T, 64, device=dev); rel_w = torch.randn(B, H, T, 64, device=dev)
+out = ops._empty_bf2((B, T, E), dev)
+trace = torch.zeros(32 * 16, dtype=torch.int64, device=dev)
+lib = _lib.load()
+P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+lo = prec == 3
+for it in range(3):
+    rc = lib.hipie_attention_tc_traced(P(S.hi), P(S.lo) if lo else None, T * 2 * E, 2 * E, 0, E, P(S.hi[:, E:]), P(S.lo[:, E:]) if lo else None, T * 2 * E, 2 * E, 0, E,
+                                       P(Vs.hi), P(Vs.lo) if lo else None, B * T, P(rel_h), P(rel_w), 64, 64, None, P(out.hi), P(out.lo) if lo else None,
+                                       T * E, E, B, H, T, hd, hd ** -0.5, prec, P(trace), None)
+    assert rc == 0, lib.hipie_last_error()
+torch.cuda.synchronize()
+t = trace.cpu().view(32, 16)
+t0 = int(t[8, 0])
+names = ["sm:start", "sm:S ready", "sm:ldtm done", "sm:xchg done", "sm:exp done", "sm:P free", "sm:P stored", "mm:iter start", "mm:k/sempty ok", "mm:QK issued",
+         "mm:pv start", "mm:p_full ok", "mm:v ok", "mm:PV issued"]
+print("tile " + " ".join(f"{n[:12]:>12s}" for n in names))
+for j in range(8, 20):
+    print(f"{j:4d} " + " ".join(f"{int(t[j, k]) - t0:12d}" for k in range(14)))
