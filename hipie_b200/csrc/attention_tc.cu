@@ -201,13 +201,59 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             if (trm) p.trace[j * 16 + 13] = clock64();
             __syncwarp();
         };
+        // PV(j) (accumulator O) and QK(j+2) (accumulator S[j&1]) are independent chains: small-N MMAs into the same
+        // accumulator are latency bound (~70 cycles each, measured), so the two chains are issued interleaved.
+        auto issue_pv_qk = [&](int jp, int jq) {
+            const int stp = jp % FA_STAGES, sbp = jp & 1;
+            const int stq = jq % FA_STAGES, sbq = jq & 1;
+            mbar_wait(&k_full[stq], (jq / FA_STAGES) & 1);
+            mbar_wait(&s_empty[sbq], ((jq >> 1) & 1) ^ 1);
+            mbar_wait(&v_full[stp], (jp / FA_STAGES) & 1);
+            mbar_wait(&p_full[sbp], (jp >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t vb = smem_u32(smem + SM::OFF_V + stp * SM::V_STAGE);
+                const uint32_t kb = smem_u32(smem + stq * SM::K_STAGE);
+                const uint32_t dO = tmem_base + TM_O, dS = tmem_base + TM_S + sbq * FA_BN;
+                const uint32_t tp_hi = tmem_base + TM_P + sbp * 64, tp_lo = tp_hi + 32;
+                const uint64_t v_hi = make_kmajor_desc<128>(vb), v_lo = make_kmajor_desc<128>(vb + SM::VT);
+                const uint64_t k64h = make_kmajor_desc<128>(kb), k16h = make_kmajor_desc<32>(kb + SM::K64);
+                const uint64_t k64l = make_kmajor_desc<128>(kb + SM::K64 + SM::K16), k16l = make_kmajor_desc<32>(kb + 2 * SM::K64 + SM::K16);
+                const uint32_t acc0 = jp > 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    umma_f16_ts(dO, tp_hi + 8 * k, v_hi + 2 * k, idesc_pv, k > 0 ? 1u : acc0);
+                    umma_f16_ts(dS, tq_hi + 8 * k, k64h + 2 * k, idesc_qk, k > 0);
+                }
+                umma_f16_ts(dS, tq_hi + 32, k16h, idesc_qk, 1);
+                if (PREC == 3) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        umma_f16_ts(dO, tp_hi + 8 * k, v_lo + 2 * k, idesc_pv, 1);
+                        umma_f16_ts(dS, tq_hi + 8 * k, k64l + 2 * k, idesc_qk, 1);
+                    }
+                    umma_f16_ts(dS, tq_hi + 32, k16l, idesc_qk, 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        umma_f16_ts(dO, tp_lo + 8 * k, v_hi + 2 * k, idesc_pv, 1);
+                        umma_f16_ts(dS, tq_lo + 8 * k, k64h + 2 * k, idesc_qk, 1);
+                    }
+                    umma_f16_ts(dS, tq_lo + 32, k16h, idesc_qk, 1);
+                }
+                umma_commit(&pv_done[sbp]);
+                umma_commit(&v_empty[stp]);
+                umma_commit(&s_full[sbq]);
+                umma_commit(&k_empty[stq]);
+            }
+            __syncwarp();
+        };
         mbar_wait(q_ready, 0);
         tc_fence_after();
         issue_qk(0);
         if (ntiles > 1) issue_qk(1);
         for (int j = 0; j < ntiles; ++j) {
-            issue_pv(j);                            // needs P(j) from the softmax warps
-            if (j + 2 < ntiles) issue_qk(j + 2);    // score buffer j&1 was released when softmax(j) loaded its scores
+            if (j + 2 < ntiles) issue_pv_qk(j, j + 2);
+            else issue_pv(j);
         }
     } else {
         // ===================== softmax / epilogue (warps 2..9) =====================
