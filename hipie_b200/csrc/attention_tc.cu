@@ -149,7 +149,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
             tc_fence_after();
             if (trq) p.trace[j * 16 + 8] = clock64();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t kb = smem_u32(smem + st * SM::K_STAGE);
                 const uint32_t d = tmem_base + TM_S + sb * FA_BN;
                 const uint64_t k64h = make_kmajor_desc<128>(kb), k16h = make_kmajor_desc<32>(kb + SM::K64);
@@ -180,7 +180,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             mbar_wait(&v_full[st], (j / FA_STAGES) & 1);
             tc_fence_after();
             if (trm) p.trace[j * 16 + 12] = clock64();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t vb = smem_u32(smem + SM::OFF_V + st * SM::V_STAGE);
                 const uint32_t d = tmem_base + TM_O;
                 const uint32_t tp_hi = tmem_base + TM_P + sb * 64, tp_lo = tp_hi + 32;
@@ -211,7 +211,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             mbar_wait(&v_full[stp], (jp / FA_STAGES) & 1);
             mbar_wait(&p_full[sbp], (jp >> 1) & 1);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t vb = smem_u32(smem + SM::OFF_V + stp * SM::V_STAGE);
                 const uint32_t kb = smem_u32(smem + stq * SM::K_STAGE);
                 const uint32_t dO = tmem_base + TM_O, dS = tmem_base + TM_S + sbq * FA_BN;

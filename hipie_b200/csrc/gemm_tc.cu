@@ -317,7 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t st = smem_u32(stage_base + s * Cfg::STAGE);
                     const uint64_t a_hi = make_kmajor_desc<Cfg::SWZ>(st);
                     const uint64_t w_hi = make_kmajor_desc<Cfg::SWZ>(st + Cfg::A_TILE);
