@@ -128,7 +128,8 @@ class HIPIE_IMG(nn.Module):
         if task == "grounding":
             lm = lang["masks"].float()
             lang_feat_pool = ((lang["hidden"] * lm.unsqueeze(-1)).sum(1) / lm.sum(-1, keepdim=True)).unsqueeze(1)   # pre-fusion (:809-811)
-        di = eng.detr_inputs(feats, pad_mask, B)
+        any_pad = any(tuple(s) != tuple(tensor.shape[-2:]) for s in image_sizes)      # host-side: no device sync
+        di = eng.detr_inputs(feats, pad_mask, B, any_pad=any_pad)
         tr = eng.detr_transformer(di, lang, B, forced_topk=forced.get("topk_fg"))
         md = eng.maskdino(feats, B, forced_topk=forced.get("topk_md"))
         nd = hp.get("dec_layers", 6)
