@@ -151,6 +151,21 @@ attention_kernel(const AttnParams p) {
     const float* kb = p.key_bias ? p.key_bias + (int64_t)b * p.Tk : nullptr;
     // one KV tile == one key row of the grid (kw == 64): rel_w terms are tile-invariant -> registers
     const bool hoist = has_rel && p.kw == ATT_BN;
+    // otherwise (14x14 windows, 80-wide grids): the CTA's 64 x (kh + kw) table rows are staged in shared memory once,
+    // so the per-score bias is two LDS instead of two scattered global loads
+    const int rel_ld = p.kh + p.kw + 1;
+    float* rel_s = reinterpret_cast<float*>(smem + 2 * STAGE);
+    if (has_rel && !hoist) {
+        for (int i = threadIdx.x; i < ATT_BM * (p.kh + p.kw); i += 128) {
+            const int rr = i / (p.kh + p.kw), c = i - rr * (p.kh + p.kw);
+            const int qq = min(q0 + rr, p.Tq - 1);
+            const int64_t rowi = ((int64_t)b * p.H + h) * p.Tq + qq;
+            rel_s[rr * rel_ld + c] = c < p.kh ? __ldg(p.rel_h + rowi * p.kh + c) : __ldg(p.rel_w + rowi * p.kw + (c - p.kh));
+        }
+        __syncthreads();
+    }
+    const float* rs0 = rel_s + (warp * 16 + (lane >> 2)) * rel_ld;
+    const float* rs1 = rs0 + 8 * rel_ld;
     float rw[ATT_BN / 8][4];
     if (hoist) {
 #pragma unroll
@@ -215,8 +230,8 @@ attention_kernel(const AttnParams p) {
                         add1 = rh1 + rw[j][2 + e];
                     } else if (has_rel) {
                         const int khi = kk / p.kw, kwi = kk - khi * p.kw;
-                        add0 = __ldg(relh_r[0] + khi) + __ldg(relw_r[0] + kwi);
-                        add1 = __ldg(relh_r[1] + khi) + __ldg(relw_r[1] + kwi);
+                        add0 = rs0[khi] + rs0[p.kh + kwi];
+                        add1 = rs1[khi] + rs1[p.kh + kwi];
                     }
                     if (kb) { const float kbv = __ldg(kb + kk); add0 += kbv; add1 += kbv; }
                 }
@@ -449,11 +464,14 @@ relpos_mma_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* _
 template <int HD, int PREC>
 static int launch_attn(const AttnParams& p, cudaStream_t st) {
     constexpr int ROWB = HD * 2 + 16;
-    constexpr int SMEM = 2 * (PREC == 3 ? 4 : 2) * ATT_BN * ROWB;
-    static bool attr = false;
-    if (!attr) {
+    constexpr int SMEM_KV = 2 * (PREC == 3 ? 4 : 2) * ATT_BN * ROWB;
+    const bool tables = p.rel_h != nullptr && p.kw != ATT_BN;
+    const int SMEM = SMEM_KV + (tables ? ATT_BM * (p.kh + p.kw + 1) * (int)sizeof(float) : 0);
+    HIPIE_CHECK_ARG(SMEM <= 200 * 1024, "hipie_attention: rel-pos grid %dx%d too large for the shared-memory tables", p.kh, p.kw);
+    static int attr = 0;
+    if (SMEM > attr) {
         HIPIE_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<HD, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr = true;
+        attr = SMEM;
     }
     dim3 grid((p.Tq + ATT_BM - 1) / ATT_BM, p.H, p.B);
     attention_kernel<HD, PREC><<<grid, 128, SMEM, st>>>(p);

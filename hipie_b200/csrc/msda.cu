@@ -172,36 +172,66 @@ msda_fast_kernel(const void* __restrict__ value, const int64_t* __restrict__ sha
         }
     }
 
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int64_t pixstride = (int64_t)M * D;
-    const int64_t vb = (int64_t)b * S * pixstride + (int64_t)m * D + dsub * 4;
-    const int src_base = lane & 24;
+    // ---- tap preparation: this lane turns its two points into 4 element offsets + 4 fused weights each (attention
+    //      weight x bilinear weight; out-of-range taps get weight 0 and a clamped in-range address, so the gather loop is
+    //      branch free), staged in shared memory for the 8 lanes of the head group.
+    extern __shared__ __align__(16) uint8_t msda_smem[];
+    const int warp_in_blk = threadIdx.x >> 5;
+    // per warp: 4 head groups x (16 points x 8 words + 4 pad words)  -> distinct banks for the 4 broadcast addresses
+    constexpr int GROUP_WORDS = 16 * 8 + 4;
+    uint32_t* wsm = reinterpret_cast<uint32_t*>(msda_smem) + warp_in_blk * 4 * GROUP_WORDS;
+    const int pixstride_i = M * D;
+    {
+        const int lown = dsub >> 1;
+        int Hown = Hl[0], Wown = Wl[0];
+        int64_t stown = st[0];
+#pragma unroll
+        for (int l = 1; l < L; ++l)
+            if (lown == l) { Hown = Hl[l]; Wown = Wl[l]; stown = st[l]; }
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+            const float x = pp ? x1p : x0p, y = pp ? y1p : y0p, w = pp ? w1p : w0p;
+            const float yf = floorf(y), xf = floorf(x);
+            const float ly = y - yf, lx = x - xf, hy = 1.f - ly, hx = 1.f - lx;
+            // clamp the integer corner so that int conversion is safe for wild offsets
+            const int yi = (int)fminf(fmaxf(yf, -2.f), (float)Hown), xi = (int)fminf(fmaxf(xf, -2.f), (float)Wown);
+            const bool inside = y > -1.f && x > -1.f && y < (float)Hown && x < (float)Wown;
+            const bool t = inside && yi >= 0, btm = inside && yi + 1 <= Hown - 1, lft = xi >= 0, rgt = xi + 1 <= Wown - 1;
+            const int yc0 = min(max(yi, 0), Hown - 1), yc1 = min(max(yi + 1, 0), Hown - 1);
+            const int xc0 = min(max(xi, 0), Wown - 1), xc1 = min(max(xi + 1, 0), Wown - 1);
+            const int base = (int)stown * pixstride_i + m * D;
+            uint4 offs;
+            offs.x = base + (yc0 * Wown + xc0) * pixstride_i;
+            offs.y = base + (yc0 * Wown + xc1) * pixstride_i;
+            offs.z = base + (yc1 * Wown + xc0) * pixstride_i;
+            offs.w = base + (yc1 * Wown + xc1) * pixstride_i;
+            float4 wt;
+            wt.x = (t && lft) ? w * hy * hx : 0.f;
+            wt.y = (t && rgt) ? w * hy * lx : 0.f;
+            wt.z = (btm && lft) ? w * ly * hx : 0.f;
+            wt.w = (btm && rgt) ? w * ly * lx : 0.f;
+            uint32_t* dst = wsm + hsub * GROUP_WORDS + (dsub * 2 + pp) * 8;
+            *reinterpret_cast<uint4*>(dst) = offs;
+            *reinterpret_cast<float4*>(dst + 4) = wt;
+        }
+    }
+    __syncwarp();
 
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t vb = (int64_t)b * S * pixstride_i + dsub * 4;
+    const uint32_t* gsm = wsm + hsub * GROUP_WORDS;
 #pragma unroll
     for (int p = 0; p < L * P; ++p) {
-        const int l = p >> 2;
-        const int src = src_base | (p >> 1);
-        const float x = __shfl_sync(0xffffffffu, (p & 1) ? x1p : x0p, src);
-        const float y = __shfl_sync(0xffffffffu, (p & 1) ? y1p : y0p, src);
-        const float w = __shfl_sync(0xffffffffu, (p & 1) ? w1p : w0p, src);
-        const int H = Hl[l], W = Wl[l];
-        if (y > -1.f && x > -1.f && y < (float)H && x < (float)W) {
-            const float yf = floorf(y), xf = floorf(x);
-            const int yi = (int)yf, xi = (int)xf;
-            const float ly = y - yf, lx = x - xf, hy = 1.f - ly, hx = 1.f - lx;
-            const int64_t base = vb + (st[l] + (int64_t)yi * W + xi) * pixstride;
-            const bool t = yi >= 0, btm = yi + 1 <= H - 1, lft = xi >= 0, rgt = xi + 1 <= W - 1;
-            float4 v1 = make_float4(0, 0, 0, 0), v2 = v1, v3 = v1, v4 = v1;
-            if (t && lft) v1 = ValLoad<BF16V>::ld(value, base);
-            if (t && rgt) v2 = ValLoad<BF16V>::ld(value, base + pixstride);
-            if (btm && lft) v3 = ValLoad<BF16V>::ld(value, base + (int64_t)W * pixstride);
-            if (btm && rgt) v4 = ValLoad<BF16V>::ld(value, base + (int64_t)(W + 1) * pixstride);
-            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-            acc.x += w * (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x);
-            acc.y += w * (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y);
-            acc.z += w * (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z);
-            acc.w += w * (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w);
-        }
+        const uint4 offs = *reinterpret_cast<const uint4*>(gsm + p * 8);
+        const float4 wt = *reinterpret_cast<const float4*>(gsm + p * 8 + 4);
+        const float4 v1 = ValLoad<BF16V>::ld(value, vb + offs.x);
+        const float4 v2 = ValLoad<BF16V>::ld(value, vb + offs.y);
+        const float4 v3 = ValLoad<BF16V>::ld(value, vb + offs.z);
+        const float4 v4 = ValLoad<BF16V>::ld(value, vb + offs.w);
+        acc.x += wt.x * v1.x + wt.y * v2.x + wt.z * v3.x + wt.w * v4.x;
+        acc.y += wt.x * v1.y + wt.y * v2.y + wt.z * v3.y + wt.w * v4.y;
+        acc.z += wt.x * v1.z + wt.y * v2.z + wt.z * v3.z + wt.w * v4.z;
+        acc.w += wt.x * v1.w + wt.y * v2.w + wt.z * v3.w + wt.w * v4.w;
     }
 
     const int64_t o = bq * (int64_t)(M * D) + m * D + dsub * 4;
@@ -224,7 +254,7 @@ static int launch_fast(const void* value, const int64_t* shapes, const int64_t* 
     const int64_t warps = (int64_t)N * Lq * (M / 4);
     const int64_t blocks = (warps + 7) / 8;
     if (blocks == 0) return HIPIE_OK;
-    msda_fast_kernel<BF16V, FUSED, REFDIM, SPLIT><<<(unsigned)blocks, 256, 0, st>>>(
+    msda_fast_kernel<BF16V, FUSED, REFDIM, SPLIT><<<(unsigned)blocks, 256, 8 * 4 * (16 * 8 + 4) * 4, st>>>(
         value, shapes, lstart, loc, attw, refp, out, (__nv_bfloat16*)out_hi,
         (__nv_bfloat16*)out_lo, N, S, M, Lq);
     HIPIE_CHECK_LAUNCH();
