@@ -165,6 +165,13 @@ class Engine:
             self._maps[key] = (tok2win, win2tok, nW)
         return self._maps[key]
 
+    def _dev_const(self, values, dtype):
+        """Small host lists as cached device tensors (no H2D copy inside a CUDA-graph capture)."""
+        key = ("const", dtype, repr(values))
+        if key not in self._maps:
+            self._maps[key] = torch.tensor(values, dtype=dtype, device=self.device)
+        return self._maps[key]
+
     def _zero_bf2(self, key, shape):
         if key not in self._bufs:
             self._bufs[key] = BF2(torch.zeros(shape, dtype=torch.bfloat16, device=self.device),
@@ -577,8 +584,8 @@ class Engine:
             _, Hh, Ww = m.shape
             vr.append(torch.stack([torch.sum(~m[:, 0, :], 1).float() / Ww, torch.sum(~m[:, :, 0], 1).float() / Hh], -1))
         valid_ratios = torch.stack(vr, 1)
-        shapes_t = torch.tensor(shapes, dtype=torch.long, device=self.device)
-        lsi_t = torch.tensor(starts, dtype=torch.long, device=self.device)
+        shapes_t = self._dev_const([list(x) for x in shapes], torch.long)
+        lsi_t = self._dev_const(list(starts), torch.long)
         return dict(src=src, pos=pos, mask_flat=mask_flat, any_pad=any_pad, valid_ratios=valid_ratios,
                     shapes=shapes, shapes_t=shapes_t, lsi_t=lsi_t, S=S, starts=starts)
 
@@ -659,7 +666,7 @@ class Engine:
         Q = hs_s.hi.shape[1]
         params = self.mlp(hs_s.view(B * Q, 256), "detr.controller", 3).view(B, Q, 169)
         ref_points = tr["refs"][-2][:, :, :2]
-        scale = torch.tensor([[float(s[1]), float(s[0])] for s in image_sizes], device=self.device).view(B, 1, 2)
+        scale = self._dev_const([[float(s[1]), float(s[0])] for s in image_sizes], torch.float32).view(B, 1, 2)
         ref_px = (ref_points * scale).contiguous()
         lv = [memory[:, starts[l]:starts[l] + shapes[l][0] * shapes[l][1]].reshape(B, shapes[l][0], shapes[l][1], 256) for l in range(3)]
         mh = "detr.mask_head"
@@ -710,8 +717,8 @@ class Engine:
         pos = torch.cat([_sine_pos(zeros[l], 128, 0.0) + lvl_embed[l].view(1, 1, -1) for l in range(4)], 1).contiguous()
         ones_vr = torch.ones(B, 4, 2, device=self.device)
         ref_enc = self.encoder_reference_points(shapes, ones_vr, self.device)
-        shapes_t = torch.tensor(shapes, dtype=torch.long, device=self.device)
-        lsi_t = torch.tensor(starts, dtype=torch.long, device=self.device)
+        shapes_t = self._dev_const([list(x) for x in shapes], torch.long)
+        lsi_t = self._dev_const(list(starts), torch.long)
         _, src_s = ops.add_split(src)
         for i in range(hp.get("md_enc_layers", 6)):
             src, src_s = self.encoder_layer(f"{pd}.transformer.encoder.layers.{i}", src, src_s, pos, ref_enc, None, shapes_t, lsi_t, B, S)
@@ -741,8 +748,8 @@ class Engine:
             dstarts.append(dstarts[-1] + h * w)
         mem = torch.cat([src[:, starts[i]:starts[i] + shapes[i][0] * shapes[i][1]] for i in order], 1).contiguous()
         _, mem_s = ops.add_split(mem)
-        dshapes_t = torch.tensor(dshapes, dtype=torch.long, device=self.device)
-        dlsi_t = torch.tensor(dstarts, dtype=torch.long, device=self.device)
+        dshapes_t = self._dev_const([list(x) for x in dshapes], torch.long)
+        dlsi_t = self._dev_const(list(dstarts), torch.long)
         zmask = torch.zeros(B, S, dtype=torch.bool, device=self.device)
         props, valid = self.proposals(dshapes, zmask, B, self.device)
         om = mem.masked_fill(~valid, 0.0)
