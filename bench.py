@@ -225,10 +225,8 @@ def run_product(args):
             lang = model.forward_text(ids_d, am_d)
             out = model.coco_inference(dev_imgs, pad_mask, sizes, lang, task="detection")
         if world > 1:     # the only collective of the data-parallel path: all-gather of the fixed-shape logits / boxes
-            for k in ("pred_logits", "pred_boxes", "pred_logits_maskdino"):
-                t = out[k].contiguous()
-                gathered = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=dev)
-                dist.all_gather_into_tensor(gathered, t)
+            from hipie_b200.parallel import all_gather_outputs
+            all_gather_outputs(out, ["pred_logits", "pred_boxes", "pred_boxious", "pred_logits_maskdino", "pred_boxes_maskdino"])
         return out
 
     def e2e_step():
