@@ -63,6 +63,7 @@ class HIPIE_IMG(nn.Module):
         self.num_bg, self.num_fg = hp.get("num_bg", 10), hp.get("num_queries", 900)
         self.mask_stride, self.mask_thres = 4, 0.5
         self.pano_temp, self.object_mask_threshold, self.overlap_threshold = 0.06, 0.25, 0.8
+        self.fused_postprocess = True      # semantic/panoptic tensor work in one kernel (ops.seg_postprocess)
         self.max_pool, self.bg_cls_agnostic, self.use_bg_for_pano = hp.get("max_pool", False), hp.get("bg_cls_agnostic", False), False
         self._sd = OrderedDict()
         self.engine = None
@@ -188,19 +189,38 @@ class HIPIE_IMG(nn.Module):
         return replay
 
     # ---- post-processing (hipie_img.py:537-766, 473-535, 870-878, 1025-1052); device-side torch glue for now ("next" tier)
-    @staticmethod
-    def convert_grounding_to_od_logits(logits, num_classes, positive_map, is_thing, mode=None, max_pool=False):
-        scores = torch.zeros(logits.shape[0], logits.shape[1], num_classes, device=logits.device)
-        for label_j in positive_map:
-            idx = torch.as_tensor(positive_map[label_j], dtype=torch.long, device=logits.device)
-            if max_pool:
-                scores[:, :, label_j - 1] = logits[:, :, idx].max(-1)[0]
-            else:
-                scores[:, :, label_j - 1] = logits[:, :, idx].mean(-1)
-            if mode == "FG" and (not is_thing.get(label_j, True)):
-                scores[:, :, label_j - 1] = -9999.0
-            elif mode == "BG" and is_thing.get(label_j, True):
-                scores[:, :, label_j - 1] = -9999.0
+    def _pool_tables(self, positive_map, num_classes, Lt, is_thing, device):
+        """Token->class pooling as dense tables, built once per vocabulary (hipie_img.py:1025-1052 loops over classes with
+        host index tensors; here: one (Lt, C) mean matrix, a padded (C, maxlen) index table for max-pooling, class masks)."""
+        key = (tuple((k, tuple(v)) for k, v in sorted(positive_map.items())), num_classes, Lt, tuple(sorted(is_thing.items())))
+        cache = self.__dict__.setdefault("_pool_cache", {})
+        if key not in cache:
+            cache.clear()
+            mean_m = torch.zeros(Lt, num_classes)
+            maxlen = max(len(v) for v in positive_map.values())
+            idx = torch.zeros(num_classes, maxlen, dtype=torch.long)
+            has = torch.zeros(num_classes, dtype=torch.bool)
+            for label_j, toks in positive_map.items():
+                mean_m[toks, label_j - 1] = 1.0 / len(toks)
+                idx[label_j - 1, :len(toks)] = torch.tensor(toks)
+                idx[label_j - 1, len(toks):] = toks[0]
+                has[label_j - 1] = True
+            thing = torch.tensor([bool(is_thing.get(c + 1, True)) for c in range(num_classes)])
+            cache[key] = (mean_m.to(device), idx.to(device), has.to(device), thing.to(device))
+        return cache[key]
+
+    def convert_grounding_to_od_logits(self, logits, num_classes, positive_map, is_thing, mode=None, max_pool=False):
+        """logits (bs, Q, Lt) -> (bs, Q, C): per-class mean (or max) over its token span, -9999 for masked classes."""
+        mean_m, idx, has, thing = self._pool_tables(positive_map, num_classes, logits.shape[-1], is_thing, logits.device)
+        if max_pool:
+            scores = logits[:, :, idx].max(-1)[0]
+        else:
+            scores = torch.matmul(logits, mean_m)
+        scores = torch.where(has, scores, torch.zeros_like(scores))
+        if mode == "FG":
+            scores = torch.where(thing, scores, torch.full_like(scores, -9999.0))
+        elif mode == "BG":
+            scores = torch.where(thing, torch.full_like(scores, -9999.0), scores)
         return scores
 
     def semantic_inference(self, mask_cls, mask_pred):
@@ -243,6 +263,37 @@ class HIPIE_IMG(nn.Module):
                 panoptic_seg[inter[k]] = current_segment_id
                 segments_info.append({"id": current_segment_id, "isthing": bool(isthing), "category_id": int(pred_class)})
         return panoptic_seg, segments_info
+
+    def fused_sem_pano(self, mask_cls, mask_low, is_thing, image_size):
+        """semantic_inference + panoptic_inference (hipie_img.py:880-1023) from the 1/4-resolution logits in one kernel
+        (ops.seg_postprocess); only the segment-merge loop over the kept queries stays on the host."""
+        Hc, Wc = int(image_size[0]), int(image_size[1])
+        sem, ids, areas, scores, labels = ops.seg_postprocess(mask_low, mask_cls, self.object_mask_threshold, Hc, Wc,
+                                                              stride=self.mask_stride)
+        Q = mask_cls.shape[0]
+        host = torch.cat([areas, labels.to(torch.int32).unsqueeze(0), (scores > self.object_mask_threshold).to(torch.int32).unsqueeze(0)]).cpu()
+        mask_area, original_area, inter_area, classes, keep = host.tolist()
+        lut = [0] * (2 * Q + 1)           # ids+1 -> segment id (odd entries = argmax winner with sigmoid >= .5)
+        segments_info, stuff_memory_list, current_segment_id = [], {}, 0
+        for k in range(Q):
+            if not keep[k]:
+                continue
+            pred_class = classes[k]
+            isthing = is_thing.get(int(pred_class + 1), True)
+            if mask_area[k] > 0 and original_area[k] > 0 and inter_area[k] > 0:
+                if mask_area[k] / original_area[k] < self.overlap_threshold:
+                    continue
+                if not isthing:
+                    if int(pred_class) in stuff_memory_list:
+                        lut[2 * k + 2] = stuff_memory_list[int(pred_class)]
+                        continue
+                    stuff_memory_list[int(pred_class)] = current_segment_id + 1
+                current_segment_id += 1
+                lut[2 * k + 2] = current_segment_id
+                segments_info.append({"id": current_segment_id, "isthing": bool(isthing), "category_id": int(pred_class)})
+        lut_d = torch.tensor(lut, dtype=torch.int32, device=ids.device)
+        panoptic_seg = lut_d[(ids + 1).long()]
+        return sem, (panoptic_seg, segments_info)
 
     @torch.no_grad()
     def inference(self, out, image_sizes, positive_map, num_classes, task, is_thing, sizes):
@@ -287,9 +338,17 @@ class HIPIE_IMG(nn.Module):
                 mask_all = torch.cat([mask_pred[i][keep_indices], mask_pred_bg[i]], dim=0)
                 N, C, H, Wd = mask_all.shape
                 logits_all = F.softmax(logits_all.sigmoid() / self.pano_temp, dim=-1)
+                if (self.fused_postprocess and self.mask_stride == 4 and logits_all.shape[1] <= 136 and N <= 8192
+                        and tuple(sizes[i]) == tuple(image_size)):
+                    sem, pano = self.fused_sem_pano(logits_all, mask_all[:, 0], is_thing[i], image_size)
+                    results.append(dict(instances=result, panoptic_seg=pano, sem_seg=sem))
+                    continue
                 mask_all = F.interpolate(mask_all, size=(H * self.mask_stride, Wd * self.mask_stride), mode="bilinear", align_corners=False)
                 mask_all = mask_all[:, :, :image_size[0], :image_size[1]]
-                mask_up = F.interpolate(mask_all, size=sizes[i], mode="bilinear", align_corners=False)[:, 0]
+                if tuple(mask_all.shape[-2:]) == tuple(sizes[i]):
+                    mask_up = mask_all[:, 0]          # same size: the bilinear resize is the identity
+                else:
+                    mask_up = F.interpolate(mask_all, size=sizes[i], mode="bilinear", align_corners=False)[:, 0]
                 sem = self.semantic_inference(logits_all, mask_up)
                 pano = self.panoptic_inference(logits_all, mask_up, is_thing[i])
             results.append(dict(instances=result, panoptic_seg=pano, sem_seg=sem))

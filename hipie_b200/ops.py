@@ -420,3 +420,28 @@ def condinst_masks(feats_nhwc, params, ref_px, Hf, Wf, stride=8):
         _lib.check(_lib.load().hipie_condinst_masks(_p(feats_nhwc.contiguous()), _p(params.contiguous()), _p(ref_px.contiguous()),
                                                     _p(out), B, Q, Hf, Wf, stride, _stream()), "condinst_masks")
     return out
+
+
+def seg_postprocess(masks_low, cls_prob, threshold, Hc, Wc, stride=4):
+    """Fused semantic + panoptic tensor work for one image (hipie_seg_postprocess).
+    masks_low (Q,h,w) f32 logits, cls_prob (Q,C) f32.  Returns sem (C,Hc,Wc), ids (Hc,Wc) i32 [-1 | 2q+inter], areas (3,Q) i32,
+    scores (Q), labels (Q)."""
+    Q, h, w = masks_low.shape
+    C = cls_prob.shape[1]
+    dev = masks_low.device
+    Qpad = (Q + 63) // 64 * 64
+    rows = 80 if C <= 80 else 136
+    pt = torch.zeros((rows, Qpad), dtype=torch.float32, device=dev)
+    pt[:C, :Q] = cls_prob.t()
+    hi = pt.to(torch.bfloat16)
+    lo = (pt - hi.float()).to(torch.bfloat16)
+    scores, labels = cls_prob.max(-1)
+    sc = torch.full((Qpad,), -1.0, dtype=torch.float32, device=dev)
+    sc[:Q] = torch.where(scores > threshold, scores, torch.full_like(scores, -1.0))
+    sem = torch.empty((C, Hc, Wc), dtype=torch.float32, device=dev)
+    ids = torch.empty((Hc, Wc), dtype=torch.int32, device=dev)
+    areas = torch.empty((3, Q), dtype=torch.int32, device=dev)
+    with _timed("seg_postprocess", float(masks_low.numel() + sem.numel() + ids.numel()) * 4):
+        _lib.check(_lib.load().hipie_seg_postprocess(_p(masks_low.contiguous()), _p(hi), _p(lo), _p(sc), _p(sem), _p(ids), _p(areas),
+                                                     Q, Qpad, C, h, w, stride, Hc, Wc, _stream()), "seg_postprocess")
+    return sem, ids, areas, scores, labels

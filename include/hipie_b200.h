@@ -216,6 +216,17 @@ int hipie_relpos_bias_tc(const void* q_hi, const void* q_lo, int64_t q_bs, int64
 int hipie_condinst_masks(const float* feats, const float* params, const float* ref_px, float* out,
                          int B, int Q, int Hf, int Wf, int stride, void* stream);
 
+/* Fused semantic + panoptic post-processing for one image (replaces the upsample / sigmoid / einsum / argmax / area chain of
+ * projects/HIPIE/hipie/models/hipie_img.py:880-1023: semantic_inference + the tensor part of panoptic_inference).
+ *   masks  (Q, h, w) f32   mask logits at 1/stride resolution (stride must be 4)
+ *   pt_hi, pt_lo (ceil8(C) [10 or 17 rows of 8], Qpad) bf16  class probabilities transposed, bf16 hi/lo split, zero padded
+ *   scores (Qpad) f32      per-query max class probability, negative for queries that are not kept (score <= threshold / padding)
+ *   sem    (C, Hc, Wc) f32 out: sum_q prob[q,c] * sigmoid(up(masks[q]))      (crop of the 4x upsampled map)
+ *   ids    (Hc, Wc) i32    out: -1 if no query is kept, else 2*q + (sigmoid_q >= 0.5), q = argmax_q score_q * sigmoid_q
+ *   areas  (3, Q) i32      out: [pixels won by q, pixels with sigmoid_q >= 0.5, pixels won by q with sigmoid_q >= 0.5] */
+int hipie_seg_postprocess(const float* masks, const void* pt_hi, const void* pt_lo, const float* scores, float* sem, int* ids,
+                          int* areas, int Q, int Qpad, int C, int h, int w, int stride, int Hc, int Wc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -430,3 +430,45 @@ def test_condinst_fused(ops, cuda):
     ref = dynamic_mask_with_coords(feats, ref_px, params, stride=8)       # (B, Q, 2Hf, 2Wf)
     out = ops.condinst_masks(feats.permute(0, 2, 3, 1).contiguous().to(cuda), params.to(cuda), ref_px.to(cuda), Hf, Wf).cpu()
     assert (out - ref).abs().max() < 2e-3 * ref.abs().max()
+
+
+# ------------------------------------------------------------------------------------------ fused semantic / panoptic
+@pytest.mark.parametrize("Q,C,h,w,Hc,Wc", [(70, 13, 24, 20, 90, 77), (200, 100, 16, 16, 64, 64), (64, 80, 12, 40, 48, 160)])
+def test_seg_postprocess_fused(ops, cuda, Q, C, h, w, Hc, Wc):
+    """hipie_seg_postprocess vs the reference op chain (upsample x4 -> crop -> sigmoid -> einsum / argmax / areas,
+    H/models/hipie_img.py:880-1023) evaluated on the CPU in fp64."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(Q + C)
+    masks = torch.randn(Q, h, w, generator=g) * 4
+    cls = F.softmax(torch.randn(Q, C, generator=g) * 3, dim=-1)
+    thr = 0.25
+    sem, ids, areas, scores, labels = ops.seg_postprocess(masks.to(cuda), cls.to(cuda), thr, Hc, Wc)
+    up = F.interpolate(masks[:, None], size=(4 * h, 4 * w), mode="bilinear", align_corners=False)[:, 0, :Hc, :Wc]
+    sg = up.double().sigmoid()
+    sem_ref = torch.einsum("qc,qhw->chw", cls.double(), sg)
+    assert (sem.cpu().double() - sem_ref).abs().max() < 2e-4 * max(1.0, float(sem_ref.abs().max()))
+    sc, lb = cls.max(-1)
+    assert torch.equal(lb, labels.cpu())
+    keep = sc > thr
+    kidx = keep.nonzero()[:, 0]
+    ids_c = ids.cpu().long()
+    if kidx.numel() == 0:
+        assert (ids_c == -1).all()
+        return
+    prob = sc[keep].double().view(-1, 1, 1) * sg[keep]
+    win = kidx[prob.argmax(0)]
+    got = ids_c >> 1
+    mism = got != win
+    # near-ties may resolve differently in fp32; wherever the winner differs the two products must be equal to 1e-5
+    if mism.any():
+        pg = (sc[got[mism]].double() * sg[got[mism], mism.nonzero()[:, 0], mism.nonzero()[:, 1]])
+        pw = prob.max(0)[0][mism]
+        assert (pg - pw).abs().max() < 1e-5 and mism.float().mean() < 1e-3
+    inter_flag = (ids_c & 1).bool()
+    sg_w = sg.gather(0, got.unsqueeze(0))[0]
+    assert ((sg_w >= 0.5) != inter_flag).float().mean() < 1e-3
+    own = got.unsqueeze(0) == torch.arange(Q).view(Q, 1, 1)
+    ref_area = torch.stack([own.flatten(1).sum(1), (sg >= 0.5).flatten(1).sum(1), (own & (sg >= 0.5)).flatten(1).sum(1)])
+    a = areas.cpu().long()
+    assert (a[:, keep] - ref_area[:, keep]).abs().max() <= 2
+    assert (a[1] - ref_area[1]).abs().max() <= 2
