@@ -436,8 +436,8 @@ def seg_postprocess(masks_low, cls_prob, threshold, Hc, Wc, stride=4):
     hi = pt.to(torch.bfloat16)
     lo = (pt - hi.float()).to(torch.bfloat16)
     scores, labels = cls_prob.max(-1)
-    sc = torch.full((Qpad,), -1.0, dtype=torch.float32, device=dev)
-    sc[:Q] = torch.where(scores > threshold, scores, torch.full_like(scores, -1.0))
+    sc = torch.zeros((Qpad,), dtype=torch.float32, device=dev)
+    sc[:Q] = torch.where(scores > threshold, scores, torch.zeros_like(scores))
     sem = torch.empty((C, Hc, Wc), dtype=torch.float32, device=dev)
     ids = torch.empty((Hc, Wc), dtype=torch.int32, device=dev)
     areas = torch.empty((3, Q), dtype=torch.int32, device=dev)

@@ -220,7 +220,7 @@ int hipie_condinst_masks(const float* feats, const float* params, const float* r
  * projects/HIPIE/hipie/models/hipie_img.py:880-1023: semantic_inference + the tensor part of panoptic_inference).
  *   masks  (Q, h, w) f32   mask logits at 1/stride resolution (stride must be 4)
  *   pt_hi, pt_lo (ceil8(C) [10 or 17 rows of 8], Qpad) bf16  class probabilities transposed, bf16 hi/lo split, zero padded
- *   scores (Qpad) f32      per-query max class probability, negative for queries that are not kept (score <= threshold / padding)
+ *   scores (Qpad) f32      per-query max class probability, 0 for queries that are not kept (score <= threshold / padding)
  *   sem    (C, Hc, Wc) f32 out: sum_q prob[q,c] * sigmoid(up(masks[q]))      (crop of the 4x upsampled map)
  *   ids    (Hc, Wc) i32    out: -1 if no query is kept, else 2*q + (sigmoid_q >= 0.5), q = argmax_q score_q * sigmoid_q
  *   areas  (3, Q) i32      out: [pixels won by q, pixels with sigmoid_q >= 0.5, pixels won by q with sigmoid_q >= 0.5] */
