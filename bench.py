@@ -269,7 +269,9 @@ def run_product(args):
             model.coco_inference(dev_imgs, pad_mask, sizes, lang, task="detection")
         prof = ops.profiler.stop()
         # end-to-end through the public API with host buffers
-        e2e_iters = max(1, min(args.steps, 3))
+        e2e_iters = max(1, min(args.steps, 5))
+        model.enable_cuda_graphs(not args.no_graph)      # serving mode of the public API: forward() replays its own graph
+        e2e_step()
         e2e_step()
         barrier()
         t0 = time.perf_counter()

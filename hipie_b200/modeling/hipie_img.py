@@ -64,6 +64,8 @@ class HIPIE_IMG(nn.Module):
         self.mask_stride, self.mask_thres = 4, 0.5
         self.pano_temp, self.object_mask_threshold, self.overlap_threshold = 0.06, 0.25, 0.8
         self.fused_postprocess = True      # semantic/panoptic tensor work in one kernel (ops.seg_postprocess)
+        self.use_cuda_graphs = False       # see enable_cuda_graphs()
+        self._graphs = {}
         self.max_pool, self.bg_cls_agnostic, self.use_bg_for_pano = hp.get("max_pool", False), hp.get("bg_cls_agnostic", False), False
         self._sd = OrderedDict()
         self.engine = None
@@ -187,6 +189,28 @@ class HIPIE_IMG(nn.Module):
         replay.launches_per_replay = launches
         replay.graph = graph
         return replay
+
+    def enable_cuda_graphs(self, on=True):
+        """Serving mode: `forward` replays one CUDA graph per (batch shape, image sizes, task) instead of ~2000 launches."""
+        self.use_cuda_graphs = bool(on)
+        if not on:
+            self._graphs.clear()
+        return self
+
+    def _graphed_hot_path(self, tensor, pad_mask, image_sizes, ids, am, task):
+        key = (tuple(tensor.shape), tuple(ids.shape), task, tuple(tuple(int(v) for v in s) for s in image_sizes))
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 4:           # static buffers are large; keep a handful of shapes
+                self._graphs.pop(next(iter(self._graphs)))
+            st = dict(tensor=tensor.clone(), pad=pad_mask.clone(), ids=ids.to(self.device_).clone(), am=am.to(self.device_).clone())
+            st["replay"] = self.capture_hot_path(st["tensor"], st["pad"], image_sizes, st["ids"], st["am"], task=task)
+            self._graphs[key] = ent = st
+        ent["tensor"].copy_(tensor)
+        ent["pad"].copy_(pad_mask)
+        ent["ids"].copy_(ids, non_blocking=True)
+        ent["am"].copy_(am, non_blocking=True)
+        return ent["replay"]()
 
     # ---- post-processing (hipie_img.py:537-766, 473-535, 870-878, 1025-1052); device-side torch glue for now ("next" tier, SURVEY §8f)
     def _pool_tables(self, positive_map, num_classes, Lt, is_thing, device):
@@ -396,8 +420,11 @@ class HIPIE_IMG(nn.Module):
             enc = tok.batch_encode_plus([x["expressions"] for x in batched_inputs], max_length=self.hp["max_query_len"],
                                         padding="max_length", return_tensors="pt", truncation=True)
             ids, am = enc.input_ids, enc.attention_mask
-        lang = self.forward_text(ids, am)
-        out = self.coco_inference(tensor, pad_mask, image_sizes, lang, task=task, forced=forced)
+        if self.use_cuda_graphs and forced is None:
+            out = self._graphed_hot_path(tensor, pad_mask, image_sizes, ids, am, task)
+        else:
+            lang = self.forward_text(ids, am)
+            out = self.coco_inference(tensor, pad_mask, image_sizes, lang, task=task, forced=forced)
         is_thing = [x["is_thing"] for x in batched_inputs]
         sizes = [(x.get("height", s[0]), x.get("width", s[1])) for x, s in zip(batched_inputs, image_sizes)]
         results = self.inference(out, image_sizes, positive_map, num_classes, task, is_thing, sizes)

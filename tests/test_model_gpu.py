@@ -128,6 +128,39 @@ def test_fast_mode_runs_and_is_close(setup):
     assert rel < 0.25, rel
 
 
+def test_cuda_graph_forward_matches_eager(setup):
+    """enable_cuda_graphs(): forward() replays a captured graph; results equal the eager launch sequence (same kernels)."""
+    model = setup["model"]
+    eager = model(setup["inputs"])
+    model.enable_cuda_graphs(True)
+    try:
+        first = model(setup["inputs"])       # captures
+        again = model(setup["inputs"])       # replays
+    finally:
+        model.enable_cuda_graphs(False)
+    for re_, r1, r2 in zip(eager, first, again):
+        for r in (r1, r2):
+            assert torch.equal(re_["instances"].pred_classes, r["instances"].pred_classes)
+            assert (re_["instances"].scores - r["instances"].scores).abs().max() < 1e-6
+            assert (re_["sem_seg"] - r["sem_seg"]).abs().max() < 1e-5
+            assert torch.equal(re_["panoptic_seg"][0], r["panoptic_seg"][0])
+
+
+def test_fused_postprocess_matches_op_chain(setup):
+    """the fused semantic/panoptic kernel against the same model with the torch op chain (upsample -> sigmoid -> einsum / argmax)"""
+    model = setup["model"]
+    fused = model(setup["inputs"])
+    model.fused_postprocess = False
+    try:
+        chain = model(setup["inputs"])
+    finally:
+        model.fused_postprocess = True
+    for rf, rc in zip(fused, chain):
+        assert (rf["sem_seg"] - rc["sem_seg"]).abs().max() < 1e-3 * max(1.0, rc["sem_seg"].abs().max().item())
+        assert [s["category_id"] for s in rf["panoptic_seg"][1]] == [s["category_id"] for s in rc["panoptic_seg"][1]]
+        assert (rf["panoptic_seg"][0] == rc["panoptic_seg"][0]).float().mean() > 0.9995
+
+
 def test_wide_image_uses_tcgen05_attention(cuda):
     """128 x 1024 input -> 8 x 64 token grid: the global blocks take the tcgen05 flash-attention path (kw == 64, T % 128 == 0,
     V emitted transposed by the GEMM); rel-pos tables are interpolated 127 -> 15 along the height axis."""
