@@ -7,13 +7,13 @@
 // einsum("bqc,bchw->bqhw") (.../maskdino/transformer_decoder/maskdino_decoder.py:520-529) with the
 // sigmoid-threshold fused as a bit-packed output.
 //
-// Structure (one CTA per SM, 320 threads):
+// Structure (one CTA per SM, 576 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles of A / W into a 4-stage 128B/64B-swizzled
 //               shared-memory ring, completion on mbarriers (expect_tx)
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a
 //               double-buffered fp32 accumulator in tensor memory; tcgen05.commit releases the
 //               smem stage / publishes the accumulator
-//   warps 2-9   epilogue: tcgen05.ld the accumulator (32 lanes x 32 columns per warp), transpose
+//   warps 2-17  epilogue: tcgen05.ld the accumulator (32 lanes x 32 columns per warp), transpose
 //               through padded smem so global stores are row-contiguous, fused bias / activation /
 //               layer-scale / residual / fp32 + bf16-split + bit-packed outputs
 //
@@ -30,9 +30,10 @@ namespace hipie {
 using namespace ptx;
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int GEMM_EPI_WARPS = 16;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // TMA warp, MMA warp, 16 epilogue warps
 constexpr int GEMM_STAGES = 4;
-constexpr int EPI_LD = 20;  // padded row length (floats) of the epilogue transpose buffer (16 cols + 4)
+constexpr int EPI_LD = 16;  // row length (floats) of the epilogue transpose buffer; 16-byte groups are XOR-swizzled by row
 
 struct GemmParams {
     const float* bias;
@@ -61,7 +62,7 @@ struct GemmCfg {
     static constexpr int W_TILE = BN * BK * 2;
     static constexpr int NPLANES = PREC == 3 ? 2 : 1;
     static constexpr int STAGE = NPLANES * (A_TILE + W_TILE);
-    static constexpr int EPI_BYTES = 8 * 32 * EPI_LD * 4;
+    static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 32 * EPI_LD * 4;
     static constexpr int SMEM = GEMM_STAGES * STAGE + EPI_BYTES + 256 + 1024;
     static constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : (2 * BN >= 128 ? 128 : 64));
 };
@@ -82,6 +83,72 @@ __device__ __forceinline__ float act_apply_t(float v) {
     return v;
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+
+// Interior-tile row epilogue: all 32 rows and all columns of the warp's slice are in range, rows are 16-byte aligned and
+// not remapped.  No per-element predicates, 32-bit offsets from one tile base, the next chunk's tcgen05.ld is in flight
+// while the current chunk is converted and stored.
+template <int ACT>
+__device__ __forceinline__ void epilogue_rows_fast(const GemmParams& p, uint32_t taddr, uint32_t es, int b, int m0, int n0,
+                                                   int col_begin, int col_end, int lane) {
+    const int rsub = lane >> 2, c4 = (lane & 3) * 4;
+    const int64_t tile_c = (int64_t)b * p.c_bstride + (int64_t)m0 * p.ldc + n0 + c4;
+    const float* res_t = p.residual ? p.residual + (int64_t)b * p.r_bstride + (int64_t)m0 * p.ldr + n0 + c4 : nullptr;
+    float* cf_t = p.c_f32 ? p.c_f32 + tile_c : nullptr;
+    __nv_bfloat16* chi_t = p.c_hi ? p.c_hi + tile_c : nullptr;
+    __nv_bfloat16* clo_t = p.c_lo ? p.c_lo + tile_c : nullptr;
+    const float* bias_t = p.bias ? p.bias + n0 + c4 : nullptr;
+    const float* cs_t = p.colscale ? p.colscale + n0 + c4 : nullptr;
+    const int ldc = (int)p.ldc, ldr = (int)p.ldr;
+    const float alpha = p.alpha;
+    const uint32_t wr = es + lane * (EPI_LD * 4);
+    const uint32_t wsw = (lane >> 1) & 3;
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(taddr + col_begin, v);
+#pragma unroll 1
+    for (int cb = col_begin; cb < col_end; cb += 16) {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts128(wr + ((j ^ wsw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        if (cb + 16 < col_end) tmem_ld_32x32b_x16(taddr + cb + 16, v);      // lands while this chunk is processed
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (bias_t) bias = *reinterpret_cast<const float4*>(bias_t + cb);
+        if (cs_t) cs = *reinterpret_cast<const float4*>(cs_t + cb);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + rsub;
+            float4 x = lds128(es + rr * (EPI_LD * 4) + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
+            x.x = act_apply_t<ACT>(fmaf(x.x, alpha, bias.x));
+            x.y = act_apply_t<ACT>(fmaf(x.y, alpha, bias.y));
+            x.z = act_apply_t<ACT>(fmaf(x.z, alpha, bias.z));
+            x.w = act_apply_t<ACT>(fmaf(x.w, alpha, bias.w));
+            if (cs_t) { x.x *= cs.x; x.y *= cs.y; x.z *= cs.z; x.w *= cs.w; }
+            if (res_t) {
+                const float4 rv = *reinterpret_cast<const float4*>(res_t + rr * ldr + cb);
+                x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
+            }
+            const int off = rr * ldc + cb;
+            if (cf_t) *reinterpret_cast<float4*>(cf_t + off) = x;
+            if (chi_t) {
+                uint2 hi, lo;
+                split2(x.x, x.y, hi.x, lo.x);
+                split2(x.z, x.w, hi.y, lo.y);
+                *reinterpret_cast<uint2*>(chi_t + off) = hi;
+                if (clo_t) *reinterpret_cast<uint2*>(clo_t + off) = lo;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Row-major epilogue for one warp: `nch` chunks of 32 columns starting at chunk c0.  The accumulator rows
 // (one per lane) are transposed through padded smem; afterwards lanes 0-7 cover one row with float4s, so a
 // warp stores four fully coalesced 128-byte row segments per instruction.
@@ -95,6 +162,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
     const int rsub = lane >> 2, c4 = (lane & 3) * 4;   // 8 rows x 16 columns per warp instruction
     const bool vec_ok = ((p.ldc & 3) == 0) && (!res_b || (p.ldr & 3) == 0);
     const int rmax = min(32, p.M - m0);
+    if (vec_ok && !p.row_map && rmax == 32 && n0 + col_end <= p.N && 32 * p.ldc < (1ll << 30) && ((n0 & 3) == 0)) {
+        epilogue_rows_fast<ACT>(p, taddr, smem_u32(my_epi), b, m0, n0, col_begin, col_end, lane);
+        return;
+    }
 #pragma unroll 1
     for (int cb = col_begin; cb < col_end; cb += 16) {
         const int nbase = n0 + cb;
@@ -103,8 +174,9 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
         tmem_ld_32x32b_x16(taddr + cb, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<uint4*>(my_epi + lane * EPI_LD + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 16; j += 4)     // 16-byte group g of row r lives at group g ^ ((r >> 1) & 3): conflict-free both ways
+            *reinterpret_cast<uint4*>(my_epi + lane * EPI_LD + (((j >> 2) ^ ((lane >> 1) & 3)) << 2)) =
+                make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
         const int col = nbase + c4;
         float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -129,7 +201,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
         for (int it = 0; it < 4; ++it) {
             const int rr = it * 8 + rsub;
             if (rr >= rmax || col >= p.N) continue;
-            float4 x = *reinterpret_cast<const float4*>(my_epi + rr * EPI_LD + c4);
+            float4 x = *reinterpret_cast<const float4*>(my_epi + rr * EPI_LD + (((lane & 3) ^ ((rr >> 1) & 3)) << 2));
             x.x = act_apply_t<ACT>(x.x * p.alpha + bias.x) * cs.x;
             x.y = act_apply_t<ACT>(x.y * p.alpha + bias.y) * cs.y;
             x.z = act_apply_t<ACT>(x.z * p.alpha + bias.z) * cs.z;
@@ -265,7 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&tfull_bar[i], 1);
-                mbar_init(&tempty_bar[i], 8);
+                mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);
             }
             fence_barrier_init();
         }
@@ -343,16 +415,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
     } else {
-        // ===================== epilogue (warps 2..9) =====================
-        // warp w may only touch TMEM lanes [32*(w%4), +32); two warps share a lane quarter and split
-        // the BN columns between them.
+        // ===================== epilogue (warps 2..17) =====================
+        // warp w may only touch TMEM lanes [32*(w%4), +32); four warps share a lane quarter and split
+        // the BN columns between them (the epilogue is latency-bound: more warps = more loads in flight).
         const int quarter = warp & 3;
-        const int ew = warp - 2;                 // 0..7
-        const int chalf = ew >> 2;               // which half of the column chunks
+        const int ew = warp - 2;                 // 0..15
+        const int cgroup = ew >> 2;              // which slice of the BN columns
         float* my_epi = epi + ew * 32 * EPI_LD;
-        constexpr int COLS_PER = BN >= 64 ? BN / 2 : BN;     // columns per warp of a lane-quarter pair
-        const bool active = BN >= 64 || chalf == 0;
-        const int cbeg = chalf * COLS_PER, cend = cbeg + COLS_PER;
+        constexpr int COLS_PER = BN / 4 >= 32 ? BN / 4 : 32;   // columns per warp (multiple of the 32-column transposed chunk)
+        const bool active = cgroup * COLS_PER < BN;
+        const int cbeg = cgroup * COLS_PER, cend = cbeg + COLS_PER;
         int acc = 0;
         uint32_t acc_ph = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {

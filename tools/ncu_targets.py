@@ -46,5 +46,17 @@ if which in ("all", "maskembed"):
     Em = ops.split(torch.randn(B * Q, C, device=dev) * 0.1)
     for _ in range(2):
         ops.gemm(Fm, Em, M=HW, N=Q, K=C, batch=B, lda=C, ldw=C, a_bstride=HW * C, w_bstride=Q * C, transposed=True, bits_threshold=0.0)
+if which in ("ffn1",):      # deformable-encoder FFN1: K=256, epilogue / store heavy
+    a = torch.randn(174080, 256, device=dev)
+    w = torch.randn(2048, 256, device=dev) * 0.05
+    A, W = ops.split(a), ops.split_weight(w)
+    for _ in range(2):
+        ops.gemm(A, W, act=ops.ACT_RELU, want_f32=False, want_split=True)
+if which in ("proj256",):   # 174080 x 256 x 256 with f32 + split out
+    a = torch.randn(174080, 256, device=dev)
+    w = torch.randn(256, 256, device=dev) * 0.05
+    A, W = ops.split(a), ops.split_weight(w)
+    for _ in range(2):
+        ops.gemm(A, W, want_f32=True, want_split=True)
 torch.cuda.synchronize()
 print("done", which)
