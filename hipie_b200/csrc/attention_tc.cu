@@ -3,20 +3,23 @@
 //   softmax((q*scale) k^T + rel_h[q, kh] + rel_w[q, kw]) v      (/root/reference/projects/HIPIE/hipie/backbone/vit.py:67-83,
 //                                                                 backbone/utils.py:96-125)
 //
-// One CTA = 128 query rows of one (batch, head); 320 threads.  Both A operands of the two MMAs live in TENSOR MEMORY
-// (TS-mode tcgen05.mma), so the tensor core only streams the small K / V^T tiles from shared memory:
+// One CTA = 256 query rows (two 128-row tiles) of one (batch, head); 320 threads:
 //   warp 0      TMA producer: K tiles (64 keys x 80) and V^T tiles (80 x 64 keys) into a 3-stage, hardware-swizzled
-//               shared-memory ring (head dim 80 = one 128B-swizzled 64-wide box + one 32B-swizzled 16-wide box)
-//   warp 1      MMA issuer: S_j = Q K_j^T (A = Q in TMEM, M=128, N=64, K=80) into one of two TMEM score buffers and
-//               O += P_j V_j (A = P_j in TMEM, M=128, N=80, K=64); QK runs two tiles ahead of PV
-//   warps 2-9   softmax, two warps per TMEM lane quarter (each owns 32 of the tile's 64 key columns): load their Q row
-//               from global once and park it in TMEM as packed bf16 pairs; per tile tcgen05.ld the scores, scale +
-//               rel-pos bias (rel_w hoisted in registers, one prefetched rel_h scalar per tile since a 64-key tile is one
-//               key row of the 64-wide grid), online softmax with lazy rescaling of the TMEM accumulator, and P written
-//               back to TMEM with tcgen05.st (double buffered) as the A operand of the PV MMA
+//               shared-memory ring (head dim 80 = one 128B-swizzled 64-wide box + one 32B-swizzled 16-wide box), plus the
+//               two Q lo tiles once
+//   warp 1      MMA issuer: S_t = Q_t K_j^T (M=128, N=64, K=80; A = Q hi in TENSOR MEMORY, TS mode) and O_t += P_t V_j
+//               (M=128, N=80, K=64; A = P in tensor memory).  The two query tiles alternate: while tile 0's scores are in
+//               the softmax warps the tensor pipe runs tile 1's MMAs, and PV_t(j) is interleaved with QK_t(j+1)
+//   warps 2-5   softmax of tile 0, warps 6-9 softmax of tile 1: ONE THREAD PER QUERY ROW (no cross-warp max exchange):
+//               tcgen05.ld the 64 scores, scale + rel-pos bias (rel_w hoisted in registers, one prefetched rel_h scalar per
+//               tile since a 64-key tile is one key row of the 64-wide grid), online softmax with lazy rescaling of the TMEM
+//               accumulator, P written back to TMEM with tcgen05.st as the A operand of the PV MMA
 // Precision: PREC==3 evaluates Qh.Kh + Qh.Kl + Ql.Kh and Ph.Vh + Ph.Vl + Pl.Vh (bf16x3, fp32-class); PREC==1 plain bf16.
-// History (profiles/): the first version kept Q and P in shared memory; ncu + a clock64 trace showed the tensor
-// pipe starved re-reading the 4 KB A tile for every small-N instruction (≈1000 cycles per MMA batch), hence this layout.
+// Tensor memory (512 columns): per tile S 64 | P hi/lo 64 | O 80 | Q hi 40; Q lo does not fit and is the one A operand
+// read from shared memory (5 of the 30 MMAs per key tile).
+// History (profiles/): v1 kept Q and P in shared memory (tensor pipe starved on A re-reads); v2 moved both to
+// TMEM with one query tile per CTA and two softmax warps per row quarter (max exchange through smem + named barriers) and
+// sat at ~45 % of the MMA peak, softmax-latency bound; this v3 is the two-tile ping-pong.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -27,14 +30,17 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols
                    int64_t bstride, int box_rows, int box_cols);
 
 constexpr int FA_BM = 128, FA_BN = 64, FA_HD = 80, FA_STAGES = 3;
-// tensor-memory map (columns)
-constexpr int TM_S = 0;            // 2 x 64 fp32 score columns
+constexpr int FA_QT = 2;           // query tiles per CTA (ping-pong: one in softmax while the other is in the tensor pipe)
+// tensor-memory map (columns), per query tile t at column 256 * t
+constexpr int TM_TILE = 256;
+constexpr int TM_S = 0;            // 64 fp32 score columns
+constexpr int TM_P = 64;           // P hi: 32 columns of packed bf16 pairs, P lo: next 32
 constexpr int TM_O = 128;          // 80 fp32 output columns
-constexpr int TM_Q = 208;          // Q hi: 40 cols of packed bf16 pairs, Q lo: next 40
-constexpr int TM_P = 288;          // P: [buf][hi 32 cols | lo 32 cols]
+constexpr int TM_Q = 208;          // Q hi: 40 columns of packed bf16 pairs (Q lo stays in shared memory)
 
 struct FaMaps {
     CUtensorMap k64[2], k16[2], vt[2];   // [hi, lo]
+    CUtensorMap q64, q16;                // Q lo plane (A operand of the Ql.Kh pass, shared memory)
 };
 
 struct FaParams {
@@ -58,9 +64,12 @@ struct FaSmem {
     static constexpr int VT = FA_HD * 128;
     static constexpr int K_STAGE = NPL * (K64 + K16);
     static constexpr int V_STAGE = NPL * VT;
+    static constexpr int Q64 = FA_BM * 128, Q16 = FA_BM * 32;
+    static constexpr int Q_TILE = PREC == 3 ? Q64 + Q16 : 0;
     static constexpr int OFF_V = FA_STAGES * K_STAGE;
-    static constexpr int OFF_BAR = OFF_V + FA_STAGES * V_STAGE;
-    static constexpr int TOTAL = OFF_BAR + 256 + 3 * 2 * FA_BM * 4 + 1024;
+    static constexpr int OFF_Q = OFF_V + FA_STAGES * V_STAGE;
+    static constexpr int OFF_BAR = OFF_Q + FA_QT * Q_TILE;
+    static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
 template <int PREC>
@@ -71,20 +80,19 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
-    uint64_t* q_ready = bars;                      // [1]  Q parked in TMEM (8 warps)
-    uint64_t* k_full = bars + 1;                   // [STAGES]
+    uint64_t* k_full = bars;                       // [STAGES]
     uint64_t* k_empty = k_full + FA_STAGES;
     uint64_t* v_full = k_empty + FA_STAGES;
     uint64_t* v_empty = v_full + FA_STAGES;
-    uint64_t* s_full = v_empty + FA_STAGES;        // [2]
-    uint64_t* s_empty = s_full + 2;                // [2]
-    uint64_t* p_full = s_empty + 2;                // [2]
-    uint64_t* pv_done = p_full + 2;                // [2]  PV(j) commits to pv_done[j & 1]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
-    float* xchg = reinterpret_cast<float*>(smem + SM::OFF_BAR + 256);   // [3][2][128] max / row-sum exchange
+    uint64_t* q_ready = v_empty + FA_STAGES;       // [2]  Q hi parked in TMEM (4 warps per tile)
+    uint64_t* qlo_full = q_ready + FA_QT;          // [2]  Q lo tile landed in shared memory (TMA)
+    uint64_t* s_full = qlo_full + FA_QT;           // [2]  QK(j) of tile t complete (and, in issue order, PV(j-1) too)
+    uint64_t* p_full = s_full + FA_QT;             // [2]  P(j) of tile t written (4 warps)
+    uint64_t* o_done = p_full + FA_QT;             // [2]  last PV of tile t complete
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + FA_QT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * FA_BM, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * (FA_QT * FA_BM), h = blockIdx.y, b = blockIdx.z;
     const int ntiles = p.T / FA_BN;
     const bool trace_cta = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
@@ -92,17 +100,17 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         for (int i = 0; i < NPL; ++i) {
             prefetch_tmap(&maps.k64[i]); prefetch_tmap(&maps.k16[i]); prefetch_tmap(&maps.vt[i]);
         }
+        if (PREC == 3) { prefetch_tmap(&maps.q64); prefetch_tmap(&maps.q16); }
     }
     if (warp == 1) {
         if (lane == 0) {
-            mbar_init(q_ready, 8);
             for (int i = 0; i < FA_STAGES; ++i) {
                 mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
                 mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
             }
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
-                mbar_init(&p_full[i], 8); mbar_init(&pv_done[i], 1);
+            for (int i = 0; i < FA_QT; ++i) {
+                mbar_init(&q_ready[i], 4); mbar_init(&qlo_full[i], 1);
+                mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_done[i], 1);
             }
             fence_barrier_init();
         }
@@ -118,6 +126,14 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            if (PREC == 3) {
+                for (int t = 0; t < FA_QT; ++t) {
+                    uint8_t* qb = smem + SM::OFF_Q + t * SM::Q_TILE;
+                    mbar_arrive_expect_tx(&qlo_full[t], SM::Q_TILE);
+                    tma_load_3d(qb, &maps.q64, &qlo_full[t], p.q_col0 + h * FA_HD, q0 + t * FA_BM, b);
+                    tma_load_3d(qb + SM::Q64, &maps.q16, &qlo_full[t], p.q_col0 + h * FA_HD + 64, q0 + t * FA_BM, b);
+                }
+            }
             int s = 0;
             uint32_t ph = 0;
             for (int j = 0; j < ntiles; ++j) {
@@ -138,216 +154,194 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // Per query tile t and key tile j:  S_t = Q_t K_j^T  (A = Q hi in TMEM; the Ql.Kh pass takes Q lo from shared memory)
+        //                                   O_t += P_t V_j   (A = P in TMEM)
+        // PV_t(j) and QK_t(j+1) are independent accumulator chains and are issued interleaved (a chain of small-N MMAs
+        // into one accumulator is latency bound); tile 0 and tile 1 alternate, so while one tile's scores are in the
+        // softmax warps the tensor pipe works on the other tile.
         constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BM, FA_BN);
         constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BM, FA_HD);
-        const uint32_t tq_hi = tmem_base + TM_Q, tq_lo = tmem_base + TM_Q + 40;
-        auto issue_qk = [&](int j) {
-            const int st = j % FA_STAGES, sb = j & 1;
-            const bool trq = trace_cta && lane == 0 && j < 32;
-            if (trq) p.trace[j * 16 + 7] = clock64();
-            mbar_wait(&k_full[st], (j / FA_STAGES) & 1);
-            mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
-            tc_fence_after();
-            if (trq) p.trace[j * 16 + 8] = clock64();
+        auto kdesc = [&](int st, uint64_t& k64h, uint64_t& k16h, uint64_t& k64l, uint64_t& k16l) {
+            const uint32_t kb = smem_u32(smem + st * SM::K_STAGE);
+            k64h = make_kmajor_desc<128>(kb); k16h = make_kmajor_desc<32>(kb + SM::K64);
+            k64l = make_kmajor_desc<128>(kb + SM::K64 + SM::K16); k16l = make_kmajor_desc<32>(kb + 2 * SM::K64 + SM::K16);
+        };
+        auto issue_qk = [&](int t, int j) {            // prologue: QK only
+            const int st = j % FA_STAGES;
             if (elect_one()) {
-                const uint32_t kb = smem_u32(smem + st * SM::K_STAGE);
-                const uint32_t d = tmem_base + TM_S + sb * FA_BN;
-                const uint64_t k64h = make_kmajor_desc<128>(kb), k16h = make_kmajor_desc<32>(kb + SM::K64);
+                const uint32_t tb = tmem_base + t * TM_TILE;
+                const uint32_t dS = tb + TM_S, tq = tb + TM_Q;
+                uint64_t k64h, k16h, k64l, k16l;
+                kdesc(st, k64h, k16h, k64l, k16l);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16_ts(d, tq_hi + 8 * k, k64h + 2 * k, idesc_qk, k > 0);
-                umma_f16_ts(d, tq_hi + 32, k16h, idesc_qk, 1);
+                for (int k = 0; k < 4; ++k) umma_f16_ts(dS, tq + 8 * k, k64h + 2 * k, idesc_qk, k > 0);
+                umma_f16_ts(dS, tq + 32, k16h, idesc_qk, 1);
                 if (PREC == 3) {
-                    const uint64_t k64l = make_kmajor_desc<128>(kb + SM::K64 + SM::K16), k16l = make_kmajor_desc<32>(kb + 2 * SM::K64 + SM::K16);
+                    const uint32_t qb = smem_u32(smem + SM::OFF_Q + t * SM::Q_TILE);
+                    const uint64_t q64l = make_kmajor_desc<128>(qb), q16l = make_kmajor_desc<32>(qb + SM::Q64);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16_ts(d, tq_hi + 8 * k, k64l + 2 * k, idesc_qk, 1);
-                    umma_f16_ts(d, tq_hi + 32, k16l, idesc_qk, 1);
+                    for (int k = 0; k < 4; ++k) umma_f16_ts(dS, tq + 8 * k, k64l + 2 * k, idesc_qk, 1);
+                    umma_f16_ts(dS, tq + 32, k16l, idesc_qk, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16_ts(d, tq_lo + 8 * k, k64h + 2 * k, idesc_qk, 1);
-                    umma_f16_ts(d, tq_lo + 32, k16h, idesc_qk, 1);
+                    for (int k = 0; k < 4; ++k) umma_f16(dS, q64l + 2 * k, k64h + 2 * k, idesc_qk, 1);
+                    umma_f16(dS, q16l, k16h, idesc_qk, 1);
                 }
-                umma_commit(&s_full[sb]);
-                umma_commit(&k_empty[st]);
+                umma_commit(&s_full[t]);
+                if (t == FA_QT - 1) umma_commit(&k_empty[st]);
             }
-            if (trq) p.trace[j * 16 + 9] = clock64();
             __syncwarp();
         };
-        auto issue_pv = [&](int j) {
-            const int st = j % FA_STAGES, sb = j & 1;
-            const bool trm = trace_cta && lane == 0 && j < 32;
-            if (trm) p.trace[j * 16 + 10] = clock64();
-            mbar_wait(&p_full[sb], (j >> 1) & 1);
-            if (trm) p.trace[j * 16 + 11] = clock64();
-            mbar_wait(&v_full[st], (j / FA_STAGES) & 1);
-            tc_fence_after();
-            if (trm) p.trace[j * 16 + 12] = clock64();
+        auto issue_pv_qk = [&](int t, int j, bool with_qk) {     // PV_t(j) [+ QK_t(j+1)]
+            const int stv = j % FA_STAGES, stk = (j + 1) % FA_STAGES;
             if (elect_one()) {
-                const uint32_t vb = smem_u32(smem + SM::OFF_V + st * SM::V_STAGE);
-                const uint32_t d = tmem_base + TM_O;
-                const uint32_t tp_hi = tmem_base + TM_P + sb * 64, tp_lo = tp_hi + 32;
-                const uint64_t v_hi = make_kmajor_desc<128>(vb);
-                uint32_t accum = j > 0;
-#pragma unroll
-                for (int k = 0; k < FA_BN / 16; ++k) { umma_f16_ts(d, tp_hi + 8 * k, v_hi + 2 * k, idesc_pv, accum); accum = 1; }
-                if (PREC == 3) {
-                    const uint64_t v_lo = make_kmajor_desc<128>(vb + SM::VT);
-#pragma unroll
-                    for (int k = 0; k < FA_BN / 16; ++k) umma_f16_ts(d, tp_hi + 8 * k, v_lo + 2 * k, idesc_pv, 1);
-#pragma unroll
-                    for (int k = 0; k < FA_BN / 16; ++k) umma_f16_ts(d, tp_lo + 8 * k, v_hi + 2 * k, idesc_pv, 1);
-                }
-                umma_commit(&pv_done[sb]);
-                umma_commit(&v_empty[st]);
-            }
-            if (trm) p.trace[j * 16 + 13] = clock64();
-            __syncwarp();
-        };
-        // PV(j) (accumulator O) and QK(j+2) (accumulator S[j&1]) are independent chains: small-N MMAs into the same
-        // accumulator are latency bound (~70 cycles each, measured), so the two chains are issued interleaved.
-        auto issue_pv_qk = [&](int jp, int jq) {
-            const int stp = jp % FA_STAGES, sbp = jp & 1;
-            const int stq = jq % FA_STAGES, sbq = jq & 1;
-            mbar_wait(&k_full[stq], (jq / FA_STAGES) & 1);
-            mbar_wait(&s_empty[sbq], ((jq >> 1) & 1) ^ 1);
-            mbar_wait(&v_full[stp], (jp / FA_STAGES) & 1);
-            mbar_wait(&p_full[sbp], (jp >> 1) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t vb = smem_u32(smem + SM::OFF_V + stp * SM::V_STAGE);
-                const uint32_t kb = smem_u32(smem + stq * SM::K_STAGE);
-                const uint32_t dO = tmem_base + TM_O, dS = tmem_base + TM_S + sbq * FA_BN;
-                const uint32_t tp_hi = tmem_base + TM_P + sbp * 64, tp_lo = tp_hi + 32;
+                const uint32_t tb = tmem_base + t * TM_TILE;
+                const uint32_t dO = tb + TM_O, dS = tb + TM_S, tq = tb + TM_Q, tp_hi = tb + TM_P, tp_lo = tb + TM_P + 32;
+                const uint32_t vb = smem_u32(smem + SM::OFF_V + stv * SM::V_STAGE);
                 const uint64_t v_hi = make_kmajor_desc<128>(vb), v_lo = make_kmajor_desc<128>(vb + SM::VT);
-                const uint64_t k64h = make_kmajor_desc<128>(kb), k16h = make_kmajor_desc<32>(kb + SM::K64);
-                const uint64_t k64l = make_kmajor_desc<128>(kb + SM::K64 + SM::K16), k16l = make_kmajor_desc<32>(kb + 2 * SM::K64 + SM::K16);
-                const uint32_t acc0 = jp > 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    umma_f16_ts(dO, tp_hi + 8 * k, v_hi + 2 * k, idesc_pv, k > 0 ? 1u : acc0);
-                    umma_f16_ts(dS, tq_hi + 8 * k, k64h + 2 * k, idesc_qk, k > 0);
-                }
-                umma_f16_ts(dS, tq_hi + 32, k16h, idesc_qk, 1);
-                if (PREC == 3) {
+                const uint32_t acc0 = j > 0;
+                if (with_qk) {
+                    uint64_t k64h, k16h, k64l, k16l;
+                    kdesc(stk, k64h, k16h, k64l, k16l);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        umma_f16_ts(dO, tp_hi + 8 * k, v_lo + 2 * k, idesc_pv, 1);
-                        umma_f16_ts(dS, tq_hi + 8 * k, k64l + 2 * k, idesc_qk, 1);
+                        umma_f16_ts(dO, tp_hi + 8 * k, v_hi + 2 * k, idesc_pv, k > 0 ? 1u : acc0);
+                        umma_f16_ts(dS, tq + 8 * k, k64h + 2 * k, idesc_qk, k > 0);
                     }
-                    umma_f16_ts(dS, tq_hi + 32, k16l, idesc_qk, 1);
+                    umma_f16_ts(dS, tq + 32, k16h, idesc_qk, 1);
+                    if (PREC == 3) {
+                        const uint32_t qb = smem_u32(smem + SM::OFF_Q + t * SM::Q_TILE);
+                        const uint64_t q64l = make_kmajor_desc<128>(qb), q16l = make_kmajor_desc<32>(qb + SM::Q64);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_f16_ts(dO, tp_lo + 8 * k, v_hi + 2 * k, idesc_pv, 1);
-                        umma_f16_ts(dS, tq_lo + 8 * k, k64h + 2 * k, idesc_qk, 1);
+                        for (int k = 0; k < 4; ++k) {
+                            umma_f16_ts(dO, tp_hi + 8 * k, v_lo + 2 * k, idesc_pv, 1);
+                            umma_f16_ts(dS, tq + 8 * k, k64l + 2 * k, idesc_qk, 1);
+                        }
+                        umma_f16_ts(dS, tq + 32, k16l, idesc_qk, 1);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_f16_ts(dO, tp_lo + 8 * k, v_hi + 2 * k, idesc_pv, 1);
+                            umma_f16(dS, q64l + 2 * k, k64h + 2 * k, idesc_qk, 1);
+                        }
+                        umma_f16(dS, q16l, k16h, idesc_qk, 1);
                     }
-                    umma_f16_ts(dS, tq_lo + 32, k16h, idesc_qk, 1);
+                    umma_commit(&s_full[t]);
+                    if (t == FA_QT - 1) umma_commit(&k_empty[stk]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16_ts(dO, tp_hi + 8 * k, v_hi + 2 * k, idesc_pv, k > 0 ? 1u : acc0);
+                    if (PREC == 3) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16_ts(dO, tp_hi + 8 * k, v_lo + 2 * k, idesc_pv, 1);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16_ts(dO, tp_lo + 8 * k, v_hi + 2 * k, idesc_pv, 1);
+                    }
+                    umma_commit(&o_done[t]);
                 }
-                umma_commit(&pv_done[sbp]);
-                umma_commit(&v_empty[stp]);
-                umma_commit(&s_full[sbq]);
-                umma_commit(&k_empty[stq]);
+                if (t == FA_QT - 1) umma_commit(&v_empty[stv]);
             }
             __syncwarp();
         };
-        mbar_wait(q_ready, 0);
-        tc_fence_after();
-        issue_qk(0);
-        if (ntiles > 1) issue_qk(1);
+        mbar_wait(&k_full[0], 0);
+        for (int t = 0; t < FA_QT; ++t) {
+            mbar_wait(&q_ready[t], 0);
+            if (PREC == 3) mbar_wait(&qlo_full[t], 0);
+            tc_fence_after();
+            issue_qk(t, 0);
+        }
         for (int j = 0; j < ntiles; ++j) {
-            if (j + 2 < ntiles) issue_pv_qk(j, j + 2);
-            else issue_pv(j);
+            const bool more = j + 1 < ntiles;
+            for (int t = 0; t < FA_QT; ++t) {
+                if (t == 0) {
+                    mbar_wait(&v_full[j % FA_STAGES], (j / FA_STAGES) & 1);
+                    if (more) mbar_wait(&k_full[(j + 1) % FA_STAGES], ((j + 1) / FA_STAGES) & 1);
+                }
+                mbar_wait(&p_full[t], j & 1);
+                tc_fence_after();
+                issue_pv_qk(t, j, more);
+            }
         }
     } else {
-        // ===================== softmax / epilogue (warps 2..9) =====================
-        const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int r = quarter * 32 + lane;            // row of the Q tile == TMEM lane
-        const int qrow = q0 + r;
-        const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // ===================== softmax / epilogue: warps 2-5 own query tile 0, warps 6-9 tile 1; one thread per row ==========
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int t = (warp - 2) >> 2;
+        const int r = quarter * 32 + lane;            // row of the query tile == TMEM lane
+        const int qrow = q0 + t * FA_BM + r;
+        const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * TM_TILE;
         const bool has_rel = p.rel_h != nullptr;
-        constexpr int HC = FA_BN / 2;                 // 32 key columns per thread
         constexpr float LOG2E = 1.4426950408889634f;
-        // ---- park this thread's half of the Q row in TMEM (packed bf16 pairs = the TS-mode A operand layout) ----
+        // ---- park this row of Q hi in TMEM (packed bf16 pairs = the TS-mode A operand layout) ----
         {
-            const int64_t qoff = (int64_t)b * p.q_bs + (int64_t)qrow * p.q_ts + p.q_col0 + h * FA_HD + half * 40;
-            for (int pl = 0; pl < NPL; ++pl) {
-                const uint4* src = reinterpret_cast<const uint4*>((pl == 0 ? p.q_hi : p.q_lo) + qoff);
+            const int64_t qoff = (int64_t)b * p.q_bs + (int64_t)qrow * p.q_ts + p.q_col0 + h * FA_HD;
+            const uint4* src = reinterpret_cast<const uint4*>(p.q_hi + qoff);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
                 uint32_t w[16];
-                const uint4 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3], a4 = src[4];
+                const uint4 a0 = src[4 * c], a1 = src[4 * c + 1], a2 = src[4 * c + 2], a3 = src[4 * c + 3];
                 w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
                 w[8] = a2.x; w[9] = a2.y; w[10] = a2.z; w[11] = a2.w; w[12] = a3.x; w[13] = a3.y; w[14] = a3.z; w[15] = a3.w;
-                tmem_st_32x32b_x16(tm + TM_Q + pl * 40 + half * 20, w);
-                tmem_st_32x32b_x4(tm + TM_Q + pl * 40 + half * 20 + 16, a4.x, a4.y, a4.z, a4.w);
+                tmem_st_32x32b_x16(tm + TM_Q + 16 * c, w);
             }
+            const uint4 a8 = src[8], a9 = src[9];
+            tmem_st_32x32b_x4(tm + TM_Q + 32, a8.x, a8.y, a8.z, a8.w);
+            tmem_st_32x32b_x4(tm + TM_Q + 36, a9.x, a9.y, a9.z, a9.w);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(q_ready);
+            if (lane == 0) mbar_arrive(&q_ready[t]);
         }
-        float rw[HC];
+        float rw[FA_BN];
         const float* relh_row = nullptr;
         if (has_rel) {
             const int64_t rowi = ((int64_t)b * p.H + h) * p.T + qrow;
-            const float* rwp = p.rel_w + rowi * FA_BN + half * HC;
+            const float* rwp = p.rel_w + rowi * FA_BN;
 #pragma unroll
-            for (int i = 0; i < HC; i += 4) {
+            for (int i = 0; i < FA_BN; i += 4) {
                 const float4 v = *reinterpret_cast<const float4*>(rwp + i);
                 rw[i] = v.x * LOG2E; rw[i + 1] = v.y * LOG2E; rw[i + 2] = v.z * LOG2E; rw[i + 3] = v.w * LOG2E;
             }
             relh_row = p.rel_h + rowi * p.kh;
         }
         float m = -INFINITY, l = 0.f;          // m: running reference max (log2 domain, incl. rel-pos terms)
-        const int o_c0 = half == 0 ? 0 : 48, o_c1 = half == 0 ? 48 : FA_HD;   // output columns owned (x16 granules)
         float rh_next = has_rel ? __ldg(relh_row) * LOG2E : 0.f;
         for (int j = 0; j < ntiles; ++j) {
-            const int s = j & 1;
-            const bool tr = trace_cta && warp == 2 && lane == 0 && j < 32;
+            const bool tr = trace_cta && lane == 0 && (warp == 2 || warp == 6) && j < 32;
             const float rh = rh_next;
             if (has_rel && j + 1 < ntiles) rh_next = __ldg(relh_row + j + 1) * LOG2E;   // prefetch for the next tile
-            if (tr) p.trace[j * 16 + 0] = clock64();
-            mbar_wait(&s_full[s], (j >> 1) & 1);
+            if (tr) p.trace[(j * 2 + t) * 8 + 0] = clock64();
+            mbar_wait(&s_full[t], j & 1);
             tc_fence_after();
-            if (tr) p.trace[j * 16 + 1] = clock64();
-            uint32_t sv[HC];
-            tmem_ld_32x32b_x32(tm + TM_S + s * FA_BN + half * HC, sv);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[s]);   // score buffer may be overwritten by QK(j+2)
-            if (tr) p.trace[j * 16 + 2] = clock64();
-            // t_i = s_i*scale*log2e + rel_w_i ; rel_h is uniform over the tile -> folded into the max / exponent offset
-            float tmax = -INFINITY;
-            float t[HC];
+            if (tr) p.trace[(j * 2 + t) * 8 + 1] = clock64();
+            float tv[FA_BN];
+            {
+                uint32_t sv[32];
+                tmem_ld_32x32b_x32(tm + TM_S, sv);
+                tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < HC; ++i) {
-                t[i] = fmaf(__uint_as_float(sv[i]), p.scale_log2e, has_rel ? rw[i] : 0.f);
-                tmax = fmaxf(tmax, t[i]);
+                for (int i = 0; i < 32; ++i) tv[i] = fmaf(__uint_as_float(sv[i]), p.scale_log2e, has_rel ? rw[i] : 0.f);
+                tmem_ld_32x32b_x32(tm + TM_S + 32, sv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) tv[32 + i] = fmaf(__uint_as_float(sv[i]), p.scale_log2e, has_rel ? rw[32 + i] : 0.f);
             }
-            tmax += rh;
-            xchg[(s * 2 + half) * FA_BM + r] = tmax;    // exchange the tile max with the partner warp (other column half)
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-            tmax = fmaxf(tmax, xchg[(s * 2 + (half ^ 1)) * FA_BM + r]);
-            if (tr) p.trace[j * 16 + 3] = clock64();
+            // t_i = s_i*scale*log2e + rel_w_i ; rel_h is uniform over the tile -> folded into the max / exponent offset
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < FA_BN; i += 4) {
+                mx[0] = fmaxf(mx[0], tv[i]); mx[1] = fmaxf(mx[1], tv[i + 1]);
+                mx[2] = fmaxf(mx[2], tv[i + 2]); mx[3] = fmaxf(mx[3], tv[i + 3]);
+            }
+            const float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + rh;
             // lazy rescale: keep the running reference max unless the tile exceeds it by more than 2^8
-            float corr = 1.f;
             const bool need = tmax > m + 8.f;
+            float corr = 1.f;
             if (need) {
                 corr = ex2_approx(m - tmax);   // m == -inf -> 0
                 m = tmax;
                 l *= corr;
             }
-            const float off = m - rh;
-            float rowsum = 0.f;
-#pragma unroll
-            for (int i = 0; i < HC; ++i) {
-                t[i] = ex2_approx(t[i] - off);
-                rowsum += t[i];
-            }
-            l += rowsum;
-            if (tr) p.trace[j * 16 + 4] = clock64();
-            if (j > 0 && __any_sync(0xffffffffu, need)) {
-                // O must reflect PV(j-1) before it is rescaled (rare once the running max has settled)
-                mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-                tc_fence_after();
-                for (int c = o_c0; c < o_c1; c += 16) {
+            if (j > 0 && __any_sync(0xffffffffu, need)) {      // warp-uniform: tcgen05.ld/st are warp-collective
+                // s_full(j) was committed after PV_t(j-1) in issue order, so O already holds it (rare once the max settles)
+                for (int c = 0; c < FA_HD; c += 16) {
                     uint32_t o[16];
                     tmem_ld_32x32b_x16(tm + TM_O + c, o);
                     tmem_ld_wait();
@@ -355,37 +349,40 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                     for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
                     tmem_st_32x32b_x16(tm + TM_O + c, o);
                 }
-                tmem_st_wait();
             }
-            // P buffer s is free once PV(j-2) has retired
-            mbar_wait(&pv_done[s], ((j >> 1) & 1) ^ 1);
-            tc_fence_after();
-            if (tr) p.trace[j * 16 + 5] = clock64();
-            {
-                uint32_t ph_[16], pl_[16];
+            if (tr) p.trace[(j * 2 + t) * 8 + 2] = clock64();
+            const float off = m - rh;
+            float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (PREC == 3) split2(t[2 * i], t[2 * i + 1], ph_[i], pl_[i]);
-                    else ph_[i] = pack_bf16x2(t[2 * i], t[2 * i + 1]);
+            for (int c = 0; c < FA_BN; c += 16) {
+                uint32_t ph_[8], pl_[8];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const float e0 = ex2_approx(tv[c + i] - off), e1 = ex2_approx(tv[c + i + 1] - off);
+                    rs[(i >> 1) & 3] += e0 + e1;
+                    if (PREC == 3) split2(e0, e1, ph_[i >> 1], pl_[i >> 1]);
+                    else ph_[i >> 1] = pack_bf16x2(e0, e1);
                 }
-                tmem_st_32x32b_x16(tm + TM_P + s * 64 + half * 16, ph_);
-                if (PREC == 3) tmem_st_32x32b_x16(tm + TM_P + s * 64 + 32 + half * 16, pl_);
-                tmem_st_wait();
+                tmem_st_32x32b_x4(tm + TM_P + (c >> 1), ph_[0], ph_[1], ph_[2], ph_[3]);
+                tmem_st_32x32b_x4(tm + TM_P + (c >> 1) + 4, ph_[4], ph_[5], ph_[6], ph_[7]);
+                if (PREC == 3) {
+                    tmem_st_32x32b_x4(tm + TM_P + 32 + (c >> 1), pl_[0], pl_[1], pl_[2], pl_[3]);
+                    tmem_st_32x32b_x4(tm + TM_P + 32 + (c >> 1) + 4, pl_[4], pl_[5], pl_[6], pl_[7]);
+                }
             }
+            l += (rs[0] + rs[1]) + (rs[2] + rs[3]);
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[s]);
-            if (tr) p.trace[j * 16 + 6] = clock64();
+            if (lane == 0) mbar_arrive(&p_full[t]);
+            if (tr) p.trace[(j * 2 + t) * 8 + 3] = clock64();
         }
-        // ---- epilogue: O / l (row sum = both halves) ----
-        xchg[(2 * 2 + half) * FA_BM + r] = l;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-        l += xchg[(2 * 2 + (half ^ 1)) * FA_BM + r];
-        mbar_wait(&pv_done[(ntiles - 1) & 1], ((ntiles - 1) >> 1) & 1);
+        // ---- epilogue: O / l ----
+        mbar_wait(&o_done[t], 0);
         tc_fence_after();
         const float inv = 1.f / l;
         const int64_t obase = (int64_t)b * p.o_bs + (int64_t)qrow * p.o_ts + (int64_t)h * FA_HD;
-        for (int c = o_c0; c < o_c1; c += 16) {
+        for (int c = 0; c < FA_HD; c += 16) {
             uint32_t o[16];
             tmem_ld_32x32b_x16(tm + TM_O + c, o);
             tmem_ld_wait();
@@ -428,7 +425,7 @@ static int launch_fa(const FaMaps& maps, const FaParams& p, cudaStream_t st) {
         HIPIE_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
         attr = true;
     }
-    dim3 grid(p.T / FA_BM, p.H, p.B);
+    dim3 grid(p.T / (FA_QT * FA_BM), p.H, p.B);
     attn_tc_kernel<PREC><<<grid, 320, SM::TOTAL, st>>>(maps, p);
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
@@ -446,13 +443,12 @@ extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int
     HIPIE_CHECK_ARG(q_hi && k_hi && vt_hi, "hipie_attention_tc: q/k/vt hi planes required");
     HIPIE_CHECK_ARG(prec == 1 || (prec == 3 && q_lo && k_lo && vt_lo), "hipie_attention_tc: prec/lo planes mismatch");
     HIPIE_CHECK_ARG(hd == FA_HD, "hipie_attention_tc: head dim must be 80 (got %d)", hd);
-    HIPIE_CHECK_ARG(T > 0 && T % FA_BM == 0, "hipie_attention_tc: T (%d) must be a multiple of 128", T);
+    HIPIE_CHECK_ARG(T > 0 && T % (FA_QT * FA_BM) == 0, "hipie_attention_tc: T (%d) must be a multiple of 256", T);
     HIPIE_CHECK_ARG((rel_h == nullptr) == (rel_w == nullptr), "hipie_attention_tc: rel_h and rel_w go together");
     HIPIE_CHECK_ARG(!rel_h || (kw == FA_BN && kh * kw == T), "hipie_attention_tc: rel-pos needs kw == 64 and kh*kw == T");
     HIPIE_CHECK_ARG(out_f32 || out_hi, "hipie_attention_tc: no output requested");
     HIPIE_CHECK_ARG(q_ts % 8 == 0 && q_bs % 8 == 0 && q_col0 % 8 == 0 && (reinterpret_cast<uintptr_t>(q_hi) & 15) == 0,
                     "hipie_attention_tc: q rows must be 16-byte aligned");
-    (void)q_width;
     FaMaps maps;
     int rc;
     const void* kp[2] = {k_hi, k_lo};
@@ -463,6 +459,9 @@ extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int
         if ((rc = make_tmap_bf16(&maps.vt[pl], vp[pl], (int64_t)H * FA_HD, (int64_t)B * T, vt_ld, 1, 0, FA_HD, 64))) return rc;
     }
     if (prec == 1) { maps.k64[1] = maps.k64[0]; maps.k16[1] = maps.k16[0]; maps.vt[1] = maps.vt[0]; }
+    const void* qsrc = prec == 3 ? q_lo : q_hi;     // prec 1 never loads it; keep the maps valid
+    if ((rc = make_tmap_bf16(&maps.q64, qsrc, T, q_width, q_ts, B, q_bs, FA_BM, 64))) return rc;
+    if ((rc = make_tmap_bf16(&maps.q16, qsrc, T, q_width, q_ts, B, q_bs, FA_BM, 16))) return rc;
     FaParams p;
     p.q_hi = (const __nv_bfloat16*)q_hi; p.q_lo = (const __nv_bfloat16*)q_lo; p.q_bs = q_bs; p.q_ts = q_ts;
     p.rel_h = rel_h; p.rel_w = rel_w; p.kh = kh;

@@ -210,7 +210,7 @@ class Engine:
                 _, xn, _ = ops.layernorm(x, W[blk + ".norm1.weight"], W[blk + ".norm1.bias"], 1e-6)
                 Bq, Tq, qh, qw = B, T, gh, gw
             st = (Tq * 3 * E, 3 * E, hd)
-            use_tc = (not windowed) and self.use_tc_attention and hd == 80 and Tq % 128 == 0 and qw == 64
+            use_tc = (not windowed) and self.use_tc_attention and hd == 80 and Tq % 256 == 0 and qw == 64
             if use_tc:
                 # q,k as one GEMM (N = 2E); V emitted transposed (E, B*T) so it is the K-major B operand of P.V
                 wqk, bqk, wv, bv = W.cached(("qk_v", blk), lambda: (ops.split_weight(W[blk + ".attn.qkv.weight"][:2 * E]),
