@@ -30,6 +30,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols
                    int64_t bstride, int box_rows, int box_cols);
 
 constexpr int FA_BM = 128, FA_BN = 64, FA_HD = 80, FA_STAGES = 3;
+constexpr int FA_THREADS = 352;  // TMA warp, MMA warp of tile 0, 8 softmax warps, MMA warp of tile 1
 constexpr int FA_QT = 2;           // query tiles per CTA (ping-pong: one in softmax while the other is in the tensor pipe)
 // tensor-memory map (columns), per query tile t at column 256 * t
 constexpr int TM_TILE = 256;
@@ -73,7 +74,7 @@ struct FaSmem {
 };
 
 template <int PREC>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(FA_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     using SM = FaSmem<PREC>;
     constexpr int NPL = SM::NPL;
@@ -86,10 +87,11 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     uint64_t* v_empty = v_full + FA_STAGES;
     uint64_t* q_ready = v_empty + FA_STAGES;       // [2]  Q hi parked in TMEM (4 warps per tile)
     uint64_t* qlo_full = q_ready + FA_QT;          // [2]  Q lo tile landed in shared memory (TMA)
-    uint64_t* s_full = qlo_full + FA_QT;           // [2]  QK(j) of tile t complete (and, in issue order, PV(j-1) too)
-    uint64_t* p_full = s_full + FA_QT;             // [2]  P(j) of tile t written (4 warps)
-    uint64_t* o_done = p_full + FA_QT;             // [2]  last PV of tile t complete
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + FA_QT);
+    uint64_t* s_full = qlo_full + FA_QT;           // [2]  QK(j) of tile t complete
+    uint64_t* s_empty = s_full + FA_QT;            // [2]  scores (j) of tile t are in registers (4 warps): QK(j+1) may overwrite S
+    uint64_t* p_full = s_empty + FA_QT;            // [2]  P(j) of tile t written (4 warps)
+    uint64_t* pv_done = p_full + FA_QT;            // [2]  PV(j) of tile t complete: P may be overwritten, O is current
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + FA_QT);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (FA_QT * FA_BM), h = blockIdx.y, b = blockIdx.z;
@@ -105,12 +107,13 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     if (warp == 1) {
         if (lane == 0) {
             for (int i = 0; i < FA_STAGES; ++i) {
-                mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
-                mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+                mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], FA_QT);      // released by both tiles' issuers
+                mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], FA_QT);
             }
             for (int i = 0; i < FA_QT; ++i) {
                 mbar_init(&q_ready[i], 4); mbar_init(&qlo_full[i], 1);
-                mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_done[i], 1);
+                mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+                mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1);
             }
             fence_barrier_init();
         }
@@ -152,32 +155,29 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 if (++s == FA_STAGES) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        // Per query tile t and key tile j:  S_t = Q_t K_j^T  (A = Q hi in TMEM; the Ql.Kh pass takes Q lo from shared memory)
-        //                                   O_t += P_t V_j   (A = P in TMEM)
-        // PV_t(j) and QK_t(j+1) are independent accumulator chains and are issued interleaved (a chain of small-N MMAs
-        // into one accumulator is latency bound); tile 0 and tile 1 alternate, so while one tile's scores are in the
-        // softmax warps the tensor pipe works on the other tile.
+    } else if (warp == 1 || warp == 10) {
+        // ===================== MMA issuers: warp 1 drives query tile 0, warp 10 tile 1 =====================
+        //   S_t = Q_t K_j^T  (A = Q hi in TMEM; the Ql.Kh pass takes Q lo from shared memory)     O_t += P_t V_j  (A = P in TMEM)
+        // QK_t(j+1) is issued as soon as the softmax warps have pulled S_t(j) into registers, so the next scores are ready
+        // before the current softmax finishes; PV_t(j) follows P_t(j).  The two issuers' instruction streams interleave in the
+        // tensor pipe (independent accumulators), which hides the dependent-accumulate latency of the small-N MMAs and keeps
+        // the pipe busy while one tile waits on its softmax.  Latency-critical waits poll (test_wait) instead of suspending.
+        const int t = warp == 1 ? 0 : 1;
         constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BM, FA_BN);
         constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BM, FA_HD);
-        auto kdesc = [&](int st, uint64_t& k64h, uint64_t& k16h, uint64_t& k64l, uint64_t& k16l) {
-            const uint32_t kb = smem_u32(smem + st * SM::K_STAGE);
-            k64h = make_kmajor_desc<128>(kb); k16h = make_kmajor_desc<32>(kb + SM::K64);
-            k64l = make_kmajor_desc<128>(kb + SM::K64 + SM::K16); k16l = make_kmajor_desc<32>(kb + 2 * SM::K64 + SM::K16);
-        };
-        auto issue_qk = [&](int t, int j) {            // prologue: QK only
+        const uint32_t tb = tmem_base + t * TM_TILE;
+        const uint32_t dS = tb + TM_S, dO = tb + TM_O, tq = tb + TM_Q, tp_hi = tb + TM_P, tp_lo = tb + TM_P + 32;
+        const uint32_t qb = smem_u32(smem + SM::OFF_Q + t * SM::Q_TILE);
+        auto issue_qk = [&](int j) {
             const int st = j % FA_STAGES;
             if (elect_one()) {
-                const uint32_t tb = tmem_base + t * TM_TILE;
-                const uint32_t dS = tb + TM_S, tq = tb + TM_Q;
-                uint64_t k64h, k16h, k64l, k16l;
-                kdesc(st, k64h, k16h, k64l, k16l);
+                const uint32_t kb = smem_u32(smem + st * SM::K_STAGE);
+                const uint64_t k64h = make_kmajor_desc<128>(kb), k16h = make_kmajor_desc<32>(kb + SM::K64);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_f16_ts(dS, tq + 8 * k, k64h + 2 * k, idesc_qk, k > 0);
                 umma_f16_ts(dS, tq + 32, k16h, idesc_qk, 1);
                 if (PREC == 3) {
-                    const uint32_t qb = smem_u32(smem + SM::OFF_Q + t * SM::Q_TILE);
+                    const uint64_t k64l = make_kmajor_desc<128>(kb + SM::K64 + SM::K16), k16l = make_kmajor_desc<32>(kb + 2 * SM::K64 + SM::K16);
                     const uint64_t q64l = make_kmajor_desc<128>(qb), q16l = make_kmajor_desc<32>(qb + SM::Q64);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_f16_ts(dS, tq + 8 * k, k64l + 2 * k, idesc_qk, 1);
@@ -187,83 +187,54 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                     umma_f16(dS, q16l, k16h, idesc_qk, 1);
                 }
                 umma_commit(&s_full[t]);
-                if (t == FA_QT - 1) umma_commit(&k_empty[st]);
+                umma_commit(&k_empty[st]);
             }
             __syncwarp();
         };
-        auto issue_pv_qk = [&](int t, int j, bool with_qk) {     // PV_t(j) [+ QK_t(j+1)]
-            const int stv = j % FA_STAGES, stk = (j + 1) % FA_STAGES;
+        auto issue_pv = [&](int j) {
+            const int st = j % FA_STAGES;
             if (elect_one()) {
-                const uint32_t tb = tmem_base + t * TM_TILE;
-                const uint32_t dO = tb + TM_O, dS = tb + TM_S, tq = tb + TM_Q, tp_hi = tb + TM_P, tp_lo = tb + TM_P + 32;
-                const uint32_t vb = smem_u32(smem + SM::OFF_V + stv * SM::V_STAGE);
+                const uint32_t vb = smem_u32(smem + SM::OFF_V + st * SM::V_STAGE);
                 const uint64_t v_hi = make_kmajor_desc<128>(vb), v_lo = make_kmajor_desc<128>(vb + SM::VT);
-                const uint32_t acc0 = j > 0;
-                if (with_qk) {
-                    uint64_t k64h, k16h, k64l, k16l;
-                    kdesc(stk, k64h, k16h, k64l, k16l);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_f16_ts(dO, tp_hi + 8 * k, v_hi + 2 * k, idesc_pv, k > 0 ? 1u : acc0);
-                        umma_f16_ts(dS, tq + 8 * k, k64h + 2 * k, idesc_qk, k > 0);
-                    }
-                    umma_f16_ts(dS, tq + 32, k16h, idesc_qk, 1);
-                    if (PREC == 3) {
-                        const uint32_t qb = smem_u32(smem + SM::OFF_Q + t * SM::Q_TILE);
-                        const uint64_t q64l = make_kmajor_desc<128>(qb), q16l = make_kmajor_desc<32>(qb + SM::Q64);
+                for (int k = 0; k < 4; ++k) umma_f16_ts(dO, tp_hi + 8 * k, v_hi + 2 * k, idesc_pv, (j | k) != 0);
+                if (PREC == 3) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_f16_ts(dO, tp_hi + 8 * k, v_lo + 2 * k, idesc_pv, 1);
-                            umma_f16_ts(dS, tq + 8 * k, k64l + 2 * k, idesc_qk, 1);
-                        }
-                        umma_f16_ts(dS, tq + 32, k16l, idesc_qk, 1);
+                    for (int k = 0; k < 4; ++k) umma_f16_ts(dO, tp_hi + 8 * k, v_lo + 2 * k, idesc_pv, 1);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_f16_ts(dO, tp_lo + 8 * k, v_hi + 2 * k, idesc_pv, 1);
-                            umma_f16(dS, q64l + 2 * k, k64h + 2 * k, idesc_qk, 1);
-                        }
-                        umma_f16(dS, q16l, k16h, idesc_qk, 1);
-                    }
-                    umma_commit(&s_full[t]);
-                    if (t == FA_QT - 1) umma_commit(&k_empty[stk]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16_ts(dO, tp_hi + 8 * k, v_hi + 2 * k, idesc_pv, k > 0 ? 1u : acc0);
-                    if (PREC == 3) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16_ts(dO, tp_hi + 8 * k, v_lo + 2 * k, idesc_pv, 1);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16_ts(dO, tp_lo + 8 * k, v_hi + 2 * k, idesc_pv, 1);
-                    }
-                    umma_commit(&o_done[t]);
+                    for (int k = 0; k < 4; ++k) umma_f16_ts(dO, tp_lo + 8 * k, v_hi + 2 * k, idesc_pv, 1);
                 }
-                if (t == FA_QT - 1) umma_commit(&v_empty[stv]);
+                umma_commit(&pv_done[t]);
+                umma_commit(&v_empty[st]);
             }
             __syncwarp();
         };
         mbar_wait(&k_full[0], 0);
-        for (int t = 0; t < FA_QT; ++t) {
-            mbar_wait(&q_ready[t], 0);
-            if (PREC == 3) mbar_wait(&qlo_full[t], 0);
-            tc_fence_after();
-            issue_qk(t, 0);
-        }
+        mbar_wait(&q_ready[t], 0);
+        if (PREC == 3) mbar_wait(&qlo_full[t], 0);
+        tc_fence_after();
+        issue_qk(0);
         for (int j = 0; j < ntiles; ++j) {
-            const bool more = j + 1 < ntiles;
-            for (int t = 0; t < FA_QT; ++t) {
-                if (t == 0) {
-                    mbar_wait(&v_full[j % FA_STAGES], (j / FA_STAGES) & 1);
-                    if (more) mbar_wait(&k_full[(j + 1) % FA_STAGES], ((j + 1) / FA_STAGES) & 1);
-                }
-                mbar_wait(&p_full[t], j & 1);
+            const bool trm = trace_cta && lane == 0 && j < 32;
+            if (j + 1 < ntiles) {
+                mbar_wait(&k_full[(j + 1) % FA_STAGES], ((j + 1) / FA_STAGES) & 1);
+                if (trm) p.trace[(j * 2 + t) * 8 + 4] = clock64();
+                mbar_wait_spin(&s_empty[t], j & 1);
                 tc_fence_after();
-                issue_pv_qk(t, j, more);
+                issue_qk(j + 1);
             }
+            mbar_wait(&v_full[j % FA_STAGES], (j / FA_STAGES) & 1);
+            if (trm) p.trace[(j * 2 + t) * 8 + 5] = clock64();
+            mbar_wait_spin(&p_full[t], j & 1);
+            tc_fence_after();
+            if (trm) p.trace[(j * 2 + t) * 8 + 6] = clock64();
+            issue_pv(j);
+            if (trm) p.trace[(j * 2 + t) * 8 + 7] = clock64();
         }
     } else {
         // ===================== softmax / epilogue: warps 2-5 own query tile 0, warps 6-9 tile 1; one thread per row ==========
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-        const int t = (warp - 2) >> 2;
+        const int t = (warp - 2) >> 2;                // warps 2-5: tile 0, warps 6-9: tile 1
         const int r = quarter * 32 + lane;            // row of the query tile == TMEM lane
         const int qrow = q0 + t * FA_BM + r;
         const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * TM_TILE;
@@ -308,7 +279,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             const float rh = rh_next;
             if (has_rel && j + 1 < ntiles) rh_next = __ldg(relh_row + j + 1) * LOG2E;   // prefetch for the next tile
             if (tr) p.trace[(j * 2 + t) * 8 + 0] = clock64();
-            mbar_wait(&s_full[t], j & 1);
+            mbar_wait_spin(&s_full[t], j & 1);
             tc_fence_after();
             if (tr) p.trace[(j * 2 + t) * 8 + 1] = clock64();
             float tv[FA_BN];
@@ -320,6 +291,9 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 for (int i = 0; i < 32; ++i) tv[i] = fmaf(__uint_as_float(sv[i]), p.scale_log2e, has_rel ? rw[i] : 0.f);
                 tmem_ld_32x32b_x32(tm + TM_S + 32, sv);
                 tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[t]);      // scores are in registers: QK_t(j+1) may overwrite S_t
 #pragma unroll
                 for (int i = 0; i < 32; ++i) tv[32 + i] = fmaf(__uint_as_float(sv[i]), p.scale_log2e, has_rel ? rw[32 + i] : 0.f);
             }
@@ -339,15 +313,18 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 m = tmax;
                 l *= corr;
             }
-            if (j > 0 && __any_sync(0xffffffffu, need)) {      // warp-uniform: tcgen05.ld/st are warp-collective
-                // s_full(j) was committed after PV_t(j-1) in issue order, so O already holds it (rare once the max settles)
-                for (int c = 0; c < FA_HD; c += 16) {
-                    uint32_t o[16];
-                    tmem_ld_32x32b_x16(tm + TM_O + c, o);
-                    tmem_ld_wait();
+            if (j > 0) {
+                mbar_wait(&pv_done[t], (j - 1) & 1);           // PV_t(j-1) retired: P_t is free and O_t is current (long done normally)
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, need)) {           // warp-uniform: tcgen05.ld/st are warp-collective (rare once the max settles)
+                    for (int c = 0; c < FA_HD; c += 16) {
+                        uint32_t o[16];
+                        tmem_ld_32x32b_x16(tm + TM_O + c, o);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-                    tmem_st_32x32b_x16(tm + TM_O + c, o);
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                        tmem_st_32x32b_x16(tm + TM_O + c, o);
+                    }
                 }
             }
             if (tr) p.trace[(j * 2 + t) * 8 + 2] = clock64();
@@ -378,7 +355,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             if (tr) p.trace[(j * 2 + t) * 8 + 3] = clock64();
         }
         // ---- epilogue: O / l ----
-        mbar_wait(&o_done[t], 0);
+        mbar_wait(&pv_done[t], (ntiles - 1) & 1);
         tc_fence_after();
         const float inv = 1.f / l;
         const int64_t obase = (int64_t)b * p.o_bs + (int64_t)qrow * p.o_ts + (int64_t)h * FA_HD;
@@ -426,7 +403,7 @@ static int launch_fa(const FaMaps& maps, const FaParams& p, cudaStream_t st) {
         attr = true;
     }
     dim3 grid(p.T / (FA_QT * FA_BM), p.H, p.B);
-    attn_tc_kernel<PREC><<<grid, 320, SM::TOTAL, st>>>(maps, p);
+    attn_tc_kernel<PREC><<<grid, FA_THREADS, SM::TOTAL, st>>>(maps, p);
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
 }

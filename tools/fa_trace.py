@@ -11,7 +11,7 @@ qk = torch.randn(B * T, 2 * E, device=dev); v = torch.randn(E, B * T, device=dev
 S, Vs = ops.split(qk), ops.split(v)
 rel_h = torch.randn(B, H, T, 64, device=dev); rel_w = torch.randn(B, H, T, 64, device=dev)
 out = ops._empty_bf2((B, T, E), dev)
-trace = torch.zeros(32 * 16, dtype=torch.int64, device=dev)
+trace = torch.zeros(32 * 2 * 8, dtype=torch.int64, device=dev)
 lib = _lib.load()
 P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
 lo = prec == 3
@@ -21,10 +21,10 @@ for it in range(3):
                                        T * E, E, B, H, T, hd, hd ** -0.5, prec, P(trace), None)
     assert rc == 0, lib.hipie_last_error()
 torch.cuda.synchronize()
-t = trace.cpu().view(32, 16)
-t0 = int(t[8, 0])
-names = ["sm:start", "sm:S ready", "sm:ldtm done", "sm:xchg done", "sm:exp done", "sm:P free", "sm:P stored", "mm:iter start", "mm:k/sempty ok", "mm:QK issued",
-         "mm:pv start", "mm:p_full ok", "mm:v ok", "mm:PV issued"]
-print("tile " + " ".join(f"{n[:12]:>12s}" for n in names))
-for j in range(8, 20):
-    print(f"{j:4d} " + " ".join(f"{int(t[j, k]) - t0:12d}" for k in range(14)))
+t = trace.cpu().view(32, 2, 8)
+t0 = int(t[8, 0, 0])
+names = ["sm:start", "sm:S ready", "sm:max done", "sm:P stored", "mm:k ok", "mm:QKi/v ok", "mm:p_full ok", "mm:PV issued"]
+print("tile qt " + " ".join(f"{n[:12]:>12s}" for n in names))
+for j in range(8, 18):
+    for q in range(2):
+        print(f"{j:4d} {q:2d} " + " ".join(f"{int(t[j, q, k]) - t0:12d}" for k in range(8)))
