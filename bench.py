@@ -307,8 +307,27 @@ def run_product(args):
                 entry.update(bound="tensor", achieved=rate / 1e12, unit="TFLOP/s", frac=rate / 1e12 / pk["tf_sustained"])
         kernels[tag] = entry
     tk = kernels[top[0]]
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture (profiles/r01_ncu_summary.json):
+    # the ViT-H fc1 launch (M=32768, N=5120, K=1280, GELU, bf16 hi/lo out), the largest single GEMM of the step.
+    traffic, traffic_note = None, None
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")).read().split("\n}\n"):
+            if "ncu_r01_gemm" in line:
+                rec = json.loads(line + "}")
+                tobytes = lambda v: float(v.split()[0]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[v.split()[1]]
+                traffic = tobytes(rec["dram__bytes_read.sum"]) + tobytes(rec["dram__bytes_write.sum"])
+                alg = 32768 * 1280 * 4 + 5120 * 1280 * 4 + 32768 * 5120 * 4      # A hi+lo, W hi+lo, C hi+lo (bf16 planes)
+                traffic_note = f"ncu dram read+write of the fc1 launch (32768x5120x1280); algorithmic operand+result bytes {alg/1e6:.0f} MB"
+    except Exception:
+        pass
+    passes = 3 if args.precision == "bf16x3" else 1
     roofline = {"kernel": top[0], "bound": tk.get("bound", "tensor"), "achieved": tk.get("achieved"), "peak": pk["hbm"] if tk.get("bound") == "hbm" else pk["tf_sustained"],
-                "unit": tk.get("unit"), "frac": tk.get("frac"), "traffic": None, "peak_source": pk["src"] + " (sustained figure: kernel timed inside a long step)",
+                "unit": tk.get("unit"), "frac": tk.get("frac"), "traffic": traffic, "traffic_note": traffic_note,
+                "mma_passes": passes, "executed_tflops": (tk.get("achieved") or 0.0) * passes if tk.get("bound") == "tensor" else None,
+                "executed_frac": (tk.get("frac") or 0.0) * passes if tk.get("bound") == "tensor" else None,
+                "achieved_note": "algorithmic 2MNK flops of the fp32-class GEMMs / measured kernel time; bf16x3 parity mode issues 3 bf16 MMAs per "
+                                 "algorithmic MAC (executed_* = achieved x mma_passes against the same bf16 peak)",
+                "peak_source": pk["src"] + " (sustained figure: kernel timed inside a long step)",
                 "vit_h_forward_tensor_frac": (VIT_H_FLOPS_PER_IMG * B * world * args.steps / (ms_max / 1000.0)) / 1e12 / (pk["tf_sustained"] * world),
                 "kernels": kernels}
     cpu = None
