@@ -189,6 +189,140 @@ row_softmax_kernel(const float* __restrict__ x, const float* __restrict__ colbia
     }
 }
 
+// Vectorised variants (n % 4 == 0, 16-byte aligned rows).  Same arithmetic as row_softmax_kernel.
+__device__ __forceinline__ float rs_val(float x, float pre, float cb, float clampv, int sub_rowmax) {
+    float v = fminf(fmaxf(x, -clampv), clampv);
+    if (sub_rowmax) v = fminf(fmaxf(v - pre, -clampv), clampv);
+    return v + cb;
+}
+__device__ __forceinline__ void rs_store4(float4 pv, int64_t off, __nv_bfloat16* hi, __nv_bfloat16* lo, float* p_f32) {
+    if (p_f32) *reinterpret_cast<float4*>(p_f32 + off) = pv;
+    if (hi) {
+        uint2 h, l;
+        split2(pv.x, pv.y, h.x, l.x);
+        split2(pv.z, pv.w, h.y, l.y);
+        *reinterpret_cast<uint2*>(hi + off) = h;
+        if (lo) *reinterpret_cast<uint2*>(lo + off) = l;
+    }
+}
+
+// short rows (n <= 1024): one warp per row, the row lives in registers (one global read), shuffle reductions only
+template <int NCH>   // float4 chunks per lane
+__global__ void __launch_bounds__(256)
+row_softmax_warp_kernel(const float* __restrict__ x, const float* __restrict__ colbias, int64_t rows, int64_t rows_per_batch,
+                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ p_f32, int n,
+                        float clampv, int sub_rowmax) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + row * n;
+    const float* cb = colbias ? colbias + (row / rows_per_batch) * n : nullptr;
+    float4 v[NCH];
+    float pre = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        v[i] = c < n ? *reinterpret_cast<const float4*>(xr + c) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    if (sub_rowmax) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+            if ((i * 32 + lane) * 4 < n)     // clamp is monotone: max of clamped == clamp of max
+                m = fmaxf(m, fminf(fmaxf(fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)), -clampv), clampv));
+        pre = warp_max(m);
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < n) {
+            const float4 b = cb ? *reinterpret_cast<const float4*>(cb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i].x = rs_val(v[i].x, pre, b.x, clampv, sub_rowmax);
+            v[i].y = rs_val(v[i].y, pre, b.y, clampv, sub_rowmax);
+            v[i].z = rs_val(v[i].z, pre, b.z, clampv, sub_rowmax);
+            v[i].w = rs_val(v[i].w, pre, b.w, clampv, sub_rowmax);
+            m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+        }
+    }
+    m = warp_max(m);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        if ((i * 32 + lane) * 4 < n) {
+            v[i].x = expf(v[i].x - m); v[i].y = expf(v[i].y - m); v[i].z = expf(v[i].z - m); v[i].w = expf(v[i].w - m);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < n) rs_store4(make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv), row * n + c, hi, lo, p_f32);
+    }
+}
+
+// long rows: one block per row, the row is cached in shared memory (one global read)
+__global__ void __launch_bounds__(512)
+row_softmax_smem_kernel(const float* __restrict__ x, const float* __restrict__ colbias, int64_t rows_per_batch,
+                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ p_f32, int n,
+                        float clampv, int sub_rowmax) {
+    extern __shared__ __align__(16) float rs_row[];
+    __shared__ float red[16];
+    __shared__ float bc;
+    const int64_t row = blockIdx.x;
+    const float* xr = x + row * n;
+    const float* cb = colbias ? colbias + (row / rows_per_batch) * n : nullptr;
+    const int n4 = n >> 2;
+    auto block_reduce = [&](float v, bool is_max) {
+        v = is_max ? warp_max(v) : warp_sum(v);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float r = threadIdx.x < 16 ? red[threadIdx.x] : (is_max ? -INFINITY : 0.f);
+            r = is_max ? warp_max(r) : warp_sum(r);
+            if (threadIdx.x == 0) bc = r;
+        }
+        __syncthreads();
+        const float r = bc;
+        __syncthreads();
+        return r;
+    };
+    float m0 = -INFINITY;
+    for (int c = threadIdx.x; c < n4; c += 512) {
+        const float4 a = *reinterpret_cast<const float4*>(xr + 4 * c);
+        *reinterpret_cast<float4*>(rs_row + 4 * c) = a;
+        m0 = fmaxf(m0, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+    }
+    float pre = 0.f;
+    if (sub_rowmax) pre = fminf(fmaxf(block_reduce(m0, true), -clampv), clampv);
+    else __syncthreads();
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < n4; c += 512) {
+        float4 a = *reinterpret_cast<const float4*>(rs_row + 4 * c);
+        const float4 b = cb ? *reinterpret_cast<const float4*>(cb + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a.x = rs_val(a.x, pre, b.x, clampv, sub_rowmax); a.y = rs_val(a.y, pre, b.y, clampv, sub_rowmax);
+        a.z = rs_val(a.z, pre, b.z, clampv, sub_rowmax); a.w = rs_val(a.w, pre, b.w, clampv, sub_rowmax);
+        *reinterpret_cast<float4*>(rs_row + 4 * c) = a;
+        m = fmaxf(m, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+    }
+    m = block_reduce(m, true);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < n4; c += 512) {
+        float4 a = *reinterpret_cast<const float4*>(rs_row + 4 * c);
+        a.x = expf(a.x - m); a.y = expf(a.y - m); a.z = expf(a.z - m); a.w = expf(a.w - m);
+        *reinterpret_cast<float4*>(rs_row + 4 * c) = a;
+        s += (a.x + a.y) + (a.z + a.w);
+    }
+    s = block_reduce(s, false);
+    const float inv = 1.f / s;
+    for (int c = threadIdx.x; c < n4; c += 512) {
+        const float4 a = *reinterpret_cast<const float4*>(rs_row + 4 * c);
+        rs_store4(make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv), row * n + 4 * c, hi, lo, p_f32);
+    }
+}
+
 // ---- CondInst dynamic mask head, fused (ddetrs_dn.py:1390-1502, 1806-1870) --------------------
 // feats (B, Hf*Wf, 8) NHWC fp32; params (B, Q, 169) = [w0 (8x10) | w1 (8x8) | w2 (1x8) | b0 8 | b1 8 | b2 1];
 // ref_px (B, Q, 2) reference point in pixels.  Per (b, q): 3-layer 1x1 MLP over
@@ -344,8 +478,31 @@ extern "C" int hipie_row_softmax(const float* x, const float* colbias, int64_t r
     HIPIE_CHECK_ARG(x && (hi || p_f32), "hipie_row_softmax: null pointer");
     HIPIE_CHECK_ARG(rows >= 0 && n > 0 && rows_per_batch > 0, "hipie_row_softmax: bad sizes");
     if (rows == 0) return HIPIE_OK;
-    row_softmax_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, colbias, rows_per_batch, (__nv_bfloat16*)hi,
-                                                                        (__nv_bfloat16*)lo, p_f32, n, clampv, sub_rowmax);
+    const bool aligned = n % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(colbias) |
+                                        reinterpret_cast<uintptr_t>(p_f32)) & 15) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 7) == 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (aligned && n <= 1024) {
+        const unsigned blocks = (unsigned)((rows + 7) / 8);
+        if (n <= 512)
+            row_softmax_warp_kernel<4><<<blocks, 256, 0, st>>>(x, colbias, rows, rows_per_batch, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                               p_f32, n, clampv, sub_rowmax);
+        else
+            row_softmax_warp_kernel<8><<<blocks, 256, 0, st>>>(x, colbias, rows, rows_per_batch, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                               p_f32, n, clampv, sub_rowmax);
+    } else if (aligned && (int64_t)n * 4 <= 200 * 1024) {
+        const int smem = n * 4;
+        static int smem_set = 0;
+        if (smem > smem_set) {
+            HIPIE_CHECK_CUDA(cudaFuncSetAttribute(row_softmax_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            smem_set = smem;
+        }
+        row_softmax_smem_kernel<<<(unsigned)rows, 512, smem, st>>>(x, colbias, rows_per_batch, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                                   p_f32, n, clampv, sub_rowmax);
+    } else {
+        row_softmax_kernel<<<(unsigned)rows, 256, 0, st>>>(x, colbias, rows_per_batch, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, p_f32,
+                                                           n, clampv, sub_rowmax);
+    }
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
 }

@@ -227,9 +227,11 @@ def layernorm(x, gamma, beta, eps, add=None, want_f32=False, want_split=True, wa
     y = torch.empty(oshape, dtype=torch.float32, device=x.device) if want_f32 else None
     s = out_split if out_split is not None else (_empty_bf2(oshape, x.device) if want_split else None)
     ssum = torch.empty_like(x) if (want_sum and add is not None) else None
-    _lib.check(_lib.load().hipie_layernorm(_p(x), _p(add), _p(gamma), _p(beta), float(eps), _p(ssum), _p(y),
-                                           _p(s.hi) if s else None, _p(s.lo) if (s and s.lo is not None) else None,
-                                           rows, C, _p(row_map), _stream()), "layernorm")
+    nbytes = x.numel() * 4.0 * (1 + (add is not None) + (ssum is not None) + (y is not None)) + (x.numel() * 2.0 * (2 if PREC == 3 else 1) if s else 0.0)
+    with _timed("layernorm", nbytes):
+        _lib.check(_lib.load().hipie_layernorm(_p(x), _p(add), _p(gamma), _p(beta), float(eps), _p(ssum), _p(y),
+                                               _p(s.hi) if s else None, _p(s.lo) if (s and s.lo is not None) else None,
+                                               rows, C, _p(row_map), _stream()), "layernorm")
     return y, s, ssum
 
 
@@ -307,9 +309,11 @@ def row_softmax(x, colbias=None, rows_per_batch=None, clampv=50000.0, sub_rowmax
     x = x.contiguous()
     s = _empty_bf2(x.shape, x.device) if want_split else None
     pf = torch.empty_like(x) if want_f32 else None
-    _lib.check(_lib.load().hipie_row_softmax(_p(x), _p(colbias), rows, rows_per_batch or rows, n, float(clampv),
-                                             1 if sub_rowmax else 0, _p(s.hi) if s else None,
-                                             _p(s.lo) if (s and s.lo is not None) else None, _p(pf), _stream()), "row_softmax")
+    nbytes = x.numel() * 4.0 * (1 + (pf is not None)) + (x.numel() * 2.0 * (2 if (s.lo is not None) else 1) if s else 0.0)
+    with _timed("row_softmax", nbytes):
+        _lib.check(_lib.load().hipie_row_softmax(_p(x), _p(colbias), rows, rows_per_batch or rows, n, float(clampv),
+                                                 1 if sub_rowmax else 0, _p(s.hi) if s else None,
+                                                 _p(s.lo) if (s and s.lo is not None) else None, _p(pf), _stream()), "row_softmax")
     return pf, s
 
 

@@ -301,6 +301,23 @@ def test_row_softmax(ops, cuda):
     assert (p2.double() - ref2).abs().max() < 1e-6
 
 
+@pytest.mark.parametrize("n", [512, 640, 2176, 132])
+def test_row_softmax_vectorised(ops, cuda, n):
+    """warp-per-row (n <= 1024) and smem-cached block-per-row variants against fp64"""
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.randn(3 * 7, n, device=cuda, generator=g) * 4
+    cb = torch.ones(3, n, device=cuda)
+    cb[1, n // 2:] = -9e15
+    p, s = ops.row_softmax(x, colbias=cb, rows_per_batch=7, want_f32=True)
+    ref = torch.softmax(x.double().clamp(-5e4, 5e4).view(3, 7, n) + cb.double()[:, None], -1).view(21, n)
+    assert (p.double() - ref).abs().max() < 1e-6
+    assert ((s.hi.float() + s.lo.float()).double() - ref).abs().max() < 1e-5
+    p2, _ = ops.row_softmax(x, sub_rowmax=True, want_f32=True, want_split=False)
+    xr = x.double()
+    ref2 = torch.softmax((xr - xr.max(-1, keepdim=True)[0]).clamp(-5e4, 5e4), -1)
+    assert (p2.double() - ref2).abs().max() < 1e-6
+
+
 # ------------------------------------------------------------------------------------------ attention
 def _attn_ref(q, k, v, scale, rel_h=None, rel_w=None, kh=0, kw=0, key_bias=None):
     # q,k,v: (B,H,T,hd) double
