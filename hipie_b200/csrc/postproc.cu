@@ -10,6 +10,7 @@
 // against the class-probability chunk; the argmax / area counters ride along on the same sigmoid values.
 // HBM traffic drops to the low-resolution logits (+halo) and the outputs.
 #include "common.cuh"
+#include <algorithm>
 
 namespace hipie {
 
@@ -271,6 +272,38 @@ seg_post_kernel(const float* __restrict__ masks, const __nv_bfloat16* __restrict
     }
 }
 
+// Instance masks (hipie_img.py:1003-1007): bilinear x4 (align_corners=False) of the 1/4-resolution logits, sigmoid, > threshold,
+// crop -- one pass, one byte per pixel out.  Thread = 4 consecutive pixels of one 4x4 block row (they share the 4 taps).
+__global__ void __launch_bounds__(256)
+upsample_threshold_kernel(const float* __restrict__ masks, uint8_t* __restrict__ out, int N, int h, int w, int Hc, int Wc,
+                          float thr) {
+    const int kxn = (Wc + 2 + 3) / 4;                       // 4-pixel groups [4k-2, 4k+2) per row
+    const int64_t total = (int64_t)N * Hc * kxn;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int kx = (int)(i % kxn);
+        const int y = (int)((i / kxn) % Hc);
+        const int n = (int)(i / ((int64_t)kxn * Hc));
+        const float sy = fmaxf(0.25f * (y + 0.5f) - 0.5f, 0.f);
+        const int y0 = min((int)sy, h - 1), y1 = y0 + (y0 < h - 1);
+        const float ly = sy - y0;
+        const int x0 = max(kx - 1, 0), x1 = min(kx, w - 1);
+        const float* m0 = masks + ((int64_t)n * h + y0) * w;
+        const float* m1 = masks + ((int64_t)n * h + y1) * w;
+        const float t00 = __ldg(m0 + x0), t01 = __ldg(m0 + x1), t10 = __ldg(m1 + x0), t11 = __ldg(m1 + x1);
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+            const int x = 4 * kx - 2 + dx;
+            if (x < 0 || x >= Wc) continue;
+            // same expression order as upsample_bilinear2d: h0*(w0*a + w1*b) + h1*(w0*c + w1*d)
+            float lx = 0.125f + 0.25f * dx;
+            if (kx == 0) lx = 0.f;                          // clamped source index at the left border
+            const float v = (1.f - ly) * ((1.f - lx) * t00 + lx * t01) + ly * ((1.f - lx) * t10 + lx * t11);
+            const float sg = 1.f / (1.f + expf(-v));
+            out[((int64_t)n * Hc + y) * Wc + x] = sg > thr ? 1 : 0;
+        }
+    }
+}
+
 template <int NT>
 int launch_seg_post(const float* masks, const void* pt_hi, const void* pt_lo, const float* scores, float* sem, int* ids,
                     int* areas, int Q, int Qpad, int C, int h, int w, int Hc, int Wc, cudaStream_t st) {
@@ -305,4 +338,18 @@ extern "C" int hipie_seg_postprocess(const float* masks, const void* pt_hi, cons
     if (C <= 80)
         return launch_seg_post<10>(masks, pt_hi, pt_lo, scores, sem, ids, areas, Q, Qpad, C, h, w, Hc, Wc, (cudaStream_t)stream);
     return launch_seg_post<17>(masks, pt_hi, pt_lo, scores, sem, ids, areas, Q, Qpad, C, h, w, Hc, Wc, (cudaStream_t)stream);
+}
+
+extern "C" int hipie_upsample_threshold(const float* masks, void* out_u8, int N, int h, int w, int stride, int Hc, int Wc,
+                                        float threshold, void* stream) {
+    if (N == 0) return HIPIE_OK;     // empty detections: nothing to write (pointers of empty tensors may be null)
+    HIPIE_CHECK_ARG(masks && out_u8, "hipie_upsample_threshold: null pointer");
+    HIPIE_CHECK_ARG(stride == 4, "hipie_upsample_threshold: only mask stride 4 is implemented (got %d)", stride);
+    HIPIE_CHECK_ARG(N >= 0 && h > 1 && w > 1 && Hc > 0 && Wc > 0 && Hc <= 4 * h && Wc <= 4 * w,
+                    "hipie_upsample_threshold: bad sizes N=%d h=%d w=%d Hc=%d Wc=%d", N, h, w, Hc, Wc);
+    const int64_t total = (int64_t)N * Hc * ((Wc + 5) / 4);
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 32);
+    upsample_threshold_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(masks, (uint8_t*)out_u8, N, h, w, Hc, Wc, threshold);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
 }

@@ -348,8 +348,11 @@ class HIPIE_IMG(nn.Module):
             result.pred_boxes = Boxes(box_cxcywh_to_xyxy(box_k))
             result.pred_boxes.scale(scale_x=image_size[1], scale_y=image_size[0])
             N, C, H, Wd = mask_i.shape
-            m = F.interpolate(mask_i, size=(H * self.mask_stride, Wd * self.mask_stride), mode="bilinear", align_corners=False)
-            result.pred_masks = (m.sigmoid() > self.mask_thres)[:, :, :image_size[0], :image_size[1]]
+            if self.fused_postprocess and self.mask_stride == 4:
+                result.pred_masks = ops.upsample_threshold(mask_i[:, 0], self.mask_thres, int(image_size[0]), int(image_size[1])).unsqueeze(1)
+            else:
+                m = F.interpolate(mask_i, size=(H * self.mask_stride, Wd * self.mask_stride), mode="bilinear", align_corners=False)
+                result.pred_masks = (m.sigmoid() > self.mask_thres)[:, :, :image_size[0], :image_size[1]]
             result.scores = topk_values
             result.pred_classes = labels
             sem = None
@@ -388,7 +391,10 @@ class HIPIE_IMG(nn.Module):
         boxes.clip((output_height, output_width))
         keep = boxes.nonempty()
         out.pred_boxes = Boxes(boxes.tensor[keep])
-        masks = F.interpolate(results.pred_masks.float(), size=(output_height, output_width), mode="nearest")[:, 0].to(torch.uint8)
+        if tuple(results.pred_masks.shape[-2:]) == (output_height, output_width):
+            masks = results.pred_masks[:, 0].to(torch.uint8)            # nearest resize to the same size is the identity
+        else:
+            masks = F.interpolate(results.pred_masks.float(), size=(output_height, output_width), mode="nearest")[:, 0].to(torch.uint8)
         out.pred_masks = masks[keep]
         out.scores = results.scores[keep]
         out.pred_classes = results.pred_classes[keep]

@@ -449,3 +449,13 @@ def seg_postprocess(masks_low, cls_prob, threshold, Hc, Wc, stride=4):
         _lib.check(_lib.load().hipie_seg_postprocess(_p(masks_low.contiguous()), _p(hi), _p(lo), _p(sc), _p(sem), _p(ids), _p(areas),
                                                      Q, Qpad, C, h, w, stride, Hc, Wc, _stream()), "seg_postprocess")
     return sem, ids, areas, scores, labels
+
+
+def upsample_threshold(masks_low, threshold, Hc, Wc, stride=4):
+    """(N,h,w) f32 logits -> (N,Hc,Wc) bool = sigmoid(bilinear x4) > threshold, cropped (hipie_upsample_threshold)."""
+    N, h, w = masks_low.shape
+    out = torch.empty((N, Hc, Wc), dtype=torch.bool, device=masks_low.device)
+    with _timed("upsample_threshold", float(masks_low.numel()) * 4 + out.numel()):
+        _lib.check(_lib.load().hipie_upsample_threshold(_p(masks_low.contiguous()), _p(out), N, h, w, stride, Hc, Wc, float(threshold),
+                                                        _stream()), "upsample_threshold")
+    return out

@@ -227,6 +227,11 @@ int hipie_condinst_masks(const float* feats, const float* params, const float* r
 int hipie_seg_postprocess(const float* masks, const void* pt_hi, const void* pt_lo, const float* scores, float* sem, int* ids,
                           int* areas, int Q, int Qpad, int C, int h, int w, int stride, int Hc, int Wc, void* stream);
 
+/* Instance masks of the kept detections (hipie_img.py:1003-1007): out[n, y, x] = sigmoid(bilinear_x4(masks[n]))[y, x] > threshold
+ * for the (Hc, Wc) crop; masks (N, h, w) f32 logits at 1/4 resolution, out (N, Hc, Wc) one byte per pixel (torch.bool layout). */
+int hipie_upsample_threshold(const float* masks, void* out_u8, int N, int h, int w, int stride, int Hc, int Wc,
+                             float threshold, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

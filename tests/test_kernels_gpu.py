@@ -489,3 +489,22 @@ def test_seg_postprocess_fused(ops, cuda, Q, C, h, w, Hc, Wc):
     a = areas.cpu().long()
     assert (a[:, keep] - ref_area[:, keep]).abs().max() <= 2
     assert (a[1] - ref_area[1]).abs().max() <= 2
+
+
+@pytest.mark.parametrize("N,h,w,Hc,Wc", [(7, 24, 20, 90, 77), (3, 16, 16, 64, 64), (0, 8, 8, 32, 32)])
+def test_upsample_threshold(ops, cuda, N, h, w, Hc, Wc):
+    """instance-mask kernel vs F.interpolate(bilinear, x4) -> sigmoid -> > thr -> crop (hipie_img.py:1003-1007)"""
+    import torch.nn.functional as F
+    g = torch.Generator(device="cuda").manual_seed(N + h)
+    m = torch.randn(N, h, w, device=cuda, generator=g) * 3
+    for thr in (0.5, 0.3):
+        out = ops.upsample_threshold(m, thr, Hc, Wc)
+        assert out.dtype == torch.bool and tuple(out.shape) == (N, Hc, Wc)
+        if N == 0:
+            continue
+        up = F.interpolate(m[:, None], size=(4 * h, 4 * w), mode="bilinear", align_corners=False)[:, 0, :Hc, :Wc]
+        ref = up.sigmoid() > thr
+        # pixels whose logit is within rounding of the threshold may flip; everything else must agree
+        margin = (up.double().sigmoid() - thr).abs() > 1e-6
+        assert torch.equal(out[margin], ref[margin])
+        assert (out != ref).float().mean() < 1e-4
