@@ -161,6 +161,77 @@ def test_fused_postprocess_matches_op_chain(setup):
         assert (rf["panoptic_seg"][0] == rc["panoptic_seg"][0]).float().mean() > 0.9995
 
 
+def _run_pair(cuda, inputs, ids, am, seed=0):
+    from hipie_oracle import hparams, synth
+    from hipie_oracle.model import HipieOracle
+    from hipie_b200 import ops
+    from hipie_b200.modeling.hipie_img import HIPIE_IMG
+    torch.manual_seed(seed)
+    hp = hparams.get("vit_tiny")
+    oracle = HipieOracle(hp).eval()
+    synth.perturb_(oracle, seed=seed + 1)
+    with torch.no_grad():
+        res_o, out_o = oracle(inputs, ids, am)
+    ops.set_precision(3)
+    model = HIPIE_IMG(hp=hp, state_dict=oracle.state_dict(), device="cuda:0")
+    for x, i, a in zip(inputs, ids, am):
+        x["input_ids"], x["attention_mask"] = i, a
+    forced = {"topk_fg": out_o["aux"]["topk"].to(cuda), "topk_md": out_o["md"]["topk"].to(cuda)}
+    res_g, out_g = model(inputs, forced=forced, return_raw=True)
+    return res_o, out_o, res_g, out_g
+
+
+def test_grounding_task_parity(cuda):
+    """task == "grounding" (SURVEY §8 config #4 semantics): class logit from the PRE-fusion pooled sentence feature,
+    positive_map {1: [0]}, top-1 instance, no semantic / panoptic branch."""
+    from hipie_oracle import hparams, synth
+    hp = hparams.get("vit_tiny")
+    inputs, ids, am = synth.make_batch(2, 256, 256, 1, hp["max_query_len"], task="grounding", seed=4)
+    res_o, out_o, res_g, out_g = _run_pair(cuda, inputs, ids, am, seed=2)
+    assert _err(out_g["pred_logits"], out_o["pred_logits"]) < 2e-3
+    assert _err(out_g["pred_boxes"], out_o["pred_boxes"]) < 1e-4
+    ref = out_o["pred_masks"]
+    assert _err(out_g["pred_masks"], ref) < 1e-3 * max(1.0, ref.abs().max().item())
+    for ro, rg in zip(res_o, res_g):
+        io, ig = ro["instances_post"], rg["instances"]
+        assert len(ig) == 1 and torch.equal(io["pred_classes"], ig.pred_classes.cpu())
+        assert (io["scores"] - ig.scores.cpu()).abs().max() < 1e-4
+        assert (io["pred_boxes"] - ig.pred_boxes.tensor.cpu()).abs().max() < 1e-2
+        assert (io["pred_masks"] == ig.pred_masks.cpu()).float().mean() > 0.9995
+        assert rg["sem_seg"] is None and rg["panoptic_seg"][0] is None
+
+
+def test_ragged_batch_padding_and_output_resize(cuda):
+    """two images of different sizes (zero padding to the batch max rounded to 32, real padding masks, valid ratios < 1)
+    and requested output sizes different from the input sizes (box rescale, nearest mask resize, second bilinear resize of
+    the semantic / panoptic masks: the un-fused post-processing path)."""
+    from hipie_oracle import hparams, synth
+    hp = hparams.get("vit_tiny")
+    _, ids, am = synth.make_batch(2, 256, 256, 5, hp["max_query_len"], seed=6)
+    ii, aa, pos_map, is_thing = synth.make_text(5, hp["max_query_len"], 6)
+    g = torch.Generator().manual_seed(9)
+    sizes = [(224, 256), (256, 192)]
+    outs = [(300, 343), (256, 192)]
+    inputs = [dict(image=torch.rand(3, h, w, generator=g) * 255.0, height=oh, width=ow, task="detection", is_thing=is_thing,
+                   positive_map_label_to_token=pos_map) for (h, w), (oh, ow) in zip(sizes, outs)]
+    res_o, out_o, res_g, out_g = _run_pair(cuda, inputs, ids, am, seed=5)
+    assert _err(out_g["pred_logits"], out_o["pred_logits"]) < 2e-3
+    assert _err(out_g["pred_boxes"], out_o["pred_boxes"]) < 1e-4
+    ref = out_o["pred_masks_maskdino"]
+    assert _err(out_g["pred_masks_maskdino"], ref) < 1e-3 * max(1.0, ref.abs().max().item())
+    for ro, rg, (oh, ow) in zip(res_o, res_g, outs):
+        io, ig = ro["instances_post"], rg["instances"]
+        assert tuple(ig.pred_masks.shape[-2:]) == (oh, ow)
+        assert torch.equal(io["pred_classes"], ig.pred_classes.cpu())
+        assert (io["pred_boxes"] - ig.pred_boxes.tensor.cpu()).abs().max() < 2e-2
+        assert (io["pred_masks"] == ig.pred_masks.cpu()).float().mean() > 0.9995
+        so, sg = ro["sem_seg"], rg["sem_seg"].cpu()
+        assert tuple(sg.shape[-2:]) == (oh, ow)
+        assert (so.argmax(0) == sg.argmax(0)).float().mean() > 0.9995
+        assert (so - sg).abs().max() < 1e-3 * max(1.0, so.abs().max().item())
+        assert (ro["panoptic_seg"][0] == rg["panoptic_seg"][0].cpu()).float().mean() > 0.9995
+
+
 def test_wide_image_uses_tcgen05_attention(cuda):
     """128 x 1024 input -> 8 x 64 token grid: the global blocks take the tcgen05 flash-attention path (kw == 64, T % 128 == 0,
     V emitted transposed by the GEMM); rel-pos tables are interpolated 127 -> 15 along the height axis."""
