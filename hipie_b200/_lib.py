@@ -74,6 +74,7 @@ SYMBOLS = {
                                      c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hipie_condinst_masks": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "hipie_seg_postprocess": (c_int, [c_void_p] * 7 + [c_int] * 8 + [c_void_p]),
+    "hipie_sine_embed": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hipie_upsample_threshold": (c_int, [c_void_p] * 2 + [c_int] * 6 + [c_float, c_void_p]),
 }
 

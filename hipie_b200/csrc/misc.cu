@@ -323,6 +323,31 @@ row_softmax_smem_kernel(const float* __restrict__ x, const float* __restrict__ c
     }
 }
 
+// ---- sine embedding of box reference points (deformable_transformer_dino.py:636-670, maskdino/utils/utils.py:74-100) ----
+// pos (rows, 4) = (x, y, w, h) with row stride `ld`;  out (rows, 512) = [emb(y) | emb(x) | emb(w) | emb(h)],
+// emb(v)[2k] = sin(v*2pi / 10000^(2k/128)), emb(v)[2k+1] = cos(same).  One thread per (row, k, component) pair of outputs.
+__global__ void __launch_bounds__(256)
+sine_embed_kernel(const float* __restrict__ pos, int64_t ld, int64_t rows, float* __restrict__ out,
+                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // over rows * 256 output pairs
+    if (i >= rows * 256) return;
+    const int64_t r = i >> 8;
+    const int pair = (int)(i & 255), g = pair >> 6, k = pair & 63;
+    const int comp = g == 0 ? 1 : (g == 1 ? 0 : g);                         // [y, x, w, h]
+    const float v = pos[r * ld + comp] * 6.283185307179586f;
+    const float dim_t = powf(10000.f, (float)(2 * k) / 128.f);
+    const float a = v / dim_t;
+    const float s_ = sinf(a), c_ = cosf(a);
+    const int64_t o = r * 512 + g * 128 + 2 * k;
+    if (out) *reinterpret_cast<float2*>(out + o) = make_float2(s_, c_);
+    if (hi) {
+        uint32_t h, l;
+        split2(s_, c_, h, l);
+        *reinterpret_cast<uint32_t*>(hi + o) = h;
+        if (lo) *reinterpret_cast<uint32_t*>(lo + o) = l;
+    }
+}
+
 // ---- CondInst dynamic mask head, fused (ddetrs_dn.py:1390-1502, 1806-1870) --------------------
 // feats (B, Hf*Wf, 8) NHWC fp32; params (B, Q, 169) = [w0 (8x10) | w1 (8x8) | w2 (1x8) | b0 8 | b1 8 | b2 1];
 // ref_px (B, Q, 2) reference point in pixels.  Per (b, q): 3-layer 1x1 MLP over
@@ -519,6 +544,16 @@ extern "C" int hipie_condinst_masks(const float* feats, const float* params, con
         smem_set = smem;
     }
     condinst_kernel<<<dim3(Q, B), 256, smem, (cudaStream_t)stream>>>(feats, params, ref_px, out, B, Q, Hf, Wf, stride);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+extern "C" int hipie_sine_embed(const float* pos, int64_t ld, int64_t rows, float* out, void* hi, void* lo, void* stream) {
+    if (rows == 0) return HIPIE_OK;
+    HIPIE_CHECK_ARG(pos && (out || hi) && rows > 0 && ld >= 4, "hipie_sine_embed: bad arguments");
+    const int64_t total = rows * 256;
+    sine_embed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos, ld, rows, out, (__nv_bfloat16*)hi,
+                                                                                        (__nv_bfloat16*)lo);
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
 }

@@ -629,8 +629,7 @@ class Engine:
         hs, refs = [], []
         for lid in range(nd):
             ref_in = (ref[:, :, None] * vr2[:, None]).contiguous()              # (B, Q, L, 4)
-            sine = _sine_embed_points(ref_in[:, :, 0, :]).view(B * Q, 512).contiguous()
-            _, sine_s = ops.add_split(sine)
+            _, sine_s = ops.sine_embed(ref_in[:, :, 0, :])                      # (B*Q, 512) planes, one kernel
             qpos = self.mlp(sine_s, t + ".decoder.ref_point_head", 2).view(B, Q, 256)
             tgt, tgt_s = self.decoder_layer(f"{t}.decoder.layers.{lid}", tgt, tgt_s, qpos, ref_in, memory_s, mask_flat, shapes_t, lsi_t, B, Q, S)
             tmp = self.mlp(tgt_s.view(B * Q, 256), f"detr.detr.bbox_embed.{lid}", 3).view(B, Q, 4)
@@ -772,8 +771,7 @@ class Engine:
         nl = hp.get("md_dec_layers", 9)
         for lid in range(nl):
             ref_in = (ref[:, :, None] * vr2[:, None]).contiguous()
-            sine = _sine_embed_points(ref_in[:, :, 0, :]).view(B * nq, 512).contiguous()
-            _, sine_s = ops.add_split(sine)
+            _, sine_s = ops.sine_embed(ref_in[:, :, 0, :])                      # (B*Q, 512) planes, one kernel
             qpos = self.mlp(sine_s, pr + ".decoder.ref_point_head", 2).view(B, nq, 256)
             tgt, tgt_s = self.decoder_layer(f"{pr}.decoder.layers.{lid}", tgt, tgt_s, qpos, ref_in, mem_s, None, dshapes_t, dlsi_t, B, nq, S)
             tmp = self.mlp(tgt_s.view(B * nq, 256), pr + "._bbox_embed", 3).view(B, nq, 4)

@@ -459,3 +459,17 @@ def upsample_threshold(masks_low, threshold, Hc, Wc, stride=4):
         _lib.check(_lib.load().hipie_upsample_threshold(_p(masks_low.contiguous()), _p(out), N, h, w, stride, Hc, Wc, float(threshold),
                                                         _stream()), "upsample_threshold")
     return out
+
+
+def sine_embed(pos, want_f32=False, want_split=True):
+    """pos (..., 4) f32 (last dim contiguous, uniform row stride) -> (rows, 512) sine embedding in [y, x, w, h] order."""
+    assert pos.shape[-1] == 4 and pos.stride(-1) == 1
+    rows = pos.numel() // 4
+    ld = pos.stride(-2) if pos.dim() > 1 else 4
+    if pos.dim() > 2:
+        assert pos.stride(-3) == ld * pos.shape[-2], "sine_embed: rows must be uniformly strided"
+    out = torch.empty((rows, 512), dtype=torch.float32, device=pos.device) if want_f32 else None
+    s = _empty_bf2((rows, 512), pos.device) if want_split else None
+    _lib.check(_lib.load().hipie_sine_embed(_p(pos), ld, rows, _p(out), _p(s.hi) if s else None,
+                                            _p(s.lo) if (s and s.lo is not None) else None, _stream()), "sine_embed")
+    return out, s

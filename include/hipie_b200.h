@@ -232,6 +232,11 @@ int hipie_seg_postprocess(const float* masks, const void* pt_hi, const void* pt_
 int hipie_upsample_threshold(const float* masks, void* out_u8, int N, int h, int w, int stride, int Hc, int Wc,
                              float threshold, void* stream);
 
+/* Sine embedding of box reference points (deformable_transformer_dino.py:636-670 get_sine_pos_embed; maskdino/utils/utils.py:74-100):
+ * pos (rows, 4) = (x, y, w, h) f32 with row stride ld -> (rows, 512) = [emb(y) | emb(x) | emb(w) | emb(h)], 128 features each,
+ * temperature 1e4, scale 2*pi.  out f32 and/or bf16 hi/lo planes (operand of the ref_point_head MLP). */
+int hipie_sine_embed(const float* pos, int64_t ld, int64_t rows, float* out, void* hi, void* lo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -508,3 +508,20 @@ def test_upsample_threshold(ops, cuda, N, h, w, Hc, Wc):
         margin = (up.double().sigmoid() - thr).abs() > 1e-6
         assert torch.equal(out[margin], ref[margin])
         assert (out != ref).float().mean() < 1e-4
+
+
+def test_sine_embed(ops, cuda):
+    """fused reference-point sine embedding vs the reference op chain (deformable_transformer_dino.py:636-670)"""
+    import math
+    g = torch.Generator(device="cuda").manual_seed(5)
+    pos_full = torch.rand(2, 37, 4, 4, device=cuda, generator=g)
+    pos = pos_full[:, :, 0, :]                                   # strided rows, like ref_in[:, :, 0, :]
+    out, s = ops.sine_embed(pos, want_f32=True, want_split=True)
+    dim_t = torch.arange(128, dtype=torch.float32, device=cuda)
+    dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / 128)
+    def emb(v):
+        p = (v * (2 * math.pi))[..., None] / dim_t
+        return torch.stack((p[..., 0::2].sin(), p[..., 1::2].cos()), dim=-1).flatten(-2)
+    ref = torch.cat([emb(pos[..., 1]), emb(pos[..., 0]), emb(pos[..., 2]), emb(pos[..., 3])], dim=-1).view(-1, 512)
+    assert (out - ref).abs().max() < 2e-6
+    assert ((s.hi.float() + s.lo.float()) - ref).abs().max() < 1e-4
