@@ -26,6 +26,7 @@ class GemmArgs(ctypes.Structure):
         ("c_bits", c_void_p), ("bits_threshold", c_float),
         ("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int),
         ("act", c_int), ("prec", c_int), ("alpha", c_float), ("transposed", c_int), ("c_row_map", c_void_p),
+        ("t_row_group", c_int), ("t_row_pad", c_int),
     ]
 
 

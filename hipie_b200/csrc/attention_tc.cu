@@ -73,7 +73,10 @@ struct FaSmem {
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
-template <int PREC>
+constexpr int FA_WIN = 14, FA_WIN_T = FA_WIN * FA_WIN;     // window mode: 14 x 14 tokens, keys padded to 4 x 64
+constexpr int FA_WIN_TP = 200;   // window mode: column pitch of one window in V^T (TMA box starts must be 16-byte aligned)
+
+template <int PREC, bool WIN>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     using SM = FaSmem<PREC>;
@@ -95,7 +98,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (FA_QT * FA_BM), h = blockIdx.y, b = blockIdx.z;
-    const int ntiles = p.T / FA_BN;
+    const int ntiles = WIN ? (FA_WIN_T + FA_BN - 1) / FA_BN : p.T / FA_BN;     // window mode: 196 keys in 4 tiles, tail masked
     const bool trace_cta = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
     if (warp == 0 && lane == 0) {
@@ -151,7 +154,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 mbar_arrive_expect_tx(&v_full[s], SM::V_STAGE);
                 uint8_t* vb = smem + SM::OFF_V + s * SM::V_STAGE;
                 for (int pl = 0; pl < NPL; ++pl)
-                    tma_load_3d(vb + pl * SM::VT, &maps.vt[pl], &v_full[s], b * p.T + j * FA_BN, h * FA_HD, 0);
+                    tma_load_3d(vb + pl * SM::VT, &maps.vt[pl], &v_full[s], b * (WIN ? FA_WIN_TP : p.T) + j * FA_BN, h * FA_HD, 0);
                 if (++s == FA_STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -242,17 +245,20 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         constexpr float LOG2E = 1.4426950408889634f;
         // ---- park this row of Q hi in TMEM (packed bf16 pairs = the TS-mode A operand layout) ----
         {
-            const int64_t qoff = (int64_t)b * p.q_bs + (int64_t)qrow * p.q_ts + p.q_col0 + h * FA_HD;
+            const bool qok = !WIN || qrow < p.T;                      // window mode: rows 196..255 of the tile pair are padding
+            const int64_t qoff = (int64_t)b * p.q_bs + (int64_t)(qok ? qrow : 0) * p.q_ts + p.q_col0 + h * FA_HD;
             const uint4* src = reinterpret_cast<const uint4*>(p.q_hi + qoff);
+            const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t w[16];
-                const uint4 a0 = src[4 * c], a1 = src[4 * c + 1], a2 = src[4 * c + 2], a3 = src[4 * c + 3];
+                const uint4 a0 = qok ? src[4 * c] : zero4, a1 = qok ? src[4 * c + 1] : zero4, a2 = qok ? src[4 * c + 2] : zero4,
+                            a3 = qok ? src[4 * c + 3] : zero4;
                 w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
                 w[8] = a2.x; w[9] = a2.y; w[10] = a2.z; w[11] = a2.w; w[12] = a3.x; w[13] = a3.y; w[14] = a3.z; w[15] = a3.w;
                 tmem_st_32x32b_x16(tm + TM_Q + 16 * c, w);
             }
-            const uint4 a8 = src[8], a9 = src[9];
+            const uint4 a8 = qok ? src[8] : zero4, a9 = qok ? src[9] : zero4;
             tmem_st_32x32b_x4(tm + TM_Q + 32, a8.x, a8.y, a8.z, a8.w);
             tmem_st_32x32b_x4(tm + TM_Q + 36, a9.x, a9.y, a9.z, a9.w);
             tmem_st_wait();
@@ -260,9 +266,18 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&q_ready[t]);
         }
-        float rw[FA_BN];
+        float rw[WIN ? FA_WIN : FA_BN];       // rel_w row of this query (window mode: 14 entries, global: 64), log2 domain
+        float rhw[WIN ? FA_WIN : 1];          // window mode: the rel_h row as well (global mode streams one rel_h scalar per tile)
         const float* relh_row = nullptr;
-        if (has_rel) {
+        if (WIN) {
+            const bool qok = qrow < p.T;
+            const int64_t rowi = ((int64_t)b * p.H + h) * p.T + (qok ? qrow : 0);
+#pragma unroll
+            for (int i = 0; i < FA_WIN; ++i) {
+                rw[i] = has_rel ? __ldg(p.rel_w + rowi * FA_WIN + i) * LOG2E : 0.f;
+                rhw[i] = has_rel ? __ldg(p.rel_h + rowi * FA_WIN + i) * LOG2E : 0.f;
+            }
+        } else if (has_rel) {
             const int64_t rowi = ((int64_t)b * p.H + h) * p.T + qrow;
             const float* rwp = p.rel_w + rowi * FA_BN;
 #pragma unroll
@@ -273,11 +288,22 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             relh_row = p.rel_h + rowi * p.kh;
         }
         float m = -INFINITY, l = 0.f;          // m: running reference max (log2 domain, incl. rel-pos terms)
-        float rh_next = has_rel ? __ldg(relh_row) * LOG2E : 0.f;
-        for (int j = 0; j < ntiles; ++j) {
+        float rh_next = (!WIN && has_rel) ? __ldg(relh_row) * LOG2E : 0.f;
+        // log2-domain score of key column i of tile j: global mode adds the hoisted rel_w entry (rel_h is per tile); window mode
+        // decomposes the key index into the 14 x 14 grid (indices fold to constants once the 4-tile loop is unrolled) and masks
+        // the 60 padding keys of the last tile
+        auto score = [&](uint32_t sbits, const int j, const int i) -> float {
+            if (WIN) {
+                const int k = j * FA_BN + i;
+                if (k >= FA_WIN_T) return -INFINITY;
+                return fmaf(__uint_as_float(sbits), p.scale_log2e, rhw[k / FA_WIN]) + rw[k % FA_WIN];
+            }
+            return fmaf(__uint_as_float(sbits), p.scale_log2e, has_rel ? rw[i] : 0.f);
+        };
+        auto tile_body = [&](const int j) {
             const bool tr = trace_cta && lane == 0 && (warp == 2 || warp == 6) && j < 32;
             const float rh = rh_next;
-            if (has_rel && j + 1 < ntiles) rh_next = __ldg(relh_row + j + 1) * LOG2E;   // prefetch for the next tile
+            if (!WIN && has_rel && j + 1 < ntiles) rh_next = __ldg(relh_row + j + 1) * LOG2E;   // prefetch for the next tile
             if (tr) p.trace[(j * 2 + t) * 8 + 0] = clock64();
             mbar_wait_spin(&s_full[t], j & 1);
             tc_fence_after();
@@ -288,14 +314,14 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 tmem_ld_32x32b_x32(tm + TM_S, sv);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) tv[i] = fmaf(__uint_as_float(sv[i]), p.scale_log2e, has_rel ? rw[i] : 0.f);
+                for (int i = 0; i < 32; ++i) tv[i] = score(sv[i], j, i);
                 tmem_ld_32x32b_x32(tm + TM_S + 32, sv);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_empty[t]);      // scores are in registers: QK_t(j+1) may overwrite S_t
 #pragma unroll
-                for (int i = 0; i < 32; ++i) tv[32 + i] = fmaf(__uint_as_float(sv[i]), p.scale_log2e, has_rel ? rw[32 + i] : 0.f);
+                for (int i = 0; i < 32; ++i) tv[32 + i] = score(sv[i], j, 32 + i);
             }
             // t_i = s_i*scale*log2e + rel_w_i ; rel_h is uniform over the tile -> folded into the max / exponent offset
             float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -353,12 +379,19 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
             if (tr) p.trace[(j * 2 + t) * 8 + 3] = clock64();
+        };
+        if (WIN) {
+#pragma unroll
+            for (int j = 0; j < (FA_WIN_T + FA_BN - 1) / FA_BN; ++j) tile_body(j);
+        } else {
+            for (int j = 0; j < ntiles; ++j) tile_body(j);
         }
         // ---- epilogue: O / l ----
         mbar_wait(&pv_done[t], (ntiles - 1) & 1);
         tc_fence_after();
         const float inv = 1.f / l;
         const int64_t obase = (int64_t)b * p.o_bs + (int64_t)qrow * p.o_ts + (int64_t)h * FA_HD;
+        const bool row_ok = !WIN || qrow < p.T;
         for (int c = 0; c < FA_HD; c += 16) {
             uint32_t o[16];
             tmem_ld_32x32b_x16(tm + TM_O + c, o);
@@ -366,12 +399,12 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(o[i]) * inv;
-            if (p.out_f32) {
+            if (row_ok && p.out_f32) {
 #pragma unroll
                 for (int i = 0; i < 16; i += 4)
                     *reinterpret_cast<float4*>(p.out_f32 + obase + c + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
             }
-            if (p.out_hi) {
+            if (row_ok && p.out_hi) {
                 uint4 h0, h1, l0, l1;
                 split2(f[0], f[1], h0.x, l0.x); split2(f[2], f[3], h0.y, l0.y);
                 split2(f[4], f[5], h0.z, l0.z); split2(f[6], f[7], h0.w, l0.w);
@@ -384,6 +417,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                     *reinterpret_cast<uint4*>(p.out_lo + obase + c + 8) = l1;
                 }
             }
+            __syncwarp();          // window mode: padding rows skip the stores; reconverge before the next warp-collective tcgen05.ld
         }
         tc_fence_before();
     }
@@ -394,16 +428,16 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     }
 }
 
-template <int PREC>
+template <int PREC, bool WIN>
 static int launch_fa(const FaMaps& maps, const FaParams& p, cudaStream_t st) {
     using SM = FaSmem<PREC>;
     static bool attr = false;
     if (!attr) {
-        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<PREC, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
         attr = true;
     }
-    dim3 grid(p.T / (FA_QT * FA_BM), p.H, p.B);
-    attn_tc_kernel<PREC><<<grid, FA_THREADS, SM::TOTAL, st>>>(maps, p);
+    dim3 grid(WIN ? 1 : p.T / (FA_QT * FA_BM), p.H, p.B);
+    attn_tc_kernel<PREC, WIN><<<grid, FA_THREADS, SM::TOTAL, st>>>(maps, p);
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
 }
@@ -420,9 +454,11 @@ extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int
     HIPIE_CHECK_ARG(q_hi && k_hi && vt_hi, "hipie_attention_tc: q/k/vt hi planes required");
     HIPIE_CHECK_ARG(prec == 1 || (prec == 3 && q_lo && k_lo && vt_lo), "hipie_attention_tc: prec/lo planes mismatch");
     HIPIE_CHECK_ARG(hd == FA_HD, "hipie_attention_tc: head dim must be 80 (got %d)", hd);
-    HIPIE_CHECK_ARG(T > 0 && T % (FA_QT * FA_BM) == 0, "hipie_attention_tc: T (%d) must be a multiple of 256", T);
+    const bool win = T == FA_WIN_T && kh == FA_WIN && kw == FA_WIN;      // 14 x 14 windows: one CTA per (window, head)
+    HIPIE_CHECK_ARG(win || (T > 0 && T % (FA_QT * FA_BM) == 0),
+                    "hipie_attention_tc: T (%d) must be a multiple of 256 (or 196 with a 14x14 rel-pos grid: window mode)", T);
     HIPIE_CHECK_ARG((rel_h == nullptr) == (rel_w == nullptr), "hipie_attention_tc: rel_h and rel_w go together");
-    HIPIE_CHECK_ARG(!rel_h || (kw == FA_BN && kh * kw == T), "hipie_attention_tc: rel-pos needs kw == 64 and kh*kw == T");
+    HIPIE_CHECK_ARG(win || !rel_h || (kw == FA_BN && kh * kw == T), "hipie_attention_tc: rel-pos needs kw == 64 and kh*kw == T");
     HIPIE_CHECK_ARG(out_f32 || out_hi, "hipie_attention_tc: no output requested");
     HIPIE_CHECK_ARG(q_ts % 8 == 0 && q_bs % 8 == 0 && q_col0 % 8 == 0 && (reinterpret_cast<uintptr_t>(q_hi) & 15) == 0,
                     "hipie_attention_tc: q rows must be 16-byte aligned");
@@ -433,7 +469,7 @@ extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int
     for (int pl = 0; pl < (prec == 3 ? 2 : 1); ++pl) {
         if ((rc = make_tmap_bf16(&maps.k64[pl], kp[pl], T, k_width, k_ts, B, k_bs, FA_BN, 64))) return rc;
         if ((rc = make_tmap_bf16(&maps.k16[pl], kp[pl], T, k_width, k_ts, B, k_bs, FA_BN, 16))) return rc;
-        if ((rc = make_tmap_bf16(&maps.vt[pl], vp[pl], (int64_t)H * FA_HD, (int64_t)B * T, vt_ld, 1, 0, FA_HD, 64))) return rc;
+        if ((rc = make_tmap_bf16(&maps.vt[pl], vp[pl], (int64_t)H * FA_HD, (int64_t)B * (win ? FA_WIN_TP : T), vt_ld, 1, 0, FA_HD, 64))) return rc;
     }
     if (prec == 1) { maps.k64[1] = maps.k64[0]; maps.k16[1] = maps.k16[0]; maps.vt[1] = maps.vt[0]; }
     const void* qsrc = prec == 3 ? q_lo : q_hi;     // prec 1 never loads it; keep the maps valid
@@ -447,9 +483,11 @@ extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int
     p.scale_log2e = scale * 1.4426950408889634f;
     p.trace = trace;
     cudaStream_t st = (cudaStream_t)stream;
-    return prec == 3 ? launch_fa<3>(maps, p, st) : launch_fa<1>(maps, p, st);
+    if (win) return prec == 3 ? launch_fa<3, true>(maps, p, st) : launch_fa<1, true>(maps, p, st);
+    return prec == 3 ? launch_fa<3, false>(maps, p, st) : launch_fa<1, false>(maps, p, st);
 }
 
+// Window mode (T == 196, kh == kw == 14): vt holds every window at a 200-column pitch, (H*80, B*200), pad columns zero.
 // q / k: bf16 planes viewed as (B, T, row_width) with token stride q_ts / k_ts and batch stride q_bs / k_bs (elements);
 // head h occupies columns [q_col0 + 80 h, +80).  vt: V transposed, (H*80 rows, B*T columns) planes with row stride vt_ld.
 extern "C" int hipie_attention_tc(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,

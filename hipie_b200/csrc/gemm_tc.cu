@@ -52,6 +52,7 @@ struct GemmParams {
     int transposed;  // 1: C stored as [N, ldc] (column-major output), lanes = rows
     int tiles_m, tiles_n;
     const int* row_map;
+    int t_row_group, t_row_pad;   // transposed epilogue: row r -> r + (r / group) * pad (0 = off)
 };
 
 template <int PREC, int BN>
@@ -253,8 +254,8 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, uint32_
     float* cf_b = p.c_f32 ? p.c_f32 + (int64_t)b * p.c_bstride : nullptr;
     __nv_bfloat16* chi_b = p.c_hi ? p.c_hi + (int64_t)b * p.c_bstride : nullptr;
     __nv_bfloat16* clo_b = p.c_lo ? p.c_lo + (int64_t)b * p.c_bstride : nullptr;
-    const int row = m0 + lane;
-    const bool rok = row < p.M;
+    const bool rok = m0 + lane < p.M;
+    const int row = p.t_row_group > 0 ? (m0 + lane) + ((m0 + lane) / p.t_row_group) * p.t_row_pad : m0 + lane;
 #pragma unroll 1
     for (int cb = col_begin; cb < col_end; cb += 32) {
         const int nbase = n0 + cb;
@@ -563,6 +564,8 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     p.act = a->act; p.alpha = a->alpha;
     p.transposed = a->transposed;
     p.row_map = a->c_row_map;
+    p.t_row_group = a->transposed ? a->t_row_group : 0;
+    p.t_row_pad = a->transposed ? a->t_row_pad : 0;
     p.tiles_m = (a->M + GEMM_BM - 1) / GEMM_BM;
     p.tiles_n = (a->N + BN - 1) / BN;
     const int64_t total = (int64_t)p.tiles_m * p.tiles_n * a->batch;

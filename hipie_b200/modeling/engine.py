@@ -210,7 +210,7 @@ class Engine:
                 _, xn, _ = ops.layernorm(x, W[blk + ".norm1.weight"], W[blk + ".norm1.bias"], 1e-6)
                 Bq, Tq, qh, qw = B, T, gh, gw
             st = (Tq * 3 * E, 3 * E, hd)
-            use_tc = (not windowed) and self.use_tc_attention and hd == 80 and Tq % 256 == 0 and qw == 64
+            use_tc = self.use_tc_attention and hd == 80 and ((not windowed and Tq % 256 == 0 and qw == 64) or (windowed and ws == 14))
             if use_tc:
                 # q,k as one GEMM (N = 2E); V emitted transposed (E, B*T) so it is the K-major B operand of P.V
                 wqk, bqk, wv, bv = W.cached(("qk_v", blk), lambda: (ops.split_weight(W[blk + ".attn.qkv.weight"][:2 * E]),
@@ -218,7 +218,13 @@ class Engine:
                                                                      ops.split_weight(W[blk + ".attn.qkv.weight"][2 * E:]),
                                                                      W[blk + ".attn.qkv.bias"][2 * E:].contiguous()))
                 _, qk, _ = ops.gemm(xn, wqk, bias=bqk, want_f32=False, want_split=True)              # (B*T, 2E)
-                _, vt, _ = ops.gemm(xn, wv, bias=bv, want_f32=False, want_split=True, transposed=True)  # (E, B*T)
+                if windowed:
+                    # V^T per window at a 200-column pitch (TMA box starts must be 16-byte aligned; 196 is not a multiple of 8);
+                    # the 4 pad columns of every window stay zero in this cached buffer
+                    vt = self._zero_bf2(("vtwin", E, Bq), (E, Bq * 200))
+                    ops.gemm(xn, wv, bias=bv, want_f32=False, transposed=True, ldc=Bq * 200, out_split=vt, t_row_group=Tq, t_row_pad=200 - Tq)
+                else:
+                    _, vt, _ = ops.gemm(xn, wv, bias=bv, want_f32=False, want_split=True, transposed=True)  # (E, B*T)
                 q = BF2(qk.hi[:, 0:E], None if qk.lo is None else qk.lo[:, 0:E])
                 k = BF2(qk.hi[:, E:], None if qk.lo is None else qk.lo[:, E:])
                 st = (Tq * 2 * E, 2 * E, hd)

@@ -144,7 +144,7 @@ def add_split(a, b=None, want_f32=False, want_split=True):
 def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, alpha=1.0, want_f32=True,
          want_split=False, out_f32=None, transposed=False, row_map=None, out_rows=None, bits_threshold=None,
          M=None, N=None, K=None, batch=1, lda=None, ldw=None, a_bstride=0, w_bstride=0, ldc=None, c_bstride=0,
-         ldr=None, r_bstride=0, prec=None):
+         ldr=None, r_bstride=0, prec=None, out_split=None, t_row_group=0, t_row_pad=0):
     """C = act(alpha * A.W^T + bias) * colscale + residual.
 
     A: (.., M, K) planes, W: (N, K) planes.  Default: 2-D row-major operands.  Strided / batched views
@@ -172,8 +172,12 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
         shape = (batch, rows_out, N) if batch > 1 else (rows_out, N)
         ldc_ = N if ldc is None else ldc
         cb = rows_out * N if (batch > 1 and c_bstride == 0) else c_bstride
-    c_f32 = out_f32 if out_f32 is not None else (torch.empty(shape, dtype=torch.float32, device=dev) if want_f32 else None)
-    c_split = _empty_bf2(shape, dev) if want_split else None
+    # transposed output with a padded leading dimension (e.g. a TMA consumer needs 16-byte row strides): allocate (N, ldc)
+    # and hand back the logical (N, rows_out) view
+    padded = transposed and batch == 1 and ldc is not None and ldc > rows_out
+    ashape = (N, ldc) if padded else shape
+    c_f32 = out_f32 if out_f32 is not None else (torch.empty(ashape, dtype=torch.float32, device=dev) if want_f32 else None)
+    c_split = out_split if out_split is not None else (_empty_bf2(ashape, dev) if want_split else None)
     c_bits = None
     if bits_threshold is not None:
         assert transposed
@@ -194,12 +198,17 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
         c_bits=c_bits.data_ptr() if c_bits is not None else None,
         bits_threshold=float(bits_threshold) if bits_threshold is not None else 0.0,
         M=M, N=N, K=K, batch=batch, act=act, prec=prec, alpha=float(alpha), transposed=1 if transposed else 0,
-        c_row_map=row_map.data_ptr() if row_map is not None else None)
+        c_row_map=row_map.data_ptr() if row_map is not None else None, t_row_group=t_row_group, t_row_pad=t_row_pad)
     tag = f"gemm_tc[p{prec}]" + (":mask_embed" if c_bits is not None else "")
     if profiler.enabled and profiler.shapes:
         tag += f" {M}x{N}x{K}" + (f"x{batch}" if batch > 1 else "") + ("T" if transposed else "")
     with _timed(tag, 2.0 * M * N * K * batch):
         _lib.check(lib.hipie_gemm(ctypes.byref(args), _stream()), "gemm")
+    if padded:
+        if c_f32 is not None and out_f32 is None:
+            c_f32 = c_f32[:, :rows_out]
+        if c_split is not None and out_split is None:
+            c_split = BF2(c_split.hi[:, :rows_out], None if c_split.lo is None else c_split.lo[:, :rows_out])
     return c_f32, c_split, c_bits
 
 

@@ -113,6 +113,8 @@ typedef struct hipie_gemm_args {
                                  which is then packed along M: bits[b][col][row/32] */
     const int32_t* c_row_map; /* optional (non-transposed only): GEMM row r is stored to / takes its residual
                                  from row c_row_map[r]; negative entries are skipped (window un-partition) */
+    int t_row_group;          /* transposed only, 0 = off: GEMM row r is stored at position r + (r / t_row_group) * t_row_pad of */
+    int t_row_pad;            /* each output column (groups of rows padded apart, e.g. 196-token windows at a 200 pitch)     */
 } hipie_gemm_args;
 
 int hipie_gemm(const hipie_gemm_args* args, void* stream);

@@ -436,6 +436,35 @@ def test_relpos_tc_global_grid(ops, cuda):
     assert (tw.double() - ref_w).abs().max() < 2e-4
 
 
+@pytest.mark.parametrize("prec", [3, 1])
+def test_attention_tcgen05_window_mode(ops, cuda, prec):
+    """14x14-window mode of the tcgen05 attention kernel: 196 tokens per (window, head), keys padded to 4x64 and masked,
+    decomposed rel-pos bias rel_h[q, k // 14] + rel_w[q, k % 14]; vs fp64 softmax attention."""
+    g = torch.Generator(device="cuda").manual_seed(31 + prec)
+    B, H, hd, gh, gw = 5, 3, 80, 14, 14          # 5 windows
+    T, E = gh * gw, H * hd
+    qk = torch.randn(B * T, 2 * E, device=cuda, generator=g)
+    v = torch.randn(B * T, E, device=cuda, generator=g)
+    S = ops.split(qk)
+    vpad = torch.zeros(E, B, 200, device=cuda)                    # vt: every window at a 200-column pitch, pad columns zero
+    vpad[:, :, :T] = v.t().reshape(E, B, T)
+    Vs = ops.split(vpad.view(E, B * 200))
+    q = ops.BF2(S.hi[:, :E], S.lo[:, :E])
+    k = ops.BF2(S.hi[:, E:], S.lo[:, E:])
+    rel_h = torch.randn(B, H, T, gh, device=cuda, generator=g)
+    rel_w = torch.randn(B, H, T, gw, device=cuda, generator=g)
+    o, _ = ops.attention_tc(q, k, Vs, B, H, T, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, rel_h=rel_h, rel_w=rel_w,
+                            kh=gh, kw=gw, want_f32=True, want_split=False, prec=prec)
+    if prec == 3:
+        qq, kk, vv = qk[:, :E], qk[:, E:], v
+    else:
+        qq, kk, vv = S.hi[:, :E].float(), S.hi[:, E:].float(), Vs.hi.float().view(E, B, 200)[:, :, :T].reshape(E, B * T).t()
+    sh = lambda x: x.reshape(B, T, H, hd).permute(0, 2, 1, 3).double()
+    ref = _attn_ref(sh(qq), sh(kk), sh(vv), hd ** -0.5, rel_h, rel_w, gh, gw).permute(0, 2, 1, 3).reshape(B, T, E)
+    err = (o.double() - ref).abs().max().item()
+    assert err < (3e-5 if prec == 3 else 3e-2), err
+
+
 # ------------------------------------------------------------------------------------------ CondInst
 def test_condinst_fused(ops, cuda):
     from hipie_oracle.condinst import dynamic_mask_with_coords
