@@ -373,34 +373,68 @@ condinst_kernel(const float* __restrict__ feats, const float* __restrict__ param
     const float b2 = prm[168];
     const int HW = Hf * Wf;
     const float* fb = feats + (int64_t)b * HW * 8;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-        const int y = i / Wf, x = i - y * Wf;
-        float in[10];
-        in[0] = ref[0] - (float)(x * stride + stride / 2);
-        in[1] = ref[1] - (float)(y * stride + stride / 2);
-        const float4 f0 = *reinterpret_cast<const float4*>(fb + (int64_t)i * 8);
-        const float4 f1 = *reinterpret_cast<const float4*>(fb + (int64_t)i * 8 + 4);
-        in[2] = f0.x; in[3] = f0.y; in[4] = f0.z; in[5] = f0.w;
-        in[6] = f1.x; in[7] = f1.y; in[8] = f1.z; in[9] = f1.w;
-        float h0[8], h1[8];
+    // 4 coarse pixels per thread and iteration: every (broadcast) weight read from shared memory feeds 4 FMAs, otherwise the
+    // 152 LDS per pixel make the MLP shared-memory bound (measured 3.1 ms for 8 x 910 queries; this layout ~3x faster)
+    constexpr int PX = 4;
+    for (int i0 = threadIdx.x; i0 < HW; i0 += blockDim.x * PX) {
+        float in[PX][10];
+        bool ok[PX];
+#pragma unroll
+        for (int u = 0; u < PX; ++u) {
+            const int i = i0 + u * blockDim.x;
+            ok[u] = i < HW;
+            const int ii = ok[u] ? i : 0;
+            const int y = ii / Wf, x = ii - y * Wf;
+            in[u][0] = ref[0] - (float)(x * stride + stride / 2);
+            in[u][1] = ref[1] - (float)(y * stride + stride / 2);
+            const float4 f0 = *reinterpret_cast<const float4*>(fb + (int64_t)ii * 8);
+            const float4 f1 = *reinterpret_cast<const float4*>(fb + (int64_t)ii * 8 + 4);
+            in[u][2] = f0.x; in[u][3] = f0.y; in[u][4] = f0.z; in[u][5] = f0.w;
+            in[u][6] = f1.x; in[u][7] = f1.y; in[u][8] = f1.z; in[u][9] = f1.w;
+        }
+        float h0[PX][8], h1[PX][8];
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
-            float a = b0[o];
+            float a[PX];
+            const float bb = b0[o];
 #pragma unroll
-            for (int k = 0; k < 10; ++k) a += w0[o * 10 + k] * in[k];
-            h0[o] = fmaxf(a, 0.f);
+            for (int u = 0; u < PX; ++u) a[u] = bb;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                const float wv = w0[o * 10 + k];
+#pragma unroll
+                for (int u = 0; u < PX; ++u) a[u] += wv * in[u][k];
+            }
+#pragma unroll
+            for (int u = 0; u < PX; ++u) h0[u][o] = fmaxf(a[u], 0.f);
         }
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
-            float a = b1[o];
+            float a[PX];
+            const float bb = b1[o];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a += w1[o * 8 + k] * h0[k];
-            h1[o] = fmaxf(a, 0.f);
+            for (int u = 0; u < PX; ++u) a[u] = bb;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float wv = w1[o * 8 + k];
+#pragma unroll
+                for (int u = 0; u < PX; ++u) a[u] += wv * h0[u][k];
+            }
+#pragma unroll
+            for (int u = 0; u < PX; ++u) h1[u][o] = fmaxf(a[u], 0.f);
         }
-        float a = b2;
+        float a[PX];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a += w2[k] * h1[k];
-        coarse[i] = a;
+        for (int u = 0; u < PX; ++u) a[u] = b2;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float wv = w2[k];
+#pragma unroll
+            for (int u = 0; u < PX; ++u) a[u] += wv * h1[u][k];
+        }
+#pragma unroll
+        for (int u = 0; u < PX; ++u)
+            if (ok[u]) coarse[i0 + u * blockDim.x] = a[u];
     }
     __syncthreads();
     // aligned_bilinear(factor 2): pad right/bottom by replicate -> (Hf+1, Wf+1); interpolate with
@@ -408,16 +442,27 @@ condinst_kernel(const float* __restrict__ feats, const float* __restrict__ param
     // (replicate) and crop to (2Hf, 2Wf): out[Y, X] = up[max(Y-1,0), max(X-1,0)].
     const int Ho = 2 * Hf, Wo = 2 * Wf;
     float* ob = out + ((int64_t)b * Q + q) * Ho * Wo;
-    for (int i = threadIdx.x; i < Ho * Wo; i += blockDim.x) {
-        const int Y = i / Wo, X = i - Y * Wo;
+    auto at = [&](int yy, int xx) { return coarse[min(yy, Hf - 1) * Wf + min(xx, Wf - 1)]; };
+    auto px = [&](int Y, int X) {
         const int uy = max(Y - 1, 0), ux = max(X - 1, 0);
         const int y0 = uy >> 1, x0 = ux >> 1;
         const float fy = (uy & 1) ? 0.5f : 0.f, fx = (ux & 1) ? 0.5f : 0.f;
-        const int y1 = min(y0 + 1, Hf - 1 + 1), x1 = min(x0 + 1, Wf - 1 + 1);
-        auto at = [&](int yy, int xx) { return coarse[min(yy, Hf - 1) * Wf + min(xx, Wf - 1)]; };
+        const int y1 = y0 + 1, x1 = x0 + 1;
         const float v00 = at(y0, x0), v01 = at(y0, x1), v10 = at(y1, x0), v11 = at(y1, x1);
         const float top = v00 + (v01 - v00) * fx, bot = v10 + (v11 - v10) * fx;
-        ob[i] = top + (bot - top) * fy;
+        return top + (bot - top) * fy;
+    };
+    if ((Wo & 3) == 0) {          // 4 outputs per thread, 16-byte stores (rows are 16-byte aligned: Wo % 4 == 0)
+        const int n4 = Ho * Wo / 4;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            const int Y = (i * 4) / Wo, X = i * 4 - Y * Wo;
+            *reinterpret_cast<float4*>(ob + (int64_t)i * 4) = make_float4(px(Y, X), px(Y, X + 1), px(Y, X + 2), px(Y, X + 3));
+        }
+    } else {
+        for (int i = threadIdx.x; i < Ho * Wo; i += blockDim.x) {
+            const int Y = i / Wo, X = i - Y * Wo;
+            ob[i] = px(Y, X);
+        }
     }
 }
 

@@ -288,15 +288,20 @@ class HIPIE_IMG(nn.Module):
                 segments_info.append({"id": current_segment_id, "isthing": bool(isthing), "category_id": int(pred_class)})
         return panoptic_seg, segments_info
 
-    def fused_sem_pano(self, mask_cls, mask_low, is_thing, image_size):
-        """semantic_inference + panoptic_inference (hipie_img.py:880-1023) from the 1/4-resolution logits in one kernel
-        (ops.seg_postprocess); only the segment-merge loop over the kept queries stays on the host."""
+    def fused_sem_pano_launch(self, mask_cls, mask_low, image_size):
+        """semantic_inference + the tensor part of panoptic_inference (hipie_img.py:880-1023) from the 1/4-resolution logits in
+        one kernel (ops.seg_postprocess).  Returns the device-side handles; the segment merge (a short host loop over the kept
+        queries) is finished by fused_sem_pano_finish once every image of the batch has been queued, so the device never idles
+        on a per-image host round trip."""
         Hc, Wc = int(image_size[0]), int(image_size[1])
         sem, ids, areas, scores, labels = ops.seg_postprocess(mask_low, mask_cls, self.object_mask_threshold, Hc, Wc,
                                                               stride=self.mask_stride)
-        Q = mask_cls.shape[0]
-        host = torch.cat([areas, labels.to(torch.int32).unsqueeze(0), (scores > self.object_mask_threshold).to(torch.int32).unsqueeze(0)]).cpu()
+        host_d = torch.cat([areas, labels.to(torch.int32).unsqueeze(0), (scores > self.object_mask_threshold).to(torch.int32).unsqueeze(0)])
+        return dict(sem=sem, ids=ids, host_d=host_d, Q=mask_cls.shape[0])
+
+    def fused_sem_pano_finish(self, pend, host, is_thing):
         mask_area, original_area, inter_area, classes, keep = host.tolist()
+        Q, ids = pend["Q"], pend["ids"]
         lut = [0] * (2 * Q + 1)           # ids+1 -> segment id (odd entries = argmax winner with sigmoid >= .5)
         segments_info, stuff_memory_list, current_segment_id = [], {}, 0
         for k in range(Q):
@@ -317,7 +322,7 @@ class HIPIE_IMG(nn.Module):
                 segments_info.append({"id": current_segment_id, "isthing": bool(isthing), "category_id": int(pred_class)})
         lut_d = torch.tensor(lut, dtype=torch.int32, device=ids.device)
         panoptic_seg = lut_d[(ids + 1).long()]
-        return sem, (panoptic_seg, segments_info)
+        return pend["sem"], (panoptic_seg, segments_info)
 
     @torch.no_grad()
     def inference(self, out, image_sizes, positive_map, num_classes, task, is_thing, sizes):
@@ -367,8 +372,8 @@ class HIPIE_IMG(nn.Module):
                 logits_all = F.softmax(logits_all.sigmoid() / self.pano_temp, dim=-1)
                 if (self.fused_postprocess and self.mask_stride == 4 and logits_all.shape[1] <= 136 and N <= 8192
                         and tuple(sizes[i]) == tuple(image_size)):
-                    sem, pano = self.fused_sem_pano(logits_all, mask_all[:, 0], is_thing[i], image_size)
-                    results.append(dict(instances=result, panoptic_seg=pano, sem_seg=sem))
+                    pend = self.fused_sem_pano_launch(logits_all, mask_all[:, 0], image_size)
+                    results.append(dict(instances=result, panoptic_seg=None, sem_seg=None, _pending=pend))
                     continue
                 mask_all = F.interpolate(mask_all, size=(H * self.mask_stride, Wd * self.mask_stride), mode="bilinear", align_corners=False)
                 mask_all = mask_all[:, :, :image_size[0], :image_size[1]]
@@ -379,6 +384,16 @@ class HIPIE_IMG(nn.Module):
                 sem = self.semantic_inference(logits_all, mask_up)
                 pano = self.panoptic_inference(logits_all, mask_up, is_thing[i])
             results.append(dict(instances=result, panoptic_seg=pano, sem_seg=sem))
+        pending = [(i, r.pop("_pending")) for i, r in enumerate(results) if "_pending" in r]
+        if pending:
+            # one device->host copy of all images' area counters / labels (pinned, after every kernel has been queued)
+            sizes_q = [p["host_d"].shape[1] for _, p in pending]
+            host_all = torch.cat([p["host_d"] for _, p in pending], dim=1).cpu()
+            off = 0
+            for (i, p), nq in zip(pending, sizes_q):
+                sem, pano = self.fused_sem_pano_finish(p, host_all[:, off:off + nq], is_thing[i])
+                off += nq
+                results[i]["sem_seg"], results[i]["panoptic_seg"] = sem, pano
         return results
 
     @staticmethod
