@@ -301,7 +301,7 @@ def run_product(args):
         entry = {"share_of_timed_kernels": v["ms"] / tot_prof, "launches_per_step": v["launches"] / prof_steps, "avg_ms": per}
         if v["work"] > 0:
             rate = v["work"] / v["launches"] / (per / 1000.0)
-            if tag.startswith(("msda", "condinst", "layernorm", "row_softmax", "seg_postprocess")):
+            if tag.startswith(("msda", "condinst", "layernorm", "row_softmax", "seg_postprocess")) or "mask_embed" in tag:
                 entry.update(bound="hbm", achieved=rate / 1e9, unit="GB/s", frac=rate / 1e9 / pk["hbm"])
             else:
                 entry.update(bound="tensor", achieved=rate / 1e12, unit="TFLOP/s", frac=rate / 1e12 / pk["tf_sustained"])

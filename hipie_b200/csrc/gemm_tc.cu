@@ -51,6 +51,8 @@ struct GemmParams {
     float alpha;
     int transposed;  // 1: C stored as [N, ldc] (column-major output), lanes = rows
     int tiles_m, tiles_n;
+    int m_fastest;   // tile order: 1 = the few M tiles of one N tile run back to back (concurrently on neighbouring SMs), so the
+                     // big streamed W operand is fetched from HBM once and re-read from L2 (short, wide problems)
     const int* row_map;
     int t_row_group, t_row_pad;   // transposed epilogue: row r -> r + (r / group) * pad (0 = off)
 };
@@ -82,6 +84,22 @@ __device__ __forceinline__ float act_apply_t(float v) {
     if (ACT == HIPIE_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
     if (ACT == HIPIE_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
     return v;
+}
+
+// Row-major bit-packed output: bits[b][row][col / 32], bit (col % 32) = value > threshold.  The four lanes that hold the 16
+// columns [col16, col16 + 16) of one row (4 each) combine their nibbles and lane 0 of the group stores one 16-bit half word.
+__device__ __forceinline__ void row_bits16(const GemmParams& p, const float4& x, int b, int row, int col16, int lane) {
+    uint32_t v = (x.x > p.bits_threshold ? 1u : 0u) | (x.y > p.bits_threshold ? 2u : 0u) | (x.z > p.bits_threshold ? 4u : 0u) |
+                 (x.w > p.bits_threshold ? 8u : 0u);
+    v <<= 4 * (lane & 3);
+    const uint32_t gmask = 0xfu << (lane & ~3);
+    v |= __shfl_xor_sync(gmask, v, 1);
+    v |= __shfl_xor_sync(gmask, v, 2);
+    if ((lane & 3) == 0) {
+        const int64_t words_per_row = (p.N + 31) / 32;
+        uint16_t* dst = reinterpret_cast<uint16_t*>(p.c_bits + ((int64_t)b * p.M + row) * words_per_row);
+        dst[col16 >> 4] = (uint16_t)v;
+    }
 }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -137,6 +155,7 @@ __device__ __forceinline__ void epilogue_rows_fast(const GemmParams& p, uint32_t
                 x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
             }
             const int off = rr * ldc + cb;
+            if (p.c_bits) row_bits16(p, x, b, m0 + rr, n0 + cb, lane);
             if (cf_t) *reinterpret_cast<float4*>(cf_t + off) = x;
             if (chi_t) {
                 uint2 hi, lo;
@@ -218,6 +237,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
                     const float4 rv = *reinterpret_cast<const float4*>(res_b + row * p.ldr + col);
                     x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
                 }
+                if (p.c_bits) row_bits16(p, x, b, (int)row, nbase, lane);
                 if (cf_b) *reinterpret_cast<float4*>(cf_b + off) = x;
                 if (chi_b) {
                     uint2 hi, lo;
@@ -359,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int b = t / tiles_per_batch;
                 const int r = t - b * tiles_per_batch;
-                const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+                const int mt = p.m_fastest ? r % p.tiles_m : r / p.tiles_n, nt = p.m_fastest ? r / p.tiles_m : r - mt * p.tiles_n;
                 const int m0 = mt * GEMM_BM, n0 = nt * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
@@ -431,7 +451,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int b = t / tiles_per_batch;
             const int r = t - b * tiles_per_batch;
-            const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+            const int mt = p.m_fastest ? r % p.tiles_m : r / p.tiles_n, nt = p.m_fastest ? r / p.tiles_m : r - mt * p.tiles_n;
             const int m0 = mt * GEMM_BM + quarter * 32, n0 = nt * BN;
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
@@ -568,6 +588,7 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     p.t_row_pad = a->transposed ? a->t_row_pad : 0;
     p.tiles_m = (a->M + GEMM_BM - 1) / GEMM_BM;
     p.tiles_n = (a->N + BN - 1) / BN;
+    p.m_fastest = (p.tiles_m <= 8 && p.tiles_n >= 4 * p.tiles_m) ? 1 : 0;
     const int64_t total = (int64_t)p.tiles_m * p.tiles_n * a->batch;
     static bool attr_set = false;
     if (!attr_set) {
@@ -593,7 +614,8 @@ extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
                     a->M, a->N, a->K, a->batch);
     HIPIE_CHECK_ARG(a->K % 8 == 0, "hipie_gemm: K (%d) must be a multiple of 8", a->K);
     HIPIE_CHECK_ARG(a->c_f32 || a->c_hi || a->c_bits, "hipie_gemm: no output requested");
-    HIPIE_CHECK_ARG(!a->c_bits || a->transposed, "hipie_gemm: bit-packed output requires transposed=1");
+    HIPIE_CHECK_ARG(!a->c_bits || a->transposed || (a->N % 16 == 0 && !a->c_row_map),
+                    "hipie_gemm: row-major bit-packed output needs N %% 16 == 0 and no row map");
     HIPIE_CHECK_ARG(!a->c_lo || a->c_hi, "hipie_gemm: c_lo requires c_hi");
     HIPIE_CHECK_ARG(!a->c_row_map || !a->transposed, "hipie_gemm: c_row_map is not supported with transposed=1");
     cudaStream_t st = (cudaStream_t)stream;

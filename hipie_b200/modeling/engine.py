@@ -789,9 +789,11 @@ class Engine:
         dec, dec_s, _ = ops.layernorm(hs, gn, bn, 1e-5, want_f32=True, want_split=True)
         cls_emb, cls_emb_s, _ = ops.gemm(dec_s, wc, bias=bc, want_split=True)                              # (B*nq, 256) "pred_logits" embedding
         me_s = self.mlp(dec_s, pr + ".mask_embed", 3, last_f32=False)                                      # BF2 (B*nq, 256)
-        # mask-embed contraction, transposed: out[b, q, hw] = sum_c mask_features[b, hw, c] * mask_embed[b, q, c]
-        pm, _, bits = ops.gemm(mf_s, me_s, M=HWm, N=nq, K=256, batch=B, lda=256, ldw=256, a_bstride=HWm * 256, w_bstride=nq * 256,
-                               transposed=True, bits_threshold=0.0)
+        # mask-embed contraction out[b, q, hw] = sum_c mask_embed[b, q, c] * mask_features[b, hw, c]: the queries are the (3) M tiles,
+        # the pixel map is the streamed W operand -- read from HBM once (the M tiles of one pixel tile run back to back and
+        # share it through L2), rows written with coalesced stores, sigmoid > 0.5 fused as a bit-packed second output
+        pm, _, bits = ops.gemm(me_s, mf_s, M=nq, N=HWm, K=256, batch=B, lda=256, ldw=256, a_bstride=nq * 256, w_bstride=HWm * 256,
+                               bits_threshold=0.0)
         pred_masks = pm.view(B, nq, 2 * h3, 2 * w3)
         box = (self.mlp(hs_s, pr + "._bbox_embed", 3).view(B, nq, 4) + inverse_sigmoid(refs[-2])).sigmoid()
         return dict(pred_logits_emb=cls_emb.view(B, nq, 256), pred_logits_emb_s=cls_emb_s, pred_masks=pred_masks, mask_bits=bits,

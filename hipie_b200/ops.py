@@ -179,9 +179,8 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
     c_f32 = out_f32 if out_f32 is not None else (torch.empty(ashape, dtype=torch.float32, device=dev) if want_f32 else None)
     c_split = out_split if out_split is not None else (_empty_bf2(ashape, dev) if want_split else None)
     c_bits = None
-    if bits_threshold is not None:
-        assert transposed
-        c_bits = torch.zeros((batch, N, (M + 31) // 32), dtype=torch.int32, device=dev)
+    if bits_threshold is not None:       # x > threshold, bit-packed along the contiguous output dimension
+        c_bits = torch.zeros((batch, N, (M + 31) // 32) if transposed else (batch, rows_out, (N + 31) // 32), dtype=torch.int32, device=dev)
     if residual is not None and ldr is None:
         ldr = residual.stride(-2) if not transposed else residual.stride(-2)
     args = _lib.GemmArgs(
@@ -202,7 +201,10 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
     tag = f"gemm_tc[p{prec}]" + (":mask_embed" if c_bits is not None else "")
     if profiler.enabled and profiler.shapes:
         tag += f" {M}x{N}x{K}" + (f"x{batch}" if batch > 1 else "") + ("T" if transposed else "")
-    with _timed(tag, 2.0 * M * N * K * batch):
+    work = 2.0 * M * N * K * batch
+    if c_bits is not None:   # the mask-embed contraction is HBM-bound: report algorithmic bytes instead of flops
+        work = float(batch) * ((M * K + N * K) * 2.0 * (2 if prec == 3 else 1) + M * N * 4.0 + M * N / 8.0)
+    with _timed(tag, work):
         _lib.check(lib.hipie_gemm(ctypes.byref(args), _stream()), "gemm")
     if padded:
         if c_f32 is not None and out_f32 is None:

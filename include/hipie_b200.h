@@ -109,8 +109,8 @@ typedef struct hipie_gemm_args {
     int act;                  /* HIPIE_ACT_* */
     int prec;                 /* 1 or 3 */
     float alpha;              /* scales the accumulator before bias (1.0f default) */
-    int transposed;           /* 1: C (and residual, c_hi/lo) addressed as [col * ld + row]; required for c_bits,
-                                 which is then packed along M: bits[b][col][row/32] */
+    int transposed;           /* 1: C (and residual, c_hi/lo) addressed as [col * ld + row]; c_bits is then packed along M:
+                                 bits[b][col][row/32].  0: c_bits (needs N % 16 == 0) is packed along N: bits[b][row][col/32] */
     const int32_t* c_row_map; /* optional (non-transposed only): GEMM row r is stored to / takes its residual
                                  from row c_row_map[r]; negative entries are skipped (window un-partition) */
     int t_row_group;          /* transposed only, 0 = off: GEMM row r is stored at position r + (r / t_row_group) * t_row_pad of */

@@ -554,3 +554,20 @@ def test_sine_embed(ops, cuda):
     ref = torch.cat([emb(pos[..., 1]), emb(pos[..., 0]), emb(pos[..., 2]), emb(pos[..., 3])], dim=-1).view(-1, 512)
     assert (out - ref).abs().max() < 2e-6
     assert ((s.hi.float() + s.lo.float()) - ref).abs().max() < 1e-4
+
+
+def test_gemm_row_major_bits_short_wide(ops, cuda):
+    """short-and-wide batched GEMM (the mask-embed shape class: M = 300 queries = 3 M tiles with a ragged last one, N = pixels):
+    M-fastest tile order, fp32 rows + fused (x > 0) bit-packed along N"""
+    g = torch.Generator(device="cuda").manual_seed(77)
+    B, M, N, K = 2, 300, 1024, 256
+    a = torch.randn(B * M, K, device=cuda, generator=g)
+    w = torch.randn(B * N, K, device=cuda, generator=g) * 0.1
+    A, W = ops.split(a), ops.split(w)
+    c, _, bits = ops.gemm(A, W, M=M, N=N, K=K, batch=B, lda=K, ldw=K, a_bstride=M * K, w_bstride=N * K, bits_threshold=0.0)
+    ref = torch.einsum("bmk,bnk->bmn", a.view(B, M, K).double(), w.view(B, N, K).double())
+    assert (c.double() - ref).abs().max() < 2e-4
+    want = (c > 0).view(B, M, N // 32, 32).long().cpu()
+    want = (want << torch.arange(32)).sum(-1)
+    want = torch.where(want >= 2 ** 31, want - 2 ** 32, want).int()
+    assert torch.equal(bits.cpu().view(B, M, N // 32), want)

@@ -45,7 +45,7 @@ if which in ("all", "maskembed"):
     Fm = ops.split(torch.randn(B * HW, C, device=dev))
     Em = ops.split(torch.randn(B * Q, C, device=dev) * 0.1)
     for _ in range(2):
-        ops.gemm(Fm, Em, M=HW, N=Q, K=C, batch=B, lda=C, ldw=C, a_bstride=HW * C, w_bstride=Q * C, transposed=True, bits_threshold=0.0)
+        ops.gemm(Em, Fm, M=Q, N=HW, K=C, batch=B, lda=C, ldw=C, a_bstride=Q * C, w_bstride=HW * C, bits_threshold=0.0)
 if which in ("ffn1",):      # deformable-encoder FFN1: K=256, epilogue / store heavy
     a = torch.randn(174080, 256, device=dev)
     w = torch.randn(2048, 256, device=dev) * 0.05
