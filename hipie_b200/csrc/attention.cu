@@ -385,7 +385,7 @@ relpos_mma_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* _
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int coord = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int coord = blockIdx.x, b = blockIdx.z;            // one CTA per (coordinate, batch): R[coord] is staged once for all heads
     const int G = axis == 0 ? qw : qh;                       // queries sharing this coordinate
     const int T = qh * qw;
     // stage R[coord] (kpad rows x HD), rows >= ksize zero-filled
@@ -401,7 +401,10 @@ relpos_mma_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* _
     cp_async_wait<0>();
     __syncthreads();
     const int nslabs = (G + 15) / 16;
-    for (int slab = warp; slab < nslabs; slab += 4) {
+    const int hpc = (H + gridDim.y - 1) / gridDim.y;         // heads per CTA
+    for (int wk = warp; wk < hpc * nslabs; wk += 4) {
+        const int h = blockIdx.y * hpc + wk / nslabs, slab = wk % nslabs;
+        if (h >= H) break;
         // A fragments straight from global: rows = members g of the group
         const int g0 = slab * 16 + (lane >> 2), g1 = g0 + 8;
         auto tok = [&](int g) { return axis == 0 ? coord * qw + g : g * qw + coord; };
@@ -446,15 +449,22 @@ relpos_mma_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* _
             for (int half = 0; half < 2; ++half) {
                 const float* c = half == 0 ? c0 : c1;
                 const int cc = col + half * 8;
+                const bool pair_ok = cc + 1 < ksize && (ksize & 1) == 0;     // 8-byte aligned pair -> one store
                 if (ok0) {
                     float* o = rel + ((((int64_t)b * H + h) * T) + tok(g0)) * ksize + cc;
-                    if (cc < ksize) o[0] = c[0];
-                    if (cc + 1 < ksize) o[1] = c[1];
+                    if (pair_ok) *reinterpret_cast<float2*>(o) = make_float2(c[0], c[1]);
+                    else {
+                        if (cc < ksize) o[0] = c[0];
+                        if (cc + 1 < ksize) o[1] = c[1];
+                    }
                 }
                 if (ok1) {
                     float* o = rel + ((((int64_t)b * H + h) * T) + tok(g1)) * ksize + cc;
-                    if (cc < ksize) o[0] = c[2];
-                    if (cc + 1 < ksize) o[1] = c[3];
+                    if (pair_ok) *reinterpret_cast<float2*>(o) = make_float2(c[2], c[3]);
+                    else {
+                        if (cc < ksize) o[0] = c[2];
+                        if (cc + 1 < ksize) o[1] = c[3];
+                    }
                 }
             }
         }
@@ -540,7 +550,11 @@ extern "C" int hipie_relpos_bias_tc(const void* q_hi, const void* q_lo, int64_t 
     HIPIE_CHECK_ARG(q_ts % 2 == 0 && q_hs % 2 == 0 && q_bs % 2 == 0, "hipie_relpos_bias_tc: strides must be even");
     if ((int64_t)B * H * qh * qw == 0) return HIPIE_OK;
     const int kpad = (ksize + 15) / 16 * 16;
-    dim3 grid(axis == 0 ? qh : qw, H, B);
+    // R[coord] is staged once per CTA and reused for several heads: all heads for short groups (windows: one 16-row slab per
+    // head), 4 heads per CTA for the 64-query groups of the global grid (keeps ~2000 CTAs in flight)
+    const int G = axis == 0 ? qw : qh;
+    const int hpc = G >= 32 ? 4 : 16;
+    dim3 grid(axis == 0 ? qh : qw, (H + hpc - 1) / hpc, B);
     cudaStream_t st = (cudaStream_t)stream;
 #define HIPIE_RP(HDV)                                                                                           \
     if (hd == HDV) {                                                                                            \
