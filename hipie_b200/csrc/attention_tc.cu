@@ -1,25 +1,29 @@
-// tcgen05 flash attention for the ViT-H global blocks (hd = 80, T % 128 == 0), sm_100a.
+// tcgen05 flash attention for the ViT-H blocks (hd = 80), sm_100a: global 64-wide token grids (T % 256 == 0) and the 14x14 windows.
 //
 //   softmax((q*scale) k^T + rel_h[q, kh] + rel_w[q, kw]) v      (/root/reference/projects/HIPIE/hipie/backbone/vit.py:67-83,
 //                                                                 backbone/utils.py:96-125)
 //
-// One CTA = 256 query rows (two 128-row tiles) of one (batch, head); 320 threads:
-//   warp 0      TMA producer: K tiles (64 keys x 80) and V^T tiles (80 x 64 keys) into a 3-stage, hardware-swizzled
-//               shared-memory ring (head dim 80 = one 128B-swizzled 64-wide box + one 32B-swizzled 16-wide box), plus the
-//               two Q lo tiles once
-//   warp 1      MMA issuer: S_t = Q_t K_j^T (M=128, N=64, K=80; A = Q hi in TENSOR MEMORY, TS mode) and O_t += P_t V_j
-//               (M=128, N=80, K=64; A = P in tensor memory).  The two query tiles alternate: while tile 0's scores are in
-//               the softmax warps the tensor pipe runs tile 1's MMAs, and PV_t(j) is interleaved with QK_t(j+1)
+// One CTA = 256 query rows (two 128-row tiles) of one (batch, head); 352 threads:
+//   warp 0      TMA producer: K tiles (64 keys x 80) and V^T tiles (80 x 64 keys) into a hardware-swizzled shared-memory
+//               ring (head dim 80 = one 128B-swizzled 64-wide box + one 32B-swizzled 16-wide box), plus the two Q lo tiles once
+//   warp 1 / 10 MMA issuers, one per query tile: S_t = Q_t K_j^T (M=128, N=64, K=80; A = Q hi in TENSOR MEMORY, TS mode) and
+//               O_t += P_t V_j (M=128, N=80, K=64; A = P in tensor memory).  QK_t(j+1) is issued as soon as the softmax warps
+//               hold S_t(j) in registers; the two issuers' streams interleave in the tensor pipe, so while one tile is in
+//               its softmax the pipe works for the other.  Latency-critical waits poll (mbarrier.test_wait)
 //   warps 2-5   softmax of tile 0, warps 6-9 softmax of tile 1: ONE THREAD PER QUERY ROW (no cross-warp max exchange):
-//               tcgen05.ld the 64 scores, scale + rel-pos bias (rel_w hoisted in registers, one prefetched rel_h scalar per
-//               tile since a 64-key tile is one key row of the 64-wide grid), online softmax with lazy rescaling of the TMEM
-//               accumulator, P written back to TMEM with tcgen05.st as the A operand of the PV MMA
+//               tcgen05.ld the 64 scores, scale + rel-pos bias, online softmax with lazy rescaling of the TMEM accumulator,
+//               P written back to TMEM with tcgen05.st as the A operand of the PV MMA
+//   global mode: rel_w hoisted in registers, one prefetched rel_h scalar per tile (a 64-key tile is one key row of the grid)
+//   window mode (T = 196, 14 x 14): one CTA per (window, head); keys padded to 4 x 64 and masked; the bias index
+//               (k / 14, k % 14) folds to constants in the unrolled 4-tile loop; V^T holds every window at a 200-column pitch
+//               because TMA box starts must be 16-byte aligned
 // Precision: PREC==3 evaluates Qh.Kh + Qh.Kl + Ql.Kh and Ph.Vh + Ph.Vl + Pl.Vh (bf16x3, fp32-class); PREC==1 plain bf16.
 // Tensor memory (512 columns): per tile S 64 | P hi/lo 64 | O 80 | Q hi 40; Q lo does not fit and is the one A operand
 // read from shared memory (5 of the 30 MMAs per key tile).
-// History (profiles/): v1 kept Q and P in shared memory (tensor pipe starved on A re-reads); v2 moved both to
-// TMEM with one query tile per CTA and two softmax warps per row quarter (max exchange through smem + named barriers) and
-// sat at ~45 % of the MMA peak, softmax-latency bound; this v3 is the two-tile ping-pong.
+// History (profiles/): v1 kept Q and P in shared memory (3.1 ms per global block at B = 8); v2 moved both to
+// TMEM with one query tile per CTA and two softmax warps per row quarter (2.1 ms, ~45 % of the MMA peak, softmax-latency
+// bound); v3 two-tile ping-pong with one thread per row (1.56 ms); v5 (this) per-tile issuers + early QK + polled barriers
+// (1.48 ms, tensor pipe 62 % active, softmax warps issue-bound).
 #include "common.cuh"
 #include "ptx.cuh"
 
