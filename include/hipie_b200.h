@@ -181,17 +181,23 @@ typedef struct hipie_attn_args {
 
 int hipie_attention(const hipie_attn_args* args, void* stream);
 
-/* tcgen05 flash attention for the ViT-H global blocks: hd == 80, T % 128 == 0, optional decomposed rel-pos bias
- * with kw == 64.  q / k are bf16 planes viewed as (B, T, width) rows (token stride *_ts, batch stride *_bs, head h at
- * columns [*_col0 + 80 h, +80)); vt is V transposed: (H*80, B*T) planes, row stride vt_ld (the qkv GEMM emits it with
- * transposed=1).  Output (B, T, H*80) fp32 and/or bf16 split. */
+/* tcgen05 flash attention for the ViT-H blocks (Attention.forward + add_decomposed_rel_pos, backbone/vit.py:67-83,
+ * backbone/utils.py:96-125), hd == 80.  Two modes, selected by the shapes:
+ *   global : T % 256 == 0, optional decomposed rel-pos bias with kw == 64 (kh * kw == T); one CTA per 256 queries.
+ *   window : T == 196 with kh == kw == 14 (the 14 x 14 windows; B = number of windows): one CTA per (window, head), the
+ *            60 padding keys of the last 64-key tile are masked.
+ * q / k are bf16 planes viewed as (B, T, width) rows (token stride *_ts, batch stride *_bs, head h at columns
+ * [*_col0 + 80 h, +80)); vt is V transposed, (H*80, B*T) planes with row stride vt_ld (the qkv GEMM emits it with transposed=1);
+ * in window mode every window sits at a 200-column pitch, (H*80, B*200), with zero pad columns (t_row_group = 196,
+ * t_row_pad = 4 of hipie_gemm).  rel_h (B, H, T, kh) and rel_w (B, H, T, kw) fp32.  Output (B, T, H*80) fp32 and/or bf16 split. */
 int hipie_attention_tc(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
                        const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
                        const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
                        int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
                        int H, int T, int hd, float scale, int prec, void* stream);
 
-/* Same, with an optional device buffer (32 tiles x 16 slots of clock64 stamps of CTA (0,0,0)) for pipeline debugging. */
+/* Same, with an optional device buffer (32 key tiles x 2 query tiles x 8 slots of clock64 stamps of CTA (0,0,0)) for pipeline
+ * debugging (tools/fa_trace.py). */
 int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
                               const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
                               const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
