@@ -405,24 +405,32 @@ relpos_mma_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* _
     for (int wk = warp; wk < hpc * nslabs; wk += 4) {
         const int h = blockIdx.y * hpc + wk / nslabs, slab = wk % nslabs;
         if (h >= H) break;
-        // A fragments straight from global: rows = members g of the group
+        // the slab's 16 query rows (members g of the group) -> this warp's smem region in 16-byte chunks (whole 160-byte rows,
+        // full sectors), then A fragments with ldmatrix
         const int g0 = slab * 16 + (lane >> 2), g1 = g0 + 8;
         auto tok = [&](int g) { return axis == 0 ? coord * qw + g : g * qw + coord; };
         const bool ok0 = g0 < G, ok1 = g1 < G;
-        const int64_t base0 = (int64_t)b * q_bs + (int64_t)tok(ok0 ? g0 : 0) * q_ts + (int64_t)h * q_hs + (lane & 3) * 2;
-        const int64_t base1 = (int64_t)b * q_bs + (int64_t)tok(ok1 ? g1 : 0) * q_ts + (int64_t)h * q_hs + (lane & 3) * 2;
+        const uint32_t qs = sb + 2 * kpad * ROWB + warp * (2 * 16 * ROWB);
+        __syncwarp();                                            // previous work item's ldmatrix reads are done
+        for (int i = lane; i < 2 * 16 * CHUNKS; i += 32) {
+            const int pl = i / (16 * CHUNKS), rc = i - pl * (16 * CHUNKS);
+            const int r = rc / CHUNKS, c = rc - r * CHUNKS;
+            const int g = slab * 16 + r;
+            const bool ok = g < G && (pl == 0 || q_lo != nullptr);
+            const __nv_bfloat16* src = (pl == 0 ? q_hi : (q_lo ? q_lo : q_hi)) + (int64_t)b * q_bs + (int64_t)tok(ok ? g : 0) * q_ts +
+                                       (int64_t)h * q_hs + c * 8;
+            cp_async16(qs + pl * 16 * ROWB + r * ROWB + c * 16, src, ok ? 16 : 0);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
         uint32_t ah[KSTEPS][4], al[KSTEPS][4];
+        {
+            const uint32_t arow = qs + (lane & 15) * ROWB + (lane >> 4) * 16;
 #pragma unroll
-        for (int kk = 0; kk < KSTEPS; ++kk) {
-            ah[kk][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q_hi + base0 + kk * 16) : 0u;
-            ah[kk][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q_hi + base1 + kk * 16) : 0u;
-            ah[kk][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q_hi + base0 + kk * 16 + 8) : 0u;
-            ah[kk][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q_hi + base1 + kk * 16 + 8) : 0u;
-            if (q_lo) {
-                al[kk][0] = ok0 ? *reinterpret_cast<const uint32_t*>(q_lo + base0 + kk * 16) : 0u;
-                al[kk][1] = ok1 ? *reinterpret_cast<const uint32_t*>(q_lo + base1 + kk * 16) : 0u;
-                al[kk][2] = ok0 ? *reinterpret_cast<const uint32_t*>(q_lo + base0 + kk * 16 + 8) : 0u;
-                al[kk][3] = ok1 ? *reinterpret_cast<const uint32_t*>(q_lo + base1 + kk * 16 + 8) : 0u;
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+                ldsm_x4(arow + kk * 32, ah[kk][0], ah[kk][1], ah[kk][2], ah[kk][3]);
+                if (q_lo) ldsm_x4(arow + 16 * ROWB + kk * 32, al[kk][0], al[kk][1], al[kk][2], al[kk][3]);
             }
         }
         const int key_l = (lane & 7) + (lane >> 4) * 8;
@@ -547,7 +555,8 @@ extern "C" int hipie_relpos_bias_tc(const void* q_hi, const void* q_lo, int64_t 
                                     float* rel, int B, int H, int hd, void* stream) {
     HIPIE_CHECK_ARG(q_hi && table_hi && table_lo && rel, "hipie_relpos_bias_tc: null pointer");
     HIPIE_CHECK_ARG(axis == 0 || axis == 1, "hipie_relpos_bias_tc: axis in {0,1}");
-    HIPIE_CHECK_ARG(q_ts % 2 == 0 && q_hs % 2 == 0 && q_bs % 2 == 0, "hipie_relpos_bias_tc: strides must be even");
+    HIPIE_CHECK_ARG(q_ts % 8 == 0 && q_hs % 8 == 0 && q_bs % 8 == 0 && ((reinterpret_cast<uintptr_t>(q_hi) | reinterpret_cast<uintptr_t>(q_lo)) & 15) == 0,
+                    "hipie_relpos_bias_tc: q rows must be 16-byte aligned (strides multiples of 8 elements)");
     if ((int64_t)B * H * qh * qw == 0) return HIPIE_OK;
     const int kpad = (ksize + 15) / 16 * 16;
     // R[coord] is staged once per CTA and reused for several heads: all heads for short groups (windows: one 16-row slab per
@@ -558,7 +567,7 @@ extern "C" int hipie_relpos_bias_tc(const void* q_hi, const void* q_lo, int64_t 
     cudaStream_t st = (cudaStream_t)stream;
 #define HIPIE_RP(HDV)                                                                                           \
     if (hd == HDV) {                                                                                            \
-        const int smem = 2 * kpad * (HDV * 2 + 16);                                                             \
+        const int smem = (2 * kpad + 4 * 2 * 16) * (HDV * 2 + 16);       /* R[coord] planes + per-warp Q slabs */ \
         static int smem_set = 0;                                                                                \
         if (smem > smem_set) {                                                                                  \
             HIPIE_CHECK_CUDA(cudaFuncSetAttribute(relpos_mma_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
