@@ -583,7 +583,9 @@ class Engine:
                            out_f32=src[:, starts[3]:], y_bstride=S * 256)
         masks.append(F.interpolate(masks[0][None].float(), size=shapes[3]).to(torch.bool)[0])
         lvl_embed = W[f"{dd}.transformer.level_embed"]
-        pos = torch.cat([_sine_pos(masks[l], 128, -0.5) + lvl_embed[l].view(1, 1, -1) for l in range(4)], 1).contiguous()
+        make_pos = lambda: torch.cat([_sine_pos(masks[l], 128, -0.5) + lvl_embed[l].view(1, 1, -1) for l in range(4)], 1).contiguous()
+        # without padding the masks are all-False and the encoding depends on the shapes only: computed once per resolution
+        pos = make_pos() if any_pad else W.cached(("sine_pos_detr", B, tuple(shapes)), make_pos)
         mask_flat = torch.cat([m.flatten(1) for m in masks], 1)
         vr = []
         for m in masks:
@@ -718,8 +720,10 @@ class Engine:
         ops.groupnorm_nhwc(y.view(B, Ho * Wo, 256), W[f"{pd}.input_proj.3.1.weight"], W[f"{pd}.input_proj.3.1.bias"],
                            out_f32=src[:, starts[3]:], y_bstride=S * 256)
         lvl_embed = W[pd + ".transformer.level_embed"]
-        zeros = [torch.zeros(B, h, w, dtype=torch.bool, device=self.device) for h, w in shapes]
-        pos = torch.cat([_sine_pos(zeros[l], 128, 0.0) + lvl_embed[l].view(1, 1, -1) for l in range(4)], 1).contiguous()
+        def make_pos_md():      # MaskDINO always passes mask=None (maskdino_encoder.py:82-88): shape-only, cached per resolution
+            zeros = [torch.zeros(B, h, w, dtype=torch.bool, device=self.device) for h, w in shapes]
+            return torch.cat([_sine_pos(zeros[l], 128, 0.0) + lvl_embed[l].view(1, 1, -1) for l in range(4)], 1).contiguous()
+        pos = W.cached(("sine_pos_md", B, tuple(shapes)), make_pos_md)
         ones_vr = torch.ones(B, 4, 2, device=self.device)
         ref_enc = self.encoder_reference_points(shapes, ones_vr, self.device)
         shapes_t = self._dev_const([list(x) for x in shapes], torch.long)

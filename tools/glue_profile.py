@@ -21,17 +21,16 @@ def step():
     return model.coco_inference(imgs, pad, [(1024, 1024)] * B, lang)
 with torch.no_grad():
     step(); step(); torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as pr:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as pr:
         step()
         torch.cuda.synchronize()
 agg = collections.Counter(); cnt = collections.Counter()
 for e in pr.events():
     if e.device_type.name != "CPU" or not e.name.startswith("aten::") or e.self_device_time_total <= 0:
         continue
-    frame = next((f for f in (e.stack or []) if "hipie_b200" in f and "ops.py" not in f), None) or next((f for f in (e.stack or []) if "hipie_b200" in f), "?")
-    key = (frame.split("/")[-1][:70], e.name)
+    key = (e.name, str(e.input_shapes)[:110])
     agg[key] += e.self_device_time_total; cnt[key] += 1
 tot = sum(agg.values())
 print(f"torch-op device time {tot/1e3:.2f} ms")
-for k, v in agg.most_common(45):
-    print(f"{v/1e3:7.3f} ms n={cnt[k]:4d} {k[1]:28s} {k[0]}")
+for k, v in agg.most_common(40):
+    print(f"{v/1e3:7.3f} ms n={cnt[k]:4d} {k[0]:22s} {k[1]}")
