@@ -146,6 +146,7 @@ class Engine:
         self._bufs = {}
         self.bf16_value_map = False     # fast mode: MSDeformAttn value map stored as bf16
         self.use_tc_attention = True    # tcgen05 flash attention for the global ViT blocks
+        self.taps = None                # parity harness: {"blocks": (7, 15, 31)} -> residual stream copies "vit.block<i>"
 
     # ------------------------------------------------------------ helpers
     def _window_maps(self, B, gh, gw, ws):
@@ -252,6 +253,8 @@ class Engine:
             w2, b2 = W.lin(blk + ".mlp.fc2")
             _, hmid, _ = ops.gemm(xn2, w1, bias=b1, act=ops.ACT_GELU, want_f32=False, want_split=True)
             ops.gemm(hmid, w2, bias=b2, residual=x, out_f32=x)
+            if self.taps is not None and i in self.taps.get("blocks", ()):
+                self.taps[f"vit.block{i}"] = x.view(B, gh, gw, E).clone()
         # simple FPN (vit.py:340-344,366-374): ConvT(k2,s2) / identity / maxpool
         _, xs = ops.add_split(x)
         x4 = x.view(B, gh, gw, E)
@@ -426,13 +429,15 @@ class Engine:
             x, x_s, _ = ops.layernorm(y, W[p + ".output.LayerNorm.weight"], W[p + ".output.LayerNorm.bias"], 1e-12, want_f32=True, want_split=True)
         return x.view(R, L, Hd)
 
-    def forward_text(self, input_ids, attention_mask):
+    def forward_text(self, input_ids, attention_mask, same_rows=None):
         """BertEncoder.forward (bert_model.py:32-154): rows > 512 tokens are chunked at '.'/EOS boundaries.
-        Identical prompts in a batch are encoded once."""
+        `same_rows` says whether every row of the batch holds the same prompt (the detection case, hipie_img.py:330-332):
+        then row 0 is encoded once and broadcast.  The caller decides it from the host-side token ids (no device sync, safe
+        inside a CUDA-graph capture); None = decide here from the tensors, which reads one flag back from the device."""
         L = input_ids.shape[1]
-        # the common case (one prompt for the whole batch, hipie_img.py:330-332): encode row 0 once and broadcast;
-        # decided on the device without a host sync, both branches produce identical values for identical rows
-        same = self._all_rows_equal(input_ids, attention_mask)
+        if same_rows is None:
+            same_rows = self.rows_equal(input_ids, attention_mask)
+        same = bool(same_rows) and input_ids.shape[0] > 1
         if same:
             ids_u, am_u = input_ids[:1].contiguous(), attention_mask[:1].contiguous()
         else:
@@ -442,13 +447,16 @@ class Engine:
             hid = hid.expand(input_ids.shape[0], -1, -1).contiguous()
         return {"hidden": hid, "masks": attention_mask}
 
-    def _all_rows_equal(self, input_ids, attention_mask):
-        key = (input_ids.data_ptr(), attention_mask.data_ptr(), tuple(input_ids.shape))
-        cache = self._maps.setdefault("rows_equal", {})
-        if key not in cache:       # one host read per distinct prompt tensor
-            cache.clear()
-            cache[key] = bool(((input_ids == input_ids[:1]).all() & (attention_mask == attention_mask[:1]).all()).item())
-        return cache[key]
+    @staticmethod
+    def rows_equal(input_ids, attention_mask):
+        """True when every row equals row 0 (value comparison every call: no pointer-keyed cache, the caching allocator
+        reuses addresses).  Host tensors are compared on the host; device tensors cost one sync and are refused while a
+        CUDA graph is being captured."""
+        if input_ids.shape[0] <= 1:
+            return True
+        if input_ids.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("forward_text: pass same_rows explicitly inside a CUDA-graph capture")
+        return bool(((input_ids == input_ids[:1]).all() & (attention_mask == attention_mask[:1]).all()).item())
 
     def _bert_chunked(self, input_ids, mask, sep=1012):
         CLS, EOS = 101, 102

@@ -158,15 +158,19 @@ class HIPIE_IMG(nn.Module):
                           mask_bits=md["mask_bits"])
         return out
 
-    def capture_hot_path(self, tensor, pad_mask, image_sizes, input_ids, attention_mask, task="detection", warmup=2):
+    def capture_hot_path(self, tensor, pad_mask, image_sizes, input_ids, attention_mask, task="detection", warmup=2, same_rows=None):
         """CUDA-graph the hot path (text encoder + coco_inference) for fixed-shape serving: ~2000 kernel launches per
         batch become one graph launch, which removes the host launch overhead (B200: ≈15 % of the step).
         Returns `replay() -> out` whose tensors are static buffers; refill `tensor` / `input_ids` in place between replays."""
         from .. import _lib
         ids, am = input_ids.to(self.device_), attention_mask.to(self.device_)
+        # whether all rows hold one prompt is part of the captured launch sequence (BERT on 1 row vs B rows): decided once,
+        # before the capture, and baked in -- replaying with prompts of the other kind needs its own graph (see forward)
+        if same_rows is None:
+            same_rows = self.engine.rows_equal(input_ids, attention_mask)
 
         def step():
-            lang = self.engine.forward_text(ids, am)
+            lang = self.engine.forward_text(ids, am, same_rows=same_rows)
             return self.coco_inference(tensor, pad_mask, image_sizes, lang, task=task)
 
         side = torch.cuda.Stream(device=self.device_)
@@ -197,14 +201,14 @@ class HIPIE_IMG(nn.Module):
             self._graphs.clear()
         return self
 
-    def _graphed_hot_path(self, tensor, pad_mask, image_sizes, ids, am, task):
-        key = (tuple(tensor.shape), tuple(ids.shape), task, tuple(tuple(int(v) for v in s) for s in image_sizes))
+    def _graphed_hot_path(self, tensor, pad_mask, image_sizes, ids, am, task, same_rows):
+        key = (tuple(tensor.shape), tuple(ids.shape), task, bool(same_rows), tuple(tuple(int(v) for v in s) for s in image_sizes))
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= 4:           # static buffers are large; keep a handful of shapes
                 self._graphs.pop(next(iter(self._graphs)))
             st = dict(tensor=tensor.clone(), pad=pad_mask.clone(), ids=ids.to(self.device_).clone(), am=am.to(self.device_).clone())
-            st["replay"] = self.capture_hot_path(st["tensor"], st["pad"], image_sizes, st["ids"], st["am"], task=task)
+            st["replay"] = self.capture_hot_path(st["tensor"], st["pad"], image_sizes, st["ids"], st["am"], task=task, same_rows=same_rows)
             self._graphs[key] = ent = st
         ent["tensor"].copy_(tensor)
         ent["pad"].copy_(pad_mask)
@@ -415,8 +419,10 @@ class HIPIE_IMG(nn.Module):
         out.pred_classes = results.pred_classes[keep]
         return out
 
-    def forward_text(self, input_ids, attention_mask):
-        return self.engine.forward_text(input_ids.to(self.device_), attention_mask.to(self.device_))
+    def forward_text(self, input_ids, attention_mask, same_rows=None):
+        if same_rows is None:
+            same_rows = self.engine.rows_equal(input_ids, attention_mask)     # host tensors: compared on the host
+        return self.engine.forward_text(input_ids.to(self.device_), attention_mask.to(self.device_), same_rows=same_rows)
 
     @torch.no_grad()
     def forward(self, batched_inputs, do_postprocess=True, forced=None, return_raw=False):
@@ -441,10 +447,11 @@ class HIPIE_IMG(nn.Module):
             enc = tok.batch_encode_plus([x["expressions"] for x in batched_inputs], max_length=self.hp["max_query_len"],
                                         padding="max_length", return_tensors="pt", truncation=True)
             ids, am = enc.input_ids, enc.attention_mask
+        same_rows = self.engine.rows_equal(ids, am)      # one prompt for the whole batch? (decided on the values, every call)
         if self.use_cuda_graphs and forced is None:
-            out = self._graphed_hot_path(tensor, pad_mask, image_sizes, ids, am, task)
+            out = self._graphed_hot_path(tensor, pad_mask, image_sizes, ids, am, task, same_rows)
         else:
-            lang = self.forward_text(ids, am)
+            lang = self.forward_text(ids, am, same_rows=same_rows)
             out = self.coco_inference(tensor, pad_mask, image_sizes, lang, task=task, forced=forced)
         is_thing = [x["is_thing"] for x in batched_inputs]
         sizes = [(x.get("height", s[0]), x.get("width", s[1])) for x, s in zip(batched_inputs, image_sizes)]

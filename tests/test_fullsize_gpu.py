@@ -1,0 +1,177 @@
+"""GPU: whole-model parity at the BASELINE.json sizes, UNFORCED (no selection is pinned to the oracle's) and forced.
+
+Every case builds the CPU oracle (oracle/hipie_oracle, the restatement of the reference eval forward) and the B200 engine
+from the same seeded weights, runs both on the same seeded inputs and compares
+
+  * the continuous outputs stage by stage (ViT residual stream after blocks 8/16/32, FPN features, encoder memory, fused
+    text features, decoder states, class logits, boxes, MaskDINO mask logits, CondInst logits) -- the table is written to
+    gpurun_out/parity_<case>.json for profiles/ and printed,
+  * the discrete results of the public API with NOTHING forced: pred_classes, sem_seg.argmax, panoptic categories.
+
+Cases:
+  c1   configs[1] at B=1: ViT-H (32 blocks, d=1280, T=4096), 1024x1024, 80 classes, Lt=512, task detection
+  c4   configs[3] path: ViT-H, 1280x1280 (80-wide token grid, rel-pos tables 127->159, 36 padded windows), task grounding
+  c5   configs[4] path: ViT-H, 847-class vocabulary, Lt=4096 (> 512 tokens: BertEncoder chunk path, bert_model.py:68-135),
+       max-pooled / class-agnostic-bg scoring of the ADE eval yaml, at 512x512 so the CPU oracle stays within the test budget
+
+Tolerances (written here, north-star: 1e-3 abs on mask logits, identical argmax class assignments):
+  MaskDINO mask logits 1e-3 ABS; class logits 2e-3 abs; boxes 1e-4 abs; CondInst logits are O(1e3) with seeded random
+  weights (pixel-unit relative coordinates times unit-variance dynamic filters) -- fp32 itself moves them by > 1e-3 when the
+  summation order changes, so they are asserted at 1e-4 RELATIVE to max|logit| and their absolute error is reported in
+  the table (the thresholded masks, which are what the reference emits, must agree on > 99.99 % of the pixels).
+"""
+import json
+import os
+import time
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_T0 = time.time()
+BUDGET_S = 900.0          # the whole GPU suite has to stay well inside the driver's pytest limit
+
+
+def _budget(need):
+    if time.time() - _T0 + need > BUDGET_S:
+        pytest.skip(f"time budget: {time.time() - _T0:.0f}s used, case needs ~{need:.0f}s")
+
+
+def _err(a, b):
+    return (a.detach().float().cpu() - b.detach().float().cpu()).abs().max().item()
+
+
+def _run_case(name, hp, inputs, ids, am, seed, taps=(7, 15, 31)):
+    from hipie_oracle import synth
+    from hipie_oracle.model import HipieOracle
+    from hipie_b200 import ops
+    from hipie_b200.modeling.hipie_img import HIPIE_IMG
+    torch.set_num_threads(min(32, os.cpu_count() or 8))
+    torch.manual_seed(seed)
+    t0 = time.time()
+    oracle = HipieOracle(hp).eval()
+    synth.perturb_(oracle, seed=seed + 1)
+    blocks = oracle.detr.detr.backbone[0].backbone.blocks
+    taps = tuple(t for t in taps if t < len(blocks))
+    otaps, hooks = {}, []
+    for t in taps:
+        hooks.append(blocks[t].register_forward_hook(lambda m, i, o, t=t: otaps.__setitem__(t, o.detach().clone())))
+    with torch.no_grad():
+        res_o, out_o = oracle(inputs, ids, am)
+    for h in hooks:
+        h.remove()
+    t_oracle = time.time() - t0
+    for x, i, a in zip(inputs, ids, am):
+        x["input_ids"], x["attention_mask"] = i, a
+    model = HIPIE_IMG(hp=hp, state_dict=oracle.state_dict(), device="cuda:0")
+    forced = {"topk_fg": out_o["aux"]["topk"].cuda(), "topk_md": out_o["md"]["topk"].cuda()}
+    table = {"case": name, "oracle_seconds": t_oracle, "cpu_threads": torch.get_num_threads(), "stages": {}}
+    runs = {}
+    for prec in (3, 1):
+        ops.set_precision(prec)
+        model.engine.bf16_value_map = False
+        model.engine.taps = {"blocks": taps}
+        try:
+            res_f, out_f = model(inputs, forced=forced, return_raw=True)
+            gt = dict(model.engine.taps)
+            model.engine.taps = None
+            res_u, out_u = (model(inputs, return_raw=True) if prec == 3 else (None, None))
+        finally:
+            ops.set_precision(3)
+            model.engine.taps = None
+        st = {}
+        for t in taps:
+            st[f"vit.block{t + 1}"] = (_err(gt[f"vit.block{t}"], otaps[t]), otaps[t].abs().max().item())
+        for k in ("res3", "res4", "res5"):
+            ref = out_o["features"][k].permute(0, 2, 3, 1)
+            st[f"fpn.{k}"] = (_err(out_f["aux"]["feats"][k], ref), ref.abs().max().item())
+        st["encoder.memory"] = (_err(out_f["aux"]["memory"], out_o["memory"]), out_o["memory"].abs().max().item())
+        st["text.fused"] = (_err(out_f["aux"]["lang_hidden_fused"], out_o["lang_hidden_fused"]), out_o["lang_hidden_fused"].abs().max().item())
+        st["decoder.hs_last"] = (_err(out_f["aux"]["hs"][-1], out_o["hs"][-1]), out_o["hs"][-1].abs().max().item())
+        for k in ("pred_logits", "pred_boxes", "pred_boxious", "pred_logits_maskdino", "pred_boxes_maskdino", "pred_masks_maskdino", "pred_masks"):
+            st[k] = (_err(out_f[k], out_o[k]), out_o[k].abs().max().item())
+        table["stages"][f"prec{prec}"] = {k: {"max_abs_err": v[0], "ref_max_abs": v[1]} for k, v in st.items()}
+        runs[prec] = (res_f, out_f, res_u, out_u)
+    del model
+    torch.cuda.empty_cache()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as f:
+        json.dump(table, f, indent=1)
+    print(f"\n[{name}] oracle {t_oracle:.0f}s on {table['cpu_threads']} threads")
+    for k in table["stages"]["prec3"]:
+        a, b = table["stages"]["prec3"][k], table["stages"]["prec1"][k]
+        print(f"  {k:24s} |ref|max {a['ref_max_abs']:10.3f}   bf16x3 {a['max_abs_err']:.3e}   bf16 {b['max_abs_err']:.3e}")
+    return dict(res_o=res_o, out_o=out_o, res_f=runs[3][0], out_f=runs[3][1], res_u=runs[3][2], out_u=runs[3][3], table=table)
+
+
+def _check_continuous(r, grounding=False):
+    t = r["table"]["stages"]["prec3"]
+    assert t["pred_masks_maskdino"]["max_abs_err"] < 1e-3, t["pred_masks_maskdino"]          # north-star: 1e-3 ABS
+    assert t["pred_logits"]["max_abs_err"] < 2e-3, t["pred_logits"]
+    assert t["pred_logits_maskdino"]["max_abs_err"] < 2e-3, t["pred_logits_maskdino"]
+    assert t["pred_boxes"]["max_abs_err"] < 1e-4 and t["pred_boxes_maskdino"]["max_abs_err"] < 1e-4
+    assert t["pred_masks"]["max_abs_err"] < 1e-4 * t["pred_masks"]["ref_max_abs"], t["pred_masks"]   # CondInst: relative (see header)
+    # (the plain-bf16 column of the printed table is the measurement behind the 3-pass parity mode)
+
+
+def _check_unforced(r, detection=True):
+    """identical argmax class assignments with NOTHING pinned: the engine's own top-k / NMS / top-100 selections"""
+    out_o, out_u = r["out_o"], r["out_u"]
+    tk_o, tk_u = out_o["aux"]["topk"], out_u["aux"]["topk"].cpu()
+    same_sets = [len(set(a.tolist()) & set(b.tolist())) / a.numel() for a, b in zip(tk_o, tk_u)]
+    print(f"  unforced proposal top-k overlap {same_sets}, identical order: {torch.equal(tk_o, tk_u)}")
+    assert min(same_sets) >= 0.995
+    for ro, ru in zip(r["res_o"], r["res_u"]):
+        io, iu = ro["instances_post"], ru["instances"]
+        assert torch.equal(io["pred_classes"], iu.pred_classes.cpu())
+        assert (io["scores"] - iu.scores.cpu()).abs().max() < 1e-4
+        assert (io["pred_boxes"] - iu.pred_boxes.tensor.cpu()).abs().max() < 2e-2          # pixels
+        agree = (io["pred_masks"] == iu.pred_masks.cpu()).float().mean().item()
+        assert agree > 0.9999, agree
+        if detection:
+            so, su = ro["sem_seg"], ru["sem_seg"].cpu()
+            a = (so.argmax(0) == su.argmax(0)).float().mean().item()
+            print(f"  unforced sem_seg argmax agreement {a:.6f}, instance mask agreement {agree:.6f}")
+            assert a > 0.9995, a
+            po, pu = ro["panoptic_seg"], ru["panoptic_seg"]
+            assert [s["category_id"] for s in po[1]] == [s["category_id"] for s in pu[1]]
+            assert (po[0] == pu[0].cpu()).float().mean().item() > 0.9995
+        else:
+            assert ru["sem_seg"] is None and ru["panoptic_seg"][0] is None
+
+
+def test_c1_vith_1024_coco80_lt512(cuda):
+    _budget(200)
+    from hipie_oracle import hparams, synth
+    hp = hparams.get("vit_h")
+    inputs, ids, am = synth.make_batch(1, 1024, 1024, 80, hp["max_query_len"])
+    r = _run_case("c1_vith_1024_coco80", hp, inputs, ids, am, seed=0)
+    _check_continuous(r)
+    _check_unforced(r)
+    # forced variant of the discrete results as a second assertion (selections pinned -> tensors comparable one to one)
+    for ro, rf in zip(r["res_o"], r["res_f"]):
+        assert torch.equal(ro["instances_post"]["pred_classes"], rf["instances"].pred_classes.cpu())
+
+
+def test_c4_vith_1280_grounding(cuda):
+    _budget(220)
+    from hipie_oracle import hparams, synth
+    hp = hparams.get("vit_h")
+    inputs, ids, am = synth.make_batch(1, 1280, 1280, 1, hp["max_query_len"], task="grounding", seed=3)
+    r = _run_case("c4_vith_1280_grounding", hp, inputs, ids, am, seed=4)
+    _check_continuous(r, grounding=True)
+    _check_unforced(r, detection=False)
+
+
+def test_c5_vith_ade847_lt4096_chunked_bert(cuda):
+    _budget(200)
+    from hipie_oracle import hparams, synth
+    hp = hparams.get("vit_h")
+    hp.update(max_query_len=4096, max_pool=True, bg_cls_agnostic=True)
+    inputs, ids, am = synth.make_batch(1, 512, 512, 847, 4096, seed=5)
+    assert int(am[0].sum()) > 512          # the prompt really takes the chunk path
+    r = _run_case("c5_vith_512_ade847_lt4096", hp, inputs, ids, am, seed=6)
+    _check_continuous(r)
+    _check_unforced(r)

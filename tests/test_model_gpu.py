@@ -261,3 +261,128 @@ def test_wide_image_uses_tcgen05_attention(cuda):
         assert _err(out_g["aux"]["feats"][k], ref) < 1e-3 * max(1.0, ref.abs().max().item()), k
     assert _err(out_g["pred_masks_maskdino"], out_o["pred_masks_maskdino"]) < 1e-3
     assert _err(out_g["pred_logits"], out_o["pred_logits"]) < 2e-3
+
+
+def _distinct_grounding_batch(hp, B, h, w, seed):
+    """B images with B DIFFERENT referring expressions (different token ids per row)."""
+    from hipie_oracle import synth
+    imgs = synth.make_images(B, h, w, seed)
+    rows_i, rows_a = [], []
+    for b in range(B):
+        g = torch.Generator().manual_seed(100 * seed + b)
+        n = 4 + 2 * b
+        toks = [101] + torch.randint(1996, 30000, (n,), generator=g).tolist() + [102]
+        ii = torch.zeros(hp["max_query_len"], dtype=torch.long)
+        ii[:len(toks)] = torch.tensor(toks)
+        aa = torch.zeros(hp["max_query_len"], dtype=torch.long)
+        aa[:len(toks)] = 1
+        rows_i.append(ii)
+        rows_a.append(aa)
+    inputs = [dict(image=im, height=h, width=w, task="grounding", is_thing={1: True}, positive_map_label_to_token={1: [0]}) for im in imgs]
+    return inputs, torch.stack(rows_i), torch.stack(rows_a)
+
+
+def test_distinct_prompts_after_detection_batch(setup, cuda):
+    """A detection batch (one prompt for every row) followed by a grounding batch with a different expression per row at the
+    same (B, Lt): the text encoder must encode every row (round-1 bug: a pointer-keyed 'all rows equal' cache went stale when
+    the allocator handed the new ids the old address).  Also through the CUDA-graph path, whose key carries the flag."""
+    from hipie_oracle import hparams
+    hp = hparams.get("vit_tiny")
+    model, oracle = setup["model"], setup["oracle"]
+    model(setup["inputs"])                                           # detection: same prompt in both rows
+    inputs, ids, am = _distinct_grounding_batch(hp, 2, 256, 256, seed=7)
+    assert not torch.equal(ids[0], ids[1])
+    with torch.no_grad():
+        res_o, out_o = oracle(inputs, ids, am)
+    for x, i, a in zip(inputs, ids, am):
+        x["input_ids"], x["attention_mask"] = i, a
+    forced = {"topk_fg": out_o["aux"]["topk"].to(cuda), "topk_md": out_o["md"]["topk"].to(cuda)}
+    _, out_g = model(inputs, forced=forced, return_raw=True)
+    assert _err(out_g["aux"]["lang_hidden_fused"], out_o["lang_hidden_fused"]) < 1e-3
+    assert _err(out_g["pred_logits"], out_o["pred_logits"]) < 2e-3
+    assert _err(out_g["pred_boxes"], out_o["pred_boxes"]) < 1e-4
+    # rows must differ from each other (a broadcast of row 0 would make them equal)
+    assert (out_g["pred_logits"][0] - out_g["pred_logits"][1]).abs().max() > 1e-3
+    eager = model(inputs)
+    model.enable_cuda_graphs(True)
+    try:
+        model(setup["inputs"])                                       # captures the one-prompt graph
+        g1 = model(inputs)                                           # must capture its own graph (flag is part of the key)
+        g2 = model(inputs)
+    finally:
+        model.enable_cuda_graphs(False)
+    for re_, r1, r2 in zip(eager, g1, g2):
+        for r in (r1, r2):
+            assert torch.equal(re_["instances"].pred_classes, r["instances"].pred_classes)
+            assert (re_["instances"].scores - r["instances"].scores).abs().max() < 1e-6
+            assert (re_["instances"].pred_boxes.tensor - r["instances"].pred_boxes.tensor).abs().max() < 1e-3
+
+
+def test_bert_chunk_path_over_512_tokens(cuda):
+    """MAX_QUERY_LEN 1024 with a ~700-token prompt: BertEncoder's chunking at '.'/EOS boundaries (bert_model.py:68-135) on both
+    sides; the text features, the fused features and the class logits must agree; max-pooled scoring over 300 classes."""
+    from hipie_oracle import hparams, synth
+    from hipie_oracle.model import HipieOracle
+    from hipie_b200 import ops
+    from hipie_b200.modeling.hipie_img import HIPIE_IMG
+    torch.manual_seed(11)
+    hp = hparams.get("vit_tiny")
+    hp.update(max_query_len=1024, max_pool=True, bg_cls_agnostic=True)
+    oracle = HipieOracle(hp).eval()
+    synth.perturb_(oracle, seed=12)
+    inputs, ids, am = synth.make_batch(1, 256, 256, 230, 1024, seed=13)
+    assert 512 < int(am[0].sum()) <= 1024
+    with torch.no_grad():
+        lang_o = oracle.forward_text(ids, am)
+        res_o, out_o = oracle(inputs, ids, am)
+    ops.set_precision(3)
+    model = HIPIE_IMG(hp=hp, state_dict=oracle.state_dict(), device="cuda:0")
+    lang_g = model.forward_text(ids, am)
+    assert _err(lang_g["hidden"], lang_o["hidden"]) < 1e-3
+    for x, i, a in zip(inputs, ids, am):
+        x["input_ids"], x["attention_mask"] = i, a
+    forced = {"topk_fg": out_o["aux"]["topk"].to(cuda), "topk_md": out_o["md"]["topk"].to(cuda)}
+    res_g, out_g = model(inputs, forced=forced, return_raw=True)
+    assert _err(out_g["aux"]["lang_hidden_fused"], out_o["lang_hidden_fused"]) < 1e-3
+    assert _err(out_g["pred_logits"], out_o["pred_logits"]) < 2e-3
+    assert _err(out_g["pred_masks_maskdino"], out_o["pred_masks_maskdino"]) < 1e-3
+    for ro, rg in zip(res_o, res_g):
+        assert torch.equal(ro["instances_post"]["pred_classes"], rg["instances"].pred_classes.cpu())
+        so, sg = ro["sem_seg"], rg["sem_seg"].cpu()
+        assert so.shape[0] == 230 and (so.argmax(0) == sg.argmax(0)).float().mean() > 0.9995
+        assert [s["category_id"] for s in ro["panoptic_seg"][1]] == [s["category_id"] for s in rg["panoptic_seg"][1]]
+
+
+def test_pybind_shim_through_reference_style_function(cuda):
+    """hipie_b200.MultiScaleDeformableAttention installed under the pybind module's name and called the way the reference's
+    MSDeformAttnFunction.forward does (ops/functions/ms_deform_attn_func.py:21-30: custom_fwd(cast_inputs=float32), positional
+    (value, shapes, level_start, loc, weights, im2col_step)); result == ms_deform_attn_core_pytorch (the oracle restatement)."""
+    import sys
+    from torch.autograd import Function
+    import hipie_b200.MultiScaleDeformableAttention as shim
+    from hipie_oracle.msda import ms_deform_attn_core
+    sys.modules["MultiScaleDeformableAttention"] = shim
+    import MultiScaleDeformableAttention as MSDA
+
+    class MSDeformAttnFunction(Function):
+        @staticmethod
+        @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+        def forward(ctx, value, shapes, lsi, loc, w, im2col_step):
+            return MSDA.ms_deform_attn_forward(value, shapes, lsi, loc, w, im2col_step)
+
+    g = torch.Generator().manual_seed(3)
+    N, M, D, Lq, L, P = 2, 8, 32, 50, 4, 4
+    shapes = torch.tensor([(16, 16), (8, 8), (4, 4), (2, 2)], dtype=torch.long)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    value = torch.rand(N, S, M, D, generator=g) * 0.01
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g)
+    w = torch.rand(N, Lq, M, L, P, generator=g) + 1e-5
+    w = w / w.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    ref = ms_deform_attn_core(value, shapes, loc, w)
+    out = MSDeformAttnFunction.apply(value.cuda(), shapes.cuda(), lsi.cuda(), loc.cuda(), w.cuda(), 64)
+    assert (out.cpu() - ref).abs().max() < 1e-6
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        MSDA.ms_deform_attn_forward(value, shapes, lsi, loc, w, 64)
+    with pytest.raises(RuntimeError):
+        MSDA.ms_deform_attn_forward(value.cuda()[:, ::2], shapes.cuda(), lsi.cuda(), loc.cuda(), w.cuda(), 64)
