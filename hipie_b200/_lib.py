@@ -50,6 +50,7 @@ SYMBOLS = {
     "hipie_last_error": (ctypes.c_char_p, []),
     "hipie_abi_version": (c_int, []),
     "hipie_launch_count": (c_int64, []),
+    "hipie_set_option": (c_int, [ctypes.c_char_p, c_int]),
     "hipie_msda_forward": (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_void_p]),
     "hipie_msda_fused_forward": (c_int, [c_void_p] * 5 + [c_int, c_void_p] + [c_int] * 9 + [c_void_p, c_void_p]),
     "hipie_gemm": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
@@ -95,6 +96,8 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    if os.environ.get("HIPIE_GEMM_CTA_PAIRS", "") in ("0", "1"):       # A/B switch (tools/gemm_check.py, bench)
+        lib.hipie_set_option(b"gemm_cta_pairs", int(os.environ["HIPIE_GEMM_CTA_PAIRS"]))
     return lib
 
 
@@ -102,6 +105,10 @@ def check(rc, what=""):
     if rc != 0:
         msg = load().hipie_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"hipie_b200 {what} failed (code {rc}): {msg}")
+
+
+def set_option(name: str, value: int):
+    check(load().hipie_set_option(name.encode(), int(value)), f"set_option({name})")
 
 
 def launch_count():

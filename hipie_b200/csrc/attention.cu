@@ -486,11 +486,7 @@ static int launch_attn(const AttnParams& p, cudaStream_t st) {
     const bool tables = p.rel_h != nullptr && p.kw != ATT_BN;
     const int SMEM = SMEM_KV + (tables ? ATT_BM * (p.kh + p.kw + 1) * (int)sizeof(float) : 0);
     HIPIE_CHECK_ARG(SMEM <= 200 * 1024, "hipie_attention: rel-pos grid %dx%d too large for the shared-memory tables", p.kh, p.kw);
-    static int attr = 0;
-    if (SMEM > attr) {
-        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<HD, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr = SMEM;
-    }
+    HIPIE_ENSURE_SMEM((attention_kernel<HD, PREC>), SMEM);
     dim3 grid((p.Tq + ATT_BM - 1) / ATT_BM, p.H, p.B);
     attention_kernel<HD, PREC><<<grid, 128, SMEM, st>>>(p);
     HIPIE_CHECK_LAUNCH();
@@ -568,11 +564,7 @@ extern "C" int hipie_relpos_bias_tc(const void* q_hi, const void* q_lo, int64_t 
 #define HIPIE_RP(HDV)                                                                                           \
     if (hd == HDV) {                                                                                            \
         const int smem = (2 * kpad + 4 * 2 * 16) * (HDV * 2 + 16);       /* R[coord] planes + per-warp Q slabs */ \
-        static int smem_set = 0;                                                                                \
-        if (smem > smem_set) {                                                                                  \
-            HIPIE_CHECK_CUDA(cudaFuncSetAttribute(relpos_mma_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-            smem_set = smem;                                                                                    \
-        }                                                                                                       \
+        HIPIE_ENSURE_SMEM(relpos_mma_kernel<HDV>, smem);                                                        \
         relpos_mma_kernel<HDV><<<grid, 128, smem, st>>>((const __nv_bfloat16*)q_hi, (const __nv_bfloat16*)q_lo, q_bs, q_ts, \
                                                          q_hs, (const __nv_bfloat16*)table_hi,                  \
                                                          (const __nv_bfloat16*)table_lo, axis, qh, qw, ksize, kpad, rel, B, H); \

@@ -435,11 +435,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
 template <int PREC, bool WIN>
 static int launch_fa(const FaMaps& maps, const FaParams& p, cudaStream_t st) {
     using SM = FaSmem<PREC>;
-    static bool attr = false;
-    if (!attr) {
-        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<PREC, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-        attr = true;
-    }
+    HIPIE_ENSURE_SMEM((attn_tc_kernel<PREC, WIN>), SM::TOTAL);
     dim3 grid(WIN ? 1 : p.T / (FA_QT * FA_BM), p.H, p.B);
     attn_tc_kernel<PREC, WIN><<<grid, FA_THREADS, SM::TOTAL, st>>>(maps, p);
     HIPIE_CHECK_LAUNCH();

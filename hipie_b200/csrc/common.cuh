@@ -43,15 +43,30 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_or
         ::hipie::count_launch();                                                            \
     } while (0)
 
+// Dynamic shared-memory opt-in (a per-device function attribute): raise it on the CURRENT device when a launch needs more.
+#define HIPIE_ENSURE_SMEM(func, bytes)                                                                          \
+    do {                                                                                                        \
+        static int _smem_set[64] = {};                                                                          \
+        int _dev = 0;                                                                                           \
+        HIPIE_CHECK_CUDA(cudaGetDevice(&_dev));                                                                 \
+        if (_dev < 0 || _dev >= 64) _dev = 0;                                                                   \
+        if ((int)(bytes) > _smem_set[_dev]) {                                                                   \
+            HIPIE_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            _smem_set[_dev] = (int)(bytes);                                                                     \
+        }                                                                                                       \
+    } while (0)
+
 static inline int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[64] = {};          // per device (several devices in one process see their own SM count)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (n[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n[dev] = v > 0 ? v : 148;
     }
-    return n;
+    return n[dev];
 }
 
 // ---- device helpers ------------------------------------------------------------------------

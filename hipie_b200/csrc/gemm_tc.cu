@@ -32,7 +32,6 @@ using namespace ptx;
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_EPI_WARPS = 16;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // TMA warp, MMA warp, 16 epilogue warps
-constexpr int GEMM_STAGES = 4;
 constexpr int EPI_LD = 16;  // row length (floats) of the epilogue transpose buffer; 16-byte groups are XOR-swizzled by row
 
 struct GemmParams {
@@ -57,16 +56,21 @@ struct GemmParams {
     int t_row_group, t_row_pad;   // transposed epilogue: row r -> r + (r / group) * pad (0 = off)
 };
 
-template <int PREC, int BN>
+// CTAS == 2: a CTA pair (cluster of 2, the two SMs of a TPC) computes one 256 x BN tile with cta_group::2 MMAs: each CTA stages
+// its own 128 A rows and HALF of the W tile (the hardware shares the halves between the pair), which takes the shared-memory
+// traffic per k-block from 120 KB (over the 128 B/clk port budget: tensor pipe 76 % in round 1) to 80 KB.
+template <int PREC, int BN, int CTAS>
 struct GemmCfg {
     static constexpr int BK = PREC == 3 ? 32 : 64;          // elements; BK*2 bytes == swizzle span
     static constexpr int SWZ = BK * 2;
     static constexpr int A_TILE = GEMM_BM * BK * 2;          // bytes
-    static constexpr int W_TILE = BN * BK * 2;
+    static constexpr int W_ROWS = BN / CTAS;                 // W rows staged by one CTA
+    static constexpr int W_TILE = W_ROWS * BK * 2;
     static constexpr int NPLANES = PREC == 3 ? 2 : 1;
     static constexpr int STAGE = NPLANES * (A_TILE + W_TILE);
+    static constexpr int STAGES = CTAS == 2 ? 6 : 4;
     static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 32 * EPI_LD * 4;
-    static constexpr int SMEM = GEMM_STAGES * STAGE + EPI_BYTES + 256 + 1024;
+    static constexpr int SMEM = STAGES * STAGE + EPI_BYTES + 256 + 1024;
     static constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : (2 * BN >= 128 ? 128 : 64));
 };
 
@@ -318,30 +322,37 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, uint32_
     }
 }
 
-template <int PREC, int BN>
+template <int PREC, int BN, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                const GemmParams p) {
-    using Cfg = GemmCfg<PREC, BN>;
+    using Cfg = GemmCfg<PREC, BN, CTAS>;
     constexpr int BK = Cfg::BK;
+    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
+    // same CTA-relative offsets in both CTAs of a pair (the dynamic shared window starts at the same offset in every CTA of a
+    // launch), which the pair MMA descriptors and the multicast commits rely on
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
-    float* epi = reinterpret_cast<float*>(smem + GEMM_STAGES * Cfg::STAGE);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * Cfg::STAGE + Cfg::EPI_BYTES);
-    uint64_t* full_bar = bars;                     // [STAGES]
-    uint64_t* empty_bar = bars + GEMM_STAGES;      // [STAGES]
-    uint64_t* tfull_bar = bars + 2 * GEMM_STAGES;  // [2]
-    uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+    float* epi = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE + Cfg::EPI_BYTES);
+    uint64_t* full_bar = bars;                // [STAGES]  (pair: only the leader's are used)
+    uint64_t* empty_bar = bars + STAGES;      // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;  // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;     // [2]       (pair: only the leader's are used)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     const int num_kb = (p.K + BK - 1) / BK;
-    const int tiles_per_batch = p.tiles_m * p.tiles_n;
+    const int tiles_per_batch = p.tiles_m * p.tiles_n;      // tiles_m counts (128 * CTAS)-row tiles
     const int total_tiles = tiles_per_batch * p.batch;
+    const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
 
+    if (CTAS == 2) cluster_sync();             // both CTAs of the pair are resident before the paired TMEM allocation
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_a_hi);
         prefetch_tmap(&tm_w_hi);
@@ -352,88 +363,119 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int i = 0; i < GEMM_STAGES; ++i) {
+            for (int i = 0; i < STAGES; ++i) {
                 mbar_init(&full_bar[i], 1);
                 mbar_init(&empty_bar[i], 1);
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&tfull_bar[i], 1);
-                mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);
+                mbar_init(&tempty_bar[i], GEMM_EPI_WARPS * CTAS);
             }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (CTAS == 2) {
+            tmem_alloc_2sm(tmem_ptr, Cfg::TMEM_COLS);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (one per CTA) =====================
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = tile0; t < total_tiles; t += tile_step) {
                 const int b = t / tiles_per_batch;
                 const int r = t - b * tiles_per_batch;
                 const int mt = p.m_fastest ? r % p.tiles_m : r / p.tiles_n, nt = p.m_fastest ? r / p.tiles_m : r - mt * p.tiles_n;
-                const int m0 = mt * GEMM_BM, n0 = nt * BN;
+                const int m0 = (mt * CTAS + (int)rank) * GEMM_BM, n0 = nt * BN + (int)rank * Cfg::W_ROWS;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* st = stage_base + s * Cfg::STAGE;
-                    mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
                     const int k0 = kb * BK;
-                    tma_load_3d(st, &tm_a_hi, &full_bar[s], k0, m0, b);
-                    tma_load_3d(st + Cfg::A_TILE, &tm_w_hi, &full_bar[s], k0, n0, b);
-                    if (PREC == 3) {
-                        tma_load_3d(st + Cfg::A_TILE + Cfg::W_TILE, &tm_a_lo, &full_bar[s], k0, m0, b);
-                        tma_load_3d(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tm_w_lo, &full_bar[s], k0, n0, b);
+                    if (CTAS == 1) {
+                        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
+                        tma_load_3d(st, &tm_a_hi, &full_bar[s], k0, m0, b);
+                        tma_load_3d(st + Cfg::A_TILE, &tm_w_hi, &full_bar[s], k0, n0, b);
+                        if (PREC == 3) {
+                            tma_load_3d(st + Cfg::A_TILE + Cfg::W_TILE, &tm_a_lo, &full_bar[s], k0, m0, b);
+                            tma_load_3d(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tm_w_lo, &full_bar[s], k0, n0, b);
+                        }
+                    } else {
+                        // both CTAs' loads report to the LEADER's barrier, which expects the bytes of the whole pair; the peer's
+                        // loads of this stage cannot run ahead of the phase (its empty barrier is released by the same commit)
+                        if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE);
+                        tma_load_3d_2sm(st, &tm_a_hi, &full_bar[s], k0, m0, b);
+                        tma_load_3d_2sm(st + Cfg::A_TILE, &tm_w_hi, &full_bar[s], k0, n0, b);
+                        if (PREC == 3) {
+                            tma_load_3d_2sm(st + Cfg::A_TILE + Cfg::W_TILE, &tm_a_lo, &full_bar[s], k0, m0, b);
+                            tma_load_3d_2sm(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tm_w_lo, &full_bar[s], k0, n0, b);
+                        }
                     }
-                    if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
-        int s = 0;
-        uint32_t ph = 0;
-        int acc = 0;
-        uint32_t acc_ph = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full_bar[s], ph);
+        // ===================== MMA issuer (pair: the leader CTA only) =====================
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * CTAS, BN);
+            int s = 0;
+            uint32_t ph = 0;
+            int acc = 0;
+            uint32_t acc_ph = 0;
+            for (int t = tile0; t < total_tiles; t += tile_step) {
+                mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t st = smem_u32(stage_base + s * Cfg::STAGE);
-                    const uint64_t a_hi = make_kmajor_desc<Cfg::SWZ>(st);
-                    const uint64_t w_hi = make_kmajor_desc<Cfg::SWZ>(st + Cfg::A_TILE);
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t st = smem_u32(stage_base + s * Cfg::STAGE);
+                        const uint64_t a_hi = make_kmajor_desc<Cfg::SWZ>(st);
+                        const uint64_t w_hi = make_kmajor_desc<Cfg::SWZ>(st + Cfg::A_TILE);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in addr>>4 units
-                        umma_f16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in addr>>4 units
+                            if (CTAS == 2) umma_f16_2sm(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
+                            else umma_f16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        if (PREC == 3) {
+                            const uint64_t a_lo = make_kmajor_desc<Cfg::SWZ>(st + Cfg::A_TILE + Cfg::W_TILE);
+                            const uint64_t w_lo = make_kmajor_desc<Cfg::SWZ>(st + 2 * Cfg::A_TILE + Cfg::W_TILE);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                if (CTAS == 2) umma_f16_2sm(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1);
+                                else umma_f16(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1);
+                            }
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                if (CTAS == 2) umma_f16_2sm(d_tmem, a_lo + 2 * k, w_hi + 2 * k, idesc, 1);
+                                else umma_f16(d_tmem, a_lo + 2 * k, w_hi + 2 * k, idesc, 1);
+                            }
+                        }
+                        if (CTAS == 2) {
+                            umma_commit_2sm(&empty_bar[s], 3);                         // stage free in both CTAs
+                            if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc], 3);   // accumulator halves ready in both CTAs
+                        } else {
+                            umma_commit(&empty_bar[s]);                       // smem stage free when MMAs retire
+                            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator ready
+                        }
                     }
-                    if (PREC == 3) {
-                        const uint64_t a_lo = make_kmajor_desc<Cfg::SWZ>(st + Cfg::A_TILE + Cfg::W_TILE);
-                        const uint64_t w_lo = make_kmajor_desc<Cfg::SWZ>(st + 2 * Cfg::A_TILE + Cfg::W_TILE);
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1);
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, w_hi + 2 * k, idesc, 1);
-                    }
-                    umma_commit(&empty_bar[s]);                       // smem stage free when MMAs retire
-                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator ready
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
-                __syncwarp();
-                if (++s == GEMM_STAGES) { s = 0; ph ^= 1; }
+                if (++acc == 2) { acc = 0; acc_ph ^= 1; }
             }
-            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
     } else {
         // ===================== epilogue (warps 2..17) =====================
@@ -448,15 +490,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int cbeg = cgroup * COLS_PER, cend = cbeg + COLS_PER;
         int acc = 0;
         uint32_t acc_ph = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = tile0; t < total_tiles; t += tile_step) {
             const int b = t / tiles_per_batch;
             const int r = t - b * tiles_per_batch;
             const int mt = p.m_fastest ? r % p.tiles_m : r / p.tiles_n, nt = p.m_fastest ? r / p.tiles_m : r - mt * p.tiles_n;
-            const int m0 = mt * GEMM_BM + quarter * 32, n0 = nt * BN;
+            const int m0 = (mt * CTAS + (int)rank) * GEMM_BM + quarter * 32, n0 = nt * BN;
             mbar_wait(&tfull_bar[acc], acc_ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-            if (active) {
+            if (active && m0 - quarter * 32 < p.M) {
                 if (p.transposed)
                     epilogue_transposed(p, taddr, b, m0, n0, cbeg, cend, lane);
                 else
@@ -467,19 +509,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         default: epilogue_rows<HIPIE_ACT_NONE>(p, taddr, my_epi, b, m0, n0, cbeg, cend, lane); break;
                     }
             }
-            // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+            // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp (of the leader CTA)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (CTAS == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (CTAS == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -560,16 +606,16 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols
     return HIPIE_OK;
 }
 
-template <int PREC, int BN>
+template <int PREC, int BN, int CTAS>
 static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
-    using Cfg = GemmCfg<PREC, BN>;
+    using Cfg = GemmCfg<PREC, BN, CTAS>;
     CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
     int rc;
     if ((rc = make_tmap_bf16(&ta_hi, a->a_hi, a->M, a->K, a->lda, a->batch, a->a_bstride, GEMM_BM, Cfg::BK))) return rc;
-    if ((rc = make_tmap_bf16(&tw_hi, a->w_hi, a->N, a->K, a->ldw, a->batch, a->w_bstride, BN, Cfg::BK))) return rc;
+    if ((rc = make_tmap_bf16(&tw_hi, a->w_hi, a->N, a->K, a->ldw, a->batch, a->w_bstride, Cfg::W_ROWS, Cfg::BK))) return rc;
     if (PREC == 3) {
         if ((rc = make_tmap_bf16(&ta_lo, a->a_lo, a->M, a->K, a->lda, a->batch, a->a_bstride, GEMM_BM, Cfg::BK))) return rc;
-        if ((rc = make_tmap_bf16(&tw_lo, a->w_lo, a->N, a->K, a->ldw, a->batch, a->w_bstride, BN, Cfg::BK))) return rc;
+        if ((rc = make_tmap_bf16(&tw_lo, a->w_lo, a->N, a->K, a->ldw, a->batch, a->w_bstride, Cfg::W_ROWS, Cfg::BK))) return rc;
     } else {
         ta_lo = ta_hi;
         tw_lo = tw_hi;
@@ -586,20 +632,34 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     p.row_map = a->c_row_map;
     p.t_row_group = a->transposed ? a->t_row_group : 0;
     p.t_row_pad = a->transposed ? a->t_row_pad : 0;
-    p.tiles_m = (a->M + GEMM_BM - 1) / GEMM_BM;
+    p.tiles_m = (a->M + GEMM_BM * CTAS - 1) / (GEMM_BM * CTAS);
     p.tiles_n = (a->N + BN - 1) / BN;
-    p.m_fastest = (p.tiles_m <= 8 && p.tiles_n >= 4 * p.tiles_m) ? 1 : 0;
+    p.m_fastest = (p.tiles_m * CTAS <= 8 && p.tiles_n >= 4 * p.tiles_m * CTAS) ? 1 : 0;
     const int64_t total = (int64_t)p.tiles_m * p.tiles_n * a->batch;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PREC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        attr_set = true;
+    HIPIE_ENSURE_SMEM((gemm_tc_kernel<PREC, BN, CTAS>), Cfg::SMEM);
+    const int units = num_sms() / CTAS;      // CTAs (or CTA pairs) that can be resident
+    const int grid = (int)(total < units ? total : units) * CTAS;
+    if (CTAS == 1) {
+        gemm_tc_kernel<PREC, BN, CTAS><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        HIPIE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<PREC, BN, CTAS>, ta_hi, ta_lo, tw_hi, tw_lo, p));
     }
-    const int grid = (int)(total < num_sms() ? total : num_sms());
-    gemm_tc_kernel<PREC, BN><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
 }
+
+// set by hipie_set_option("gemm_cta_pairs", 0|1): CTA-pair (cta_group::2) tiles for the large GEMMs
+int g_gemm_cta_pairs = 1;
 
 }  // namespace hipie
 
@@ -619,7 +679,20 @@ extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     HIPIE_CHECK_ARG(!a->c_lo || a->c_hi, "hipie_gemm: c_lo requires c_hi");
     HIPIE_CHECK_ARG(!a->c_row_map || !a->transposed, "hipie_gemm: c_row_map is not supported with transposed=1");
     cudaStream_t st = (cudaStream_t)stream;
-    if (a->N <= 64) return a->prec == 3 ? launch_gemm<3, 64>(a, st) : launch_gemm<1, 64>(a, st);
-    if (a->N <= 128) return a->prec == 3 ? launch_gemm<3, 128>(a, st) : launch_gemm<1, 128>(a, st);
-    return a->prec == 3 ? launch_gemm<3, 256>(a, st) : launch_gemm<1, 256>(a, st);
+    // CTA pairs for the big row counts (ViT / encoder linears); short or narrow problems stay on single-CTA tiles
+    const bool pairs = g_gemm_cta_pairs && a->M >= 1024 && a->N > 64;
+    if (a->N <= 64) return a->prec == 3 ? launch_gemm<3, 64, 1>(a, st) : launch_gemm<1, 64, 1>(a, st);
+    if (a->N <= 128) {
+        if (pairs) return a->prec == 3 ? launch_gemm<3, 128, 2>(a, st) : launch_gemm<1, 128, 2>(a, st);
+        return a->prec == 3 ? launch_gemm<3, 128, 1>(a, st) : launch_gemm<1, 128, 1>(a, st);
+    }
+    if (pairs) return a->prec == 3 ? launch_gemm<3, 256, 2>(a, st) : launch_gemm<1, 256, 2>(a, st);
+    return a->prec == 3 ? launch_gemm<3, 256, 1>(a, st) : launch_gemm<1, 256, 1>(a, st);
+}
+
+extern "C" int hipie_set_option(const char* name, int value) {
+    HIPIE_CHECK_ARG(name != nullptr, "hipie_set_option: null name");
+    if (strcmp(name, "gemm_cta_pairs") == 0) { g_gemm_cta_pairs = value ? 1 : 0; return HIPIE_OK; }
+    set_error("hipie_set_option: unknown option '%s'", name);
+    return HIPIE_EINVAL;
 }

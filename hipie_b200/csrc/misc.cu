@@ -562,11 +562,7 @@ extern "C" int hipie_row_softmax(const float* x, const float* colbias, int64_t r
                                                                p_f32, n, clampv, sub_rowmax);
     } else if (aligned && (int64_t)n * 4 <= 200 * 1024) {
         const int smem = n * 4;
-        static int smem_set = 0;
-        if (smem > smem_set) {
-            HIPIE_CHECK_CUDA(cudaFuncSetAttribute(row_softmax_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            smem_set = smem;
-        }
+        HIPIE_ENSURE_SMEM(row_softmax_smem_kernel, smem);
         row_softmax_smem_kernel<<<(unsigned)rows, 512, smem, st>>>(x, colbias, rows_per_batch, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
                                                                    p_f32, n, clampv, sub_rowmax);
     } else {
@@ -583,11 +579,7 @@ extern "C" int hipie_condinst_masks(const float* feats, const float* params, con
     HIPIE_CHECK_ARG(B > 0 && Q > 0 && Hf > 0 && Wf > 0 && (int64_t)Hf * Wf * 4 <= 200 * 1024,
                     "hipie_condinst_masks: bad sizes B=%d Q=%d Hf=%d Wf=%d", B, Q, Hf, Wf);
     const int smem = Hf * Wf * (int)sizeof(float);
-    static int smem_set = 0;
-    if (smem > smem_set) {
-        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(condinst_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
-    }
+    HIPIE_ENSURE_SMEM(condinst_kernel, smem);
     condinst_kernel<<<dim3(Q, B), 256, smem, (cudaStream_t)stream>>>(feats, params, ref_px, out, B, Q, Hf, Wf, stride);
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;

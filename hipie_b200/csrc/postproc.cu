@@ -582,11 +582,7 @@ static int launch_seg_post_tc(const float* masks, const void* pt_hi, const void*
                               int* ids, int* areas, int Q, int Qpad, int C, int h, int w, int Hc, int Wc, cudaStream_t st) {
     const int smem = PtSmem::OFF_CNT + 3 * Qpad * 4 + 1024;
     HIPIE_CHECK_ARG(smem <= 220 * 1024, "hipie_seg_postprocess: Q=%d needs %d B of shared memory", Q, smem);
-    static int smem_set = 0;
-    if (smem > smem_set) {
-        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(seg_post_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
-    }
+    HIPIE_ENSURE_SMEM(seg_post_tc_kernel, smem);
     dim3 grid(((Wc + 2 + 3) / 4 + PP_BX - 1) / PP_BX, ((Hc + 2 + 3) / 4 + PP_BY - 1) / PP_BY);
     seg_post_tc_kernel<<<grid, PT_THREADS, smem, st>>>(masks, (const __nv_bfloat16*)pt_hi, (const __nv_bfloat16*)pt_lo, scores,
                                                       sem, ids, areas, Q, Qpad, C, h, w, Hc, Wc);
@@ -631,11 +627,7 @@ int launch_seg_post(const float* masks, const void* pt_hi, const void* pt_lo, co
                     int* areas, int Q, int Qpad, int C, int h, int w, int Hc, int Wc, cudaStream_t st) {
     const int smem = 2 * PP_QC * PP_TQ * 4 + 4 * NT * 8 * PP_PQ * 2 + 2 * PP_QC * 4 + 3 * Qpad * 4;
     HIPIE_CHECK_ARG(smem <= 220 * 1024, "hipie_seg_postprocess: Q=%d needs %d B of shared memory", Q, smem);
-    static int smem_set = 0;
-    if (smem > smem_set) {
-        HIPIE_CHECK_CUDA(cudaFuncSetAttribute(seg_post_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
-    }
+    HIPIE_ENSURE_SMEM(seg_post_kernel<NT>, smem);
     dim3 grid(((Wc + 2 + 3) / 4 + PP_BX - 1) / PP_BX, ((Hc + 2 + 3) / 4 + PP_BY - 1) / PP_BY);
     seg_post_kernel<NT><<<grid, PP_THREADS, smem, st>>>(masks, (const __nv_bfloat16*)pt_hi, (const __nv_bfloat16*)pt_lo, scores,
                                                        sem, ids, areas, Q, Qpad, C, h, w, Hc, Wc);

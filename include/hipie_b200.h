@@ -56,6 +56,9 @@ const char* hipie_last_error(void);
 int hipie_abi_version(void);
 /* Number of kernel launches issued through this library by the calling process. */
 int64_t hipie_launch_count(void);
+/* Process-wide tuning switches (tests / A-B measurements).  "gemm_cta_pairs" (default 1): large GEMMs run as CTA pairs
+ * (tcgen05 cta_group::2, 256-row tiles); 0 forces single-CTA tiles.  Unknown names return HIPIE_EINVAL. */
+int hipie_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-scale deformable attention, forward.
