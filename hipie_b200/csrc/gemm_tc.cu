@@ -679,8 +679,10 @@ extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     HIPIE_CHECK_ARG(!a->c_lo || a->c_hi, "hipie_gemm: c_lo requires c_hi");
     HIPIE_CHECK_ARG(!a->c_row_map || !a->transposed, "hipie_gemm: c_row_map is not supported with transposed=1");
     cudaStream_t st = (cudaStream_t)stream;
-    // CTA pairs for the big row counts (ViT / encoder linears); short or narrow problems stay on single-CTA tiles
-    const bool pairs = g_gemm_cta_pairs && a->M >= 1024 && a->N > 64;
+    // CTA pairs where the mainloop dominates: big row counts, K >= 512, 3-pass operands (ViT / BERT / VL linears).  Measured on
+    // B200 (tools/gemm_check.py, profiles/r02_gemm_pairs.txt): fc1 32768x5120x1280 0.944 -> 0.844 ms, qk 0.489 -> 0.454 ms;
+    // K = 256 problems are epilogue/store-bound and lose 8-10 % with pairs, single-pass operands gain nothing.
+    const bool pairs = g_gemm_cta_pairs && a->M >= 1024 && a->N > 64 && a->K >= 512 && a->prec == 3;
     if (a->N <= 64) return a->prec == 3 ? launch_gemm<3, 64, 1>(a, st) : launch_gemm<1, 64, 1>(a, st);
     if (a->N <= 128) {
         if (pairs) return a->prec == 3 ? launch_gemm<3, 128, 2>(a, st) : launch_gemm<1, 128, 2>(a, st);

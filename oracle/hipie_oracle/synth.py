@@ -65,3 +65,26 @@ def make_batch(batch, h, w, num_classes, max_len, task="detection", seed=0):
         is_thing = {1: True}
     inputs = [dict(image=im, height=h, width=w, task=task, is_thing=is_thing, positive_map_label_to_token=pos_map) for im in imgs]
     return inputs, input_ids.repeat(batch, 1), attn.repeat(batch, 1)
+
+
+def fill_by_name_(module, seed=0):
+    """Deterministic parameters keyed by parameter NAME and shape (used to give a reference module and the oracle's restatement
+    of it identical weights without storing a state_dict in the fixture: the fill only agrees if names and shapes agree, so it
+    also checks state_dict compatibility).  matrices ~ N(0, 1/fan_in), norm weights ~ 1 + 0.1 N, everything else ~ 0.1 N."""
+    import zlib
+    with torch.no_grad():
+        items = list(module.named_parameters()) + [(n, b) for n, b in module.named_buffers() if b.dtype.is_floating_point]
+        for name, p in sorted(items, key=lambda kv: kv[0]):
+            g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 31))
+            r = torch.randn(p.shape, generator=g)
+            if "bg_query_refs" in name:
+                p.copy_(0.2 + 0.6 * torch.rand(p.shape, generator=g))
+            elif name.endswith("running_var"):
+                p.copy_(1.0 + 0.2 * torch.rand(p.shape, generator=g))
+            elif p.dim() > 1:
+                p.copy_(r / (p.shape[1:].numel() ** 0.5))
+            elif name.endswith("weight") and p.numel() > 1:
+                p.copy_(1.0 + 0.1 * r)
+            else:
+                p.copy_(0.1 * r)
+    return module
