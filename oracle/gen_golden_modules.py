@@ -132,6 +132,154 @@ def gen_transformer():
     print("ref_heads.pt")
 
 
+def gen_maskdino():
+    enc_mod = ref_import.ref("models.maskdino.pixel_decoder.maskdino_encoder")
+    dec_mod = ref_import.ref("models.maskdino.transformer_decoder.maskdino_decoder")
+    from detectron2.layers import ShapeSpec
+    torch.manual_seed(9)
+    c3, c4, c5, d = 24, 40, 40, 256       # 256: dino_decoder's ref_point_head consumes 4 x 128 sine features (hard-coded)
+    enc = enc_mod.MaskDINOEncoder(
+        {"res3": ShapeSpec(channels=c3, stride=8), "res4": ShapeSpec(channels=c4, stride=16), "res5": ShapeSpec(channels=c5, stride=32)},
+        transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=48, transformer_enc_layers=2, conv_dim=d, mask_dim=d,
+        norm="GN", transformer_in_features=["res3", "res4", "res5"], common_stride=4, num_feature_levels=3, total_num_feature_levels=4,
+        feature_order="low2high")
+    randomize_(enc, 10).eval()
+    g = torch.Generator().manual_seed(11)
+    feats = {"res3": torch.randn(2, c3, 12, 16, generator=g), "res4": torch.randn(2, c4, 6, 8, generator=g),
+             "res5": torch.randn(2, c5, 3, 4, generator=g)}
+    with torch.no_grad():
+        mask_features, out0, multi_scale = enc.forward_features(feats, None)
+    dec = dec_mod.MaskDINODecoder(d, True, num_classes=d, hidden_dim=d, num_queries=7, nheads=8, dim_feedforward=48, dec_layers=3, mask_dim=d,
+                                  enforce_input_project=False, two_stage=True, dn="seg", noise_scale=0.4, dn_num=100,
+                                  initialize_box_type="no", initial_pred=True, learn_tgt=False, total_num_feature_levels=4, dropout=0.0)
+    randomize_(dec, 12).eval()
+    with torch.no_grad():
+        out, _ = dec(multi_scale, mask_features, None)
+    torch.save(dict(enc_seed=10, dec_seed=12, enc_keys=sorted(enc.state_dict().keys()), dec_keys=sorted(dec.state_dict().keys()),
+                    in_channels=(c3, c4, c5), feats=feats, mask_features=mask_features, multi_scale=multi_scale,
+                    pred_logits=out["pred_logits"], pred_masks=out["pred_masks"], pred_boxes=out["pred_boxes"],
+                    interm_masks=out["interm_outputs"]["pred_masks"], interm_boxes=out["interm_outputs"]["pred_boxes"]),
+               os.path.join(OUT, "ref_maskdino.pt"))
+    print("ref_maskdino.pt", tuple(out["pred_masks"].shape), tuple(mask_features.shape))
+
+
+def gen_condinst():
+    dn = ref_import.ref("models.ddetrs_dn")
+    torch.manual_seed(13)
+    g = torch.Generator().manual_seed(14)
+    head = randomize_(dn.MaskHeadSmallConv(256, None, 256), 15).eval()
+    enc = [torch.randn(2, 256, 12, 16, generator=g), torch.randn(2, 256, 6, 8, generator=g), torch.randn(2, 256, 3, 4, generator=g)]
+    with torch.no_grad():
+        decod = head(enc, fpns=None)                           # (2, 8, 12, 16)
+    fake = types.SimpleNamespace(no_rel_pos=False, dynamic_mask_channels=8, weight_nums=[80, 64, 8], bias_nums=[8, 8, 1], mask_out_stride=4,
+                                 use_raft=False)
+    fake.mask_heads_forward = lambda *a: dn.DDETRSegmUniDN.mask_heads_forward(fake, *a)
+    nq = 5
+    params = torch.randn(2, nq, 169, generator=g)
+    ref_px = torch.rand(2, nq, 2, generator=g) * torch.tensor([128.0, 96.0])
+    with torch.no_grad():
+        logits = dn.DDETRSegmUniDN.dynamic_mask_with_coords(fake, decod, ref_px.reshape(1, 2 * nq, 2), params.reshape(1, 2 * nq, 169),
+                                                            num_insts=[nq, nq], mask_feat_stride=8, rel_coord=True, up_masks=None)
+    x = torch.randn(3, 1, 5, 7, generator=g)
+    torch.save(dict(head_seed=15, head_keys=sorted(head.state_dict().keys()), enc=enc, decod=decod, params=params, ref_px=ref_px,
+                    logits=logits.reshape(2, nq, logits.shape[-2], logits.shape[-1]), ab_in=x, ab_out=dn.aligned_bilinear(x, 2),
+                    locations=dn.compute_locations(3, 4, device="cpu", stride=8)),
+               os.path.join(OUT, "ref_condinst.pt"))
+    print("ref_condinst.pt", tuple(logits.shape))
+
+
+def gen_bert():
+    """BertEncoder.forward with a 1300-token prompt (chunk path) and a 40-token prompt (plain path) on a random-init 2-layer HF
+    BertModel: `from_pretrained` of the absent checkpoint directory is redirected to a seeded random model."""
+    import transformers
+    bm = ref_import.ref("models.deformable_detr.bert_model")
+    conf = transformers.BertConfig(vocab_size=30522, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=96,
+                                   max_position_embeddings=512, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    bm.BertConfig.from_pretrained = classmethod(lambda cls, *a, **k: conf)
+    bm.BertModel.from_pretrained = classmethod(lambda cls, *a, config=None, add_pooling_layer=False, **k: cls(config, add_pooling_layer=add_pooling_layer))
+    cfg = small_cfg()
+    cfg.MODEL.LANGUAGE_BACKBONE.MAX_QUERY_LEN = 2048
+    torch.manual_seed(16)
+    enc = bm.BertEncoder(cfg)
+    randomize_(enc, 17).eval()
+    from hipie_oracle import synth
+    ids, am, _, _ = synth.make_text(430, 2048, seed=18)
+    assert int(am.sum()) > 1024
+    ids = torch.cat([ids, ids.flip(0)[:, :1].expand(1, 2048) * 0 + ids], 0)           # batch of 2 (same prompt)
+    am = torch.cat([am, am], 0)
+    ids2, am2, _, _ = synth.make_text(12, 64, seed=19)
+    with torch.no_grad():
+        long = enc({"input_ids": ids, "attention_mask": am}, task="detection", sep=1012)
+        short = enc({"input_ids": ids2, "attention_mask": am2}, task="detection", sep=1012)
+    torch.save(dict(seed=17, keys=sorted(enc.state_dict().keys()), bert=dict(vocab=30522, hidden=64, layers=2, heads=4, inter=96, max_pos=512),
+                    ids=ids, am=am, hidden_long=long["hidden"], ids2=ids2, am2=am2, hidden_short=short["hidden"]),
+               os.path.join(OUT, "ref_bert_chunk.pt"))
+    print("ref_bert_chunk.pt", tuple(long["hidden"].shape), int(am[0].sum()))
+
+
+def gen_postproc():
+    """The reference's own HIPIE_IMG.inference (NMS / flat top-100 / x4 upsample + threshold / class pooling / softmax(sigmoid/T) /
+    semantic einsum / panoptic merge) and ddetrs.segmentation_postprocess, executed on synthetic head outputs with the REAL
+    detectron2 Instances / Boxes classes.  Two variants: mean pooling + FG/BG class masking (training yaml) and max pooling +
+    class-agnostic background (ADE eval yaml)."""
+    hi = ref_import.ref("hipie_img")
+    dd = ref_import.ref("models.ddetrs")
+    boxes_mod = ref_import._load_file("detectron2.structures.boxes", f"{ref_import.REF_ROOT}/detectron2/structures/boxes.py")
+    inst_mod = ref_import._load_file("detectron2.structures.instances", f"{ref_import.REF_ROOT}/detectron2/structures/instances.py")
+    for m in (hi, dd):
+        m.Instances, m.Boxes = inst_mod.Instances, boxes_mod.Boxes
+    hi.retry_if_cuda_oom = lambda f: f
+    g = torch.Generator().manual_seed(21)
+    B, nbg, nfg, nmd, Lt, C, h, w = 2, 3, 40, 12, 24, 6, 16, 20
+    H, W = 4 * h, 4 * w
+    pos_map = {1: [1, 2], 2: [4], 3: [6, 7, 8], 4: [10], 5: [12, 13], 6: [15]}
+    is_thing = {1: True, 2: True, 3: True, 4: True, 5: False, 6: False}
+    out = {"pred_logits": torch.randn(B, nbg + nfg, Lt, generator=g) * 2 - 1, "pred_boxes": torch.rand(B, nbg + nfg, 4, generator=g) * 0.5 + 0.2,
+           "pred_masks": torch.randn(B, nbg + nfg, 1, h, w, generator=g) * 3, "pred_boxious": torch.randn(B, nbg + nfg, 1, generator=g),
+           "pred_logits_maskdino": torch.randn(B, nmd, Lt, generator=g) * 2 - 1, "pred_masks_maskdino": torch.randn(B, nmd, h, w, generator=g) * 3,
+           "pred_boxes_maskdino": torch.rand(B, nmd, 4, generator=g)}
+    out["pred_boxes"][:, 10:14] = out["pred_boxes"][:, 5:9] + 0.003            # near-duplicates so that NMS removes something
+
+    def blobs(n):      # one soft rectangle per query (real mask logits are blob-like; pure noise never passes the overlap filter)
+        m = torch.full((B, n, h, w), -6.0)
+        for b in range(B):
+            for q in range(n):
+                y0, x0 = int(torch.randint(0, h - 5, (1,), generator=g)), int(torch.randint(0, w - 6, (1,), generator=g))
+                m[b, q, y0:y0 + int(torch.randint(3, 6, (1,), generator=g)), x0:x0 + int(torch.randint(3, 7, (1,), generator=g))] = 6.0
+        return m + torch.randn(B, n, h, w, generator=g)
+    out["pred_masks"] = blobs(nbg + nfg).unsqueeze(2)
+    out["pred_masks_maskdino"] = blobs(nmd)
+    image_sizes = [(H, W), (H - 6, W - 10)]
+    sizes = [(H, W), (50, 70)]                                                 # second image: resized semantic / panoptic output
+    variants = {}
+    for tag, max_pool, agn in (("mean_fgbg", False, False), ("maxpool_agnostic", True, True)):
+        fake = types.SimpleNamespace(num_bg=nbg, num_fg=nfg, ota=True, mode_free_inference=False, max_pool_token_test=max_pool, enable_clip=False,
+                                     demo_only=False, mask_on=True, mask_stride=4, mask_thres=0.5, use_bg_for_pano=False, bg_cls_agnostic=agn,
+                                     transform_eval=True, pano_temp=0.06, object_mask_threshold=0.25, overlap_threshold=0.8,
+                                     detr=types.SimpleNamespace(bg_query_from_lang=False, decouple_decoder=True, mask_dino_fixed_linear_head=False))
+        fake.semantic_inference = lambda *a, f=fake: hi.HIPIE_IMG.semantic_inference(f, *a)
+        fake.panoptic_inference = lambda *a, f=fake: hi.HIPIE_IMG.panoptic_inference(f, *a)
+        with torch.no_grad():
+            res = hi.HIPIE_IMG.inference(fake, out["pred_logits"].clone(), out["pred_boxes"].clone(), out["pred_masks"].clone(), image_sizes, pos_map, C,
+                                         task="detection", iou_pred=out["pred_boxious"].clone(), is_thing=[is_thing, is_thing], sizes=sizes,
+                                         output={k: v.clone() for k, v in out.items()})
+        packed = []
+        for r, (oh, ow) in zip(res, sizes):
+            inst = r["instances"]
+            raw_boxes = inst.pred_boxes.tensor.clone()        # segmentation_postprocess rescales the Boxes object in place
+            post = dd.segmentation_postprocess(inst, oh, ow)
+            packed.append(dict(pred_boxes=raw_boxes, scores=inst.scores, pred_classes=inst.pred_classes, pred_masks=inst.pred_masks,
+                               post_boxes=post.pred_boxes.tensor, post_masks=post.pred_masks, post_scores=post.scores, post_classes=post.pred_classes,
+                               sem_seg=r["sem_seg"], panoptic_seg=r["panoptic_seg"][0], segments_info=r["panoptic_seg"][1]))
+        variants[tag] = dict(max_pool=max_pool, bg_cls_agnostic=agn, results=packed)
+        print("ref_postproc", tag, [len(p["scores"]) for p in packed], [len(p["segments_info"]) for p in packed])
+    g2 = dict(logits=torch.randn(2, 5, Lt, generator=g))
+    g2["mean_fg"] = hi.convert_grounding_to_od_logits(g2["logits"], C, pos_map, is_thing=is_thing, mode="FG")
+    g2["max_bg"] = hi.convert_grounding_to_od_logits(g2["logits"], C, pos_map, is_thing=is_thing, mode="BG", max_pool=True)
+    torch.save(dict(out=out, image_sizes=image_sizes, sizes=sizes, pos_map=pos_map, is_thing=is_thing, num_classes=C, nbg=nbg, nfg=nfg,
+                    variants=variants, pool=g2), os.path.join(OUT, "ref_postproc.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or ["vit", "transformer", "maskdino", "condinst", "bert", "postproc"]

@@ -192,7 +192,8 @@ def install():
                 "models/deformable_detr/ops/functions", "models/deformable_detr/ops/modules", "models/maskdino",
                 "models/maskdino/utils", "models/maskdino/pixel_decoder", "models/maskdino/pixel_decoder/ops",
                 "models/maskdino/pixel_decoder/ops/functions", "models/maskdino/pixel_decoder/ops/modules",
-                "models/maskdino/transformer_decoder", "models/maskdino/meta_arch", "models/maskdino/backbone"):
+                "models/maskdino/transformer_decoder", "models/maskdino/meta_arch", "models/maskdino/backbone", "data/datasets", "models/sam",
+                "open_vocab"):
         if os.path.isdir(os.path.join(HIPIE, sub)):
             _mount("hipie." + sub.replace("/", "."), os.path.join(HIPIE, sub))
     for pkg in ("hipie.models.deformable_detr.ops", "hipie.models.maskdino.pixel_decoder.ops"):

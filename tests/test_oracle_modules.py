@@ -76,3 +76,96 @@ def test_heads_match_reference(golden_dir):
         assert torch.allclose(va(g["q"], g["emb"]), g["va_out"], atol=1e-5)
         mlp = fill_by_name_(detr.MLP(256, 256, 4, 3), g["mlp_seed"]).eval()
         assert torch.allclose(mlp(g["q"]), g["mlp_out"], atol=1e-5)
+
+
+def test_maskdino_encoder_decoder_match_reference(golden_dir):
+    """maskdino_encoder.py MaskDINOEncoder.forward_features (input_proj + GN, 2 MSDeformAttn encoder layers, FPN level on res3,
+    mask_features head) and maskdino_decoder.py MaskDINODecoder.forward (coarse->fine re-flattening, two-stage top-k, 3 DINO decoder
+    layers, double decoder_norm, mask-embed einsum, box refinement)"""
+    g = _load(golden_dir, "ref_maskdino.pt")
+    enc = maskdino.MaskDINOEncoder(g["in_channels"], conv_dim=256, mask_dim=256, enc_layers=2, dim_ff=48, nheads=8).eval()
+    _same_keys(enc, g["enc_keys"])
+    fill_by_name_(enc, g["enc_seed"])
+    with torch.no_grad():
+        mf, out0, ms = enc.forward_features(g["feats"])
+    assert torch.allclose(mf, g["mask_features"], atol=2e-5), (mf - g["mask_features"]).abs().max()
+    for a, b in zip(ms, g["multi_scale"]):
+        assert torch.allclose(a, b, atol=2e-5)
+    dec = maskdino.MaskDINODecoder(hidden_dim=256, num_queries=7, nheads=8, dim_feedforward=48, dec_layers=3, mask_dim=256, num_classes=256).eval()
+    _same_keys(dec, g["dec_keys"])
+    fill_by_name_(dec, g["dec_seed"])
+    with torch.no_grad():
+        out = dec(g["multi_scale"], g["mask_features"])
+    assert torch.allclose(out["pred_logits"], g["pred_logits"], atol=5e-5)
+    assert torch.allclose(out["pred_boxes"], g["pred_boxes"], atol=1e-5)
+    assert torch.allclose(out["interm_masks"], g["interm_masks"], atol=1e-4)
+    ref = g["pred_masks"]
+    assert (out["pred_masks"] - ref).abs().max() < 1e-5 * ref.abs().max() + 1e-4, (out["pred_masks"] - ref).abs().max()
+
+
+def test_condinst_matches_reference(golden_dir):
+    """ddetrs_dn.py MaskHeadSmallConv.forward, DDETRSegmUniDN.dynamic_mask_with_coords (+ mask_heads_forward, parse_dynamic_params),
+    compute_locations, aligned_bilinear"""
+    from hipie_oracle import condinst
+    from hipie_oracle.model import MaskHeadSmallConv
+    g = _load(golden_dir, "ref_condinst.pt")
+    head = MaskHeadSmallConv(256).eval()
+    _same_keys(head, g["head_keys"])
+    fill_by_name_(head, g["head_seed"])
+    with torch.no_grad():
+        decod = head(g["enc"])
+        assert torch.allclose(decod, g["decod"], atol=1e-5)
+        logits = condinst.dynamic_mask_with_coords(g["decod"], g["ref_px"], g["params"], stride=8)
+    ref = g["logits"]
+    assert (logits - ref).abs().max() < 1e-5 * ref.abs().max() + 1e-5, ((logits - ref).abs().max(), ref.abs().max())
+    assert torch.equal(condinst.aligned_bilinear(g["ab_in"], 2), g["ab_out"])
+    assert torch.equal(condinst.compute_locations(3, 4, stride=8), g["locations"])
+
+
+def test_bert_encoder_chunk_path_matches_reference(golden_dir):
+    """bert_model.py BertEncoder.forward: <= 512 tokens straight through HF BertModel; 1305 tokens through the chunking at
+    '.' / EOS boundaries with [CLS] re-insertion and scatter back (:68-135)"""
+    from hipie_oracle.model import BertEncoder
+    g = _load(golden_dir, "ref_bert_chunk.pt")
+    enc = BertEncoder({"bert": g["bert"]}).eval()
+    mine = sorted(k for k in enc.state_dict().keys())
+    assert mine == sorted(g["keys"]), sorted(set(mine) ^ set(g["keys"]))[:10]
+    fill_by_name_(enc, g["seed"])
+    with torch.no_grad():
+        long = enc({"input_ids": g["ids"], "attention_mask": g["am"]}, sep=1012)
+        short = enc({"input_ids": g["ids2"], "attention_mask": g["am2"]}, sep=1012)
+    assert torch.allclose(short["hidden"], g["hidden_short"], atol=1e-5)
+    assert torch.allclose(long["hidden"], g["hidden_long"], atol=1e-5), (long["hidden"] - g["hidden_long"]).abs().max()
+
+
+def test_postprocessing_matches_reference_inference(golden_dir):
+    """hipie_img.py HIPIE_IMG.inference (class pooling mean / max, FG / BG masking, sqrt(cls x iou), batched NMS 0.7, flat top-100,
+    x4 bilinear upsample + sigmoid > 0.5, softmax(sigmoid / 0.06), second resize, semantic einsum, panoptic merge incl. stuff merging)
+    and ddetrs.py segmentation_postprocess, both variants of the shipped yamls"""
+    import types
+    from hipie_oracle.model import HipieOracle
+    g = _load(golden_dir, "ref_postproc.pt")
+    pool = g["pool"]
+    assert torch.equal(HipieOracle.convert_grounding_to_od_logits(pool["logits"], g["num_classes"], g["pos_map"], g["is_thing"], mode="FG"), pool["mean_fg"])
+    assert torch.equal(HipieOracle.convert_grounding_to_od_logits(pool["logits"], g["num_classes"], g["pos_map"], g["is_thing"], mode="BG", max_pool=True),
+                       pool["max_bg"])
+    for tag, v in g["variants"].items():
+        fake = types.SimpleNamespace(num_bg=g["nbg"], num_fg=g["nfg"], mask_stride=4, mask_thres=0.5, pano_temp=0.06, object_mask_threshold=0.25,
+                                     overlap_threshold=0.8, max_pool=v["max_pool"], use_bg_for_pano=False, bg_cls_agnostic=v["bg_cls_agnostic"])
+        fake.convert_grounding_to_od_logits = HipieOracle.convert_grounding_to_od_logits
+        fake.semantic_inference = lambda *a, f=fake: HipieOracle.semantic_inference(f, *a)
+        fake.panoptic_inference = lambda *a, f=fake: HipieOracle.panoptic_inference(f, *a)
+        res = HipieOracle.inference(fake, {k: t.clone() for k, t in g["out"].items()}, g["image_sizes"], g["pos_map"], g["num_classes"], "detection",
+                                    [g["is_thing"], g["is_thing"]], g["sizes"])
+        for r, ref, isz, (oh, ow) in zip(res, v["results"], g["image_sizes"], g["sizes"]):
+            inst = r["instances"]
+            assert torch.equal(inst["pred_classes"], ref["pred_classes"]), tag
+            assert torch.allclose(inst["scores"], ref["scores"], atol=1e-6)
+            assert torch.allclose(inst["pred_boxes"], ref["pred_boxes"], atol=1e-4)
+            assert torch.equal(inst["pred_masks"], ref["pred_masks"])
+            post = HipieOracle.segmentation_postprocess(inst, isz, oh, ow)
+            assert torch.allclose(post["pred_boxes"], ref["post_boxes"], atol=1e-4)
+            assert torch.equal(post["pred_masks"], ref["post_masks"]) and torch.equal(post["pred_classes"], ref["post_classes"])
+            assert torch.allclose(r["sem_seg"], ref["sem_seg"], atol=1e-5)
+            assert torch.equal(r["panoptic_seg"][0], ref["panoptic_seg"])
+            assert r["panoptic_seg"][1] == ref["segments_info"] and len(ref["segments_info"]) > 0
