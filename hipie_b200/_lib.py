@@ -78,6 +78,9 @@ SYMBOLS = {
     "hipie_seg_postprocess": (c_int, [c_void_p] * 7 + [c_int] * 8 + [c_void_p]),
     "hipie_sine_embed": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hipie_upsample_threshold": (c_int, [c_void_p] * 2 + [c_int] * 6 + [c_float, c_void_p]),
+    "hipie_class_scores": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
+    "hipie_batched_nms": (c_int, [c_void_p] * 5 + [c_int, c_int, c_float, c_void_p]),
+    "hipie_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 

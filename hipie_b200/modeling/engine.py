@@ -630,7 +630,8 @@ class Engine:
         scores, _, _ = ops.gemm(om_ns, wc, bias=bc)
         scores = scores.view(B, S)
         nq = hp.get("num_queries", 900)
-        topk = torch.topk(scores, nq, dim=1)[1] if forced_topk is None else forced_topk
+        # two-stage selection on the device (ops.topk: values descending, lowest index first among exact ties -> deterministic)
+        topk = ops.topk(scores.contiguous(), nq)[1].long() if forced_topk is None else forced_topk
         # bbox_embed[nd] only on the selected rows (same values as computing all and gathering, :226-229)
         sel = torch.gather(om_n.view(B, S, 256), 1, topk.unsqueeze(-1).expand(-1, -1, 256)).reshape(B * nq, 256).contiguous()
         _, sel_s = ops.add_split(sel)
@@ -778,7 +779,7 @@ class Engine:
         cls_all, _, _ = ops.gemm(om_ns, wc, bias=bc)
         enc_scores = cls_all.view(B, S, -1).max(-1)[0]
         nq = hp.get("md_queries", 300)
-        topk = torch.topk(enc_scores, nq, dim=1)[1] if forced_topk is None else forced_topk
+        topk = ops.topk(enc_scores.contiguous(), nq)[1].long() if forced_topk is None else forced_topk
         tgt = torch.gather(om_n.view(B, S, 256), 1, topk.unsqueeze(-1).expand(-1, -1, 256)).contiguous()
         _, tgt_s = ops.add_split(tgt)
         delta = self.mlp(tgt_s.view(B * nq, 256), pr + "._bbox_embed", 3).view(B, nq, 4)

@@ -218,38 +218,42 @@ class HIPIE_IMG(nn.Module):
 
     # ---- post-processing (hipie_img.py:537-766, 473-535, 870-878, 1025-1052); device-side torch glue for now ("next" tier)
     def _pool_tables(self, positive_map, num_classes, Lt, is_thing, device):
-        """Token->class pooling as dense tables, built once per vocabulary (hipie_img.py:1025-1052 loops over classes with
-        host index tensors; here: one (Lt, C) mean matrix, a padded (C, maxlen) index table for max-pooling, class masks)."""
+        """Token->class pooling tables, built once per vocabulary (hipie_img.py:1025-1052 loops over the classes with host index
+        tensors): a padded (C, maxlen) int32 token table + token counts (0 = class absent from the positive map -> score 0, as in
+        the reference's zero-initialised `scores`) and the two -9999 masks (mode FG masks stuff classes, mode BG masks things)."""
         key = (tuple((k, tuple(v)) for k, v in sorted(positive_map.items())), num_classes, Lt, tuple(sorted(is_thing.items())))
         cache = self.__dict__.setdefault("_pool_cache", {})
         if key not in cache:
-            cache.clear()
-            mean_m = torch.zeros(Lt, num_classes)
+            if len(cache) > 8:
+                cache.clear()
             maxlen = max(len(v) for v in positive_map.values())
-            idx = torch.zeros(num_classes, maxlen, dtype=torch.long)
-            has = torch.zeros(num_classes, dtype=torch.bool)
+            tok = torch.zeros(num_classes, maxlen, dtype=torch.int32)
+            cnt = torch.zeros(num_classes, dtype=torch.int32)
+            fg = torch.zeros(num_classes, dtype=torch.int8)
+            bg = torch.zeros(num_classes, dtype=torch.int8)
             for label_j, toks in positive_map.items():
-                mean_m[toks, label_j - 1] = 1.0 / len(toks)
-                idx[label_j - 1, :len(toks)] = torch.tensor(toks)
-                idx[label_j - 1, len(toks):] = toks[0]
-                has[label_j - 1] = True
-            thing = torch.tensor([bool(is_thing.get(c + 1, True)) for c in range(num_classes)])
-            cache[key] = (mean_m.to(device), idx.to(device), has.to(device), thing.to(device))
+                if max(toks) >= Lt or min(toks) < 0:
+                    raise ValueError(f"positive map token {toks} of class {label_j} outside the {Lt} text positions")
+                tok[label_j - 1, :len(toks)] = torch.tensor(toks, dtype=torch.int32)
+                tok[label_j - 1, len(toks):] = toks[0]
+                cnt[label_j - 1] = len(toks)
+                thing = bool(is_thing.get(label_j, True))
+                fg[label_j - 1] = 0 if thing else 1
+                bg[label_j - 1] = 1 if thing else 0
+            cache[key] = (tok.to(device), cnt.to(device), fg.to(device), bg.to(device))
         return cache[key]
 
-    def convert_grounding_to_od_logits(self, logits, num_classes, positive_map, is_thing, mode=None, max_pool=False):
-        """logits (bs, Q, Lt) -> (bs, Q, C): per-class mean (or max) over its token span, -9999 for masked classes."""
-        mean_m, idx, has, thing = self._pool_tables(positive_map, num_classes, logits.shape[-1], is_thing, logits.device)
-        if max_pool:
-            scores = logits[:, :, idx].max(-1)[0]
-        else:
-            scores = torch.matmul(logits, mean_m)
-        scores = torch.where(has, scores, torch.zeros_like(scores))
-        if mode == "FG":
-            scores = torch.where(thing, scores, torch.full_like(scores, -9999.0))
-        elif mode == "BG":
-            scores = torch.where(thing, torch.full_like(scores, -9999.0), scores)
-        return scores
+    def convert_grounding_to_od_logits(self, logits, num_classes, positive_map, is_thing, mode=None, max_pool=False, iou=None):
+        """logits (bs, Q, Lt) -> scores (bs, Q, C): per-class mean (or max) over its token span, -9999 for masked classes; one kernel
+        (ops.class_scores).  With `iou` (bs, Q, 1) also returns prob = sqrt(sigmoid(score) * sigmoid(iou)), its row max and argmax."""
+        tok, cnt, fg, bg = self._pool_tables(positive_map, num_classes, logits.shape[-1], is_thing, logits.device)
+        masked = fg if mode == "FG" else (bg if mode == "BG" else None)
+        bs, Q, Lt = logits.shape
+        sc, prob, rmax, rarg = ops.class_scores(logits.reshape(bs * Q, Lt), tok, cnt, masked=masked,
+                                                iou=None if iou is None else iou.reshape(bs * Q), max_pool=max_pool, want_prob=iou is not None)
+        if iou is None:
+            return sc.view(bs, Q, num_classes)
+        return sc.view(bs, Q, num_classes), prob.view(bs, Q, num_classes), rmax.view(bs, Q), rarg.view(bs, Q)
 
     def semantic_inference(self, mask_cls, mask_pred):
         return torch.einsum("qc,qhw->chw", mask_cls, mask_pred.sigmoid())
@@ -330,26 +334,40 @@ class HIPIE_IMG(nn.Module):
 
     @torch.no_grad()
     def inference(self, out, image_sizes, positive_map, num_classes, task, is_thing, sizes):
-        import torchvision.ops as tvops
+        """HIPIE_IMG.inference (hipie_img.py:537-766, OTA path): class pooling, sqrt(cls x iou), class-aware NMS and the flat
+        top-100 run as kernels for the whole batch (ops.class_scores / batched_nms / topk); one device->host read of the kept
+        counts sizes the per-image tensors."""
         max_num_inst = 100 if task == "detection" else 1
         fg = self.num_bg
         box_cls, box_pred = out["pred_logits"][:, fg:], out["pred_boxes"][:, fg:]
         mask_pred, iou_pred = out["pred_masks"][:, fg:], out["pred_boxious"][:, fg:]
         box_cls_bg = out["pred_logits_maskdino"]
         mask_pred_bg = out["pred_masks_maskdino"].unsqueeze(2)
+        nimg = len(image_sizes)
+        Qfg = box_cls.shape[1]
+        # class scores / probabilities / NMS keys; images may carry different is_thing tables -> one launch per distinct table
+        logits_fg, prob_all, nms_scores, idxs = [None] * nimg, [None] * nimg, [None] * nimg, [None] * nimg
+        same_tables = all(is_thing[i] == is_thing[0] for i in range(nimg))
+        groups = [list(range(nimg))] if same_tables else [[i] for i in range(nimg)]
+        for grp in groups:
+            has_thing = any(is_thing[grp[0]].values())
+            sc, pr, rm, ra = self.convert_grounding_to_od_logits(box_cls[grp[0]:grp[-1] + 1], num_classes, positive_map, is_thing[grp[0]],
+                                                                 mode="FG" if has_thing else None, max_pool=self.max_pool,
+                                                                 iou=iou_pred[grp[0]:grp[-1] + 1])
+            for j, i in enumerate(grp):
+                logits_fg[i], prob_all[i], nms_scores[i], idxs[i] = sc[j], pr[j], rm[j], ra[j]
+        keep_all, nkeep = ops.batched_nms(box_pred, torch.stack(nms_scores), torch.stack(idxs), 0.7)
+        nk_host = nkeep.tolist()                       # the one host read of the selection stage
         results = []
-        for i in range(len(image_sizes)):
+        for i in range(nimg):
             image_size = image_sizes[i]
-            has_thing = any(is_thing[i].values())
-            logits_per_image = self.convert_grounding_to_od_logits(box_cls[i].unsqueeze(0), num_classes, positive_map, is_thing[i],
-                                                                   mode="FG" if has_thing else None, max_pool=self.max_pool)[0]
-            prob = torch.sqrt(logits_per_image.sigmoid() * iou_pred[i].sigmoid())
-            nms_scores, idxs = torch.max(prob, 1)
-            keep_indices = tvops.batched_nms(box_cxcywh_to_xyxy(box_pred[i]), nms_scores, idxs, 0.7)
-            prob = prob[keep_indices]
+            logits_per_image = logits_fg[i]
+            keep_indices = keep_all[i, :nk_host[i]].long()
+            prob = prob_all[i][keep_indices]
             num_inst = min(max_num_inst, prob.numel())
             box_k, mask_k = box_pred[i][keep_indices], mask_pred[i][keep_indices]
-            topk_values, topk_indexes = torch.topk(prob.view(-1), num_inst, dim=0)
+            topk_values, topk_indexes = ops.topk(prob.view(1, -1), num_inst)
+            topk_values, topk_indexes = topk_values[0], topk_indexes[0].long()
             topk_boxes = torch.div(topk_indexes, logits_per_image.shape[1], rounding_mode="floor")
             labels = topk_indexes % logits_per_image.shape[1]
             box_k, mask_i = box_k[topk_boxes], mask_k[topk_boxes]
@@ -374,8 +392,7 @@ class HIPIE_IMG(nn.Module):
                 mask_all = torch.cat([mask_pred[i][keep_indices], mask_pred_bg[i]], dim=0)
                 N, C, H, Wd = mask_all.shape
                 logits_all = F.softmax(logits_all.sigmoid() / self.pano_temp, dim=-1)
-                if (self.fused_postprocess and self.mask_stride == 4 and logits_all.shape[1] <= 136 and N <= 8192
-                        and tuple(sizes[i]) == tuple(image_size)):
+                if (self.fused_postprocess and self.mask_stride == 4 and N <= 8192 and tuple(sizes[i]) == tuple(image_size)):
                     pend = self.fused_sem_pano_launch(logits_all, mask_all[:, 0], image_size)
                     results.append(dict(instances=result, panoptic_seg=None, sem_seg=None, _pending=pend))
                     continue

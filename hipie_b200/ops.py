@@ -440,25 +440,34 @@ def condinst_masks(feats_nhwc, params, ref_px, Hf, Wf, stride=8):
 def seg_postprocess(masks_low, cls_prob, threshold, Hc, Wc, stride=4):
     """Fused semantic + panoptic tensor work for one image (hipie_seg_postprocess).
     masks_low (Q,h,w) f32 logits, cls_prob (Q,C) f32.  Returns sem (C,Hc,Wc), ids (Hc,Wc) i32 [-1 | 2q+inter], areas (3,Q) i32,
-    scores (Q), labels (Q)."""
+    scores (Q), labels (Q).  Any number of classes: vocabularies wider than one accumulator tile (80 classes on the tcgen05
+    kernel) run as class chunks of the same kernel, each writing its own rows of `sem`; the panoptic argmax / areas depend on the
+    per-query max over ALL classes only and are taken from the first chunk."""
     Q, h, w = masks_low.shape
     C = cls_prob.shape[1]
     dev = masks_low.device
     Qpad = (Q + 63) // 64 * 64
-    rows = 80 if C <= 80 else 136
-    pt = torch.zeros((rows, Qpad), dtype=torch.float32, device=dev)
-    pt[:C, :Q] = cls_prob.t()
-    hi = pt.to(torch.bfloat16)
-    lo = (pt - hi.float()).to(torch.bfloat16)
+    masks_low = masks_low.contiguous()
     scores, labels = cls_prob.max(-1)
     sc = torch.zeros((Qpad,), dtype=torch.float32, device=dev)
     sc[:Q] = torch.where(scores > threshold, scores, torch.zeros_like(scores))
     sem = torch.empty((C, Hc, Wc), dtype=torch.float32, device=dev)
     ids = torch.empty((Hc, Wc), dtype=torch.int32, device=dev)
     areas = torch.empty((3, Q), dtype=torch.int32, device=dev)
-    with _timed("seg_postprocess", float(masks_low.numel() + sem.numel() + ids.numel()) * 4):
-        _lib.check(_lib.load().hipie_seg_postprocess(_p(masks_low.contiguous()), _p(hi), _p(lo), _p(sc), _p(sem), _p(ids), _p(areas),
-                                                     Q, Qpad, C, h, w, stride, Hc, Wc, _stream()), "seg_postprocess")
+    chunk = C if C <= 136 else 80
+    for c0 in range(0, C, chunk):
+        cc = min(chunk, C - c0)
+        rows = 80 if cc <= 80 else 136
+        pt = torch.zeros((rows, Qpad), dtype=torch.float32, device=dev)
+        pt[:cc, :Q] = cls_prob[:, c0:c0 + cc].t()
+        hi = pt.to(torch.bfloat16)
+        lo = (pt - hi.float()).to(torch.bfloat16)
+        first = c0 == 0
+        ids_c = ids if first else torch.empty_like(ids)
+        areas_c = areas if first else torch.empty_like(areas)
+        with _timed("seg_postprocess", float(masks_low.numel() + cc * Hc * Wc + ids.numel()) * 4):
+            _lib.check(_lib.load().hipie_seg_postprocess(_p(masks_low), _p(hi), _p(lo), _p(sc), _p(sem[c0:c0 + cc]), _p(ids_c), _p(areas_c),
+                                                         Q, Qpad, cc, h, w, stride, Hc, Wc, _stream()), "seg_postprocess")
     return sem, ids, areas, scores, labels
 
 
@@ -484,3 +493,45 @@ def sine_embed(pos, want_f32=False, want_split=True):
     _lib.check(_lib.load().hipie_sine_embed(_p(pos), ld, rows, _p(out), _p(s.hi) if s else None,
                                             _p(s.lo) if (s and s.lo is not None) else None, _stream()), "sine_embed")
     return out, s
+
+
+def class_scores(logits, tok, cnt, masked=None, iou=None, max_pool=False, want_prob=True):
+    """Token -> class pooling + masking + sqrt(sigmoid(cls) * sigmoid(iou)) + per-row max / argmax (hipie_class_scores).
+    logits (R, Lt) f32; tok (C, maxlen) i32; cnt (C) i32; masked (C) i8 | None; iou (R) | None.
+    Returns scores (R, C), prob (R, C) | None, row_max (R) | None, row_arg (R) i32 | None."""
+    logits = logits.contiguous()
+    R, Lt = logits.shape
+    C, maxlen = tok.shape
+    dev = logits.device
+    scores = torch.empty((R, C), dtype=torch.float32, device=dev)
+    prob = torch.empty((R, C), dtype=torch.float32, device=dev) if want_prob else None
+    rmax = torch.empty((R,), dtype=torch.float32, device=dev) if want_prob else None
+    rarg = torch.empty((R,), dtype=torch.int32, device=dev) if want_prob else None
+    with _timed("class_scores"):
+        _lib.check(_lib.load().hipie_class_scores(_p(logits), _p(tok), _p(cnt), _p(masked), _p(iou.contiguous()) if iou is not None else None,
+                                                  _p(scores), _p(prob), _p(rmax), _p(rarg), R, Lt, C, maxlen, 1 if max_pool else 0, _stream()),
+                   "class_scores")
+    return scores, prob, rmax, rarg
+
+
+def batched_nms(boxes_cxcywh, scores, cls, iou_threshold):
+    """(B, N, 4) cxcywh boxes, (B, N) scores, (B, N) int32 classes -> keep (B, N) int32 (-1 padded, decreasing score), nkeep (B) int32."""
+    boxes_cxcywh, scores, cls = boxes_cxcywh.contiguous(), scores.contiguous(), cls.contiguous()
+    B, N = scores.shape
+    keep = torch.empty((B, N), dtype=torch.int32, device=scores.device)
+    nkeep = torch.empty((B,), dtype=torch.int32, device=scores.device)
+    with _timed("batched_nms"):
+        _lib.check(_lib.load().hipie_batched_nms(_p(boxes_cxcywh), _p(scores), _p(cls), _p(keep), _p(nkeep), B, N, float(iou_threshold), _stream()),
+                   "batched_nms")
+    return keep, nkeep
+
+
+def topk(values, k, n_rows=None, n_cols_per_row=0):
+    """values (R, n) f32 (row-contiguous) -> (R, k) values descending, (R, k) int32 indices; optional device-side valid row counts."""
+    assert values.dim() == 2 and values.stride(1) == 1
+    R, n = values.shape
+    ov = torch.empty((R, k), dtype=torch.float32, device=values.device)
+    oi = torch.empty((R, k), dtype=torch.int32, device=values.device)
+    with _timed("topk"):
+        _lib.check(_lib.load().hipie_topk(_p(values), values.stride(0), _p(n_rows), n_cols_per_row, R, n, k, _p(ov), _p(oi), _stream()), "topk")
+    return ov, oi

@@ -248,6 +248,31 @@ int hipie_upsample_threshold(const float* masks, void* out_u8, int N, int h, int
  * temperature 1e4, scale 2*pi.  out f32 and/or bf16 hi/lo planes (operand of the ref_point_head MLP). */
 int hipie_sine_embed(const float* pos, int64_t ld, int64_t rows, float* out, void* hi, void* lo, void* stream);
 
+/* ---- device-side selection steps of the inference post-processing (projects/HIPIE/hipie/hipie_img.py:587-657, 1025-1052) ----
+ * hipie_class_scores: token -> class pooling of grounding logits (`convert_grounding_to_od_logits`).
+ *   logits (R, Lt) f32 | tok (C, maxlen) i32 token indices of each class, cnt (C) i32 tokens per class (0 = class not in the
+ *   positive map: score 0) | masked (C) i8 or NULL: 1 = class forced to -9999 (mode FG: stuff classes, mode BG: thing classes)
+ *   iou (R) f32 logits or NULL | max_pool: 0 mean, 1 max over the class's tokens
+ *   scores (R, C) f32 out | prob (R, C) f32 out or NULL: sqrt(sigmoid(score) * sigmoid(iou)) (sigmoid(score) if iou NULL)
+ *   row_max (R) f32 / row_arg (R) i32 out or NULL: max / first argmax of prob over the classes (the NMS keys). */
+int hipie_class_scores(const float* logits, const int* tok, const int* cnt, const int8_t* masked, const float* iou,
+                       float* scores, float* prob, float* row_max, int* row_arg, int R, int Lt, int C, int maxlen,
+                       int max_pool, void* stream);
+
+/* hipie_batched_nms: torchvision.ops.batched_nms semantics (coordinate-offset trick: box + cls * (max_coord + 1), greedy in
+ * decreasing score, IoU = inter / (a + b - inter) > threshold), one launch for B images.
+ *   boxes (B, N, 4) f32 (cx, cy, w, h) | scores (B, N) f32 | cls (B, N) i32
+ *   keep (B, N) i32 out: kept indices in decreasing score order, -1 padded | nkeep (B) i32 out.  N <= ~1300. */
+int hipie_batched_nms(const float* boxes_cxcywh, const float* scores, const int* cls, int* keep, int* nkeep, int B, int N,
+                      float iou_threshold, void* stream);
+
+/* hipie_topk: k largest of each row, values descending, lowest index first among equal values (torch.topk, largest=True).
+ *   values: row r starts at values + r * row_stride; its length is n, or min(n, n_rows[r] * n_cols_per_row) when n_rows != NULL
+ *   (a compacted (rows x cols) matrix whose valid row count lives on the device).  out_val (R, k) f32, out_idx (R, k) i32;
+ *   rows shorter than k are padded with (-inf, -1).  k <= 1024. */
+int hipie_topk(const float* values, int64_t row_stride, const int* n_rows, int n_cols_per_row, int R, int n, int k,
+               float* out_val, int* out_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -571,3 +571,114 @@ def test_gemm_row_major_bits_short_wide(ops, cuda):
     want = (want << torch.arange(32)).sum(-1)
     want = torch.where(want >= 2 ** 31, want - 2 ** 32, want).int()
     assert torch.equal(bits.cpu().view(B, M, N // 32), want)
+
+
+# ------------------------------------------------------------------------------------------------ selection kernels (a20)
+@pytest.mark.parametrize("max_pool", [False, True])
+def test_class_scores_matches_reference_loop(cuda, max_pool):
+    """hipie_class_scores against the reference's per-class host loop (hipie_img.py:1025-1052, restated in the oracle)."""
+    from hipie_oracle.model import HipieOracle
+    from hipie_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    R, Lt, C = 37, 64, 11
+    pos_map, cur = {}, 1
+    for c in range(1, C + 1):
+        if c == 4:
+            continue                                   # a class missing from the positive map keeps score 0
+        n = 1 + (c % 3)
+        pos_map[c] = list(range(cur, cur + n))
+        cur += n + 1
+    is_thing = {c: c % 2 == 1 for c in range(1, C + 1)}
+    logits = torch.randn(2, R, Lt, generator=g) * 3
+    iou = torch.randn(2, R, 1, generator=g)
+    maxlen = max(len(v) for v in pos_map.values())
+    tok = torch.zeros(C, maxlen, dtype=torch.int32)
+    cnt = torch.zeros(C, dtype=torch.int32)
+    fg = torch.zeros(C, dtype=torch.int8)
+    for c, t in pos_map.items():
+        tok[c - 1, :len(t)] = torch.tensor(t, dtype=torch.int32)
+        cnt[c - 1] = len(t)
+        fg[c - 1] = 0 if is_thing[c] else 1
+    ref = HipieOracle.convert_grounding_to_od_logits(logits, C, pos_map, is_thing, mode="FG", max_pool=max_pool)
+    ref_prob = torch.sqrt(ref.sigmoid() * iou.sigmoid())
+    sc, prob, rmax, rarg = ops.class_scores(logits.view(-1, Lt).cuda(), tok.cuda(), cnt.cuda(), masked=fg.cuda(), iou=iou.view(-1).cuda(),
+                                            max_pool=max_pool)
+    assert torch.allclose(sc.cpu().view(2, R, C), ref, atol=1e-6)
+    assert torch.allclose(prob.cpu().view(2, R, C), ref_prob, atol=1e-6)
+    m, a = ref_prob.view(-1, C).max(1)
+    assert torch.allclose(rmax.cpu(), m, atol=1e-6) and torch.equal(rarg.cpu().long(), a)
+    sc2, _, _, _ = ops.class_scores(logits.view(-1, Lt).cuda(), tok.cuda(), cnt.cuda(), masked=None, iou=None, max_pool=max_pool, want_prob=False)
+    assert torch.allclose(sc2.cpu().view(2, R, C), HipieOracle.convert_grounding_to_od_logits(logits, C, pos_map, is_thing, mode=None, max_pool=max_pool), atol=1e-6)
+
+
+@pytest.mark.parametrize("N", [1, 37, 900])
+def test_batched_nms_matches_torchvision(cuda, N):
+    """hipie_batched_nms against torchvision.ops.batched_nms (what the reference calls, hipie_img.py:629) incl. near-duplicate
+    boxes, several classes and equal scores."""
+    import torchvision.ops as tvops
+    from hipie_b200 import ops
+    g = torch.Generator().manual_seed(N)
+    B = 3
+    boxes = torch.cat([torch.rand(B, N, 2, generator=g) * 0.6 + 0.2, torch.rand(B, N, 2, generator=g) * 0.3 + 0.05], -1)
+    if N > 10:
+        boxes[:, N // 2:N // 2 + N // 4] = boxes[:, :N // 4] + torch.randn(B, N // 4, 4, generator=g) * 0.01     # heavy overlaps
+    scores = torch.rand(B, N, generator=g)
+    if N > 10:
+        scores[:, 5] = scores[:, 3]                                                                              # an exact tie
+    cls = torch.randint(0, 4, (B, N), generator=g, dtype=torch.int32)
+    keep, nkeep = ops.batched_nms(boxes.cuda(), scores.cuda(), cls.cuda(), 0.7)
+    for b in range(B):
+        cx, cy, w, h = boxes[b].unbind(-1)
+        xyxy = torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
+        ref = tvops.batched_nms(xyxy, scores[b], cls[b].long(), 0.7)
+        n = int(nkeep[b])
+        assert n == len(ref), (n, len(ref))
+        assert torch.equal(keep[b, :n].cpu().long(), ref)
+        assert bool((keep[b, n:] == -1).all())
+
+
+@pytest.mark.parametrize("n,k", [(50, 100), (2400, 100), (21760, 900), (700000, 100)])
+def test_topk_matches_torch(cuda, n, k):
+    from hipie_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    v = torch.randn(3, n, generator=g)
+    v[1, : n // 2] = v[1, n // 2: n // 2 * 2]            # many exact ties
+    v[2, ::3] = -9999.0
+    ov, oi = ops.topk(v.cuda(), k)
+    kk = min(k, n)
+    rv, ri = torch.topk(v, kk, dim=1)
+    assert torch.equal(ov[:, :kk].cpu(), rv)
+    # indices: same values, and among equal values the lowest index first
+    assert torch.equal(torch.gather(v, 1, oi[:, :kk].cpu().long()), rv)
+    for r in range(3):
+        idx = oi[r, :kk].cpu().long()
+        assert len(set(idx.tolist())) == kk
+        same = rv[r, 1:] == rv[r, :-1]
+        assert bool((idx[1:][same] > idx[:-1][same]).all())
+    if k > n:
+        assert bool((oi[:, n:] == -1).all()) and bool(torch.isinf(ov[:, n:]).all())
+    # device-side row count: only the first 7 rows x 10 columns of a compacted matrix are valid
+    if n >= 100:
+        nr = torch.tensor([7, 0, 3], dtype=torch.int32)
+        ov2, oi2 = ops.topk(v.cuda(), 20, n_rows=nr.cuda(), n_cols_per_row=10)
+        assert torch.equal(ov2[0].cpu(), torch.topk(v[0, :70], 20)[0]) and bool((oi2[1] == -1).all())
+        assert torch.equal(ov2[2].cpu(), torch.topk(v[2, :30], 20)[0])
+
+
+def test_seg_postprocess_wide_vocabulary(cuda):
+    """C = 150 and 847 classes (ADE-150 / ADE-847): class chunks of the fused kernel against the op chain."""
+    from hipie_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for C, Q in ((150, 70), (847, 40)):
+        masks = torch.randn(Q, 24, 32, generator=g) * 4
+        cls = torch.softmax(torch.randn(Q, C, generator=g) * 3, -1)
+        sem, ids, areas, scores, labels = ops.seg_postprocess(masks.cuda(), cls.cuda(), 0.25, 96, 120)
+        up = torch.nn.functional.interpolate(masks[None], size=(96, 128), mode="bilinear", align_corners=False)[0][:, :, :120].sigmoid()
+        ref = torch.einsum("qc,qhw->chw", cls, up)
+        assert (sem.cpu() - ref).abs().max() < 1e-3 * max(1.0, ref.abs().max().item())
+        sc, lb = cls.max(-1)
+        keep = sc > 0.25
+        prob = torch.where(keep[:, None, None], sc[:, None, None] * up, torch.full_like(up, -1.0))
+        win = prob.argmax(0)
+        got = ids.cpu()
+        assert ((got >> 1) == win).float().mean() > 0.999 or not keep.any()
