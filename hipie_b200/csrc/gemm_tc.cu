@@ -33,6 +33,7 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_EPI_WARPS = 16;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // TMA warp, MMA warp, 16 epilogue warps
 constexpr int EPI_LD = 16;  // row length (floats) of the epilogue transpose buffer; 16-byte groups are XOR-swizzled by row
+constexpr int EPI_WARP_BYTES = 4096;   // per epilogue warp: one 32 x 32 fp32 TMA-store box (or a 32 x 32 bf16 hi box + lo box)
 
 struct GemmParams {
     const float* bias;
@@ -50,6 +51,7 @@ struct GemmParams {
     float alpha;
     int transposed;  // 1: C stored as [N, ldc] (column-major output), lanes = rows
     int tiles_m, tiles_n;
+    int tma_out;     // row-major outputs leave through TMA stores (32 x 32 boxes staged in swizzled shared memory)
     int m_fastest;   // tile order: 1 = the few M tiles of one N tile run back to back (concurrently on neighbouring SMs), so the
                      // big streamed W operand is fetched from HBM once and re-read from L2 (short, wide problems)
     const int* row_map;
@@ -68,8 +70,11 @@ struct GemmCfg {
     static constexpr int W_TILE = W_ROWS * BK * 2;
     static constexpr int NPLANES = PREC == 3 ? 2 : 1;
     static constexpr int STAGE = NPLANES * (A_TILE + W_TILE);
-    static constexpr int STAGES = CTAS == 2 ? 6 : 4;
-    static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 32 * EPI_LD * 4;
+    static constexpr int EPI_BYTES = GEMM_EPI_WARPS * EPI_WARP_BYTES;
+    static constexpr int SMEM_BUDGET = 232448 - 1024 - 256 - EPI_BYTES;                  // 227 KB per CTA
+    static constexpr int MAX_STAGES = CTAS == 2 ? 6 : 4;
+    static constexpr int STAGES = SMEM_BUDGET / STAGE < MAX_STAGES ? SMEM_BUDGET / STAGE : MAX_STAGES;
+    static_assert(STAGES >= 3, "pipeline too shallow");
     static constexpr int SMEM = STAGES * STAGE + EPI_BYTES + 256 + 1024;
     static constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : (2 * BN >= 128 ? 128 : 64));
 };
@@ -270,6 +275,96 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
     }
 }
 
+__device__ __forceinline__ float4 load4_guard(const float* p, int col, int N, float fill) {
+    if (col + 3 < N) return *reinterpret_cast<const float4*>(p + col);
+    float4 r = make_float4(fill, fill, fill, fill);
+    if (col < N) r.x = p[col];
+    if (col + 1 < N) r.y = p[col + 1];
+    if (col + 2 < N) r.z = p[col + 2];
+    return r;
+}
+
+// Row-major epilogue through TMA stores.  The warp reads 32 accumulator columns per step (lane = row), applies the fused
+// bias / activation / layer-scale in that layout, writes the 32 x 32 box into its private staging buffer in the tensor map's
+// swizzled layout (128 B rows for fp32, 64 B rows per bf16 plane: conflict-free 16-byte stores) and one lane hands the box to
+// the TMA unit: full-line global writes that do not occupy the LSU, clipped at the matrix edges by the hardware.  The bit-packed
+// (x > threshold) output falls out of the layout for free: a lane's 32 columns are one 32-bit word of its row.
+template <int ACT>
+__device__ __forceinline__ void epilogue_rows_tma(const GemmParams& p, const CUtensorMap* tm_f32, const CUtensorMap* tm_hi,
+                                                  const CUtensorMap* tm_lo, uint32_t taddr, uint32_t sbuf, int b, int m0, int n0,
+                                                  int col_begin, int col_end, int lane) {
+    if (m0 >= p.M) return;          // warp-uniform: this 32-row group lies below the matrix
+    const float alpha = p.alpha;
+    const int row = m0 + lane;
+    const int npass = (p.c_f32 ? 1 : 0) + (p.c_hi ? 1 : 0);
+#pragma unroll 1
+    for (int cb = col_begin; cb < col_end; cb += 32) {
+        const int nbase = n0 + cb;
+        if (nbase >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + cb, v);
+        tmem_ld_wait();
+#pragma unroll 1
+        for (int pass = 0; pass < npass; ++pass) {
+            const bool planes = p.c_hi && (pass == npass - 1) && !(p.c_f32 && pass == 0);
+            // the previous box must have been read out of the staging buffer before it is overwritten
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            uint32_t word = 0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const int col = nbase + 4 * g;
+                float4 x = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                       __uint_as_float(v[4 * g + 3]));
+                float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) bias = load4_guard(p.bias, col, p.N, 0.f);
+                x.x = act_apply_t<ACT>(fmaf(x.x, alpha, bias.x));
+                x.y = act_apply_t<ACT>(fmaf(x.y, alpha, bias.y));
+                x.z = act_apply_t<ACT>(fmaf(x.z, alpha, bias.z));
+                x.w = act_apply_t<ACT>(fmaf(x.w, alpha, bias.w));
+                if (p.colscale) {
+                    const float4 cs = load4_guard(p.colscale, col, p.N, 1.f);
+                    x.x *= cs.x; x.y *= cs.y; x.z *= cs.z; x.w *= cs.w;
+                }
+                if (p.c_bits && pass == 0) {
+                    word |= ((x.x > p.bits_threshold && col < p.N) ? 1u : 0u) << (4 * g);
+                    word |= ((x.y > p.bits_threshold && col + 1 < p.N) ? 1u : 0u) << (4 * g + 1);
+                    word |= ((x.z > p.bits_threshold && col + 2 < p.N) ? 1u : 0u) << (4 * g + 2);
+                    word |= ((x.w > p.bits_threshold && col + 3 < p.N) ? 1u : 0u) << (4 * g + 3);
+                }
+                if (!planes) {
+                    // fp32 box: 128-byte rows, 16-byte group g of row r at g ^ (r & 7)  (CU_TENSOR_MAP_SWIZZLE_128B)
+                    sts128(sbuf + lane * 128 + ((g ^ (lane & 7)) << 4), __float_as_uint(x.x), __float_as_uint(x.y), __float_as_uint(x.z),
+                           __float_as_uint(x.w));
+                } else {
+                    // bf16 boxes: 64-byte rows, 16-byte group c of row r at c ^ ((r >> 1) & 3)  (CU_TENSOR_MAP_SWIZZLE_64B)
+                    uint2 hi, lo;
+                    split2(x.x, x.y, hi.x, lo.x);
+                    split2(x.z, x.w, hi.y, lo.y);
+                    const uint32_t off = lane * 64 + (((g >> 1) ^ ((lane >> 1) & 3)) << 4) + ((g & 1) << 3);
+                    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sbuf + off), "r"(hi.x), "r"(hi.y) : "memory");
+                    if (p.c_lo) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sbuf + 2048 + off), "r"(lo.x), "r"(lo.y) : "memory");
+                }
+            }
+            fence_proxy_async_smem();      // generic-proxy writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                if (!planes) {
+                    tma_store_3d(tm_f32, sbuf, nbase, m0, b);
+                } else {
+                    tma_store_3d(tm_hi, sbuf, nbase, m0, b);
+                    if (p.c_lo) tma_store_3d(tm_lo, sbuf + 2048, nbase, m0, b);
+                }
+                bulk_commit();
+            }
+            if (p.c_bits && pass == 0 && row < p.M) {
+                const int64_t words_per_row = (p.N + 31) / 32;
+                p.c_bits[((int64_t)b * p.M + row) * words_per_row + (nbase >> 5)] = word;
+            }
+        }
+    }
+}
+
 // Transposed epilogue (C stored [col * ldc + row]): lanes hold 32 consecutive rows, so each register j is a
 // coalesced 128-byte store along M; optional bit-packed (x > threshold) output packed along M.
 __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, uint32_t taddr, int b, int m0, int n0,
@@ -326,7 +421,8 @@ template <int PREC, int BN, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tm_c_f32, const __grid_constant__ CUtensorMap tm_c_hi,
+               const __grid_constant__ CUtensorMap tm_c_lo, const GemmParams p) {
     using Cfg = GemmCfg<PREC, BN, CTAS>;
     constexpr int BK = Cfg::BK;
     constexpr int STAGES = Cfg::STAGES;
@@ -484,7 +580,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int quarter = warp & 3;
         const int ew = warp - 2;                 // 0..15
         const int cgroup = ew >> 2;              // which slice of the BN columns
-        float* my_epi = epi + ew * 32 * EPI_LD;
+        float* my_epi = epi + ew * (EPI_WARP_BYTES / 4);          // 4 KB per warp (1024-byte aligned: TMA swizzle atoms)
+        const uint32_t my_sbuf = smem_u32(my_epi);
+        if (p.tma_out && lane == 0) {
+            if (p.c_f32) prefetch_tmap(&tm_c_f32);
+            if (p.c_hi) prefetch_tmap(&tm_c_hi);
+            if (p.c_lo) prefetch_tmap(&tm_c_lo);
+        }
         constexpr int COLS_PER = BN / 4 >= 32 ? BN / 4 : 32;   // columns per warp (multiple of the 32-column transposed chunk)
         const bool active = cgroup * COLS_PER < BN;
         const int cbeg = cgroup * COLS_PER, cend = cbeg + COLS_PER;
@@ -501,6 +603,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             if (active && m0 - quarter * 32 < p.M) {
                 if (p.transposed)
                     epilogue_transposed(p, taddr, b, m0, n0, cbeg, cend, lane);
+                else if (p.tma_out)
+                    switch (p.act) {
+                        case HIPIE_ACT_RELU: epilogue_rows_tma<HIPIE_ACT_RELU>(p, &tm_c_f32, &tm_c_hi, &tm_c_lo, taddr, my_sbuf, b, m0, n0, cbeg, cend, lane); break;
+                        case HIPIE_ACT_GELU: epilogue_rows_tma<HIPIE_ACT_GELU>(p, &tm_c_f32, &tm_c_hi, &tm_c_lo, taddr, my_sbuf, b, m0, n0, cbeg, cend, lane); break;
+                        case HIPIE_ACT_SIGMOID: epilogue_rows_tma<HIPIE_ACT_SIGMOID>(p, &tm_c_f32, &tm_c_hi, &tm_c_lo, taddr, my_sbuf, b, m0, n0, cbeg, cend, lane); break;
+                        default: epilogue_rows_tma<HIPIE_ACT_NONE>(p, &tm_c_f32, &tm_c_hi, &tm_c_lo, taddr, my_sbuf, b, m0, n0, cbeg, cend, lane); break;
+                    }
                 else
                     switch (p.act) {
                         case HIPIE_ACT_RELU: epilogue_rows<HIPIE_ACT_RELU>(p, taddr, my_epi, b, m0, n0, cbeg, cend, lane); break;
@@ -518,6 +627,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             }
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
+        if (p.tma_out && lane == 0) bulk_wait0();     // outstanding TMA stores read this CTA's shared memory
     }
 
     tc_fence_before();
@@ -552,7 +662,7 @@ static EncodeTiledFn get_encode_fn() {
 struct TmapKey {
     const void* ptr;
     int64_t rows, cols, ld, bstride;
-    int batch, box_rows, box_cols;
+    int batch, box_rows, box_cols, esize, pad_;
     bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapKeyHash {
@@ -566,14 +676,23 @@ struct TmapKeyHash {
 
 // bf16 matrix (batch, rows, cols) with row stride ld and batch stride bstride (elements);
 // box = (box_cols along K, box_rows, 1); swizzle span == box_cols*2 bytes.
+int make_tmap(CUtensorMap* out, const void* ptr, int esize, int64_t rows, int64_t cols, int64_t ld, int batch, int64_t bstride,
+              int box_rows, int box_cols);
+
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int batch,
                    int64_t bstride, int box_rows, int box_cols) {
+    return make_tmap(out, ptr, 2, rows, cols, ld, batch, bstride, box_rows, box_cols);
+}
+
+// matrix (batch, rows, cols) of 2-byte (bf16) or 4-byte (fp32) elements; swizzle span == box_cols * esize bytes (32 / 64 / 128)
+int make_tmap(CUtensorMap* out, const void* ptr, int esize, int64_t rows, int64_t cols, int64_t ld, int batch, int64_t bstride,
+              int box_rows, int box_cols) {
     static std::mutex mu;
     static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
     TmapKey key;
     memset(&key, 0, sizeof(key));
     key.ptr = ptr; key.rows = rows; key.cols = cols; key.ld = ld; key.bstride = bstride;
-    key.batch = batch; key.box_rows = box_rows; key.box_cols = box_cols;
+    key.batch = batch; key.box_rows = box_rows; key.box_cols = box_cols; key.esize = esize;
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -582,15 +701,15 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return HIPIE_ECUDA; }
     HIPIE_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map base %p not 16B aligned", ptr);
-    HIPIE_CHECK_ARG((ld * 2) % 16 == 0, "row stride %lld elements is not a multiple of 8", (long long)ld);
-    HIPIE_CHECK_ARG(batch == 1 || (bstride * 2) % 16 == 0, "batch stride must be a multiple of 8 elements");
+    HIPIE_CHECK_ARG((ld * esize) % 16 == 0, "row stride %lld elements is not a multiple of 16 bytes", (long long)ld);
+    HIPIE_CHECK_ARG(batch == 1 || (bstride * esize) % 16 == 0, "batch stride must be a multiple of 16 bytes");
     cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? bstride : rows * ld) * 2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * esize, (cuuint64_t)(batch > 1 ? bstride : rows * ld) * esize};
     cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUtensorMapSwizzle swz = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                             : (box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUtensorMapSwizzle swz = box_cols * esize == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                             : (box_cols * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = enc(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -606,6 +725,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols
     return HIPIE_OK;
 }
 
+// hipie_set_option switches (A/B measurements, fallbacks): CTA-pair (cta_group::2) tiles, TMA-store epilogue
+int g_gemm_cta_pairs = 1;
+int g_gemm_tma_store = 1;
+
 template <int PREC, int BN, int CTAS>
 static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     using Cfg = GemmCfg<PREC, BN, CTAS>;
@@ -620,7 +743,23 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
         ta_lo = ta_hi;
         tw_lo = tw_hi;
     }
+    // row-major outputs through TMA stores when nothing needs per-element addressing (residual / row map / transposed stay on the
+    // register path) and the output rows satisfy TMA's 16-byte rules
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    bool tma_out = g_gemm_tma_store && !a->transposed && !a->c_row_map && !a->residual && al16(a->bias) && al16(a->colscale);
+    if (a->c_f32) tma_out = tma_out && al16(a->c_f32) && (a->ldc * 4) % 16 == 0 && (a->batch == 1 || (a->c_bstride * 4) % 16 == 0);
+    if (a->c_hi) tma_out = tma_out && al16(a->c_hi) && (!a->c_lo || al16(a->c_lo)) && (a->ldc * 2) % 16 == 0 &&
+                           (a->batch == 1 || (a->c_bstride * 2) % 16 == 0);
+    if (!a->c_f32 && !a->c_hi) tma_out = false;
+    CUtensorMap tc_f32 = ta_hi, tc_hi = ta_hi, tc_lo = ta_hi;
+    if (tma_out) {
+        const int64_t cbs = a->batch > 1 ? a->c_bstride : (int64_t)a->M * a->ldc;
+        if (a->c_f32 && (rc = make_tmap(&tc_f32, a->c_f32, 4, a->M, a->N, a->ldc, a->batch, cbs, 32, 32))) return rc;
+        if (a->c_hi && (rc = make_tmap(&tc_hi, a->c_hi, 2, a->M, a->N, a->ldc, a->batch, cbs, 32, 32))) return rc;
+        if (a->c_lo && (rc = make_tmap(&tc_lo, a->c_lo, 2, a->M, a->N, a->ldc, a->batch, cbs, 32, 32))) return rc;
+    }
     GemmParams p;
+    p.tma_out = tma_out ? 1 : 0;
     p.bias = a->bias; p.colscale = a->colscale; p.residual = a->residual;
     p.ldr = a->ldr; p.r_bstride = a->r_bstride;
     p.c_f32 = a->c_f32; p.c_hi = (__nv_bfloat16*)a->c_hi; p.c_lo = (__nv_bfloat16*)a->c_lo;
@@ -640,7 +779,7 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     const int units = num_sms() / CTAS;      // CTAs (or CTA pairs) that can be resident
     const int grid = (int)(total < units ? total : units) * CTAS;
     if (CTAS == 1) {
-        gemm_tc_kernel<PREC, BN, CTAS><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
+        gemm_tc_kernel<PREC, BN, CTAS><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, tc_f32, tc_hi, tc_lo, p);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
@@ -652,14 +791,11 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        HIPIE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<PREC, BN, CTAS>, ta_hi, ta_lo, tw_hi, tw_lo, p));
+        HIPIE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<PREC, BN, CTAS>, ta_hi, ta_lo, tw_hi, tw_lo, tc_f32, tc_hi, tc_lo, p));
     }
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
 }
-
-// set by hipie_set_option("gemm_cta_pairs", 0|1): CTA-pair (cta_group::2) tiles for the large GEMMs
-int g_gemm_cta_pairs = 1;
 
 }  // namespace hipie
 
@@ -695,6 +831,7 @@ extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
 extern "C" int hipie_set_option(const char* name, int value) {
     HIPIE_CHECK_ARG(name != nullptr, "hipie_set_option: null name");
     if (strcmp(name, "gemm_cta_pairs") == 0) { g_gemm_cta_pairs = value ? 1 : 0; return HIPIE_OK; }
+    if (strcmp(name, "gemm_tma_store") == 0) { g_gemm_tma_store = value ? 1 : 0; return HIPIE_OK; }
     set_error("hipie_set_option: unknown option '%s'", name);
     return HIPIE_EINVAL;
 }

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(1024) batched_nms_kernel(const float* __restri
                                                            int N, float thr) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     const int b = blockIdx.x;
-    int n2 = 1;
+    int n2 = 4;                                   // >= 4 keeps the float4 array behind key/idx 16-byte aligned
     while (n2 < N) n2 <<= 1;
     const int words = (N + 31) >> 5;
     float* key = reinterpret_cast<float*>(nms_smem);             // [n2]
@@ -309,7 +309,7 @@ extern "C" int hipie_batched_nms(const float* boxes_cxcywh, const float* scores,
     HIPIE_CHECK_ARG(boxes_cxcywh && scores && cls && keep && nkeep, "hipie_batched_nms: null pointer argument");
     HIPIE_CHECK_ARG(B >= 0 && N > 0 && N <= NMS_MAX, "hipie_batched_nms: N=%d outside (0, %d]", N, NMS_MAX);
     if (B == 0) return HIPIE_OK;
-    int n2 = 1;
+    int n2 = 4;
     while (n2 < N) n2 <<= 1;
     const int words = (N + 31) / 32;
     const int smem = n2 * 8 + N * 16 + N * words * 4 + words * 4 + 64;
