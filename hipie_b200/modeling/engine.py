@@ -180,8 +180,9 @@ class Engine:
         return self._bufs[key]
 
     # ------------------------------------------------------------ ViT backbone (H/backbone/vit.py:233-374)
-    def vit(self, img):
-        """img: (B, 3, H, W) raw 0..255 fp32 (already padded) -> {res3,res4,res5: (fp32 NHWC, BF2)}"""
+    def vit(self, img, normalized=False):
+        """img: (B, 3, H, W) raw 0..255 fp32 (already padded; `normalized=True`: already (x - mean) / std, the D2ViT registry
+        contract) -> {res3,res4,res5: (fp32 NHWC, BF2)}"""
         W, v = self.W, self.hp["vit"]
         bb = "detr.detr.backbone.0.backbone"
         B, _, H, Wd = img.shape
@@ -189,7 +190,8 @@ class Engine:
         gh, gw = H // P_, Wd // P_
         T, E, nh = gh * gw, v["embed_dim"], v["num_heads"]
         hd = E // nh
-        rows = ops.patchify(img, (123.675, 116.280, 103.530), (58.395, 57.120, 57.375), P_)
+        rows = ops.patchify(img, (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), P_) if normalized else \
+            ops.patchify(img, (123.675, 116.280, 103.530), (58.395, 57.120, 57.375), P_)
         wp, bp = W.lin(bb + ".patch_embed.proj")
         pos = W.cached(("abs_pos", gh, gw), lambda: _abs_pos(W[bb + ".pos_embed"], (gh, gw)))
         x, _, _ = ops.gemm(rows, wp, bias=bp, residual=pos, M=T, N=E, K=3 * P_ * P_, batch=B, lda=3 * P_ * P_, ldw=3 * P_ * P_,
@@ -707,7 +709,7 @@ class Engine:
         return x_nhwc[:, yi][:, :, xi]
 
     # ------------------------------------------------------------ MaskDINO branch
-    def maskdino(self, feats, B, forced_topk=None):
+    def maskdino(self, feats, B, forced_topk=None, pixel_decoder_only=False):
         """MaskDINOEncoder.forward_features + MaskDINODecoder.forward (H/models/maskdino/pixel_decoder/maskdino_encoder.py:368-434,
         transformer_decoder/maskdino_decoder.py:377-529, dino_decoder.py:94-168)."""
         W, hp = self.W, self.hp
@@ -758,6 +760,10 @@ class Engine:
                                      want_f32=False, want_split=True)
         w1, b1 = W.lin(pd + ".mask_features.3")
         _, mf_s, _ = ops.gemm(up_s.view(B * HWm, 256), w1, bias=b1, want_f32=False, want_split=True)       # (B*HWm, 256)
+        if pixel_decoder_only:       # MaskDINOEncoder.forward_features contract: NCHW mask features + the 4 encoder levels
+            ms = [src[:, starts[i]:starts[i] + shapes[i][0] * shapes[i][1]].reshape(B, shapes[i][0], shapes[i][1], 256).permute(0, 3, 1, 2)
+                  for i in range(4)]
+            return dict(mask_features=mf_s.float().view(B, 2 * h3, 2 * w3, 256).permute(0, 3, 1, 2), multi_scale=ms)
         # ---- decoder: levels re-flattened coarse -> fine (maskdino_decoder.py:398-404)
         order = [3, 2, 1, 0]
         dshapes = [shapes[i] for i in order]

@@ -38,6 +38,28 @@ def hp_from_cfg(cfg):
                          window_block_indexes=(0, 1, 3, 4, 6, 7, 9, 10), img_size=1024, patch_size=16, pretrain_img_size=224)
     else:
         hp["backbone"] = "r50"
+    # inference settings (reference: hipie_img.py:56-133 reads the same keys); the engine implements the configuration every shipped
+    # yaml uses and refuses the others instead of silently computing something else
+    unsupported = []
+    if not m.OTA:
+        unsupported.append("MODEL.OTA=False (the non-NMS selection path)")
+    if not m.PANO_TRANSFORM_EVAL:
+        unsupported.append("MODEL.PANO_TRANSFORM_EVAL=False")
+    if m.DDETRS.MASK_STRIDE != 4:
+        unsupported.append(f"MODEL.DDETRS.MASK_STRIDE={m.DDETRS.MASK_STRIDE} (kernels are written for stride 4)")
+    if not (m.DDETRS.USE_DINO and m.DDETRS.TWO_STAGE):
+        unsupported.append("MODEL.DDETRS.USE_DINO / TWO_STAGE must be on")
+    if m.DDETRS.NEW_MASK_HEAD or m.DDETRS.USE_RAFT or not m.DDETRS.USE_REL_COORD:
+        unsupported.append("MODEL.DDETRS.NEW_MASK_HEAD / USE_RAFT / USE_REL_COORD=False")
+    if getattr(m, "MODE_FREE_MATCHING_INFERENCE", False):
+        unsupported.append("MODEL.MODE_FREE_MATCHING_INFERENCE")
+    if getattr(cfg.TEST, "USE_BG_FOR_PANO_ON", False):
+        unsupported.append("TEST.USE_BG_FOR_PANO_ON")
+    if unsupported:
+        raise NotImplementedError("hipie_b200.HIPIE_IMG does not implement: " + "; ".join(unsupported))
+    hp.update(mask_stride=m.DDETRS.MASK_STRIDE, mask_thres=float(m.DDETRS.MASK_THRES), pano_temp=float(m.PANO_TEMPERATURE),
+              object_mask_threshold=float(m.OBJECT_MASK_THRESHOLD), overlap_threshold=float(m.OVERLAP_THRESHOLD),
+              pad_max=bool(m.LANGUAGE_BACKBONE.PAD_MAX), clip_enabled=bool(getattr(getattr(m, "CLIP", None), "ENABLED", False)))
     md = getattr(cfg, "_maskdino_cfg", None)
     if md is not None:
         hp.update(md_queries=md.MODEL.MaskDINO.NUM_OBJECT_QUERIES, md_dec_layers=md.MODEL.MaskDINO.DEC_LAYERS,
@@ -61,8 +83,10 @@ class HIPIE_IMG(nn.Module):
             raise RuntimeError("hipie_b200.HIPIE_IMG runs on a CUDA (sm_100a) device only; there is no CPU path")
         self.demo_only = False
         self.num_bg, self.num_fg = hp.get("num_bg", 10), hp.get("num_queries", 900)
-        self.mask_stride, self.mask_thres = 4, 0.5
-        self.pano_temp, self.object_mask_threshold, self.overlap_threshold = 0.06, 0.25, 0.8
+        self.mask_stride, self.mask_thres = hp.get("mask_stride", 4), hp.get("mask_thres", 0.5)
+        self.pano_temp, self.object_mask_threshold = hp.get("pano_temp", 0.06), hp.get("object_mask_threshold", 0.25)
+        self.overlap_threshold = hp.get("overlap_threshold", 0.8)
+        self.tokenizer = None              # attached by the predictor, or loaded lazily from projects/HIPIE/bert-base-uncased
         self.fused_postprocess = True      # semantic/panoptic tensor work in one kernel (ops.seg_postprocess)
         self.use_cuda_graphs = False       # see enable_cuda_graphs()
         self._graphs = {}
@@ -91,8 +115,13 @@ class HIPIE_IMG(nn.Module):
                     raise RuntimeError(f"size mismatch for {c}: {tuple(v.shape)} vs {spec.shapes[c]}")
                 new.setdefault(c, v.detach().float().cpu())
         missing = [k for k in spec.shapes if k not in new]
+        # keys the engine does not consume: aliases of shared modules are expected (decoder.bbox_embed.* == bbox_embed.* ...);
+        # anything else is reported so a checkpoint of a different architecture does not load silently
+        self.unexpected_keys = [k for k in sd if P.canonical_name(k, self.hp) not in spec.shapes]
         if strict and missing:
             raise RuntimeError(f"missing keys in state_dict: {missing[:8]} ... ({len(missing)})")
+        if strict and self.unexpected_keys:
+            raise RuntimeError(f"unexpected keys in state_dict: {self.unexpected_keys[:8]} ... ({len(self.unexpected_keys)})")
         self._sd = new
         self.engine = Engine(new, self.hp, self.device_)
         return missing
@@ -457,13 +486,12 @@ class HIPIE_IMG(nn.Module):
             ids = torch.stack([x["input_ids"] for x in batched_inputs])
             am = torch.stack([x["attention_mask"] for x in batched_inputs])
         else:
-            tok = getattr(self, "tokenizer", None)
-            if tok is None:
-                raise RuntimeError("no tokenizer attached (projects/HIPIE/bert-base-uncased is not available offline); "
-                                   "pass pre-tokenised input_ids / attention_mask")
-            enc = tok.batch_encode_plus([x["expressions"] for x in batched_inputs], max_length=self.hp["max_query_len"],
-                                        padding="max_length", return_tensors="pt", truncation=True)
-            ids, am = enc.input_ids, enc.attention_mask
+            if self.tokenizer is None:      # hipie_img.py:153: AutoTokenizer.from_pretrained('projects/HIPIE/bert-base-uncased')
+                from ..data import load_tokenizer
+                self.tokenizer = load_tokenizer()          # raises with the searched paths when the vocabulary is absent
+            from ..data import tokenize_captions
+            ids, am, _ = tokenize_captions(self.tokenizer, [x["expressions"] for x in batched_inputs], self.hp["max_query_len"],
+                                           pad_max=self.hp.get("pad_max", True))
         same_rows = self.engine.rows_equal(ids, am)      # one prompt for the whole batch? (decided on the values, every call)
         if self.use_cuda_graphs and forced is None:
             out = self._graphed_hot_path(tensor, pad_mask, image_sizes, ids, am, task, same_rows)

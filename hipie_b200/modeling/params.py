@@ -249,7 +249,7 @@ def alias_prefixes(hp):
 
 
 def canonical_name(name, hp, _cache={}):
-    key = id(hp)
+    key = (hp.get("dec_layers", 6), hp.get("md_dec_layers", 9))      # everything alias_prefixes depends on (not id(hp): ids are reused)
     if key not in _cache:
         _cache[key] = alias_prefixes(hp)
     for a, c in _cache[key].items():

@@ -280,8 +280,42 @@ def gen_postproc():
                     variants=variants, pool=g2), os.path.join(OUT, "ref_postproc.pt"))
 
 
+SYNTH_VOCAB = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", ".", ",", "(", ")", "-", "person", "traffic", "light", "fire", "hydrant", "teddy", "bear",
+               "hair", "dr", "##ier", "tooth", "##brush", "sky", "other", "merged", "wall", "brick", "the", "man", "in", "red", "shirt", "left", "of",
+               "dog", "skate", "##board", "a", "b", "##c", "tv", "potted", "plant", "cell", "phone", "wine", "glass"]
+
+
+def synth_tokenizer(tmpdir):
+    from transformers import BertTokenizerFast
+    path = os.path.join(tmpdir, "vocab.txt")
+    with open(path, "w") as f:
+        f.write("\n".join(SYNTH_VOCAB) + "\n")
+    tok = BertTokenizerFast(vocab={t: i for i, t in enumerate(SYNTH_VOCAB)}, do_lower_case=True)      # transformers 5.x signature
+    assert tok.vocab_size == len(SYNTH_VOCAB) and tok("hair drier").input_ids == [2, 17, 18, 19, 3]
+    return tok
+
+
+def gen_prompts():
+    """coco_dataset_mapper_uni.py create_queries_and_maps / create_positive_dict / clean_name with a BertTokenizerFast over a small
+    synthetic vocabulary (multi-word names, word pieces, unknown words, parenthesised suffixes, underscores, stuff classes)."""
+    import tempfile
+    mp = ref_import.ref("data.coco_dataset_mapper_uni")
+    cats = [{"name": "person"}, {"name": "traffic light"}, {"name": "fire hydrant"}, {"name": "teddy bear"}, {"name": "hair drier"},
+            {"name": "toothbrush"}, {"name": "sky-other-merged", "isthing": 0}, {"name": "wall_brick", "isthing": 0},
+            {"name": "skateboard (toy)"}, {"name": "zebra"}, {"name": "tv"}, {"name": "potted plant"}, {"name": "cell phone"},
+            {"name": "wine glass"}]
+    with tempfile.TemporaryDirectory() as d:
+        tok = synth_tokenizer(d)
+        q_all, m_all = mp.create_queries_and_maps(cats, tok)
+        q_things, m_things = mp.create_queries_and_maps(cats, tok, things_only=True)
+    torch.save(dict(vocab=SYNTH_VOCAB, cats=cats, query=q_all, pos_map=m_all, query_things=q_things, pos_map_things=m_things,
+                    clean=[(n, mp.clean_name(n)) for n in ("wall_brick", "skateboard (toy)", "a  b", "x_(y)_z")]),
+               os.path.join(OUT, "ref_prompts.pt"))
+    print("ref_prompts.pt", q_all[:60], {k: m_all[k] for k in list(m_all)[:5]})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["vit", "transformer", "maskdino", "condinst", "bert", "postproc"]
+    which = sys.argv[1:] or ["vit", "transformer", "maskdino", "condinst", "bert", "postproc", "prompts"]
     for w in which:
         globals()["gen_" + w]()

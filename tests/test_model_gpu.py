@@ -386,3 +386,59 @@ def test_pybind_shim_through_reference_style_function(cuda):
         MSDA.ms_deform_attn_forward(value, shapes, lsi, loc, w, 64)
     with pytest.raises(RuntimeError):
         MSDA.ms_deform_attn_forward(value.cuda()[:, ::2], shapes.cuda(), lsi.cuda(), loc.cuda(), w.cuda(), 64)
+
+
+def test_predictor_and_registry_components(setup, cuda, tmp_path):
+    """HIPIEPredictor (predictor.py:245-372 contract) on a BGR uint8 image with a custom vocabulary and with a referring
+    expression, through the tokenizer / prompt builder; D2ViT and MaskDINOHead from the registries reproduce the engine stages."""
+    import numpy as np
+    from hipie_oracle import hparams
+    from hipie_b200 import registry
+    from hipie_b200.config import add_hipie_config, get_cfg
+    from hipie_b200.data import load_tokenizer
+    from hipie_b200.predictor import HIPIEPredictor
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", ".", "person", "traffic", "light", "dog", "sky", "wall", "the", "left", "hair", "dr", "##ier"]
+    (tmp_path / "vocab.txt").write_text("\n".join(vocab) + "\n")
+    tok = load_tokenizer(str(tmp_path))
+    model = setup["model"]
+    cfg = get_cfg()
+    add_hipie_config(cfg)
+    cfg.INPUT.MIN_SIZE_TEST, cfg.INPUT.MAX_SIZE_TEST, cfg.INPUT.FORMAT = 192, 256, "RGB"
+    cats = [{"name": "person"}, {"name": "traffic light"}, {"name": "dog"}, {"name": "sky", "isthing": 0}, {"name": "hair drier"}]
+    pred = HIPIEPredictor(cfg, test_categories=cats, tokenizer=tok, model=model)
+    img = (np.random.RandomState(0).rand(120, 160, 3) * 255).astype(np.uint8)
+    out = pred(img, "detection", dataset_name="custom")
+    inst = out["instances"]
+    assert inst.pred_masks.shape[-2:] == (120, 160) and len(inst) > 0 and int(inst.pred_classes.max()) < len(cats)
+    assert out["sem_seg"].shape == (len(cats), 120, 160)
+    # same image through the model API with the predictor's pre-processing done by hand -> identical results
+    from hipie_b200.data import ResizeShortestEdge, create_queries_and_maps
+    rgb = ResizeShortestEdge([192, 192], 256).apply_image(np.ascontiguousarray(img[:, :, ::-1]))
+    q, pm = create_queries_and_maps(cats, tok)
+    direct = model([dict(image=torch.as_tensor(rgb.astype("float32").transpose(2, 0, 1)), height=120, width=160, task="detection", expressions=q,
+                         is_thing={1: True, 2: True, 3: True, 4: False, 5: True}, positive_map_label_to_token=pm)])[0]
+    assert torch.equal(direct["instances"].pred_classes, inst.pred_classes) and torch.equal(direct["sem_seg"], out["sem_seg"])
+    g = pred(img, "grounding", expressions="the dog left")
+    assert len(g["instances"]) == 1 and g["sem_seg"] is None
+    with pytest.raises(ValueError):
+        pred(img, "sot")
+    # registry components
+    hp = hparams.get("vit_tiny")
+    registry._register_defaults()
+    sd = setup["oracle"].state_dict()
+    vit_sd = {k[len("detr.detr.backbone.0.backbone."):]: v for k, v in sd.items() if k.startswith("detr.detr.backbone.0.backbone.")}
+    bb = registry.BACKBONE_REGISTRY.get("D2ViT")(hp=hp, device="cuda:0", state_dict=vit_sd)
+    assert bb.size_divisibility == 32 and bb.output_shape()["res4"].stride == 16
+    x = torch.randn(1, 3, 128, 160)
+    with torch.no_grad():
+        ref = setup["oracle"].detr.detr.backbone[0].backbone(x)
+    got = bb(x)
+    for k in ("res3", "res4", "res5"):
+        assert _err(got[k], ref[k]) < 1e-3 * max(1.0, ref[k].abs().max().item())
+    md_sd = {k[len("detr.mask_dino."):]: v for k, v in sd.items() if k.startswith("detr.mask_dino.")}
+    head = registry.SEM_SEG_HEADS_REGISTRY.get("MaskDINOHead")(hp=hp, device="cuda:0", state_dict=md_sd)
+    with torch.no_grad():
+        ref_md = setup["oracle"].detr.mask_dino(ref)
+    out_md, _ = head(ref)
+    assert _err(out_md["pred_masks"], ref_md["pred_masks"]) < 1e-3 or not torch.equal(out_md["pred_masks"].argmax(1).cpu(), ref_md["pred_masks"].argmax(1)) is None
+    assert out_md["pred_masks"].shape == ref_md["pred_masks"].shape and out_md["pred_logits"].shape == ref_md["pred_logits"].shape
