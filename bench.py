@@ -1,15 +1,20 @@
 #!/usr/bin/env python
-"""Benchmark of the HIPIE inference hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+"""Benchmark of the HIPIE inference hot path on B200 (contract: see the task statement / DESIGN.md §6).
 
-  python bench.py --gpus N --steps K --warmup W           # product arm (one process per GPU under torchrun for N>1)
-  python bench.py --impl reference --gpus N --steps K ... # reference arm: the CPU oracle of the same path, rank 0 only
+  python bench.py --gpus N --steps K --warmup W [--config C]          # product arm (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ... [--config C]  # reference arm: the CPU oracle of the same path, rank 0 only
 
-Workload = BASELINE.json configs[1]: ViT-H, 8 x 1024x1024 synthetic images per GPU, 80-class COCO-style vocabulary
-(Lt = 512), task "detection", random-init weights of that architecture, synthetic token ids.
-A step = one pass of the hot path (preprocess -> ViT-H -> BERT -> VL fusion -> deformable encoder/decoder -> MaskDINO
-pixel decoder/decoder + mask-embed contraction -> CondInst masks) over the per-GPU batch with
-inputs resident in HBM.  `e2e` times the public API call (HIPIE_IMG.forward incl. post-processing, rows a20-a23) from
-pinned host images, H2D and D2H inside the timed region.
+Workloads (BASELINE.json `configs`; per-GPU shards of the image-sharded global batches):
+  --config 1 (default, the configuration the metric is quoted on)  ViT-H, 8 x 1024x1024, 80-class COCO vocabulary (Lt = 512), detection
+  --config 2   ViT-H, 8 x 1024x1024 per GPU (64 over 8 GPUs), 150-class ADE vocabulary, Lt = 4096, max-pooled / class-agnostic-bg scoring
+  --config 3   ViT-H, 4 x 1280x1280 per GPU (16 over 4 GPUs), one referring expression per image (task grounding), Lt = 512
+  --config 4   ViT-H, 4 x 1024x1024 per GPU (32 over 8 GPUs), 847-class ADE vocabulary, Lt = 4096 (> 512 tokens: chunked BERT)
+Synthetic images, random-init weights of that architecture, synthetic token ids.
+
+A step = one pass of the hot path (preprocess -> ViT-H -> BERT -> VL fusion -> deformable encoder/decoder -> MaskDINO pixel
+decoder/decoder + mask-embed contraction -> CondInst masks) over the per-GPU batch with inputs resident
+in HBM.  `e2e` times the public API call (HIPIE_IMG.forward incl. post-processing, rows a20-a23) from pinned host images, H2D and
+D2H inside the timed region.
 """
 import argparse
 import json
@@ -23,19 +28,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "images/sec at 1024x1024, ViT-H HIPIE inference hot path (synthetic batch)"
-PER_GPU_BATCH = 8
-IMG = 1024
-NUM_CLASSES = 80
-VIT_H_FLOPS_PER_IMG = 7.41e12      # SURVEY §8d / BASELINE.md §3 (patch-embed + 32 blocks + FPN @1024^2)
+
+CONFIGS = {
+    1: dict(name="configs[1]", img=1024, batch=8, classes=80, lt=512, task="detection", max_pool=False, bg_agnostic=False,
+            vit_flops=7.41e12, desc="ViT-H, batch 8 x 1024x1024 synthetic per GPU, 80-class COCO-style vocab (Lt=512), task detection"),
+    2: dict(name="configs[2]", img=1024, batch=8, classes=150, lt=4096, task="detection", max_pool=True, bg_agnostic=True,
+            vit_flops=7.41e12, desc="ViT-H, batch 8 x 1024x1024 synthetic per GPU (64 over 8 GPUs), 150-class ADE vocab (Lt=4096), task detection"),
+    3: dict(name="configs[3]", img=1280, batch=4, classes=1, lt=512, task="grounding", max_pool=False, bg_agnostic=False,
+            vit_flops=13.33e12, desc="ViT-H, batch 4 x 1280x1280 synthetic per GPU (16 over 4 GPUs), one referring expression per image, task grounding"),
+    4: dict(name="configs[4]", img=1024, batch=4, classes=847, lt=4096, task="detection", max_pool=True, bg_agnostic=True,
+            vit_flops=7.41e12, desc="ViT-H, batch 4 x 1024x1024 synthetic per GPU (32 over 8 GPUs), 847-class ADE vocab (Lt=4096, chunked BERT), task detection"),
+}
 
 
-def vit_h_hp():
+def vit_h_hp(cfg):
     bert = dict(vocab=30522, hidden=768, layers=12, heads=12, inter=3072, max_pos=512)
     return dict(backbone="vit",
                 vit=dict(embed_dim=1280, depth=32, num_heads=16, window_size=14, window_block_indexes=(0, 1, 3, 4, 6, 7, 9, 10),
                          img_size=1024, patch_size=16, pretrain_img_size=224),
                 hidden_dim=256, enc_layers=6, dec_layers=6, dim_ff=2048, num_queries=900, num_bg=10, vl_hidden=2048, lang_dim=768,
-                md_queries=300, md_dec_layers=9, md_enc_layers=6, md_dim_ff=2048, bert=bert, max_query_len=512)
+                md_queries=300, md_dec_layers=9, md_enc_layers=6, md_dim_ff=2048, bert=bert, max_query_len=cfg["lt"],
+                max_pool=cfg["max_pool"], bg_cls_agnostic=cfg["bg_agnostic"])
 
 
 def synth_text(num_classes, max_len, seed=0):
@@ -45,6 +58,8 @@ def synth_text(num_classes, max_len, seed=0):
     ids, pos_map = [101], {}
     for c in range(1, num_classes + 1):
         n = int(torch.randint(1, 4, (1,), generator=g))
+        if len(ids) + n + 2 > max_len:
+            n = 1
         toks = torch.randint(1996, 30000, (n,), generator=g).tolist()
         pos_map[c] = list(range(len(ids), len(ids) + n))
         ids += toks + [1012]
@@ -58,14 +73,38 @@ def synth_text(num_classes, max_len, seed=0):
     return input_ids, attn, pos_map, {c: c <= n_thing for c in range(1, num_classes + 1)}
 
 
+def synth_expression(max_len, seed):
+    """a referring expression of 5-12 random word pieces: [CLS] w1 .. wn [SEP]"""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    n = int(torch.randint(5, 13, (1,), generator=g))
+    ids = [101] + torch.randint(1996, 30000, (n,), generator=g).tolist() + [102]
+    input_ids = torch.zeros(max_len, dtype=torch.long)
+    input_ids[:len(ids)] = torch.tensor(ids)
+    attn = torch.zeros(max_len, dtype=torch.long)
+    attn[:len(ids)] = 1
+    return input_ids, attn
+
+
+def batch_text(cfg, B, seed_base=0):
+    """-> ids (B, Lt), am (B, Lt), positive map, is_thing.  Detection: one vocabulary prompt for the whole batch; grounding: a
+    different expression per image (the text encoder really runs on B rows)."""
+    import torch
+    if cfg["task"] == "grounding":
+        rows = [synth_expression(cfg["lt"], seed_base + b) for b in range(B)]
+        return torch.stack([r[0] for r in rows]), torch.stack([r[1] for r in rows]), {1: [0]}, {1: True}
+    ids, am, pos_map, is_thing = synth_text(cfg["classes"], cfg["lt"])
+    return ids.unsqueeze(0).repeat(B, 1), am.unsqueeze(0).repeat(B, 1), pos_map, is_thing
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index=0):
-        self.index, self.samples, self._stop = index, [], threading.Event()
+    def __init__(self, index=0, enabled=True):
+        self.index, self.samples, self._stop, self.enabled = index, [], threading.Event(), enabled
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
@@ -80,12 +119,14 @@ class ClockSampler:
             self._stop.wait(0.2)
 
     def __enter__(self):
-        self.t.start()
+        if self.enabled:
+            self.t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self.t.join(timeout=6)
+        if self.enabled:
+            self.t.join(timeout=6)
 
     def summary(self):
         sm = sorted(float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit())
@@ -106,89 +147,87 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------ CPU oracle arm
-def cpu_oracle_seconds_per_image(verbose=False):
-    """Times the CPU oracle (oracle/, the restatement of the reference eval forward; the unmodified reference cannot
-    run on CPU: its MSDeformAttn op throws and detectron2/fvcore/timm are absent — DESIGN.md) on ONE 1024^2 image.
-    Bounded sample: the 32-block ViT-H is timed on 1 windowed + 1 global block and scaled to 8 + 24 blocks; everything
-    else on the path (patch embed, FPN, BERT, VL fusion, deformable encoder/decoder, MaskDINO, CondInst) runs in full."""
+def cpu_oracle_seconds_per_image(cfg, verbose=False):
+    """Times the CPU oracle (oracle/, the restatement of the reference eval forward; the unmodified reference cannot run on CPU:
+    its MSDeformAttn op throws and detectron2/fvcore/timm are absent -- DESIGN.md) on ONE image of the workload: the whole hot path
+    a1-a19 in full (all 32 ViT-H blocks, BERT, VL fusion, deformable encoder/decoder, MaskDINO, CondInst), no extrapolation.
+    Threads: min(32, cores) -- on the 128-core boxes more threads are slower for this B=1 problem size."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from hipie_oracle import hparams, synth
     from hipie_oracle.model import HipieOracle
-    torch.set_num_threads(os.cpu_count())
+    threads = min(32, os.cpu_count() or 8)
+    torch.set_num_threads(threads)
     hp = hparams.get("vit_h")
-    hp["vit"] = dict(hp["vit"], depth=2, window_block_indexes=(0,))       # block 0 windowed, block 1 global
+    hp.update(max_query_len=cfg["lt"], max_pool=cfg["max_pool"], bg_cls_agnostic=cfg["bg_agnostic"])
     torch.manual_seed(0)
     model = HipieOracle(hp).eval()
     synth.perturb_(model)
-    inputs, ids, am = synth.make_batch(1, IMG, IMG, NUM_CLASSES, hp["max_query_len"])
-    vit = model.detr.detr.backbone[0].backbone
-    times = {"win": 0.0, "glob": 0.0}
-    import types
-
-    def timed_block(blk, kind):
-        orig = blk.forward
-
-        def fwd(self, x):
-            t0 = time.perf_counter()
-            y = orig(x)
-            times[kind] += time.perf_counter() - t0
-            return y
-        blk.forward = types.MethodType(fwd, blk)
-    for i, blk in enumerate(vit.blocks):
-        timed_block(blk, "win" if i < 1 else "glob")
+    inputs, ids, am = synth.make_batch(1, cfg["img"], cfg["img"], cfg["classes"], cfg["lt"], task=cfg["task"])
     with torch.no_grad():
         tensor, mask, sizes = model.preprocess([x["image"] for x in inputs])
         t0 = time.perf_counter()
         lang = model.forward_text(ids, am)
-        out = model.coco_inference(tensor, mask, sizes, lang, task="detection")
+        model.coco_inference(tensor, mask, sizes, lang, task=cfg["task"])
         total = time.perf_counter() - t0
-    rest = total - times["win"] - times["glob"]
-    full = rest + times["win"] * 8 + times["glob"] * 24
     if verbose:
-        print(f"[cpu oracle] measured {total:.1f}s: window blk {times['win']:.2f}s, global blk {times['glob']:.2f}s, rest {rest:.1f}s"
-              f" -> scaled {full:.1f}s/img", file=sys.stderr)
-    return full, total, "1 image 1024^2: ViT-H timed on 1 windowed + 1 global block and scaled to 8 + 24, rest of the path " \
-                        "(BERT, VL fusion, deformable enc/dec, MaskDINO, CondInst) run once in full"
+        print(f"[cpu oracle] {cfg['name']}: {total:.1f} s/img on {threads} threads", file=sys.stderr)
+    sample = f"1 image {cfg['img']}^2 of {cfg['name']}: the whole hot path a1-a19 in full (32 ViT-H blocks, BERT, VL fusion, deformable enc/dec, " \
+             f"MaskDINO, CondInst), {threads} torch threads"
+    return total, threads, sample
 
 
-def run_reference(args):
+def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    secs = []
-    sample = ""
+    secs, sample, threads = [], "", 0
     t_start = time.perf_counter()
-    warm = min(args.warmup, 1)           # one untimed sample warms the allocator / thread pool
-    done = 0
+    warm = 1 if (args.warmup > 0 and args.ref_budget_s >= 150) else 0      # one untimed sample warms the allocator / thread pool
     for i in range(warm + args.steps):
-        full, measured, sample = cpu_oracle_seconds_per_image(verbose=True)
+        total, threads, sample = cpu_oracle_seconds_per_image(cfg, verbose=True)
         if i >= warm:
-            secs.append(full)
-            done += 1
-        if secs and time.perf_counter() - t_start > args.ref_budget_s:
+            secs.append(total)
+        if secs and time.perf_counter() - t_start + 1.2 * total > args.ref_budget_s:
             break                        # keep the whole reference run within a few minutes
     spi = sorted(secs)[len(secs) // 2]
     val = 1.0 / spi
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": spi * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": len(secs),
+            "warmup": warm, "ms_per_step": spi * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: ViT-H, 1024x1024 synthetic, 80-class vocab (Lt=512), CPU oracle of the reference path",
-                       "note": f"each step is a bounded sample (see cpu_baseline.sample); {done} timed samples (median) within a "
-                               f"{args.ref_budget_s:.0f}s wall-clock budget, {warm} warm-up sample"},
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "config": {"workload": f"{cfg['name']}: {cfg['desc']} -- CPU oracle of the reference path, one image per step",
+                       "note": f"{len(secs)} timed samples (median) of {args.steps} requested within a {args.ref_budget_s:.0f}s wall-clock budget, "
+                               f"{warm} warm-up sample; each sample = the full hot path on one image (no extrapolation)"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample,
+                             "host_cores": os.cpu_count()},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ product arm
-def run_product(args):
+def ncu_traffic(kernel_tag):
+    """DRAM bytes per launch of the dominant kernel class from the committed `ncu --set full` capture of THIS round
+    (profiles/r02_ncu_summary.json, keyed by the same tags the live profiler uses); None when no capture of that class is committed."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_summary.json")
+    try:
+        d = json.load(open(p))
+        e = d.get(kernel_tag)
+        if e:
+            return e["dram_bytes_per_launch"], f"committed ncu capture profiles/r02_ncu_summary.json[{kernel_tag}] ({e.get('launch', '')}, commit {d.get('_commit', '?')}): " \
+                                               f"dram__bytes_read.sum + dram__bytes_write.sum of one launch; not re-measured in this run"
+    except Exception:
+        pass
+    return None, None
+
+
+def run_product(args, cfg):
     import torch
     import torch.distributed as dist
     from hipie_b200 import _lib, ops
     from hipie_b200.modeling import params as P
     from hipie_b200.modeling.hipie_img import HIPIE_IMG
+    from hipie_b200.parallel import PackedAllGather
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,49 +237,53 @@ def run_product(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (printed to stdout at VERSION level) out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     prec = 1 if args.precision == "bf16" else 3
     ops.set_precision(prec)
-    hp = vit_h_hp()
+    hp = vit_h_hp(cfg)
     model = HIPIE_IMG(hp=hp, state_dict=P.random_state_dict(hp, seed=0), device=str(dev))
     model.engine.bf16_value_map = prec == 1
-    B = PER_GPU_BATCH
+    B, IMG, task = cfg["batch"], cfg["img"], cfg["task"]
     g = torch.Generator().manual_seed(1234 + rank)
     host_imgs = [(torch.rand(3, IMG, IMG, generator=g) * 255.0).pin_memory() for _ in range(B)]
-    ids, am, pos_map, is_thing = synth_text(NUM_CLASSES, hp["max_query_len"])
+    ids, am, pos_map, is_thing = batch_text(cfg, B, seed_base=100 * rank)
+    same_rows = task == "detection"
     dev_imgs = torch.stack(host_imgs).to(dev)
-    ids_d, am_d = ids.unsqueeze(0).repeat(B, 1).to(dev), am.unsqueeze(0).repeat(B, 1).to(dev)
+    ids_d, am_d = ids.to(dev), am.to(dev)
     pad_mask = torch.zeros(B, IMG, IMG, dtype=torch.bool, device=dev)
     sizes = [(IMG, IMG)] * B
+    gather_keys = ["pred_logits", "pred_boxes", "pred_boxious", "pred_logits_maskdino", "pred_boxes_maskdino"]
 
     graphed = None
     if not args.no_graph:
         with torch.no_grad():
-            graphed = model.capture_hot_path(dev_imgs, pad_mask, sizes, ids_d, am_d, task="detection")
+            graphed = model.capture_hot_path(dev_imgs, pad_mask, sizes, ids_d, am_d, task=task, same_rows=same_rows)
+    gather = PackedAllGather() if world > 1 else None
 
     def hot_step():
         if graphed is not None:
             out = graphed()
         else:
-            lang = model.forward_text(ids_d, am_d)
-            out = model.coco_inference(dev_imgs, pad_mask, sizes, lang, task="detection")
-        if world > 1:     # the only collective of the data-parallel path: all-gather of the fixed-shape logits / boxes
-            from hipie_b200.parallel import all_gather_outputs
-            all_gather_outputs(out, ["pred_logits", "pred_boxes", "pred_boxious", "pred_logits_maskdino", "pred_boxes_maskdino"])
+            lang = model.engine.forward_text(ids_d, am_d, same_rows=same_rows)
+            out = model.coco_inference(dev_imgs, pad_mask, sizes, lang, task=task)
+        if gather is not None:     # the only collective of the data-parallel path: ONE all-gather of the packed fixed-shape outputs
+            gather(out, gather_keys)
         return out
 
     def e2e_step():
-        batched = [dict(image=im, height=IMG, width=IMG, task="detection", is_thing=is_thing, positive_map_label_to_token=pos_map,
-                        input_ids=ids, attention_mask=am) for im in host_imgs]
+        batched = [dict(image=im, height=IMG, width=IMG, task=task, is_thing=is_thing, positive_map_label_to_token=pos_map,
+                        input_ids=ids[b], attention_mask=am[b]) for b, im in enumerate(host_imgs)]
         res = model(batched)
         host = []
         for r in res:
             inst = r["instances"]
-            host.append((inst.pred_boxes.tensor.cpu(), inst.scores.cpu(), inst.pred_classes.cpu(), r["panoptic_seg"][0].cpu(),
-                         r["sem_seg"].argmax(0).to(torch.uint8).cpu()))
+            item = [inst.pred_boxes.tensor.cpu(), inst.scores.cpu(), inst.pred_classes.cpu()]
+            if task == "detection":
+                sem = r["sem_seg"].argmax(0)
+                item += [r["panoptic_seg"][0].cpu(), sem.to(torch.uint8 if r["sem_seg"].shape[0] <= 256 else torch.int16).cpu()]
+            else:
+                item.append(inst.pred_masks.cpu())
+            host.append(tuple(item))
         return host
 
     def barrier():
@@ -253,7 +296,7 @@ def run_product(args):
             hot_step()
         barrier()
         launches0 = _lib.launch_count()
-        with ClockSampler(local) as clk:
+        with ClockSampler(local, enabled=rank == 0) as clk:      # one nvidia-smi poller per job, not per rank
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             for _ in range(args.steps):
@@ -268,8 +311,8 @@ def run_product(args):
         ops.profiler.start()
         prof_steps = max(1, min(2, args.steps))
         for _ in range(prof_steps):      # eager (un-graphed) so that each launch can be bracketed by events
-            lang = model.forward_text(ids_d, am_d)
-            model.coco_inference(dev_imgs, pad_mask, sizes, lang, task="detection")
+            lang = model.engine.forward_text(ids_d, am_d, same_rows=same_rows)
+            model.coco_inference(dev_imgs, pad_mask, sizes, lang, task=task)
         prof = ops.profiler.stop()
         # end-to-end through the public API with host buffers
         e2e_iters = max(1, min(args.steps, 5))
@@ -295,10 +338,10 @@ def run_product(args):
     value = imgs_total / (ms_max / 1000.0)
     h2d = B * 3 * IMG * IMG * 4 + 2 * B * hp["max_query_len"] * 8
     d2h = sum(sum(t.numel() * t.element_size() for t in h) for h in host)
-    # dominant kernel of the step
     tot_prof = sum(v["ms"] for v in prof.values()) or 1.0
     top = max(prof.items(), key=lambda kv: kv[1]["ms"])
     kernels = {}
+    passes = 3 if args.precision == "bf16x3" else 1
     for tag, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
         per = v["ms"] / v["launches"]
         entry = {"share_of_timed_kernels": v["ms"] / tot_prof, "launches_per_step": v["launches"] / prof_steps, "avg_ms": per}
@@ -310,44 +353,40 @@ def run_product(args):
                 entry.update(bound="tensor", achieved=rate / 1e12, unit="TFLOP/s", frac=rate / 1e12 / pk["tf_sustained"])
         kernels[tag] = entry
     tk = kernels[top[0]]
-    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture (profiles/r01_ncu_summary.json):
-    # the ViT-H fc1 launch (M=32768, N=5120, K=1280, GELU, bf16 hi/lo out), the largest single GEMM of the step.
-    traffic, traffic_note = None, None
-    try:
-        for line in open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")).read().split("\n}\n"):
-            if "ncu_r01_gemm" in line:
-                rec = json.loads(line + "}")
-                tobytes = lambda v: float(v.split()[0]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[v.split()[1]]
-                traffic = tobytes(rec["dram__bytes_read.sum"]) + tobytes(rec["dram__bytes_write.sum"])
-                alg = 32768 * 1280 * 4 + 5120 * 1280 * 4 + 32768 * 5120 * 4      # A hi+lo, W hi+lo, C hi+lo (bf16 planes)
-                traffic_note = f"ncu dram read+write of the fc1 launch (32768x5120x1280); algorithmic operand+result bytes {alg/1e6:.0f} MB"
-    except Exception:
-        pass
-    passes = 3 if args.precision == "bf16x3" else 1
-    roofline = {"kernel": top[0], "bound": tk.get("bound", "tensor"), "achieved": tk.get("achieved"), "peak": pk["hbm"] if tk.get("bound") == "hbm" else pk["tf_sustained"],
+    traffic, traffic_note = ncu_traffic(top[0])
+    roofline = {"kernel": top[0], "bound": tk.get("bound", "tensor"), "achieved": tk.get("achieved"),
+                "peak": pk["hbm"] if tk.get("bound") == "hbm" else pk["tf_sustained"],
                 "unit": tk.get("unit"), "frac": tk.get("frac"), "traffic": traffic, "traffic_note": traffic_note,
                 "mma_passes": passes, "executed_tflops": (tk.get("achieved") or 0.0) * passes if tk.get("bound") == "tensor" else None,
                 "executed_frac": (tk.get("frac") or 0.0) * passes if tk.get("bound") == "tensor" else None,
-                "achieved_note": "algorithmic 2MNK flops of the fp32-class GEMMs / measured kernel time; bf16x3 parity mode issues 3 bf16 MMAs per "
-                                 "algorithmic MAC (executed_* = achieved x mma_passes against the same bf16 peak)",
+                "achieved_note": "algorithmic 2MNK flops of the fp32-class GEMMs / measured kernel time (CUDA events on the launching stream, "
+                                 "eager steps after the timed region); the bf16x3 parity mode issues 3 bf16 MMAs per algorithmic MAC "
+                                 "(executed_* = achieved x mma_passes against the same bf16 peak); attention QK^T / PV run single-pass fp16 "
+                                 "when the precision map allows (DESIGN.md 3)",
                 "peak_source": pk["src"] + " (sustained figure: kernel timed inside a long step)",
-                "vit_h_forward_tensor_frac": (VIT_H_FLOPS_PER_IMG * B * world * args.steps / (ms_max / 1000.0)) / 1e12 / (pk["tf_sustained"] * world),
+                "vit_h_forward_tensor_frac": (cfg["vit_flops"] * B * world * args.steps / (ms_max / 1000.0)) / 1e12 / (pk["tf_sustained"] * world),
+                "north_star_hbm": {k: {"achieved_gbs": kernels[k]["achieved"], "frac": kernels[k]["frac"], "avg_ms": kernels[k]["avg_ms"]}
+                                   for k in kernels if (k.startswith("msda_fused") or "mask_embed" in k) and "achieved" in kernels[k]},
                 "kernels": kernels}
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            full, measured, sample = cpu_oracle_seconds_per_image(verbose=True)
-            cpu = {"value": 1.0 / full, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample,
-                   "seconds_per_image_scaled": full, "seconds_measured": measured}
+            total, threads, sample = cpu_oracle_seconds_per_image(cfg, verbose=True)
+            cpu = {"value": 1.0 / total, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample,
+                   "seconds_per_image": total, "host_cores": os.cpu_count()}
         except Exception as ex:  # the CPU leg must never take the GPU number down with it
-            cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+            cpu = {"value": None, "unit": "images/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+    bert_rows = 1 if same_rows else B
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (split-bf16 tensor-core operands, fp32 accumulate; fp32-class results)" if prec == 3 else "bf16",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: ViT-H, batch 8 x 1024x1024 synthetic per GPU, 80-class COCO-style vocab (Lt=512), task detection",
-                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world} (image sharding, all-gather of logits)",
-                       "value_scope": "SURVEY 8a rows a1-a19: preprocess, ViT-H, BERT, VL fusion, deformable enc/dec, MaskDINO + mask-embed, CondInst masks",
+            "config": {"workload": f"{cfg['name']}: {cfg['desc']}",
+                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world} (image sharding, one packed all-gather of logits / boxes)",
+                       "value_scope": "SURVEY 8a rows a1-a19: preprocess, ViT-H, BERT, VL fusion, deformable enc/dec, MaskDINO + mask-embed, CondInst masks; "
+                                      f"the text encoder runs on {bert_rows} row(s) per step "
+                                      + ("(all images of a detection batch share one vocabulary prompt, hipie_img.py:330-332: encoded once and broadcast)"
+                                         if same_rows else "(one expression per image)"),
                        "e2e_scope": "HIPIE_IMG.forward (public API) incl. post-processing rows a20-a23, pinned-host images in, results out",
                        "l2": "per-step working set (>= 1 GB activations per block) exceeds the 126 MB L2; no explicit flush",
                        "precision_mode": args.precision,
@@ -366,16 +405,22 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE.json configs[N] (default 1: the headline workload)")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"],
                     help="bf16x3 = parity-grade split precision (default, the headline); bf16 = fast mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the hot step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--ref-budget-s", type=float, default=200.0, help="wall-clock budget of the --impl reference run")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="wall-clock budget of the --impl reference run")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line.  NCCL_DEBUG is left as the caller set it (the driver reads the NCCL log for its
+    # evidence); NCCL prints its log to stdout by default, so it is routed to stderr instead of being silenced.
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("NCCL_DEBUG", ""):
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfg)
     else:
-        run_product(args)
+        run_product(args, cfg)
 
 
 if __name__ == "__main__":

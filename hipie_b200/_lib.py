@@ -26,7 +26,7 @@ class GemmArgs(ctypes.Structure):
         ("c_bits", c_void_p), ("bits_threshold", c_float),
         ("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int),
         ("act", c_int), ("prec", c_int), ("alpha", c_float), ("transposed", c_int), ("c_row_map", c_void_p),
-        ("t_row_group", c_int), ("t_row_pad", c_int),
+        ("t_row_group", c_int), ("t_row_pad", c_int), ("c_fp16", c_int),
     ]
 
 
@@ -74,6 +74,8 @@ SYMBOLS = {
                                   c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hipie_relpos_bias_tc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "hipie_relpos_bias_tc_f16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hipie_condinst_masks": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "hipie_seg_postprocess": (c_int, [c_void_p] * 7 + [c_int] * 8 + [c_void_p]),
     "hipie_sine_embed": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -30,6 +30,17 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool F16>
+__device__ __forceinline__ void mma_16b(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if (F16) mma_f16(c, a, b0, b1);
+    else mma_bf16(c, a, b0, b1);
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -373,7 +384,8 @@ relpos_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __res
 // group; R[coord] (bf16 hi/lo, K-major) is staged in shared memory, each warp computes m16 slabs with
 // mma.sync in bf16x3 (fp32-class) and stores fp32.
 // ------------------------------------------------------------------------------------------
-template <int HD>
+// F16: q is one IEEE fp16 plane and the table planes are fp16 hi/lo (q.Rh + q.Rl): the companion of the single-pass fp16 attention.
+template <int HD, bool F16>
 __global__ void __launch_bounds__(128)
 relpos_mma_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __restrict__ q_lo, int64_t q_bs,
                   int64_t q_ts, int64_t q_hs, const __nv_bfloat16* __restrict__ R_hi,
@@ -441,16 +453,16 @@ relpos_mma_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* _
             for (int kk = 0; kk < KSTEPS; ++kk) {
                 uint32_t b0, b1, b2, b3;
                 ldsm_x4(sb + (j * 8 + key_l) * ROWB + kk * 32 + cb, b0, b1, b2, b3);
-                mma_bf16(c0, ah[kk], b0, b1);
-                mma_bf16(c1, ah[kk], b2, b3);
+                mma_16b<F16>(c0, ah[kk], b0, b1);
+                mma_16b<F16>(c1, ah[kk], b2, b3);
                 if (q_lo) {
-                    mma_bf16(c0, al[kk], b0, b1);
-                    mma_bf16(c1, al[kk], b2, b3);
+                    mma_16b<F16>(c0, al[kk], b0, b1);
+                    mma_16b<F16>(c1, al[kk], b2, b3);
                 }
                 uint32_t d0, d1, d2, d3;
                 ldsm_x4(sb + kpad * ROWB + (j * 8 + key_l) * ROWB + kk * 32 + cb, d0, d1, d2, d3);
-                mma_bf16(c0, ah[kk], d0, d1);
-                mma_bf16(c1, ah[kk], d2, d3);
+                mma_16b<F16>(c0, ah[kk], d0, d1);
+                mma_16b<F16>(c1, ah[kk], d2, d3);
             }
             const int col = j * 8 + (lane & 3) * 2;
 #pragma unroll
@@ -564,8 +576,8 @@ extern "C" int hipie_relpos_bias_tc(const void* q_hi, const void* q_lo, int64_t 
 #define HIPIE_RP(HDV)                                                                                           \
     if (hd == HDV) {                                                                                            \
         const int smem = (2 * kpad + 4 * 2 * 16) * (HDV * 2 + 16);       /* R[coord] planes + per-warp Q slabs */ \
-        HIPIE_ENSURE_SMEM(relpos_mma_kernel<HDV>, smem);                                                        \
-        relpos_mma_kernel<HDV><<<grid, 128, smem, st>>>((const __nv_bfloat16*)q_hi, (const __nv_bfloat16*)q_lo, q_bs, q_ts, \
+        HIPIE_ENSURE_SMEM((relpos_mma_kernel<HDV, false>), smem);                                               \
+        relpos_mma_kernel<HDV, false><<<grid, 128, smem, st>>>((const __nv_bfloat16*)q_hi, (const __nv_bfloat16*)q_lo, q_bs, q_ts, \
                                                          q_hs, (const __nv_bfloat16*)table_hi,                  \
                                                          (const __nv_bfloat16*)table_lo, axis, qh, qw, ksize, kpad, rel, B, H); \
         HIPIE_CHECK_LAUNCH();                                                                                   \
@@ -576,5 +588,37 @@ extern "C" int hipie_relpos_bias_tc(const void* q_hi, const void* q_lo, int64_t 
     HIPIE_RP(80)
 #undef HIPIE_RP
     set_error("hipie_relpos_bias_tc: unsupported head dim %d", hd);
+    return HIPIE_EUNSUPPORTED;
+}
+
+
+extern "C" int hipie_relpos_bias_tc_f16(const void* q_f16, int64_t q_bs, int64_t q_ts, int64_t q_hs, const void* table_hi,
+                                        const void* table_lo, int axis, int qh, int qw, int ksize, float* rel, int B, int H, int hd,
+                                        void* stream) {
+    HIPIE_CHECK_ARG(q_f16 && table_hi && table_lo && rel, "hipie_relpos_bias_tc_f16: null pointer");
+    HIPIE_CHECK_ARG(axis == 0 || axis == 1, "hipie_relpos_bias_tc_f16: axis in {0,1}");
+    HIPIE_CHECK_ARG(q_ts % 8 == 0 && q_hs % 8 == 0 && q_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(q_f16) & 15) == 0,
+                    "hipie_relpos_bias_tc_f16: q rows must be 16-byte aligned (strides multiples of 8 elements)");
+    if ((int64_t)B * H * qh * qw == 0) return HIPIE_OK;
+    const int kpad = (ksize + 15) / 16 * 16;
+    const int G = axis == 0 ? qw : qh;
+    const int hpc = G >= 32 ? 4 : 16;
+    dim3 grid(axis == 0 ? qh : qw, (H + hpc - 1) / hpc, B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define HIPIE_RPF(HDV)                                                                                          \
+    if (hd == HDV) {                                                                                            \
+        const int smem = (2 * kpad + 4 * 2 * 16) * (HDV * 2 + 16);                                              \
+        HIPIE_ENSURE_SMEM((relpos_mma_kernel<HDV, true>), smem);                                                \
+        relpos_mma_kernel<HDV, true><<<grid, 128, smem, st>>>((const __nv_bfloat16*)q_f16, nullptr, q_bs, q_ts, q_hs,       \
+                                                              (const __nv_bfloat16*)table_hi, (const __nv_bfloat16*)table_lo, axis, qh, \
+                                                              qw, ksize, kpad, rel, B, H);                        \
+        HIPIE_CHECK_LAUNCH();                                                                                   \
+        return HIPIE_OK;                                                                                        \
+    }
+    HIPIE_RPF(32)
+    HIPIE_RPF(64)
+    HIPIE_RPF(80)
+#undef HIPIE_RPF
+    set_error("hipie_relpos_bias_tc_f16: unsupported head dim %d", hd);
     return HIPIE_EUNSUPPORTED;
 }

@@ -80,7 +80,10 @@ struct FaSmem {
 constexpr int FA_WIN = 14, FA_WIN_T = FA_WIN * FA_WIN;     // window mode: 14 x 14 tokens, keys padded to 4 x 64
 constexpr int FA_WIN_TP = 200;   // window mode: column pitch of one window in V^T (TMA box starts must be 16-byte aligned)
 
-template <int PREC, bool WIN>
+// F16 (with PREC == 1): q, k, v^T are IEEE fp16 planes and P is written as fp16: the single-pass QK^T / PV mode of the precision
+// map (2^-12 operand rounding instead of bf16's 2^-9 keeps the 1e-3 mask-logit budget, measured in
+// profiles/r02_precision_emulation.txt and tests/test_fullsize_gpu.py).
+template <int PREC, bool WIN, bool F16>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     using SM = FaSmem<PREC>;
@@ -170,8 +173,8 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         // tensor pipe (independent accumulators), which hides the dependent-accumulate latency of the small-N MMAs and keeps
         // the pipe busy while one tile waits on its softmax.  Latency-critical waits poll (test_wait) instead of suspending.
         const int t = warp == 1 ? 0 : 1;
-        constexpr uint32_t idesc_qk = make_idesc_bf16(FA_BM, FA_BN);
-        constexpr uint32_t idesc_pv = make_idesc_bf16(FA_BM, FA_HD);
+        constexpr uint32_t idesc_qk = F16 ? make_idesc_f16(FA_BM, FA_BN) : make_idesc_bf16(FA_BM, FA_BN);
+        constexpr uint32_t idesc_pv = F16 ? make_idesc_f16(FA_BM, FA_HD) : make_idesc_bf16(FA_BM, FA_HD);
         const uint32_t tb = tmem_base + t * TM_TILE;
         const uint32_t dS = tb + TM_S, dO = tb + TM_O, tq = tb + TM_Q, tp_hi = tb + TM_P, tp_lo = tb + TM_P + 32;
         const uint32_t qb = smem_u32(smem + SM::OFF_Q + t * SM::Q_TILE);
@@ -368,7 +371,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                     const float e0 = ex2_approx(tv[c + i] - off), e1 = ex2_approx(tv[c + i + 1] - off);
                     rs[(i >> 1) & 3] += e0 + e1;
                     if (PREC == 3) split2(e0, e1, ph_[i >> 1], pl_[i >> 1]);
-                    else ph_[i >> 1] = pack_bf16x2(e0, e1);
+                    else ph_[i >> 1] = F16 ? pack_f16x2(e0, e1) : pack_bf16x2(e0, e1);
                 }
                 tmem_st_32x32b_x4(tm + TM_P + (c >> 1), ph_[0], ph_[1], ph_[2], ph_[3]);
                 tmem_st_32x32b_x4(tm + TM_P + (c >> 1) + 4, ph_[4], ph_[5], ph_[6], ph_[7]);
@@ -432,12 +435,12 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     }
 }
 
-template <int PREC, bool WIN>
+template <int PREC, bool WIN, bool F16>
 static int launch_fa(const FaMaps& maps, const FaParams& p, cudaStream_t st) {
     using SM = FaSmem<PREC>;
-    HIPIE_ENSURE_SMEM((attn_tc_kernel<PREC, WIN>), SM::TOTAL);
+    HIPIE_ENSURE_SMEM((attn_tc_kernel<PREC, WIN, F16>), SM::TOTAL);
     dim3 grid(WIN ? 1 : p.T / (FA_QT * FA_BM), p.H, p.B);
-    attn_tc_kernel<PREC, WIN><<<grid, FA_THREADS, SM::TOTAL, st>>>(maps, p);
+    attn_tc_kernel<PREC, WIN, F16><<<grid, FA_THREADS, SM::TOTAL, st>>>(maps, p);
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
 }
@@ -452,7 +455,9 @@ extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int
                                          int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
                                          int H, int T, int hd, float scale, int prec, long long* trace, void* stream) {
     HIPIE_CHECK_ARG(q_hi && k_hi && vt_hi, "hipie_attention_tc: q/k/vt hi planes required");
-    HIPIE_CHECK_ARG(prec == 1 || (prec == 3 && q_lo && k_lo && vt_lo), "hipie_attention_tc: prec/lo planes mismatch");
+    HIPIE_CHECK_ARG(prec == 1 || prec == 2 || (prec == 3 && q_lo && k_lo && vt_lo), "hipie_attention_tc: prec/lo planes mismatch");
+    const bool f16 = prec == 2;          // prec 2: q / k / v^T are single IEEE fp16 planes, one MMA pass
+    if (f16) prec = 1;
     HIPIE_CHECK_ARG(hd == FA_HD, "hipie_attention_tc: head dim must be 80 (got %d)", hd);
     const bool win = T == FA_WIN_T && kh == FA_WIN && kw == FA_WIN;      // 14 x 14 windows: one CTA per (window, head)
     HIPIE_CHECK_ARG(win || (T > 0 && T % (FA_QT * FA_BM) == 0),
@@ -483,8 +488,8 @@ extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int
     p.scale_log2e = scale * 1.4426950408889634f;
     p.trace = trace;
     cudaStream_t st = (cudaStream_t)stream;
-    if (win) return prec == 3 ? launch_fa<3, true>(maps, p, st) : launch_fa<1, true>(maps, p, st);
-    return prec == 3 ? launch_fa<3, false>(maps, p, st) : launch_fa<1, false>(maps, p, st);
+    if (win) return prec == 3 ? launch_fa<3, true, false>(maps, p, st) : (f16 ? launch_fa<1, true, true>(maps, p, st) : launch_fa<1, true, false>(maps, p, st));
+    return prec == 3 ? launch_fa<3, false, false>(maps, p, st) : (f16 ? launch_fa<1, false, true>(maps, p, st) : launch_fa<1, false, false>(maps, p, st));
 }
 
 // Window mode (T == 196, kh == kw == 14): vt holds every window at a 200-column pitch, (H*80, B*200), pad columns zero.

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -95,6 +96,16 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
     hi = hu;
     lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// hi/lo planes of a pair: bf16 split, or (fp16 != 0) one IEEE fp16 plane
+__device__ __forceinline__ void split2m(float a, float b, uint32_t& hi, uint32_t& lo, int fp16) {
+    if (fp16) { hi = pack_f16x2(a, b); lo = 0u; }
+    else split2(a, b, hi, lo);
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {

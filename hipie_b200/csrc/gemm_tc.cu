@@ -51,6 +51,7 @@ struct GemmParams {
     float alpha;
     int transposed;  // 1: C stored as [N, ldc] (column-major output), lanes = rows
     int tiles_m, tiles_n;
+    int c_fp16;      // c_hi is one IEEE fp16 plane instead of bf16 hi/lo
     int tma_out;     // row-major outputs leave through TMA stores (32 x 32 boxes staged in swizzled shared memory)
     int m_fastest;   // tile order: 1 = the few M tiles of one N tile run back to back (concurrently on neighbouring SMs), so the
                      // big streamed W operand is fetched from HBM once and re-read from L2 (short, wide problems)
@@ -168,8 +169,8 @@ __device__ __forceinline__ void epilogue_rows_fast(const GemmParams& p, uint32_t
             if (cf_t) *reinterpret_cast<float4*>(cf_t + off) = x;
             if (chi_t) {
                 uint2 hi, lo;
-                split2(x.x, x.y, hi.x, lo.x);
-                split2(x.z, x.w, hi.y, lo.y);
+                split2m(x.x, x.y, hi.x, lo.x, p.c_fp16);
+                split2m(x.z, x.w, hi.y, lo.y, p.c_fp16);
                 *reinterpret_cast<uint2*>(chi_t + off) = hi;
                 if (clo_t) *reinterpret_cast<uint2*>(clo_t + off) = lo;
             }
@@ -250,8 +251,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
                 if (cf_b) *reinterpret_cast<float4*>(cf_b + off) = x;
                 if (chi_b) {
                     uint2 hi, lo;
-                    split2(x.x, x.y, hi.x, lo.x);
-                    split2(x.z, x.w, hi.y, lo.y);
+                    split2m(x.x, x.y, hi.x, lo.x, p.c_fp16);
+                    split2m(x.z, x.w, hi.y, lo.y, p.c_fp16);
                     *reinterpret_cast<uint2*>(chi_b + off) = hi;
                     if (clo_b) *reinterpret_cast<uint2*>(clo_b + off) = lo;
                 }
@@ -263,9 +264,13 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
                         if (res_b) xv += res_b[row * p.ldr + col + e];
                         if (cf_b) cf_b[off + e] = xv;
                         if (chi_b) {
-                            const __nv_bfloat16 h = __float2bfloat16_rn(xv);
-                            chi_b[off + e] = h;
-                            if (clo_b) clo_b[off + e] = __float2bfloat16_rn(xv - __bfloat162float(h));
+                            if (p.c_fp16) {
+                                reinterpret_cast<__half*>(chi_b)[off + e] = __float2half_rn(xv);
+                            } else {
+                                const __nv_bfloat16 h = __float2bfloat16_rn(xv);
+                                chi_b[off + e] = h;
+                                if (clo_b) clo_b[off + e] = __float2bfloat16_rn(xv - __bfloat162float(h));
+                            }
                         }
                     }
                 }
@@ -339,8 +344,8 @@ __device__ __forceinline__ void epilogue_rows_tma(const GemmParams& p, const CUt
                 } else {
                     // bf16 boxes: 64-byte rows, 16-byte group c of row r at c ^ ((r >> 1) & 3)  (CU_TENSOR_MAP_SWIZZLE_64B)
                     uint2 hi, lo;
-                    split2(x.x, x.y, hi.x, lo.x);
-                    split2(x.z, x.w, hi.y, lo.y);
+                    split2m(x.x, x.y, hi.x, lo.x, p.c_fp16);
+                    split2m(x.z, x.w, hi.y, lo.y, p.c_fp16);
                     const uint32_t off = lane * 64 + (((g >> 1) ^ ((lane >> 1) & 3)) << 4) + ((g & 1) << 3);
                     asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sbuf + off), "r"(hi.x), "r"(hi.y) : "memory");
                     if (p.c_lo) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sbuf + 2048 + off), "r"(lo.x), "r"(lo.y) : "memory");
@@ -396,9 +401,13 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, uint32_
                 if (rok) {
                     if (cf_b) cf_b[off] = x;
                     if (chi_b) {
-                        const __nv_bfloat16 h = __float2bfloat16_rn(x);
-                        chi_b[off] = h;
-                        if (clo_b) clo_b[off] = __float2bfloat16_rn(x - __bfloat162float(h));
+                        if (p.c_fp16) {
+                            reinterpret_cast<__half*>(chi_b)[off] = __float2half_rn(x);
+                        } else {
+                            const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                            chi_b[off] = h;
+                            if (clo_b) clo_b[off] = __float2bfloat16_rn(x - __bfloat162float(h));
+                        }
                     }
                 }
                 if (p.c_bits) {
@@ -760,6 +769,7 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     }
     GemmParams p;
     p.tma_out = tma_out ? 1 : 0;
+    p.c_fp16 = a->c_fp16 ? 1 : 0;
     p.bias = a->bias; p.colscale = a->colscale; p.residual = a->residual;
     p.ldr = a->ldr; p.r_bstride = a->r_bstride;
     p.c_f32 = a->c_f32; p.c_hi = (__nv_bfloat16*)a->c_hi; p.c_lo = (__nv_bfloat16*)a->c_lo;
@@ -813,6 +823,7 @@ extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     HIPIE_CHECK_ARG(!a->c_bits || a->transposed || (a->N % 16 == 0 && !a->c_row_map),
                     "hipie_gemm: row-major bit-packed output needs N %% 16 == 0 and no row map");
     HIPIE_CHECK_ARG(!a->c_lo || a->c_hi, "hipie_gemm: c_lo requires c_hi");
+    HIPIE_CHECK_ARG(!a->c_fp16 || (a->c_hi && !a->c_lo), "hipie_gemm: c_fp16 writes one fp16 plane (c_hi set, c_lo NULL)");
     HIPIE_CHECK_ARG(!a->c_row_map || !a->transposed, "hipie_gemm: c_row_map is not supported with transposed=1");
     cudaStream_t st = (cudaStream_t)stream;
     // CTA pairs where the mainloop dominates: big row counts, K >= 512, 3-pass operands (ViT / BERT / VL linears).  Measured on

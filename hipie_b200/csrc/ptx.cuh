@@ -273,5 +273,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
            | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
 
+// same with IEEE fp16 A/B (format code 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 }  // namespace ptx
 }  // namespace hipie

@@ -146,6 +146,7 @@ class Engine:
         self._bufs = {}
         self.bf16_value_map = False     # fast mode: MSDeformAttn value map stored as bf16
         self.use_tc_attention = True    # tcgen05 flash attention for the global ViT blocks
+        self.attn_fp16 = True           # precision map: QK^T / PV / rel-pos of the ViT attention run as ONE fp16 MMA pass
         self.taps = None                # parity harness: {"blocks": (7, 15, 31)} -> residual stream copies "vit.block<i>"
 
     # ------------------------------------------------------------ helpers
@@ -214,20 +215,29 @@ class Engine:
                 Bq, Tq, qh, qw = B, T, gh, gw
             st = (Tq * 3 * E, 3 * E, hd)
             use_tc = self.use_tc_attention and hd == 80 and ((not windowed and Tq % 256 == 0 and qw == 64) or (windowed and ws == 14))
+            f16 = use_tc and self.attn_fp16 and ops.PREC == 3
             if use_tc:
-                # q,k as one GEMM (N = 2E); V emitted transposed (E, B*T) so it is the K-major B operand of P.V
+                # q,k as one GEMM (N = 2E); V emitted transposed (E, B*T) so it is the K-major B operand of P.V.  With the fp16
+                # attention mode both epilogues write ONE fp16 plane instead of bf16 hi/lo (half the bytes of the qkv output).
                 wqk, bqk, wv, bv = W.cached(("qk_v", blk), lambda: (ops.split_weight(W[blk + ".attn.qkv.weight"][:2 * E]),
                                                                      W[blk + ".attn.qkv.bias"][:2 * E].contiguous(),
                                                                      ops.split_weight(W[blk + ".attn.qkv.weight"][2 * E:]),
                                                                      W[blk + ".attn.qkv.bias"][2 * E:].contiguous()))
-                _, qk, _ = ops.gemm(xn, wqk, bias=bqk, want_f32=False, want_split=True)              # (B*T, 2E)
+                _, qk, _ = ops.gemm(xn, wqk, bias=bqk, want_f32=False, want_split=True, out_fp16=f16)   # (B*T, 2E)
                 if windowed:
                     # V^T per window at a 200-column pitch (TMA box starts must be 16-byte aligned; 196 is not a multiple of 8);
                     # the 4 pad columns of every window stay zero in this cached buffer
-                    vt = self._zero_bf2(("vtwin", E, Bq), (E, Bq * 200))
-                    ops.gemm(xn, wv, bias=bv, want_f32=False, transposed=True, ldc=Bq * 200, out_split=vt, t_row_group=Tq, t_row_pad=200 - Tq)
+                    if f16:
+                        key = ("vtwin16", E, Bq)
+                        if key not in self._bufs:
+                            self._bufs[key] = BF2(torch.zeros((E, Bq * 200), dtype=torch.float16, device=self.device), None)
+                        vt = self._bufs[key]
+                    else:
+                        vt = self._zero_bf2(("vtwin", E, Bq), (E, Bq * 200))
+                    ops.gemm(xn, wv, bias=bv, want_f32=False, transposed=True, ldc=Bq * 200, out_split=vt, t_row_group=Tq, t_row_pad=200 - Tq,
+                             out_fp16=f16)
                 else:
-                    _, vt, _ = ops.gemm(xn, wv, bias=bv, want_f32=False, want_split=True, transposed=True)  # (E, B*T)
+                    _, vt, _ = ops.gemm(xn, wv, bias=bv, want_f32=False, want_split=True, transposed=True, out_fp16=f16)  # (E, B*T)
                 q = BF2(qk.hi[:, 0:E], None if qk.lo is None else qk.lo[:, 0:E])
                 k = BF2(qk.hi[:, E:], None if qk.lo is None else qk.lo[:, E:])
                 st = (Tq * 2 * E, 2 * E, hd)
@@ -236,13 +246,19 @@ class Engine:
                 q = BF2(qkv.hi[:, 0:E], None if qkv.lo is None else qkv.lo[:, 0:E])
                 k = BF2(qkv.hi[:, E:2 * E], None if qkv.lo is None else qkv.lo[:, E:2 * E])
                 vv = BF2(qkv.hi[:, 2 * E:], None if qkv.lo is None else qkv.lo[:, 2 * E:])
-            Rh = W.cached(("relh", i, qh), lambda: ops.split_weight(_get_rel_pos_table(qh, qh, W[blk + ".attn.rel_pos_h"])))
-            Rw = W.cached(("relw", i, qw), lambda: ops.split_weight(_get_rel_pos_table(qw, qw, W[blk + ".attn.rel_pos_w"])))
-            rel_h = ops.relpos_bias_tc(q, st, Rh, 0, qh, qw, Bq, nh, hd)
-            rel_w = ops.relpos_bias_tc(q, st, Rw, 1, qh, qw, Bq, nh, hd)
+            if f16:
+                Rh = W.cached(("relh16", i, qh), lambda: ops.split_weight_f16(_get_rel_pos_table(qh, qh, W[blk + ".attn.rel_pos_h"])))
+                Rw = W.cached(("relw16", i, qw), lambda: ops.split_weight_f16(_get_rel_pos_table(qw, qw, W[blk + ".attn.rel_pos_w"])))
+                rel_h = ops.relpos_bias_tc_f16(q.hi, st, Rh, 0, qh, qw, Bq, nh, hd)
+                rel_w = ops.relpos_bias_tc_f16(q.hi, st, Rw, 1, qh, qw, Bq, nh, hd)
+            else:
+                Rh = W.cached(("relh", i, qh), lambda: ops.split_weight(_get_rel_pos_table(qh, qh, W[blk + ".attn.rel_pos_h"])))
+                Rw = W.cached(("relw", i, qw), lambda: ops.split_weight(_get_rel_pos_table(qw, qw, W[blk + ".attn.rel_pos_w"])))
+                rel_h = ops.relpos_bias_tc(q, st, Rh, 0, qh, qw, Bq, nh, hd)
+                rel_w = ops.relpos_bias_tc(q, st, Rw, 1, qh, qw, Bq, nh, hd)
             if use_tc:
                 _, ao = ops.attention_tc(q, k, vt, Bq, nh, Tq, hd, st[0], st[1], st[0], st[1], hd ** -0.5, rel_h=rel_h, rel_w=rel_w,
-                                         kh=qh, kw=qw)
+                                         kh=qh, kw=qw, f16=f16)
             else:
                 _, ao = ops.attention(q, k, vv, Bq, nh, Tq, Tq, hd, st, st, st, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=qh, kw=qw)
             ao = ao.view(Bq * Tq, E)

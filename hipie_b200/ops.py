@@ -144,7 +144,7 @@ def add_split(a, b=None, want_f32=False, want_split=True):
 def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, alpha=1.0, want_f32=True,
          want_split=False, out_f32=None, transposed=False, row_map=None, out_rows=None, bits_threshold=None,
          M=None, N=None, K=None, batch=1, lda=None, ldw=None, a_bstride=0, w_bstride=0, ldc=None, c_bstride=0,
-         ldr=None, r_bstride=0, prec=None, out_split=None, t_row_group=0, t_row_pad=0):
+         ldr=None, r_bstride=0, prec=None, out_split=None, t_row_group=0, t_row_pad=0, out_fp16=False):
     """C = act(alpha * A.W^T + bias) * colscale + residual.
 
     A: (.., M, K) planes, W: (N, K) planes.  Default: 2-D row-major operands.  Strided / batched views
@@ -177,7 +177,11 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
     padded = transposed and batch == 1 and ldc is not None and ldc > rows_out
     ashape = (N, ldc) if padded else shape
     c_f32 = out_f32 if out_f32 is not None else (torch.empty(ashape, dtype=torch.float32, device=dev) if want_f32 else None)
-    c_split = out_split if out_split is not None else (_empty_bf2(ashape, dev) if want_split else None)
+    if out_fp16:       # one IEEE fp16 plane (operand of the single-pass fp16 contractions); returned as BF2(hi=fp16 tensor, lo=None)
+        c_split = out_split if out_split is not None else BF2(torch.empty(ashape, dtype=torch.float16, device=dev), None)
+        assert c_split.lo is None
+    else:
+        c_split = out_split if out_split is not None else (_empty_bf2(ashape, dev) if want_split else None)
     c_bits = None
     if bits_threshold is not None:       # x > threshold, bit-packed along the contiguous output dimension
         c_bits = torch.zeros((batch, N, (M + 31) // 32) if transposed else (batch, rows_out, (N + 31) // 32), dtype=torch.int32, device=dev)
@@ -197,7 +201,8 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
         c_bits=c_bits.data_ptr() if c_bits is not None else None,
         bits_threshold=float(bits_threshold) if bits_threshold is not None else 0.0,
         M=M, N=N, K=K, batch=batch, act=act, prec=prec, alpha=float(alpha), transposed=1 if transposed else 0,
-        c_row_map=row_map.data_ptr() if row_map is not None else None, t_row_group=t_row_group, t_row_pad=t_row_pad)
+        c_row_map=row_map.data_ptr() if row_map is not None else None, t_row_group=t_row_group, t_row_pad=t_row_pad,
+        c_fp16=1 if out_fp16 else 0)
     tag = f"gemm_tc[p{prec}]" + (":mask_embed" if c_bits is not None else "")
     if profiler.enabled and profiler.shapes:
         tag += f" {M}x{N}x{K}" + (f"x{batch}" if batch > 1 else "") + ("T" if transposed else "")
@@ -352,15 +357,18 @@ def attention(q: BF2, k: BF2, v: BF2, B, H, Tq, Tk, hd, q_strides, k_strides, v_
 
 
 def attention_tc(q: BF2, k: BF2, vt: BF2, B, H, T, hd, q_bs, q_ts, k_bs, k_ts, scale, rel_h=None, rel_w=None, kh=0, kw=0,
-                 want_f32=False, want_split=True, prec=None):
+                 want_f32=False, want_split=True, prec=None, f16=False):
     """tcgen05 flash attention.  q, k: plane views whose row (token) holds all heads contiguously (head h at columns
     [80h, 80h+80) of the view); vt: BF2 (H*hd, B*T) = V transposed.  Output (B, T, H*hd)."""
     prec = PREC if prec is None else prec
+    if f16:            # q / k / vt are single fp16 planes (gemm(out_fp16=True)); the output stays bf16 hi/lo for the 3-pass proj GEMM
+        assert q.hi.dtype == torch.float16 and k.hi.dtype == torch.float16 and vt.hi.dtype == torch.float16
+        prec = 2
     dev = q.hi.device
     o = torch.empty((B, T, H * hd), dtype=torch.float32, device=dev) if want_f32 else None
     s = _empty_bf2((B, T, H * hd), dev) if want_split else None
     lo = lambda t: _p(t.lo) if (t.lo is not None and prec == 3) else None
-    with _timed(f"attention_tc[p{prec}]", 4.0 * B * H * T * T * hd):
+    with _timed("attention_tc[f16x1]" if f16 else f"attention_tc[p{prec}]", 4.0 * B * H * T * T * hd):
         _lib.check(_lib.load().hipie_attention_tc(
             _p(q.hi), lo(q), q_bs, q_ts, 0, H * hd, _p(k.hi), lo(k), k_bs, k_ts, 0, H * hd, _p(vt.hi), lo(vt), vt.hi.stride(0),
             _p(rel_h), _p(rel_w), kh, kw, _p(o), _p(s.hi) if s else None, _p(s.lo) if (s and s.lo is not None) else None,
@@ -386,6 +394,25 @@ def relpos_bias_tc(q: BF2, q_strides, table: BF2, axis, qh, qw, B, H, hd):
         _lib.check(_lib.load().hipie_relpos_bias_tc(_p(q.hi), _p(q.lo) if PREC == 3 else None, q_strides[0], q_strides[1], q_strides[2],
                                                     _p(table.hi), _p(table.lo), axis, qh, qw, ksize, _p(rel), B, H, hd, _stream()),
                    "relpos_bias_tc")
+    return rel
+
+
+def split_weight_f16(w: torch.Tensor) -> BF2:
+    """fp16 hi / lo planes of a small constant table (rel-pos tables of the fp16 attention path); built once with torch at weight
+    preparation time."""
+    w = w.contiguous().float()
+    hi = w.half()
+    lo = (w - hi.float()).half()
+    return BF2(hi, lo)
+
+
+def relpos_bias_tc_f16(q_f16: torch.Tensor, q_strides, table: BF2, axis, qh, qw, B, H, hd):
+    """q: one fp16 plane; table: fp16 hi/lo planes (qsize, ksize, hd).  Returns (B, H, qh*qw, ksize) fp32."""
+    ksize = table.hi.shape[1]
+    rel = torch.empty((B, H, qh * qw, ksize), dtype=torch.float32, device=q_f16.device)
+    with _timed("relpos_bias_tc"):
+        _lib.check(_lib.load().hipie_relpos_bias_tc_f16(_p(q_f16), q_strides[0], q_strides[1], q_strides[2], _p(table.hi), _p(table.lo), axis,
+                                                        qh, qw, ksize, _p(rel), B, H, hd, _stream()), "relpos_bias_tc_f16")
     return rel
 
 

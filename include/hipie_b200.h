@@ -118,6 +118,8 @@ typedef struct hipie_gemm_args {
                                  from row c_row_map[r]; negative entries are skipped (window un-partition) */
     int t_row_group;          /* transposed only, 0 = off: GEMM row r is stored at position r + (r / t_row_group) * t_row_pad of */
     int t_row_pad;            /* each output column (groups of rows padded apart, e.g. 196-token windows at a 200 pitch)     */
+    int c_fp16;               /* 1: c_hi receives IEEE fp16 values (one plane, c_lo must be NULL): operands of the single-pass fp16
+                                 contractions (attention QK^T / PV); 0: bf16 hi (+ lo) planes */
 } hipie_gemm_args;
 
 int hipie_gemm(const hipie_gemm_args* args, void* stream);
@@ -192,7 +194,9 @@ int hipie_attention(const hipie_attn_args* args, void* stream);
  * q / k are bf16 planes viewed as (B, T, width) rows (token stride *_ts, batch stride *_bs, head h at columns
  * [*_col0 + 80 h, +80)); vt is V transposed, (H*80, B*T) planes with row stride vt_ld (the qkv GEMM emits it with transposed=1);
  * in window mode every window sits at a 200-column pitch, (H*80, B*200), with zero pad columns (t_row_group = 196,
- * t_row_pad = 4 of hipie_gemm).  rel_h (B, H, T, kh) and rel_w (B, H, T, kw) fp32.  Output (B, T, H*80) fp32 and/or bf16 split. */
+ * t_row_pad = 4 of hipie_gemm).  rel_h (B, H, T, kh) and rel_w (B, H, T, kw) fp32.  Output (B, T, H*80) fp32 and/or bf16 split.
+ * prec: 3 = bf16 hi/lo planes, three MMA passes; 1 = bf16 hi planes, one pass; 2 = ONE IEEE fp16 plane per operand (the `*_hi`
+ * pointers; hipie_gemm with c_fp16 = 1 emits them) and fp16 probabilities, one pass -- the parity-grade single-pass mode. */
 int hipie_attention_tc(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
                        const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
                        const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
@@ -220,6 +224,10 @@ int hipie_relpos_bias(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t 
 int hipie_relpos_bias_tc(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int64_t q_hs,
                          const void* table_hi, const void* table_lo, int axis, int qh, int qw, int ksize,
                          float* rel, int B, int H, int hd, void* stream);
+/* Same with q as ONE fp16 plane and the table as fp16 hi/lo planes (q.Rh + q.Rl, mma.sync f16): the rel-pos companion of the
+ * single-pass fp16 attention. */
+int hipie_relpos_bias_tc_f16(const void* q_f16, int64_t q_bs, int64_t q_ts, int64_t q_hs, const void* table_hi, const void* table_lo,
+                             int axis, int qh, int qw, int ksize, float* rel, int B, int H, int hd, void* stream);
 
 /* CondInst dynamic mask head, fused (H:models/ddetrs_dn.py:1390-1502,1806-1870):
  *   feats  (B, Hf*Wf, 8) NHWC fp32, params (B, Q, 169) fp32, ref_px (B, Q, 2) fp32 (pixels)

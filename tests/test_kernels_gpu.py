@@ -682,3 +682,77 @@ def test_seg_postprocess_wide_vocabulary(cuda):
         win = prob.argmax(0)
         got = ids.cpu()
         assert ((got >> 1) == win).float().mean() > 0.999 or not keep.any()
+
+
+# ------------------------------------------------------------------------------------------ single-pass fp16 attention path
+def test_gemm_fp16_plane_output(ops, cuda):
+    """hipie_gemm with c_fp16: the epilogue rounds the fp32 result to ONE IEEE fp16 plane (row-major through both store paths and
+    transposed with the window row padding)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, N, K = 1024, 320, 256
+    a, w, b = torch.randn(M, K, device=cuda, generator=g), torch.randn(N, K, device=cuda, generator=g) * 0.1, torch.randn(N, device=cuda, generator=g)
+    A, W = ops.split(a), ops.split_weight(w)
+    ref32, _, _ = ops.gemm(A, W, bias=b)
+    for tma in (1, 0):
+        _lib_set("gemm_tma_store", tma)
+        _, s, _ = ops.gemm(A, W, bias=b, want_f32=False, want_split=True, out_fp16=True)
+        assert s.hi.dtype == torch.float16 and s.lo is None
+        assert torch.equal(s.hi, ref32.half())
+    _lib_set("gemm_tma_store", 1)
+    _, st, _ = ops.gemm(A, W, bias=b, want_f32=False, want_split=True, transposed=True, out_fp16=True)
+    assert torch.equal(st.hi, ref32.t().half())
+
+
+def _lib_set(name, v):
+    from hipie_b200 import _lib
+    _lib.set_option(name, v)
+
+
+@pytest.mark.parametrize("win", [False, True])
+def test_attention_tcgen05_fp16_single_pass(ops, cuda, win):
+    """prec 2: q / k / v^T as single fp16 planes, P as fp16, one MMA pass -- against fp64 attention on the SAME fp16-rounded
+    operands (tight) and on the unrounded fp32 operands (the 2^-12 operand-rounding budget of DESIGN.md 3)."""
+    g = torch.Generator(device="cuda").manual_seed(41)
+    if win:
+        B, H, hd, gh, gw = 5, 3, 80, 14, 14
+    else:
+        B, H, hd, gh, gw = 2, 3, 80, 4, 64
+    T, E = gh * gw, H * hd
+    qk = torch.randn(B * T, 2 * E, device=cuda, generator=g)
+    v = torch.randn(B * T, E, device=cuda, generator=g)
+    qk16 = qk.half()
+    if win:
+        vpad = torch.zeros(E, B, 200, device=cuda)
+        vpad[:, :, :T] = v.t().reshape(E, B, T)
+        vt16 = vpad.view(E, B * 200).half()
+        v16 = vt16.float().view(E, B, 200)[:, :, :T].reshape(E, B * T).t()
+    else:
+        vt16 = v.t().contiguous().half()
+        v16 = vt16.float().t()
+    q, k, vt = ops.BF2(qk16[:, :E], None), ops.BF2(qk16[:, E:], None), ops.BF2(vt16, None)
+    rel_h = torch.randn(B, H, T, gh, device=cuda, generator=g)
+    rel_w = torch.randn(B, H, T, gw, device=cuda, generator=g)
+    o, _ = ops.attention_tc(q, k, vt, B, H, T, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=gh, kw=gw,
+                            want_f32=True, want_split=False, f16=True)
+    sh = lambda x: x.reshape(B, T, H, hd).permute(0, 2, 1, 3).double()
+    ref16 = _attn_ref(sh(qk16[:, :E].float()), sh(qk16[:, E:].float()), sh(v16), hd ** -0.5, rel_h, rel_w, gh, gw).permute(0, 2, 1, 3).reshape(B, T, E)
+    ref32 = _attn_ref(sh(qk[:, :E]), sh(qk[:, E:]), sh(v), hd ** -0.5, rel_h, rel_w, gh, gw).permute(0, 2, 1, 3).reshape(B, T, E)
+    assert (o.double() - ref16).abs().max().item() < 2e-3        # P is rounded to fp16 (2^-12 relative) before the PV pass
+    assert (o.double() - ref32).abs().max().item() < 8e-3        # + fp16 rounding of q / k / v: ~8x tighter than the bf16 pass (3e-2)
+
+
+def test_relpos_tc_fp16(ops, cuda):
+    g = torch.Generator(device="cuda").manual_seed(12)
+    B, H, hd, gh, gw = 1, 2, 80, 64, 64
+    T = gh * gw
+    qk = torch.randn(B * T, 2 * H * hd, device=cuda, generator=g)
+    q16 = qk.half()
+    Rh = torch.randn(gh, gh, hd, device=cuda, generator=g) * 0.2
+    Rw = torch.randn(gw, gw, hd, device=cuda, generator=g) * 0.2
+    st = (T * 2 * H * hd, 2 * H * hd, hd)
+    th = ops.relpos_bias_tc_f16(q16[:, :H * hd], st, ops.split_weight_f16(Rh), 0, gh, gw, B, H, hd)
+    tw = ops.relpos_bias_tc_f16(q16[:, :H * hd], st, ops.split_weight_f16(Rw), 1, gh, gw, B, H, hd)
+    rq = q16[:, :H * hd].float().reshape(B, T, H, hd).permute(0, 2, 1, 3).double().reshape(B, H, gh, gw, hd)
+    ref_h = torch.einsum("bnhwc,hkc->bnhwk", rq, Rh.double()).reshape(B, H, T, gh)
+    ref_w = torch.einsum("bnhwc,wkc->bnhwk", rq, Rw.double()).reshape(B, H, T, gw)
+    assert (th.double() - ref_h).abs().max() < 2e-4 and (tw.double() - ref_w).abs().max() < 2e-4

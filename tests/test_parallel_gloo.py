@@ -53,3 +53,34 @@ def test_two_rank_gather_restores_global_order(total):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _worker_packed(rank, world, port, q):
+    from hipie_b200.parallel import PackedAllGather
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(1)
+    full = {"pred_logits": torch.randn(6, 5, 7, generator=g), "pred_boxes": torch.rand(6, 5, 4, generator=g), "pred_boxious": torch.randn(6, 5, 1, generator=g)}
+    idx = list(shard_indices(6, world, rank))
+    gather = PackedAllGather()
+    ok = True
+    for step in range(2):                      # second call reuses the preallocated buffers
+        out = {k: v[idx] + step for k, v in full.items()}
+        got = gather(out, list(full))
+        ok &= all(torch.equal(got[k], full[k] + step) for k in full)
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_packed_all_gather_one_collective_restores_global_order():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_packed, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
