@@ -53,6 +53,7 @@ SYMBOLS = {
     "hipie_set_option": (c_int, [ctypes.c_char_p, c_int]),
     "hipie_msda_forward": (c_int, [c_void_p] * 6 + [c_int] * 9 + [c_void_p]),
     "hipie_msda_fused_forward": (c_int, [c_void_p] * 5 + [c_int, c_void_p] + [c_int] * 9 + [c_void_p, c_void_p]),
+    "hipie_msda_encoder_forward": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p, c_int, c_void_p]),
     "hipie_gemm": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     "hipie_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "hipie_layernorm": (c_int, [c_void_p] * 4 + [c_float] + [c_void_p] * 4 + [c_int64, c_int, c_void_p, c_void_p]),

@@ -738,6 +738,30 @@ int make_tmap(CUtensorMap* out, const void* ptr, int esize, int64_t rows, int64_
 int g_gemm_cta_pairs = 1;
 int g_gemm_tma_store = 1;
 
+// fp32 tensor of rank 5 (dims / strides innermost first, strides in BYTES for dims 1..4), dense unswizzled boxes: the value-map
+// windows of the shared-memory MSDeformAttn kernel (msda.cu).  Not cached: built once per launch from host-side geometry.
+int make_tmap_f32_5d(CUtensorMap* out, const void* ptr, const uint64_t dims[5], const uint64_t strides_bytes[4], const uint32_t box[5]) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return HIPIE_ECUDA; }
+    HIPIE_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map base %p not 16B aligned", ptr);
+    cuuint64_t d[5], st[4];
+    cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < 5; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i < 4; ++i) {
+        HIPIE_CHECK_ARG(strides_bytes[i] % 16 == 0, "tensor map stride %llu not a multiple of 16 bytes", (unsigned long long)strides_bytes[i]);
+        st[i] = strides_bytes[i];
+    }
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (5-d) failed (%d): dims %llu %llu %llu %llu %llu box %u %u %u %u %u", (int)r, (unsigned long long)d[0],
+                  (unsigned long long)d[1], (unsigned long long)d[2], (unsigned long long)d[3], (unsigned long long)d[4], bx[0], bx[1], bx[2],
+                  bx[3], bx[4]);
+        return HIPIE_ECUDA;
+    }
+    return HIPIE_OK;
+}
+
 template <int PREC, int BN, int CTAS>
 static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     using Cfg = GemmCfg<PREC, BN, CTAS>;

@@ -302,7 +302,7 @@ class Engine:
         C = wk.hi.shape[0]
         return (f.view(B, Ho, Wo, C) if f is not None else None), (s.view(B, Ho, Wo, C) if s is not None else None)
 
-    def msda_layer(self, prefix, query_s, ref, value_src_s, value_mask, shapes_t, lsi_t, B, Lq, S, want_split=True):
+    def msda_layer(self, prefix, query_s, ref, value_src_s, value_mask, shapes_t, lsi_t, B, Lq, S, want_split=True, shapes_host=None):
         """MSDeformAttn.forward (H/models/deformable_detr/ops/modules/ms_deform_attn.py:79-116) minus output_proj.
         query_s: BF2 (B*Lq, 256); value_src_s: BF2 (B*S, 256); ref (B, Lq, 4, 2|4) fp32."""
         W = self.W
@@ -319,7 +319,7 @@ class Engine:
                     value = value.bfloat16()
         wol, bol = W.lin_cat(prefix + ".offs_logits", [prefix + ".sampling_offsets", prefix + ".attention_weights"])
         ol, _, _ = ops.gemm(query_s, wol, bias=bol)
-        return ops.msda_fused(value, shapes_t, lsi_t, ol.view(B, Lq, 384), ref, want_split=want_split)
+        return ops.msda_fused(value, shapes_t, lsi_t, ol.view(B, Lq, 384), ref, want_split=want_split, shapes_host=shapes_host)
 
     def mlp(self, x_s, prefix, n, last_f32=True):
         """MLP with ReLU between layers (deformable_transformer_dino.py:599-633).  x_s BF2 (rows, in)."""
@@ -342,11 +342,12 @@ class Engine:
         y, _, _ = ops.gemm(h, w2, bias=b2, residual=x)
         return ops.layernorm(y, W[f"{prefix}.{n2}.weight"], W[f"{prefix}.{n2}.bias"], 1e-5, want_f32=True, want_split=True)[:2]
 
-    def encoder_layer(self, prefix, src, src_s, pos, ref, mask_flat, shapes_t, lsi_t, B, S):
+    def encoder_layer(self, prefix, src, src_s, pos, ref, mask_flat, shapes_t, lsi_t, B, S, shapes_host=None):
         """DeformableTransformerEncoderLayer (deformable_transformer_dino.py:354-394) == MaskDINO's (:117-157)."""
         W = self.W
         _, q_s = ops.add_split(src, pos)
-        a_s = self.msda_layer(prefix + ".self_attn", q_s.view(B * S, 256), ref, src_s.view(B * S, 256), mask_flat, shapes_t, lsi_t, B, S, S)
+        a_s = self.msda_layer(prefix + ".self_attn", q_s.view(B * S, 256), ref, src_s.view(B * S, 256), mask_flat, shapes_t, lsi_t, B, S, S,
+                              shapes_host=shapes_host)
         wo, bo = W.lin(prefix + ".self_attn.output_proj")
         y, _, _ = ops.gemm(a_s.view(B * S, 256), wo, bias=bo, residual=src.view(B * S, 256))
         x, x_s, _ = ops.layernorm(y, W[prefix + ".norm1.weight"], W[prefix + ".norm1.bias"], 1e-5, want_f32=True, want_split=True)
@@ -634,7 +635,7 @@ class Engine:
         # layer 0: VL fusion, then the deformable encoder layers
         src, src_s, lang_hidden = self.vl_fuse(src, lang["hidden"], lang["masks"], B, S)
         for i in range(hp.get("enc_layers", 6)):
-            src, src_s = self.encoder_layer(f"{t}.encoder.layers.{i}", src, src_s, pos, ref_enc, mask_flat, shapes_t, lsi_t, B, S)
+            src, src_s = self.encoder_layer(f"{t}.encoder.layers.{i}", src, src_s, pos, ref_enc, mask_flat, shapes_t, lsi_t, B, S, shapes_host=shapes)
         memory, memory_s = src, src_s
         # two-stage proposals (:222-230): enc_output + LN on masked memory, Still_Classifier score, top-k
         props, valid = self.proposals(shapes, di["mask_flat"], B, self.device)
@@ -757,7 +758,8 @@ class Engine:
         lsi_t = self._dev_const(list(starts), torch.long)
         _, src_s = ops.add_split(src)
         for i in range(hp.get("md_enc_layers", 6)):
-            src, src_s = self.encoder_layer(f"{pd}.transformer.encoder.layers.{i}", src, src_s, pos, ref_enc, None, shapes_t, lsi_t, B, S)
+            src, src_s = self.encoder_layer(f"{pd}.transformer.encoder.layers.{i}", src, src_s, pos, ref_enc, None, shapes_t, lsi_t, B, S,
+                                            shapes_host=shapes)
         # FPN level on res3 (:418-427): lateral 1x1+GN, + out[0] (same size -> bilinear resize is the identity), 3x3+GN+ReLU
         h3, w3 = shapes[0]
         lat = self.conv1x1_gn(lv[0][1], pd + ".adapter_1", pd + ".adapter_1.norm", bias=False)              # (B, hw, 256)

@@ -430,9 +430,14 @@ def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, a
     return out
 
 
+MSDA_WINDOWS = True      # encoder calls gather from TMA-staged shared-memory windows (msda_win_kernel); False = flat kernel (A/B)
+
+
 def msda_fused(value, spatial_shapes, level_start_index, offs_logits, reference_points, M=8, D=32, L=4, P=4,
-               want_split=True):
-    """value (N,S,M*D) fp32|bf16; offs_logits (N,Lq,M*L*P*3) fp32; reference_points (N,Lq,L,2|4) fp32."""
+               want_split=True, shapes_host=None):
+    """value (N,S,M*D) fp32|bf16; offs_logits (N,Lq,M*L*P*3) fp32; reference_points (N,Lq,L,2|4) fp32.
+    shapes_host: the level (H, W) list on the host -- with it, encoder calls (Lq == S, 2-d reference points, fp32 value map) run the
+    shared-memory window kernel."""
     N, S = value.shape[0], value.shape[1]
     Lq = offs_logits.shape[1]
     ref_dim = reference_points.shape[-1]
@@ -447,11 +452,22 @@ def msda_fused(value, spatial_shapes, level_start_index, offs_logits, reference_
     fv = 2 if vdt == 2 else 4
     # algorithmic bytes: value map + offsets/logits (3 floats per sample) + output
     alg = float(N) * (S * M * D * fv + Lq * M * L * P * 3 * 4 + Lq * M * D * 4)
+    offs_logits, reference_points = offs_logits.contiguous(), reference_points.contiguous()
     with _timed("msda_fused" + (":enc" if Lq == S else ":dec"), alg):
-        _lib.check(_lib.load().hipie_msda_fused_forward(_p(value), _p(spatial_shapes), _p(level_start_index),
-                                                        _p(offs_logits.contiguous()), _p(reference_points.contiguous()), ref_dim,
-                                                        _p(out), N, S, M, D, L, Lq, P, vdt, 1 if want_split else 0, _p(out_lo),
-                                                        _stream()), "msda_fused_forward")
+        done = False
+        if MSDA_WINDOWS and shapes_host is not None and Lq == S and ref_dim == 2 and vdt == 0 and L == 4:
+            sh = (ctypes.c_int * 8)(*[int(v) for hw in shapes_host for v in hw])
+            rc = _lib.load().hipie_msda_encoder_forward(_p(value), sh, _p(offs_logits), _p(reference_points), _p(out), N, S, M, D, L, P,
+                                                        1 if want_split else 0, _p(out_lo), 0, _stream())
+            if rc == 0:
+                done = True
+            elif rc != -3:           # HIPIE_EUNSUPPORTED: windows do not fit -> flat kernel
+                _lib.check(rc, "msda_encoder_forward")
+        if not done:
+            _lib.check(_lib.load().hipie_msda_fused_forward(_p(value), _p(spatial_shapes), _p(level_start_index),
+                                                            _p(offs_logits), _p(reference_points), ref_dim,
+                                                            _p(out), N, S, M, D, L, Lq, P, vdt, 1 if want_split else 0, _p(out_lo),
+                                                            _stream()), "msda_fused_forward")
     return s if want_split else out
 
 

@@ -122,6 +122,16 @@ typedef struct hipie_gemm_args {
                                  contractions (attention QK^T / PV); 0: bf16 hi (+ lo) planes */
 } hipie_gemm_args;
 
+/* Encoder form of the fused MSDeformAttn op (Lq == S: the queries are the pixels of the four levels; 2-d reference points; fp32
+ * value map): one work item = (image, head, 16x16-pixel region of the finest level); the region's windows of all four levels are
+ * staged in shared memory by TMA (zero fill outside a level = the sampling's zero padding) and the region's queries gather from
+ * shared memory; taps outside the halo take the global path, so results equal hipie_msda_fused_forward bit for bit.
+ *   shapes_hw_host: HOST array of 4 (H_l, W_l) pairs (sizes the TMA boxes); halo: pixels around the region (0 = default 5, reduced
+ *   automatically until the windows fit).  Returns HIPIE_EUNSUPPORTED when the windows cannot fit: use the flat kernel then. */
+int hipie_msda_encoder_forward(const void* value, const int* shapes_hw_host, const float* offs_logits, const float* reference_points,
+                               void* out, int N, int S, int M, int D, int L, int P, int out_split_bf16, void* out_lo, int halo,
+                               void* stream);
+
 int hipie_gemm(const hipie_gemm_args* args, void* stream);
 
 /* fp32 -> bf16 hi (+ lo = bf16(x - hi)) split of a contiguous array of n elements. */

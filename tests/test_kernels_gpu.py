@@ -756,3 +756,47 @@ def test_relpos_tc_fp16(ops, cuda):
     ref_h = torch.einsum("bnhwc,hkc->bnhwk", rq, Rh.double()).reshape(B, H, T, gh)
     ref_w = torch.einsum("bnhwc,wkc->bnhwk", rq, Rw.double()).reshape(B, H, T, gw)
     assert (th.double() - ref_h).abs().max() < 2e-4 and (tw.double() - ref_w).abs().max() < 2e-4
+
+
+# ------------------------------------------------------------------------------------------ MSDeformAttn encoder: window kernel
+@pytest.mark.parametrize("shapes,offs_scale", [([(32, 32), (16, 16), (8, 8), (4, 4)], 1.5), ([(40, 56), (20, 28), (10, 14), (5, 7)], 1.5),
+                                               ([(24, 20), (12, 10), (6, 5), (3, 3)], 12.0), ([(64, 64), (32, 32), (16, 16), (8, 8)], 3.0)])
+def test_msda_encoder_window_kernel(ops, cuda, shapes, offs_scale):
+    """hipie_msda_encoder_forward (TMA-staged shared-memory windows, Lq == S, encoder reference points) against the flat fused
+    kernel -- bit for bit -- and against the oracle core; ragged level sizes, borders, and offsets far larger than the halo (the
+    global fallback path) included."""
+    from hipie_oracle.msda import ms_deform_attn_core
+    from hipie_b200 import ops as O
+    g = torch.Generator().manual_seed(7)
+    shapes_t = torch.as_tensor(shapes)
+    S = int(shapes_t.prod(1).sum())
+    N, M, L, P = 2, 8, 4, 4
+    value = torch.randn(N, S, M * 32, generator=g)
+    offs = torch.randn(N, S, M, L, P, 2, generator=g) * offs_scale
+    logits = torch.randn(N, S, M, L * P, generator=g)
+    # encoder reference points: the query's own pixel centre, the same normalised point on every level (valid ratios 1)
+    refs = []
+    for (H_, W_) in shapes:
+        ry, rx = torch.meshgrid(torch.linspace(0.5, H_ - 0.5, H_) / H_, torch.linspace(0.5, W_ - 0.5, W_) / W_, indexing="ij")
+        refs.append(torch.stack((rx.reshape(-1), ry.reshape(-1)), -1))
+    refp = torch.cat(refs, 0)[None, :, None, :].repeat(N, 1, L, 1).contiguous()
+    norm = torch.stack([shapes_t[:, 1], shapes_t[:, 0]], -1).float()
+    loc = refp[:, :, None, :, None, :] + offs / norm[None, None, None, :, None, :]
+    w = torch.softmax(logits, -1).view(N, S, M, L, P)
+    ref = ms_deform_attn_core(value.view(N, S, M, 32).double(), shapes_t, loc.double(), w.double()).float()
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    packed = torch.cat([offs.reshape(N, S, -1), logits.reshape(N, S, -1)], -1).to(cuda)
+    args = (value.to(cuda), shapes_t.to(cuda), lsi.to(cuda), packed, refp.to(cuda))
+    O.MSDA_WINDOWS = False
+    try:
+        flat = ops.msda_fused(*args, want_split=False)
+        flat_s = ops.msda_fused(*args, want_split=True)
+    finally:
+        O.MSDA_WINDOWS = True
+    ops.profiler.start()
+    win = ops.msda_fused(*args, want_split=False, shapes_host=shapes)
+    win_s = ops.msda_fused(*args, want_split=True, shapes_host=shapes)
+    assert "msda_fused:enc" in ops.profiler.stop()
+    assert (win.cpu() - ref).abs().max() < 2e-5
+    assert torch.equal(win, flat)
+    assert torch.equal(win_s.hi, flat_s.hi) and torch.equal(win_s.lo, flat_s.lo)
