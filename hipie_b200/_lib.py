@@ -26,7 +26,7 @@ class GemmArgs(ctypes.Structure):
         ("c_bits", c_void_p), ("bits_threshold", c_float),
         ("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int),
         ("act", c_int), ("prec", c_int), ("alpha", c_float), ("transposed", c_int), ("c_row_map", c_void_p),
-        ("t_row_group", c_int), ("t_row_pad", c_int), ("c_fp16", c_int),
+        ("t_row_group", c_int), ("t_row_pad", c_int), ("relu_after_residual", c_int), ("c_fp16", c_int),
     ]
 
 
@@ -63,6 +63,7 @@ SYMBOLS = {
     "hipie_im2col_nhwc": (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     "hipie_pixel_shuffle2": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "hipie_maxpool2_nhwc": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
+    "hipie_maxpool3x3s2_nhwc": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "hipie_row_softmax": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hipie_attention": (c_int, [ctypes.POINTER(AttnArgs), c_void_p]),
     "hipie_attention_tc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,

@@ -51,6 +51,7 @@ struct GemmParams {
     float alpha;
     int transposed;  // 1: C stored as [N, ldc] (column-major output), lanes = rows
     int tiles_m, tiles_n;
+    int relu_post;   // ReLU after the residual add
     int c_fp16;      // c_hi is one IEEE fp16 plane instead of bf16 hi/lo
     int tma_out;     // row-major outputs leave through TMA stores (32 x 32 boxes staged in swizzled shared memory)
     int m_fastest;   // tile order: 1 = the few M tiles of one N tile run back to back (concurrently on neighbouring SMs), so the
@@ -164,6 +165,7 @@ __device__ __forceinline__ void epilogue_rows_fast(const GemmParams& p, uint32_t
                 const float4 rv = *reinterpret_cast<const float4*>(res_t + rr * ldr + cb);
                 x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
             }
+            if (p.relu_post) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
             const int off = rr * ldc + cb;
             if (p.c_bits) row_bits16(p, x, b, m0 + rr, n0 + cb, lane);
             if (cf_t) *reinterpret_cast<float4*>(cf_t + off) = x;
@@ -247,6 +249,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
                     const float4 rv = *reinterpret_cast<const float4*>(res_b + row * p.ldr + col);
                     x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
                 }
+                if (p.relu_post) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
                 if (p.c_bits) row_bits16(p, x, b, (int)row, nbase, lane);
                 if (cf_b) *reinterpret_cast<float4*>(cf_b + off) = x;
                 if (chi_b) {
@@ -262,6 +265,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
                     if (col + e < p.N) {
                         float xv = e == 0 ? x.x : (e == 1 ? x.y : (e == 2 ? x.z : x.w));
                         if (res_b) xv += res_b[row * p.ldr + col + e];
+                        if (p.relu_post) xv = fmaxf(xv, 0.f);
                         if (cf_b) cf_b[off + e] = xv;
                         if (chi_b) {
                             if (p.c_fp16) {
@@ -794,6 +798,7 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     GemmParams p;
     p.tma_out = tma_out ? 1 : 0;
     p.c_fp16 = a->c_fp16 ? 1 : 0;
+    p.relu_post = a->relu_after_residual ? 1 : 0;
     p.bias = a->bias; p.colscale = a->colscale; p.residual = a->residual;
     p.ldr = a->ldr; p.r_bstride = a->r_bstride;
     p.c_f32 = a->c_f32; p.c_hi = (__nv_bfloat16*)a->c_hi; p.c_lo = (__nv_bfloat16*)a->c_lo;
@@ -847,6 +852,7 @@ extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     HIPIE_CHECK_ARG(!a->c_bits || a->transposed || (a->N % 16 == 0 && !a->c_row_map),
                     "hipie_gemm: row-major bit-packed output needs N %% 16 == 0 and no row map");
     HIPIE_CHECK_ARG(!a->c_lo || a->c_hi, "hipie_gemm: c_lo requires c_hi");
+    HIPIE_CHECK_ARG(!a->relu_after_residual || (a->residual && !a->transposed), "hipie_gemm: relu_after_residual needs a row-major residual");
     HIPIE_CHECK_ARG(!a->c_fp16 || (a->c_hi && !a->c_lo), "hipie_gemm: c_fp16 writes one fp16 plane (c_hi set, c_lo NULL)");
     HIPIE_CHECK_ARG(!a->c_row_map || !a->transposed, "hipie_gemm: c_row_map is not supported with transposed=1");
     cudaStream_t st = (cudaStream_t)stream;

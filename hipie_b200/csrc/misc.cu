@@ -102,6 +102,41 @@ pixel_shuffle2_kernel(const float* __restrict__ g, float* __restrict__ y, __nv_b
     }
 }
 
+// F.max_pool2d(kernel 3, stride 2, padding 1) on NHWC (the ResNet stem, detectron2 resnet.py:362-365): padding never wins the max
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ hi,
+                         __nv_bfloat16* __restrict__ lo, int B, int H, int W, int C) {
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const int64_t total = (int64_t)B * Ho * Wo * C / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i * 4;
+        const int c = (int)(e % C);
+        const int64_t row = e / C;
+        const int ox = (int)(row % Wo), oy = (int)((row / Wo) % Ho), b = (int)(row / ((int64_t)Wo * Ho));
+        float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = 2 * oy - 1 + dy;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = 2 * ox - 1 + dx;
+                if (ix < 0 || ix >= W) continue;
+                const float4 a = *reinterpret_cast<const float4*>(x + (((int64_t)b * H + iy) * W + ix) * C + c);
+                v.x = fmaxf(v.x, a.x); v.y = fmaxf(v.y, a.y); v.z = fmaxf(v.z, a.z); v.w = fmaxf(v.w, a.w);
+            }
+        }
+        if (y) *reinterpret_cast<float4*>(y + e) = v;
+        if (hi) {
+            uint2 h, l;
+            split2(v.x, v.y, h.x, l.x);
+            split2(v.z, v.w, h.y, l.y);
+            *reinterpret_cast<uint2*>(hi + e) = h;
+            if (lo) *reinterpret_cast<uint2*>(lo + e) = l;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 maxpool2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ hi,
                      __nv_bfloat16* __restrict__ lo, int B, int H, int W, int C) {
@@ -539,6 +574,16 @@ extern "C" int hipie_maxpool2_nhwc(const float* x, float* y, void* hi, void* lo,
     const int64_t total = (int64_t)B * (H / 2) * (W / 2) * C / 4;
     maxpool2_nhwc_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, y, (__nv_bfloat16*)hi,
                                                                            (__nv_bfloat16*)lo, B, H, W, C);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
+extern "C" int hipie_maxpool3x3s2_nhwc(const float* x, float* y, void* hi, void* lo, int B, int H, int W, int C, void* stream) {
+    HIPIE_CHECK_ARG(x && (y || hi), "hipie_maxpool3x3s2_nhwc: null pointer");
+    HIPIE_CHECK_ARG(C % 4 == 0 && H > 0 && W > 0, "hipie_maxpool3x3s2_nhwc: bad sizes");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const int64_t total = (int64_t)B * Ho * Wo * C / 4;
+    maxpool3x3s2_nhwc_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, y, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, B, H, W, C);
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
 }

@@ -282,6 +282,64 @@ class Engine:
         r5, r5s = ops.maxpool2_nhwc(x4, want_f32=True, want_split=True)
         return {"res3": (r3, r3s), "res4": (x4, xs.view(B, gh, gw, E)), "res5": (r5, r5s)}
 
+    # ------------------------------------------------------------ ResNet-50 backbone (config #1; detectron2 resnet.py:105-205,329-366,614-694)
+    def _conv_bn(self, prefix, ksz):
+        """(BF2 weight (cout, ksz*ksz*cin) in (ky, kx, c) column order, bias) with FrozenBatchNorm2d folded in
+        (batch_norm.py:13-118: y = x * (w * rsqrt(var + eps)) + (b - mean * w * rsqrt(var + eps)), eps 1e-5)."""
+        W = self.W
+
+        def mk():
+            w = W[prefix + ".weight"]
+            scale = W[prefix + ".norm.weight"] * (W[prefix + ".norm.running_var"] + 1e-5).rsqrt()
+            bias = W[prefix + ".norm.bias"] - W[prefix + ".norm.running_mean"] * scale
+            w = w * scale.view(-1, 1, 1, 1)
+            if w.shape[1] % 8:                                   # stem: 3 input channels padded to 8 (GEMM rows need 16-byte strides)
+                w = F.pad(w, (0, 0, 0, 0, 0, 8 - w.shape[1] % 8))
+            return ops.split_weight(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)), bias.contiguous()
+        return W.cached(("convbn", prefix, ksz), mk)
+
+    def resnet50(self, img):
+        """img: (B, 3, H, W) raw 0..255 fp32 -> {res3, res4, res5: (fp32 NHWC, BF2)}.  Every convolution is a GEMM over NHWC rows
+        (1x1: plain / strided row subsampling through im2col with k = 1; 3x3 and the 7x7 stem: im2col) with the frozen BN folded into
+        weights and bias, ReLU in the epilogue, and the bottleneck's relu(conv3 + shortcut) as residual + post-ReLU in the epilogue."""
+        bb = "detr.detr.backbone.0.backbone"
+        B, _, H, Wd = img.shape
+        mean = self._dev_const([123.675, 116.280, 103.530], torch.float32).view(1, 3, 1, 1)
+        std = self._dev_const([58.395, 57.120, 57.375], torch.float32).view(1, 3, 1, 1)
+        x = ((img - mean) / std).permute(0, 2, 3, 1)
+        x = F.pad(x, (0, 5)).contiguous()                        # NHWC, channels 3 -> 8 (zeros)
+        cols, Ho, Wo = ops.im2col_nhwc(x, 7, 2, 3)
+        w, b = self._conv_bn(bb + ".stem.conv1", 7)
+        y, _, _ = ops.gemm(cols, w, bias=b, act=ops.ACT_RELU)
+        x, x_s = ops.maxpool3x3s2_nhwc(y.view(B, Ho, Wo, 64), want_f32=True, want_split=True)
+        outs = {}
+        for name, n, first_stride in (("res2", 3, 1), ("res3", 4, 2), ("res4", 6, 2), ("res5", 3, 2)):
+            for i in range(n):
+                p_ = f"{bb}.{name}.{i}"
+                stride = first_stride if i == 0 else 1
+                Bc, Hc, Wc, Cin = x.shape
+                w1, b1 = self._conv_bn(p_ + ".conv1", 1)
+                y1, _, _ = ops.gemm(x_s.view(-1, Cin), w1, bias=b1, act=ops.ACT_RELU)                    # f32 for the 3x3 im2col
+                bott = w1.hi.shape[0]
+                cols, Ho, Wo = ops.im2col_nhwc(y1.view(Bc, Hc, Wc, bott), 3, stride, 1)
+                w2, b2 = self._conv_bn(p_ + ".conv2", 3)
+                _, y2, _ = ops.gemm(cols, w2, bias=b2, act=ops.ACT_RELU, want_f32=False, want_split=True)
+                if (p_ + ".shortcut.weight") in self.W.f:
+                    ws, bs = self._conv_bn(p_ + ".shortcut", 1)
+                    if stride == 1:
+                        sc, _, _ = ops.gemm(x_s.view(-1, Cin), ws, bias=bs)
+                    else:
+                        sub, _, _ = ops.im2col_nhwc(x, 1, stride, 0)                                     # strided 1x1 = row subsampling
+                        sc, _, _ = ops.gemm(sub, ws, bias=bs)
+                else:
+                    sc = x.view(-1, Cin)
+                w3, b3 = self._conv_bn(p_ + ".conv3", 1)
+                y3, y3_s, _ = ops.gemm(y2, w3, bias=b3, residual=sc, relu_after_residual=True, want_split=True)
+                x, x_s = y3.view(Bc, Ho, Wo, -1), y3_s.view(Bc, Ho, Wo, -1)
+            if name != "res2":
+                outs[name] = (x, x_s)
+        return outs
+
     # ------------------------------------------------------------ generic pieces
     def conv1x1_gn(self, feat_s, prefix_conv, prefix_gn, out_view=None, y_bstride=None, relu=False, bias=True):
         """1x1 conv (GEMM over NHWC rows) + GroupNorm(32).  feat_s: BF2 (B, h, w, Cin)."""
@@ -546,6 +604,13 @@ class Engine:
         out_l = BF2(torch.empty(B * Lt, E, dtype=torch.bfloat16, device=self.device),
                     torch.empty(B * Lt, E, dtype=torch.bfloat16, device=self.device) if ops.PREC == 3 else None)
         sub = lambda a, r0, r1, c0, c1: BF2(a.hi[r0:r1, c0:c1], None if a.lo is None else a.lo[r0:r1, c0:c1])
+        # the text->image P.V contraction runs over K = S pixels; TMA rows need 16-byte strides, i.e. a pixel count that is a multiple
+        # of 8.  Image sizes whose level sum is not (e.g. 192 x 256 -> S = 1020) get zero-padded operand pitches (zeros add nothing).
+        Sp = (S + 7) // 8 * 8
+        padS = lambda a, rows: a if Sp == S else BF2(F.pad(a.hi.reshape(rows, -1, S), (0, Sp - S)).reshape(rows, -1),
+                                                     None if a.lo is None else F.pad(a.lo.reshape(rows, -1, S), (0, Sp - S)).reshape(rows, -1))
+        if Sp != S:
+            vvT = padS(vvT, E)                                   # (E, B*Sp): every image at an Sp pitch
         for h in range(nh):
             c0, c1 = h * hd, (h + 1) * hd
             qh, kh = sub(q_s, 0, B * S, c0, c1), sub(k_s, 0, B * Lt, c0, c1)
@@ -554,13 +619,15 @@ class Engine:
             scT, _, _ = ops.gemm(kh, qh, M=Lt, N=S, K=hd, batch=B, lda=E, ldw=E, a_bstride=Lt * E, w_bstride=S * E)
             _, pv = ops.row_softmax(sc.view(B * S, Lt), colbias=colbias, rows_per_batch=S)          # softmax over text
             _, pl = ops.row_softmax(scT.view(B * Lt, S), sub_rowmax=True)                            # softmax over pixels
+            if Sp != S:
+                pl = padS(pl, B * Lt)                            # (B*Lt, Sp)
             # out_v[b, s, c0:c1] = P_v[b] (S x Lt) . value_l[b]^T ; value_l^T rows c0:c1 of vlT, cols b*Lt..
             ov = BF2(out_v.hi[:, c0:c1], None if out_v.lo is None else out_v.lo[:, c0:c1])
             ol = BF2(out_l.hi[:, c0:c1], None if out_l.lo is None else out_l.lo[:, c0:c1])
             self._gemm_into(pv, sub(vlT, c0, c1, 0, B * Lt), ov, M=S, N=hd, K=Lt, batch=B, lda=Lt, ldw=B * Lt, a_bstride=S * Lt,
                             w_bstride=Lt, ldc=E, c_bstride=S * E)
-            self._gemm_into(pl, sub(vvT, c0, c1, 0, B * S), ol, M=Lt, N=hd, K=S, batch=B, lda=S, ldw=B * S, a_bstride=Lt * S,
-                            w_bstride=S, ldc=E, c_bstride=Lt * E)
+            self._gemm_into(pl, sub(vvT, c0, c1, 0, B * Sp), ol, M=Lt, N=hd, K=Sp, batch=B, lda=Sp, ldw=B * Sp, a_bstride=Lt * Sp,
+                            w_bstride=Sp, ldc=E, c_bstride=Lt * E)
         wov, bov = W.lin(p + ".attn.out_v_proj")
         wol, bol = W.lin(p + ".attn.out_l_proj")
         new_v, new_v_s, _ = ops.gemm(out_v, wov, bias=bov, colscale=W[p + ".gamma_v"], residual=v, want_split=True)
@@ -579,7 +646,7 @@ class Engine:
                              bias=None, colscale=None, residual=None, ldr=0, r_bstride=0, c_f32=None, c_hi=out.hi.data_ptr(),
                              c_lo=out.lo.data_ptr() if out.lo is not None else None, ldc=kw["ldc"], c_bstride=kw["c_bstride"],
                              c_bits=None, bits_threshold=0.0, M=kw["M"], N=kw["N"], K=kw["K"], batch=kw["batch"], act=0, prec=prec,
-                             alpha=1.0, transposed=0, c_row_map=None)
+                             alpha=1.0, transposed=0, c_row_map=None, t_row_group=0, t_row_pad=0, relu_after_residual=0, c_fp16=0)
         _lib.check(_lib.load().hipie_gemm(ctypes.byref(args), ops._stream()), "gemm")
 
 

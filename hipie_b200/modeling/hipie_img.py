@@ -154,9 +154,7 @@ class HIPIE_IMG(nn.Module):
         forced = forced or {}
         eng, hp = self.engine, self.hp
         B = tensor.shape[0]
-        if hp["backbone"] != "vit":
-            raise RuntimeError("the B200 engine implements the ViT backbones; the R50 configuration (#1) is CPU plumbing only")
-        feats = eng.vit(tensor)
+        feats = eng.vit(tensor) if hp["backbone"] == "vit" else eng.resnet50(tensor)
         if task == "grounding":
             lm = lang["masks"].float()
             lang_feat_pool = ((lang["hidden"] * lm.unsqueeze(-1)).sum(1) / lm.sum(-1, keepdim=True)).unsqueeze(1)   # pre-fusion (:809-811)

@@ -144,7 +144,7 @@ def add_split(a, b=None, want_f32=False, want_split=True):
 def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, alpha=1.0, want_f32=True,
          want_split=False, out_f32=None, transposed=False, row_map=None, out_rows=None, bits_threshold=None,
          M=None, N=None, K=None, batch=1, lda=None, ldw=None, a_bstride=0, w_bstride=0, ldc=None, c_bstride=0,
-         ldr=None, r_bstride=0, prec=None, out_split=None, t_row_group=0, t_row_pad=0, out_fp16=False):
+         ldr=None, r_bstride=0, prec=None, out_split=None, t_row_group=0, t_row_pad=0, out_fp16=False, relu_after_residual=False):
     """C = act(alpha * A.W^T + bias) * colscale + residual.
 
     A: (.., M, K) planes, W: (N, K) planes.  Default: 2-D row-major operands.  Strided / batched views
@@ -202,7 +202,7 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
         bits_threshold=float(bits_threshold) if bits_threshold is not None else 0.0,
         M=M, N=N, K=K, batch=batch, act=act, prec=prec, alpha=float(alpha), transposed=1 if transposed else 0,
         c_row_map=row_map.data_ptr() if row_map is not None else None, t_row_group=t_row_group, t_row_pad=t_row_pad,
-        c_fp16=1 if out_fp16 else 0)
+        relu_after_residual=1 if relu_after_residual else 0, c_fp16=1 if out_fp16 else 0)
     tag = f"gemm_tc[p{prec}]" + (":mask_embed" if c_bits is not None else "")
     if profiler.enabled and profiler.shapes:
         tag += f" {M}x{N}x{K}" + (f"x{batch}" if batch > 1 else "") + ("T" if transposed else "")
@@ -316,6 +316,17 @@ def maxpool2_nhwc(x, want_f32=True, want_split=False):
     _lib.check(_lib.load().hipie_maxpool2_nhwc(_p(x), _p(y), _p(s.hi) if s else None,
                                                _p(s.lo) if (s and s.lo is not None) else None, B, H, W, C, _stream()),
                "maxpool2_nhwc")
+    return y, s
+
+
+def maxpool3x3s2_nhwc(x, want_f32=True, want_split=False):
+    B, H, W, C = x.shape
+    x = x.contiguous()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((B, Ho, Wo, C), dtype=torch.float32, device=x.device) if want_f32 else None
+    s = _empty_bf2((B, Ho, Wo, C), x.device) if want_split else None
+    _lib.check(_lib.load().hipie_maxpool3x3s2_nhwc(_p(x), _p(y), _p(s.hi) if s else None, _p(s.lo) if (s and s.lo is not None) else None,
+                                                   B, H, W, C, _stream()), "maxpool3x3s2_nhwc")
     return y, s
 
 

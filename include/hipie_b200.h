@@ -118,6 +118,7 @@ typedef struct hipie_gemm_args {
                                  from row c_row_map[r]; negative entries are skipped (window un-partition) */
     int t_row_group;          /* transposed only, 0 = off: GEMM row r is stored at position r + (r / t_row_group) * t_row_pad of */
     int t_row_pad;            /* each output column (groups of rows padded apart, e.g. 196-token windows at a 200 pitch)     */
+    int relu_after_residual;  /* 1: ReLU applied AFTER the residual add (ResNet bottleneck: relu(conv3(x) + shortcut)); `act` is applied before */
     int c_fp16;               /* 1: c_hi receives IEEE fp16 values (one plane, c_lo must be NULL): operands of the single-pass fp16
                                  contractions (attention QK^T / PV); 0: bf16 hi (+ lo) planes */
 } hipie_gemm_args;
@@ -165,6 +166,8 @@ int hipie_pixel_shuffle2(const float* g, float* y, void* hi, void* lo, int B, in
                          void* stream);
 int hipie_maxpool2_nhwc(const float* x, float* y, void* hi, void* lo, int B, int H, int W, int C,
                         void* stream);
+/* F.max_pool2d(kernel 3, stride 2, padding 1) on NHWC fp32 (ResNet stem); output (B, (H-1)/2+1, (W-1)/2+1, C) fp32 and/or bf16 split. */
+int hipie_maxpool3x3s2_nhwc(const float* x, float* y, void* hi, void* lo, int B, int H, int W, int C, void* stream);
 /* p = softmax(clamp(x [- rowmax], +-clampv) + colbias[row / rows_per_batch, :]) over the last dim. */
 int hipie_row_softmax(const float* x, const float* colbias, int64_t rows, int64_t rows_per_batch,
                       int n, float clampv, int sub_rowmax, void* hi, void* lo, float* p_f32,

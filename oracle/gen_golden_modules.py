@@ -314,8 +314,27 @@ def gen_prompts():
     print("ref_prompts.pt", q_all[:60], {k: m_all[k] for k in list(m_all)[:5]})
 
 
+def gen_r50():
+    """detectron2/modeling/backbone/resnet.py: BasicStem + ResNet.make_default_stages(50, FrozenBN, stride_in_1x1=False), the
+    backbone of BASELINE configs[0] (training/r50.yaml: RESNETS.DEPTH 50, STRIDE_IN_1X1 False, OUT_FEATURES res3-res5)."""
+    ref_import.install()
+    import detectron2.modeling as d2m
+    import detectron2.modeling.backbone.backbone as bbmod
+    bbmod.Backbone = d2m.Backbone
+    r = ref_import._load_file("detectron2.modeling.backbone.resnet", f"{ref_import.REF_ROOT}/detectron2/modeling/backbone/resnet.py")
+    m = r.ResNet(r.BasicStem(3, 64, norm="FrozenBN"), r.ResNet.make_default_stages(50, norm="FrozenBN", stride_in_1x1=False),
+                 out_features=["res3", "res4", "res5"])
+    randomize_(m, 23).eval()
+    x = torch.randn(2, 3, 96, 72, generator=torch.Generator().manual_seed(24))
+    with torch.no_grad():
+        out = m(x)
+    sub = lambda t: t[:, ::8].contiguous()           # every 8th channel is enough to pin the arithmetic and keeps the fixture small
+    torch.save(dict(seed=23, keys=sorted(m.state_dict().keys()), x=x, out={k: sub(v) for k, v in out.items()}), os.path.join(OUT, "ref_r50.pt"))
+    print("ref_r50.pt", {k: tuple(v.shape) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["vit", "transformer", "maskdino", "condinst", "bert", "postproc", "prompts"]
+    which = sys.argv[1:] or ["vit", "transformer", "maskdino", "condinst", "bert", "postproc", "prompts", "r50"]
     for w in which:
         globals()["gen_" + w]()

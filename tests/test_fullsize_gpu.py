@@ -53,7 +53,7 @@ def _run_case(name, hp, inputs, ids, am, seed, taps=(7, 15, 31)):
     t0 = time.time()
     oracle = HipieOracle(hp).eval()
     synth.perturb_(oracle, seed=seed + 1)
-    blocks = oracle.detr.detr.backbone[0].backbone.blocks
+    blocks = getattr(oracle.detr.detr.backbone[0].backbone, "blocks", [])      # ViT only; the R50 case has no residual-stream taps
     taps = tuple(t for t in taps if t < len(blocks))
     otaps, hooks = {}, []
     for t in taps:
@@ -251,6 +251,19 @@ def test_c5_vith_ade847_lt4096_chunked_bert(cuda):
     inputs, ids, am = synth.make_batch(1, 512, 512, 847, 4096, seed=5)
     assert int(am[0].sum()) > 512          # the prompt really takes the chunk path
     r = _run_case("c5_vith_512_ade847_lt4096", hp, inputs, ids, am, seed=6)
+    _check_continuous(r)
+    _check_unforced(r)
+    _check_forced(r)
+
+
+def test_c0_r50_512_three_queries(cuda):
+    """BASELINE configs[0]: ResNet-50 backbone, 1 x 512 x 512, 3 text queries (the reference's CPU-runnable plumbing case) through
+    the same public entry point, on the engine's R50 path (convolutions as GEMMs, frozen BN folded, bottleneck ReLU after the residual)."""
+    _budget(120)
+    from hipie_oracle import hparams, synth
+    hp = hparams.get("r50")
+    inputs, ids, am = synth.make_batch(1, 512, 512, 3, hp["max_query_len"], seed=8)
+    r = _run_case("c0_r50_512_3queries", hp, inputs, ids, am, seed=9, taps=())
     _check_continuous(r)
     _check_unforced(r)
     _check_forced(r)

@@ -169,3 +169,18 @@ def test_postprocessing_matches_reference_inference(golden_dir):
             assert torch.allclose(r["sem_seg"], ref["sem_seg"], atol=1e-5)
             assert torch.equal(r["panoptic_seg"][0], ref["panoptic_seg"])
             assert r["panoptic_seg"][1] == ref["segments_info"] and len(ref["segments_info"]) > 0
+
+
+def test_resnet50_matches_reference(golden_dir):
+    """detectron2 ResNet-50 (BasicStem, 16 BottleneckBlocks with FrozenBatchNorm2d, stride in the 3x3) on a 96x72 input"""
+    from hipie_oracle.resnet import ResNet50
+    g = _load(golden_dir, "ref_r50.pt")
+    m = ResNet50().eval()
+    _same_keys(m, g["keys"])
+    fill_by_name_(m, g["seed"])
+    with torch.no_grad():
+        out = m(g["x"])
+    for k in ("res3", "res4", "res5"):
+        ref = g["out"][k]
+        got = out[k][:, ::8]
+        assert (got - ref).abs().max() < 1e-5 * ref.abs().max() + 1e-5, (k, (got - ref).abs().max())
