@@ -64,7 +64,7 @@ SYMBOLS = {
     "hipie_pixel_shuffle2": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "hipie_maxpool2_nhwc": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "hipie_maxpool3x3s2_nhwc": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
-    "hipie_row_softmax": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hipie_row_softmax": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "hipie_attention": (c_int, [ctypes.POINTER(AttnArgs), c_void_p]),
     "hipie_attention_tc": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                    c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -51,6 +51,7 @@ struct GemmParams {
     float alpha;
     int transposed;  // 1: C stored as [N, ldc] (column-major output), lanes = rows
     int tiles_m, tiles_n;
+    int f16_ops;     // operands are IEEE fp16 planes (single pass): fp16 instruction descriptor
     int relu_post;   // ReLU after the residual add
     int c_fp16;      // c_hi is one IEEE fp16 plane instead of bf16 hi/lo
     int tma_out;     // row-major outputs leave through TMA stores (32 x 32 boxes staged in swizzled shared memory)
@@ -536,7 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer (pair: the leader CTA only) =====================
         if (leader) {
-            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * CTAS, BN);
+            const uint32_t idesc = p.f16_ops ? make_idesc_f16(GEMM_BM * CTAS, BN) : make_idesc_bf16(GEMM_BM * CTAS, BN);
             int s = 0;
             uint32_t ph = 0;
             int acc = 0;
@@ -799,6 +800,7 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     p.tma_out = tma_out ? 1 : 0;
     p.c_fp16 = a->c_fp16 ? 1 : 0;
     p.relu_post = a->relu_after_residual ? 1 : 0;
+    p.f16_ops = a->prec == 2 ? 1 : 0;
     p.bias = a->bias; p.colscale = a->colscale; p.residual = a->residual;
     p.ldr = a->ldr; p.r_bstride = a->r_bstride;
     p.c_f32 = a->c_f32; p.c_hi = (__nv_bfloat16*)a->c_hi; p.c_lo = (__nv_bfloat16*)a->c_lo;
@@ -843,8 +845,8 @@ using namespace hipie;
 extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     HIPIE_CHECK_ARG(a != nullptr, "hipie_gemm: null args");
     HIPIE_CHECK_ARG(a->a_hi && a->w_hi, "hipie_gemm: a_hi / w_hi required");
-    HIPIE_CHECK_ARG(a->prec == 1 || a->prec == 3, "hipie_gemm: prec must be 1 or 3 (got %d)", a->prec);
-    HIPIE_CHECK_ARG(a->prec == 1 || (a->a_lo && a->w_lo), "hipie_gemm: prec 3 needs a_lo and w_lo");
+    HIPIE_CHECK_ARG(a->prec == 1 || a->prec == 2 || a->prec == 3, "hipie_gemm: prec must be 1, 2 or 3 (got %d)", a->prec);
+    HIPIE_CHECK_ARG(a->prec != 3 || (a->a_lo && a->w_lo), "hipie_gemm: prec 3 needs a_lo and w_lo");
     HIPIE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "hipie_gemm: bad sizes M=%d N=%d K=%d batch=%d",
                     a->M, a->N, a->K, a->batch);
     HIPIE_CHECK_ARG(a->K % 8 == 0, "hipie_gemm: K (%d) must be a multiple of 8", a->K);
@@ -860,13 +862,14 @@ extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     // B200 (tools/gemm_check.py, profiles/r02_gemm_pairs.txt): fc1 32768x5120x1280 0.944 -> 0.844 ms, qk 0.489 -> 0.454 ms;
     // K = 256 problems are epilogue/store-bound and lose 8-10 % with pairs, single-pass operands gain nothing.
     const bool pairs = g_gemm_cta_pairs && a->M >= 1024 && a->N > 64 && a->K >= 512 && a->prec == 3;
-    if (a->N <= 64) return a->prec == 3 ? launch_gemm<3, 64, 1>(a, st) : launch_gemm<1, 64, 1>(a, st);
+    const bool p3 = a->prec == 3;          // prec 1 (bf16) and prec 2 (fp16) share the single-plane kernels; the MMA kind differs
+    if (a->N <= 64) return p3 ? launch_gemm<3, 64, 1>(a, st) : launch_gemm<1, 64, 1>(a, st);
     if (a->N <= 128) {
-        if (pairs) return a->prec == 3 ? launch_gemm<3, 128, 2>(a, st) : launch_gemm<1, 128, 2>(a, st);
-        return a->prec == 3 ? launch_gemm<3, 128, 1>(a, st) : launch_gemm<1, 128, 1>(a, st);
+        if (pairs) return p3 ? launch_gemm<3, 128, 2>(a, st) : launch_gemm<1, 128, 2>(a, st);
+        return p3 ? launch_gemm<3, 128, 1>(a, st) : launch_gemm<1, 128, 1>(a, st);
     }
-    if (pairs) return a->prec == 3 ? launch_gemm<3, 256, 2>(a, st) : launch_gemm<1, 256, 2>(a, st);
-    return a->prec == 3 ? launch_gemm<3, 256, 1>(a, st) : launch_gemm<1, 256, 1>(a, st);
+    if (pairs) return p3 ? launch_gemm<3, 256, 2>(a, st) : launch_gemm<1, 256, 2>(a, st);
+    return p3 ? launch_gemm<3, 256, 1>(a, st) : launch_gemm<1, 256, 1>(a, st);
 }
 
 extern "C" int hipie_set_option(const char* name, int value) {

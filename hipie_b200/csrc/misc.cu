@@ -174,7 +174,7 @@ maxpool2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bf
 __global__ void __launch_bounds__(256)
 row_softmax_kernel(const float* __restrict__ x, const float* __restrict__ colbias, int64_t rows_per_batch,
                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ p_f32,
-                   int n, float clampv, int sub_rowmax) {
+                   int n, float clampv, int sub_rowmax, int fp16) {
     __shared__ float red[8];
     __shared__ float bc;
     const int64_t row = blockIdx.x;
@@ -217,9 +217,13 @@ row_softmax_kernel(const float* __restrict__ x, const float* __restrict__ colbia
         const float pv = expf(val(c) - m) * inv;
         if (p_f32) p_f32[row * n + c] = pv;
         if (hi) {
-            const __nv_bfloat16 h = __float2bfloat16_rn(pv);
-            hi[row * n + c] = h;
-            if (lo) lo[row * n + c] = __float2bfloat16_rn(pv - __bfloat162float(h));
+            if (fp16) {
+                reinterpret_cast<__half*>(hi)[row * n + c] = __float2half_rn(pv);
+            } else {
+                const __nv_bfloat16 h = __float2bfloat16_rn(pv);
+                hi[row * n + c] = h;
+                if (lo) lo[row * n + c] = __float2bfloat16_rn(pv - __bfloat162float(h));
+            }
         }
     }
 }
@@ -230,12 +234,12 @@ __device__ __forceinline__ float rs_val(float x, float pre, float cb, float clam
     if (sub_rowmax) v = fminf(fmaxf(v - pre, -clampv), clampv);
     return v + cb;
 }
-__device__ __forceinline__ void rs_store4(float4 pv, int64_t off, __nv_bfloat16* hi, __nv_bfloat16* lo, float* p_f32) {
+__device__ __forceinline__ void rs_store4(float4 pv, int64_t off, __nv_bfloat16* hi, __nv_bfloat16* lo, float* p_f32, int fp16) {
     if (p_f32) *reinterpret_cast<float4*>(p_f32 + off) = pv;
     if (hi) {
         uint2 h, l;
-        split2(pv.x, pv.y, h.x, l.x);
-        split2(pv.z, pv.w, h.y, l.y);
+        split2m(pv.x, pv.y, h.x, l.x, fp16);
+        split2m(pv.z, pv.w, h.y, l.y, fp16);
         *reinterpret_cast<uint2*>(hi + off) = h;
         if (lo) *reinterpret_cast<uint2*>(lo + off) = l;
     }
@@ -246,7 +250,7 @@ template <int NCH>   // float4 chunks per lane
 __global__ void __launch_bounds__(256)
 row_softmax_warp_kernel(const float* __restrict__ x, const float* __restrict__ colbias, int64_t rows, int64_t rows_per_batch,
                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ p_f32, int n,
-                        float clampv, int sub_rowmax) {
+                        float clampv, int sub_rowmax, int fp16) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -294,7 +298,7 @@ row_softmax_warp_kernel(const float* __restrict__ x, const float* __restrict__ c
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
         const int c = (i * 32 + lane) * 4;
-        if (c < n) rs_store4(make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv), row * n + c, hi, lo, p_f32);
+        if (c < n) rs_store4(make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv), row * n + c, hi, lo, p_f32, fp16);
     }
 }
 
@@ -302,7 +306,7 @@ row_softmax_warp_kernel(const float* __restrict__ x, const float* __restrict__ c
 __global__ void __launch_bounds__(512)
 row_softmax_smem_kernel(const float* __restrict__ x, const float* __restrict__ colbias, int64_t rows_per_batch,
                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ p_f32, int n,
-                        float clampv, int sub_rowmax) {
+                        float clampv, int sub_rowmax, int fp16) {
     extern __shared__ __align__(16) float rs_row[];
     __shared__ float red[16];
     __shared__ float bc;
@@ -354,7 +358,7 @@ row_softmax_smem_kernel(const float* __restrict__ x, const float* __restrict__ c
     const float inv = 1.f / s;
     for (int c = threadIdx.x; c < n4; c += 512) {
         const float4 a = *reinterpret_cast<const float4*>(rs_row + 4 * c);
-        rs_store4(make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv), row * n + 4 * c, hi, lo, p_f32);
+        rs_store4(make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv), row * n + 4 * c, hi, lo, p_f32, fp16);
     }
 }
 
@@ -589,7 +593,9 @@ extern "C" int hipie_maxpool3x3s2_nhwc(const float* x, float* y, void* hi, void*
 }
 
 extern "C" int hipie_row_softmax(const float* x, const float* colbias, int64_t rows, int64_t rows_per_batch, int n,
-                                 float clampv, int sub_rowmax, void* hi, void* lo, float* p_f32, void* stream) {
+                                 float clampv, int sub_rowmax, void* hi, void* lo, float* p_f32, int out_fp16, void* stream) {
+    const int fp16 = out_fp16 ? 1 : 0;
+    HIPIE_CHECK_ARG(!fp16 || (hi && !lo), "hipie_row_softmax: out_fp16 writes one fp16 plane (hi set, lo NULL)");
     HIPIE_CHECK_ARG(x && (hi || p_f32), "hipie_row_softmax: null pointer");
     HIPIE_CHECK_ARG(rows >= 0 && n > 0 && rows_per_batch > 0, "hipie_row_softmax: bad sizes");
     if (rows == 0) return HIPIE_OK;
@@ -601,18 +607,18 @@ extern "C" int hipie_row_softmax(const float* x, const float* colbias, int64_t r
         const unsigned blocks = (unsigned)((rows + 7) / 8);
         if (n <= 512)
             row_softmax_warp_kernel<4><<<blocks, 256, 0, st>>>(x, colbias, rows, rows_per_batch, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
-                                                               p_f32, n, clampv, sub_rowmax);
+                                                               p_f32, n, clampv, sub_rowmax, fp16);
         else
             row_softmax_warp_kernel<8><<<blocks, 256, 0, st>>>(x, colbias, rows, rows_per_batch, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
-                                                               p_f32, n, clampv, sub_rowmax);
+                                                               p_f32, n, clampv, sub_rowmax, fp16);
     } else if (aligned && (int64_t)n * 4 <= 200 * 1024) {
         const int smem = n * 4;
         HIPIE_ENSURE_SMEM(row_softmax_smem_kernel, smem);
         row_softmax_smem_kernel<<<(unsigned)rows, 512, smem, st>>>(x, colbias, rows_per_batch, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
-                                                                   p_f32, n, clampv, sub_rowmax);
+                                                                   p_f32, n, clampv, sub_rowmax, fp16);
     } else {
         row_softmax_kernel<<<(unsigned)rows, 256, 0, st>>>(x, colbias, rows_per_batch, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, p_f32,
-                                                           n, clampv, sub_rowmax);
+                                                           n, clampv, sub_rowmax, fp16);
     }
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;

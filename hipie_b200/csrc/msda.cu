@@ -279,7 +279,7 @@ struct MsdaWinParams {
 };
 struct MsdaWinMaps { CUtensorMap l[4]; };
 
-constexpr int MW_THREADS = 256;
+constexpr int MW_THREADS = 512;                  // 16 warps: 64 (query, head) pairs in flight per step
 constexpr int MW_GROUP_WORDS = 16 * 8 + 4;       // per (warp, quarter): 16 points x (4 offsets + 4 weights), padded
 constexpr uint32_t MW_GLOBAL = 0x80000000u;      // record flag: offsets are global element offsets, not window byte offsets
 
@@ -290,8 +290,8 @@ msda_win_kernel(const __grid_constant__ MsdaWinMaps maps, const MsdaWinParams p)
     constexpr int D = 32, L = 4, P = 4;
     extern __shared__ uint8_t mw_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mw_raw) + 127) & ~uintptr_t(127));
-    uint32_t* recs = reinterpret_cast<uint32_t*>(smem + p.win_bytes);                      // [8 warps][4][MW_GROUP_WORDS]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.win_bytes + 8 * 4 * MW_GROUP_WORDS * 4);
+    uint32_t* recs = reinterpret_cast<uint32_t*>(smem + p.win_bytes);                      // [16 warps][4][MW_GROUP_WORDS]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.win_bytes + (MW_THREADS / 32) * 4 * MW_GROUP_WORDS * 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hsub = lane >> 3, dsub = lane & 7;
     const uint32_t win_s = smem_u32(smem);
     if (tid == 0) {
@@ -328,33 +328,47 @@ msda_win_kernel(const __grid_constant__ MsdaWinMaps maps, const MsdaWinParams p)
             for (int l = 0; l < L; ++l) tma_load_5d(smem + p.wbase[l], &maps.l[l], bar, 0, m, wx0[l], wy0[l], b);
         }
         bool landed = false;
-        for (int g0 = 0; g0 < nq; g0 += 32) {
+        // the front-half inputs of a group (offsets, logits, reference point: global loads with ~1 us latency) are fetched one
+        // group ahead, so the latency hides behind the previous group's gather
+        struct Fetch { float4 o; float2 lg; float rx, ry; int q; bool valid; };
+        const int lown = dsub >> 1;
+        auto fetch = [&](int g0) {
+            Fetch f;
             const int qi = g0 + warp * 4 + hsub;
-            const bool qvalid = qi < nq;
-            int q = 0;                         // query index inside the image (level-major, row-major: the encoder's token order)
-            {
-                const int qc = qvalid ? qi : 0;
-                int lq = 0;
+            f.valid = qi < nq;
+            const int qc = f.valid ? qi : 0;
+            int lq = 0;
 #pragma unroll
-                for (int l = 1; l < L; ++l) lq += (qc >= cum[l]) ? 1 : 0;
-                int r = qc, twl = tw[0], ysl = ys[0], xsl = xs[0], Wl = p.W[0], base = p.lsi[0];
+            for (int l = 1; l < L; ++l) lq += (qc >= cum[l]) ? 1 : 0;
+            int r = qc, twl = tw[0], ysl = ys[0], xsl = xs[0], Wl = p.W[0], base = p.lsi[0];
 #pragma unroll
-                for (int l = 1; l < L; ++l)
-                    if (lq == l) { r = qc - cum[l]; twl = tw[l]; ysl = ys[l]; xsl = xs[l]; Wl = p.W[l]; base = p.lsi[l]; }
-                twl = max(twl, 1);
-                q = base + (ysl + r / twl) * Wl + xsl + r % twl;
-            }
-            const int64_t bq = (int64_t)b * p.S + q;
+            for (int l = 1; l < L; ++l)
+                if (lq == l) { r = qc - cum[l]; twl = tw[l]; ysl = ys[l]; xsl = xs[l]; Wl = p.W[l]; base = p.lsi[l]; }
+            twl = max(twl, 1);
+            f.q = base + (ysl + r / twl) * Wl + xsl + r % twl;      // query index inside the image (level-major, row-major)
+            const int64_t bq = (int64_t)b * p.S + f.q;
+            const float* row = p.offs_logits + bq * (int64_t)(p.M * L * P * 3);
+            f.o = *reinterpret_cast<const float4*>(row + m * (L * P * 2) + dsub * 4);
+            f.lg = *reinterpret_cast<const float2*>(row + p.M * L * P * 2 + m * (L * P) + dsub * 2);
+            const float* rp = p.refp + (bq * L + lown) * 2;
+            f.rx = rp[0];
+            f.ry = rp[1];
+            return f;
+        };
+        Fetch nxt = fetch(0);
+        for (int g0 = 0; g0 < nq; g0 += MW_THREADS / 8) {
+            const Fetch cur = nxt;
+            if (g0 + MW_THREADS / 8 < nq) nxt = fetch(g0 + MW_THREADS / 8);
+            const bool qvalid = cur.valid;
+            const int64_t bq = (int64_t)b * p.S + cur.q;
             // ---- front half for head m: this lane owns points 2*dsub, 2*dsub+1 (level dsub >> 1) of its quarter's query
-            const int lown = dsub >> 1;
             int Hown = p.H[0], Wown = p.W[0], stown = p.lsi[0], wwown = p.ww[0], whown = p.wh[0], wbown = p.wbase[0], wx = wx0[0], wy = wy0[0];
 #pragma unroll
             for (int l = 1; l < L; ++l)
                 if (lown == l) { Hown = p.H[l]; Wown = p.W[l]; stown = p.lsi[l]; wwown = p.ww[l]; whown = p.wh[l]; wbown = p.wbase[l]; wx = wx0[l]; wy = wy0[l]; }
             const float Wf = (float)Wown, Hf = (float)Hown;
-            const float* row = p.offs_logits + bq * (int64_t)(p.M * L * P * 3);
-            const float4 o = *reinterpret_cast<const float4*>(row + m * (L * P * 2) + dsub * 4);
-            const float2 lg = *reinterpret_cast<const float2*>(row + p.M * L * P * 2 + m * (L * P) + dsub * 2);
+            const float4 o = cur.o;
+            const float2 lg = cur.lg;
             float mx = fmaxf(lg.x, lg.y);
 #pragma unroll
             for (int s = 1; s < 8; s <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
@@ -364,8 +378,7 @@ msda_win_kernel(const __grid_constant__ MsdaWinMaps maps, const MsdaWinParams p)
             for (int s = 1; s < 8; s <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
             const float inv = 1.0f / sum;
             const float w0p = e0 * inv, w1p = e1 * inv;
-            const float* rp = p.refp + (bq * L + lown) * 2;
-            const float rx = rp[0], ry = rp[1];
+            const float rx = cur.rx, ry = cur.ry;
             const float x0p = (rx + o.x / Wf) * Wf - 0.5f, y0p = (ry + o.y / Hf) * Hf - 0.5f;
             const float x1p = (rx + o.z / Wf) * Wf - 0.5f, y1p = (ry + o.w / Hf) * Hf - 0.5f;
             uint32_t* wsm = recs + (warp * 4 + hsub) * MW_GROUP_WORDS;
@@ -570,8 +583,8 @@ extern "C" int hipie_msda_encoder_forward(const void* value, const int* shapes_h
     HIPIE_CHECK_ARG(tot == S, "hipie_msda_encoder_forward: level shapes sum to %d, S = %d", tot, S);
     HIPIE_CHECK_ARG((int64_t)S * M * D < (1ll << 30), "hipie_msda_encoder_forward: value map too large for 31-bit element offsets");
     p.nty = (p.H[0] + 15) / 16; p.ntx = (p.W[0] + 15) / 16;       // regions of 16 x 16 finest-level queries
-    const int rec_bytes = 8 * 4 * MW_GROUP_WORDS * 4;
-    int h = halo > 0 ? halo : 5;
+    const int rec_bytes = (MW_THREADS / 32) * 4 * MW_GROUP_WORDS * 4;
+    int h = halo > 0 ? halo : 4;
     for (; h >= 2; --h) {
         int bytes = 0;
         for (int l = 0; l < 4; ++l) {

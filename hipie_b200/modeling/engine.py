@@ -585,17 +585,22 @@ class Engine:
         v, v_s, _ = ops.layernorm(src.view(B * S, 256), W[p + ".layer_norm_v.weight"], W[p + ".layer_norm_v.bias"], 1e-5, want_f32=True, want_split=True)
         l, l_s, _ = ops.layernorm(lang_hidden.reshape(B * Lt, Ld), W[p + ".layer_norm_l.weight"], W[p + ".layer_norm_l.bias"], 1e-5, want_f32=True, want_split=True)
         scale = hd ** -0.5
+        # Precision map: the S x Lt score and P.V contractions of the bi-attention run as ONE fp16 MMA pass (operands
+        # rounded at 2^-12: measured 2e-5 on the encoder memory, 7e-6 on the class logits, tools/prec_emulate.py); the six projections
+        # around them stay 3-pass.  q / k / value maps leave their projection GEMMs as single fp16 planes, the softmaxes write fp16.
+        f16 = self.attn_fp16 and ops.PREC == 3
+        aprec = 2 if f16 else ops.PREC
         # (v_proj(v) * scale): scale = 256^-0.5 = 2^-4 for the shipped embed 2048 / 8 heads -> exact to fold into W and b
         wq, bq = W.cached(("vlq", p), lambda: (ops.split_weight(W[p + ".attn.v_proj.weight"] * scale),
                                                (W[p + ".attn.v_proj.bias"] * scale).contiguous()))
-        _, q_s, _ = ops.gemm(v_s, wq, bias=bq, want_f32=False, want_split=True)                      # (B*S, E)
+        _, q_s, _ = ops.gemm(v_s, wq, bias=bq, want_f32=False, want_split=True, out_fp16=f16)                      # (B*S, E)
         wk, bk = W.lin(p + ".attn.l_proj")
-        _, k_s, _ = ops.gemm(l_s, wk, bias=bk, want_f32=False, want_split=True)                      # (B*Lt, E)
+        _, k_s, _ = ops.gemm(l_s, wk, bias=bk, want_f32=False, want_split=True, out_fp16=f16)                      # (B*Lt, E)
         wvv, bvv = W.lin(p + ".attn.values_v_proj")
         wvl, bvl = W.lin(p + ".attn.values_l_proj")
         # value maps are needed K-major for the P.V GEMMs -> emit them transposed: (E, B*S) and (E, B*Lt)
-        _, vvT, _ = ops.gemm(v_s, wvv, bias=bvv, want_f32=False, want_split=True, transposed=True)   # (E, B*S)
-        _, vlT, _ = ops.gemm(l_s, wvl, bias=bvl, want_f32=False, want_split=True, transposed=True)   # (E, B*Lt)
+        _, vvT, _ = ops.gemm(v_s, wvv, bias=bvv, want_f32=False, want_split=True, transposed=True, out_fp16=f16)   # (E, B*S)
+        _, vlT, _ = ops.gemm(l_s, wvl, bias=bvl, want_f32=False, want_split=True, transposed=True, out_fp16=f16)   # (E, B*Lt)
         # additive text mask: valid tokens +1, invalid -9e15 (fuse_helper.py:96-107)
         am = lang_mask.float()
         colbias = torch.where(am == 0, torch.full_like(am, -9e15), am).contiguous()
@@ -615,19 +620,19 @@ class Engine:
             c0, c1 = h * hd, (h + 1) * hd
             qh, kh = sub(q_s, 0, B * S, c0, c1), sub(k_s, 0, B * Lt, c0, c1)
             # scores (B, S, Lt) and its transpose (B, Lt, S): two GEMMs instead of a transpose pass
-            sc, _, _ = ops.gemm(qh, kh, M=S, N=Lt, K=hd, batch=B, lda=E, ldw=E, a_bstride=S * E, w_bstride=Lt * E)
-            scT, _, _ = ops.gemm(kh, qh, M=Lt, N=S, K=hd, batch=B, lda=E, ldw=E, a_bstride=Lt * E, w_bstride=S * E)
-            _, pv = ops.row_softmax(sc.view(B * S, Lt), colbias=colbias, rows_per_batch=S)          # softmax over text
-            _, pl = ops.row_softmax(scT.view(B * Lt, S), sub_rowmax=True)                            # softmax over pixels
+            sc, _, _ = ops.gemm(qh, kh, M=S, N=Lt, K=hd, batch=B, lda=E, ldw=E, a_bstride=S * E, w_bstride=Lt * E, prec=aprec)
+            scT, _, _ = ops.gemm(kh, qh, M=Lt, N=S, K=hd, batch=B, lda=E, ldw=E, a_bstride=Lt * E, w_bstride=S * E, prec=aprec)
+            _, pv = ops.row_softmax(sc.view(B * S, Lt), colbias=colbias, rows_per_batch=S, out_fp16=f16)          # softmax over text
+            _, pl = ops.row_softmax(scT.view(B * Lt, S), sub_rowmax=True, out_fp16=f16)                            # softmax over pixels
             if Sp != S:
                 pl = padS(pl, B * Lt)                            # (B*Lt, Sp)
             # out_v[b, s, c0:c1] = P_v[b] (S x Lt) . value_l[b]^T ; value_l^T rows c0:c1 of vlT, cols b*Lt..
             ov = BF2(out_v.hi[:, c0:c1], None if out_v.lo is None else out_v.lo[:, c0:c1])
             ol = BF2(out_l.hi[:, c0:c1], None if out_l.lo is None else out_l.lo[:, c0:c1])
             self._gemm_into(pv, sub(vlT, c0, c1, 0, B * Lt), ov, M=S, N=hd, K=Lt, batch=B, lda=Lt, ldw=B * Lt, a_bstride=S * Lt,
-                            w_bstride=Lt, ldc=E, c_bstride=S * E)
+                            w_bstride=Lt, ldc=E, c_bstride=S * E, prec=aprec)
             self._gemm_into(pl, sub(vvT, c0, c1, 0, B * Sp), ol, M=Lt, N=hd, K=Sp, batch=B, lda=Sp, ldw=B * Sp, a_bstride=Lt * Sp,
-                            w_bstride=Sp, ldc=E, c_bstride=Lt * E)
+                            w_bstride=Sp, ldc=E, c_bstride=Lt * E, prec=aprec)
         wov, bov = W.lin(p + ".attn.out_v_proj")
         wol, bol = W.lin(p + ".attn.out_l_proj")
         new_v, new_v_s, _ = ops.gemm(out_v, wov, bias=bov, colscale=W[p + ".gamma_v"], residual=v, want_split=True)
@@ -639,7 +644,7 @@ class Engine:
         """GEMM whose bf16-split output lands in a strided view `out` (used to assemble multi-head outputs)."""
         import ctypes
         from .. import _lib
-        prec = ops.PREC
+        prec = kw.get("prec", ops.PREC)
         args = _lib.GemmArgs(a_hi=a.hi.data_ptr(), a_lo=a.lo.data_ptr() if (a.lo is not None and prec == 3) else None,
                              lda=kw["lda"], a_bstride=kw["a_bstride"], w_hi=w.hi.data_ptr(),
                              w_lo=w.lo.data_ptr() if (w.lo is not None and prec == 3) else None, ldw=kw["ldw"], w_bstride=kw["w_bstride"],

@@ -155,6 +155,8 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
     prec = PREC if prec is None else prec
     if prec == 3 and (a.lo is None or w.lo is None):
         raise RuntimeError("gemm: prec=3 needs lo planes")
+    if prec == 2 and not (a.hi.dtype == torch.float16 and w.hi.dtype == torch.float16):
+        raise RuntimeError("gemm: prec=2 takes fp16 planes (gemm(out_fp16=True) / row_softmax(out_fp16=True) / split_weight_f16)")
     dev = a.hi.device
     if M is None:
         assert a.hi.dim() == 2 and w.hi.dim() == 2
@@ -203,7 +205,7 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
         M=M, N=N, K=K, batch=batch, act=act, prec=prec, alpha=float(alpha), transposed=1 if transposed else 0,
         c_row_map=row_map.data_ptr() if row_map is not None else None, t_row_group=t_row_group, t_row_pad=t_row_pad,
         relu_after_residual=1 if relu_after_residual else 0, c_fp16=1 if out_fp16 else 0)
-    tag = f"gemm_tc[p{prec}]" + (":mask_embed" if c_bits is not None else "")
+    tag = ("gemm_tc[f16x1]" if prec == 2 else f"gemm_tc[p{prec}]") + (":mask_embed" if c_bits is not None else "")
     if profiler.enabled and profiler.shapes:
         tag += f" {M}x{N}x{K}" + (f"x{batch}" if batch > 1 else "") + ("T" if transposed else "")
     work = 2.0 * M * N * K * batch
@@ -330,17 +332,21 @@ def maxpool3x3s2_nhwc(x, want_f32=True, want_split=False):
     return y, s
 
 
-def row_softmax(x, colbias=None, rows_per_batch=None, clampv=50000.0, sub_rowmax=False, want_split=True, want_f32=False):
+def row_softmax(x, colbias=None, rows_per_batch=None, clampv=50000.0, sub_rowmax=False, want_split=True, want_f32=False, out_fp16=False):
     n = x.shape[-1]
     rows = x.numel() // n
     x = x.contiguous()
-    s = _empty_bf2(x.shape, x.device) if want_split else None
+    if out_fp16:
+        s = BF2(torch.empty(x.shape, dtype=torch.float16, device=x.device), None)
+    else:
+        s = _empty_bf2(x.shape, x.device) if want_split else None
     pf = torch.empty_like(x) if want_f32 else None
     nbytes = x.numel() * 4.0 * (1 + (pf is not None)) + (x.numel() * 2.0 * (2 if (s.lo is not None) else 1) if s else 0.0)
     with _timed("row_softmax", nbytes):
         _lib.check(_lib.load().hipie_row_softmax(_p(x), _p(colbias), rows, rows_per_batch or rows, n, float(clampv),
                                                  1 if sub_rowmax else 0, _p(s.hi) if s else None,
-                                                 _p(s.lo) if (s and s.lo is not None) else None, _p(pf), _stream()), "row_softmax")
+                                                 _p(s.lo) if (s and s.lo is not None) else None, _p(pf), 1 if out_fp16 else 0, _stream()),
+                   "row_softmax")
     return pf, s
 
 

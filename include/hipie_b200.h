@@ -110,7 +110,8 @@ typedef struct hipie_gemm_args {
     uint32_t* c_bits; float bits_threshold;
     int M, N, K, batch;
     int act;                  /* HIPIE_ACT_* */
-    int prec;                 /* 1 or 3 */
+    int prec;                 /* 3: bf16 hi/lo planes, Ah.Wh + Ah.Wl + Al.Wh (fp32-class); 1: bf16 hi planes, one pass;
+                                 2: a_hi / w_hi are IEEE fp16 planes, one pass (the parity-grade single-pass mode) */
     float alpha;              /* scales the accumulator before bias (1.0f default) */
     int transposed;           /* 1: C (and residual, c_hi/lo) addressed as [col * ld + row]; c_bits is then packed along M:
                                  bits[b][col][row/32].  0: c_bits (needs N % 16 == 0) is packed along N: bits[b][row][col/32] */
@@ -169,9 +170,10 @@ int hipie_maxpool2_nhwc(const float* x, float* y, void* hi, void* lo, int B, int
 /* F.max_pool2d(kernel 3, stride 2, padding 1) on NHWC fp32 (ResNet stem); output (B, (H-1)/2+1, (W-1)/2+1, C) fp32 and/or bf16 split. */
 int hipie_maxpool3x3s2_nhwc(const float* x, float* y, void* hi, void* lo, int B, int H, int W, int C, void* stream);
 /* p = softmax(clamp(x [- rowmax], +-clampv) + colbias[row / rows_per_batch, :]) over the last dim. */
+/* out_fp16 = 1: the probabilities are written as ONE IEEE fp16 plane (hi; lo NULL) for the single-pass fp16 contractions. */
 int hipie_row_softmax(const float* x, const float* colbias, int64_t rows, int64_t rows_per_batch,
                       int n, float clampv, int sub_rowmax, void* hi, void* lo, float* p_f32,
-                      void* stream);
+                      int out_fp16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head attention with optional decomposed relative-position bias

@@ -20,6 +20,16 @@ if which in ("all", "attn"):
     rel_w = torch.randn(B, H, T, 64, device=dev)
     for _ in range(2):
         ops.attention_tc(q, k, Vs, B, H, T, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=64, kw=64)
+if which in ("all", "attn16"):      # the single-pass fp16 mode of the precision map (B = 8: one full global block)
+    B, H, hd, T = 8, 16, 80, 4096
+    E = H * hd
+    qk16 = torch.randn(B * T, 2 * E, device=dev).half()
+    vt16 = torch.randn(E, B * T, device=dev).half()
+    q, k, vt = ops.BF2(qk16[:, :E], None), ops.BF2(qk16[:, E:], None), ops.BF2(vt16, None)
+    rel_h = torch.randn(B, H, T, 64, device=dev)
+    rel_w = torch.randn(B, H, T, 64, device=dev)
+    for _ in range(2):
+        ops.attention_tc(q, k, vt, B, H, T, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=64, kw=64, f16=True)
 if which in ("all", "gemm"):
     a = torch.randn(32768, 1280, device=dev)
     w = torch.randn(5120, 1280, device=dev) * 0.02
@@ -38,8 +48,8 @@ if which in ("all", "msda"):
         ys, xs = torch.meshgrid(torch.linspace(0.5, h - 0.5, h, device=dev) / h, torch.linspace(0.5, w_ - 0.5, w_, device=dev) / w_, indexing="ij")
         refs.append(torch.stack([xs.reshape(-1), ys.reshape(-1)], -1))
     refp = torch.cat(refs, 0)[None, :, None, :].repeat(B, 1, 4, 1).contiguous()
-    for _ in range(2):
-        ops.msda_fused(value, shapes, lsi, packed, refp)
+    for _ in range(2):      # encoder call: shared-memory window kernel (shapes known on the host)
+        ops.msda_fused(value, shapes, lsi, packed, refp, shapes_host=[(128, 128), (64, 64), (32, 32), (16, 16)])
 if which in ("all", "maskembed"):
     B, HW, Q, C = 8, 65536, 300, 256
     Fm = ops.split(torch.randn(B * HW, C, device=dev))
