@@ -48,20 +48,25 @@ def test_panoptic_merge_from_counters_matches_oracle(seed):
     assert torch.equal(seg, ref_seg)
 
 
-@pytest.mark.parametrize("max_pool", [False, True])
-@pytest.mark.parametrize("mode", [None, "FG", "BG"])
-def test_token_to_class_pooling_matches_oracle(mode, max_pool):
+def test_token_to_class_tables_match_the_positive_map():
+    """the pooling itself is a kernel now (hipie_class_scores, GPU test test_class_scores_matches_reference_loop); the host part is
+    the table construction: token lists, counts (0 = class absent -> score 0 like the reference's zero-initialised tensor) and the
+    FG / BG -9999 masks (hipie_img.py:1041-1049), cached by vocabulary CONTENT"""
     from hipie_oracle import synth
-    from hipie_oracle.model import HipieOracle
     _, _, pos_map, is_thing = synth.make_text(9, 64, seed=3)
-    g = torch.Generator().manual_seed(5)
-    logits = torch.randn(2, 11, 64, generator=g)
+    del pos_map[4]                                   # a class without tokens
     m = _host_model()
-    got = m.convert_grounding_to_od_logits(logits, 9, pos_map, is_thing, mode=mode, max_pool=max_pool)
-    ref = HipieOracle.convert_grounding_to_od_logits(logits, 9, pos_map, is_thing, mode=mode, max_pool=max_pool)
-    assert torch.allclose(got, ref, atol=1e-6)
-    # cached tables are keyed by content: a different vocabulary must not reuse them
+    tok, cnt, fg, bg = m._pool_tables(pos_map, 9, 64, is_thing, torch.device("cpu"))
+    assert tok.dtype == torch.int32 and cnt.dtype == torch.int32 and fg.dtype == torch.int8
+    for c in range(1, 10):
+        if c in pos_map:
+            assert tok[c - 1, :len(pos_map[c])].tolist() == pos_map[c] and int(cnt[c - 1]) == len(pos_map[c])
+            assert bool(fg[c - 1]) == (not is_thing[c]) and bool(bg[c - 1]) == is_thing[c]
+        else:
+            assert int(cnt[c - 1]) == 0 and not bool(fg[c - 1]) and not bool(bg[c - 1])
     _, _, pos_map2, is_thing2 = synth.make_text(9, 64, seed=4)
-    got2 = m.convert_grounding_to_od_logits(logits, 9, pos_map2, is_thing2, mode=mode, max_pool=max_pool)
-    ref2 = HipieOracle.convert_grounding_to_od_logits(logits, 9, pos_map2, is_thing2, mode=mode, max_pool=max_pool)
-    assert torch.allclose(got2, ref2, atol=1e-6)
+    tok2, cnt2, _, _ = m._pool_tables(pos_map2, 9, 64, is_thing2, torch.device("cpu"))
+    assert not (torch.equal(tok, tok2) and torch.equal(cnt, cnt2))
+    assert m._pool_tables(pos_map, 9, 64, is_thing, torch.device("cpu"))[0] is tok      # cache hit on identical content
+    with pytest.raises(ValueError):
+        m._pool_tables({1: [70]}, 1, 64, {1: True}, torch.device("cpu"))                 # token index outside the text length
