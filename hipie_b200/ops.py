@@ -447,7 +447,8 @@ def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, a
     return out
 
 
-MSDA_WINDOWS = True      # encoder calls gather from TMA-staged shared-memory windows (msda_win_kernel); False = flat kernel (A/B)
+MSDA_WINDOWS = False     # True: encoder calls gather from TMA-staged shared-memory windows (msda_win_kernel, bit-identical results);
+                         # measured slower than the flat kernel so far (tools/msda_micro.py, profiles/r02_msda_micro.txt): off by default
 
 
 def msda_fused(value, spatial_shapes, level_start_index, offs_logits, reference_points, M=8, D=32, L=4, P=4,

@@ -8,7 +8,7 @@ from hipie_b200.modeling import params as P
 from hipie_b200.modeling.hipie_img import HIPIE_IMG
 prec = 1 if (len(sys.argv) > 1 and sys.argv[1] == "bf16") else 3
 ops.set_precision(prec)
-hp = bench.vit_h_hp()
+hp = bench.vit_h_hp(bench.CONFIGS[1])
 model = HIPIE_IMG(hp=hp, state_dict=P.random_state_dict(hp, seed=0), device="cuda:0")
 model.engine.bf16_value_map = prec == 1
 B = 8

@@ -8,7 +8,7 @@ from hipie_b200.modeling import params as P
 from hipie_b200.modeling.hipie_img import HIPIE_IMG
 from torch.profiler import profile, ProfilerActivity
 ops.set_precision(3)
-hp = bench.vit_h_hp()
+hp = bench.vit_h_hp(bench.CONFIGS[1])
 model = HIPIE_IMG(hp=hp, state_dict=P.random_state_dict(hp, seed=0), device="cuda:0")
 B = 8
 dev = torch.device("cuda:0")

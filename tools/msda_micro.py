@@ -36,4 +36,4 @@ for (img, B) in ((1024, 8), (1280, 4)):
             res[name] = (ms, out)
             print(f"{img}^2 B={B} offsets sigma={sigma} px  {name:6s}: {ms:.3f} ms  {alg/ms/1e6:.0f} GB/s algorithmic", flush=True)
         assert torch.equal(res["flat"][1].hi, res["window"][1].hi)
-ops.MSDA_WINDOWS = True
+ops.MSDA_WINDOWS = False

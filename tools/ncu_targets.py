@@ -48,8 +48,27 @@ if which in ("all", "msda"):
         ys, xs = torch.meshgrid(torch.linspace(0.5, h - 0.5, h, device=dev) / h, torch.linspace(0.5, w_ - 0.5, w_, device=dev) / w_, indexing="ij")
         refs.append(torch.stack([xs.reshape(-1), ys.reshape(-1)], -1))
     refp = torch.cat(refs, 0)[None, :, None, :].repeat(B, 1, 4, 1).contiguous()
+    import hipie_b200.ops as O
+    O.MSDA_WINDOWS = True
     for _ in range(2):      # encoder call: shared-memory window kernel (shapes known on the host)
         ops.msda_fused(value, shapes, lsi, packed, refp, shapes_host=[(128, 128), (64, 64), (32, 32), (16, 16)])
+if which in ("msda_flat",):      # the same encoder call on the flat L1-gather kernel (A/B of the window kernel)
+    import hipie_b200.ops as O
+    O.MSDA_WINDOWS = False
+    B = 8
+    hw = [(128, 128), (64, 64), (32, 32), (16, 16)]
+    shapes = torch.tensor(hw, device=dev)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    Sx = int(shapes.prod(1).sum())
+    value = torch.randn(B, Sx, 256, device=dev)
+    packed = torch.cat([torch.randn(B, Sx, 256, device=dev) * 2.0, torch.randn(B, Sx, 128, device=dev)], -1)
+    refs = []
+    for (h, w_) in hw:
+        ys, xs = torch.meshgrid(torch.linspace(0.5, h - 0.5, h, device=dev) / h, torch.linspace(0.5, w_ - 0.5, w_, device=dev) / w_, indexing="ij")
+        refs.append(torch.stack([xs.reshape(-1), ys.reshape(-1)], -1))
+    refp = torch.cat(refs, 0)[None, :, None, :].repeat(B, 1, 4, 1).contiguous()
+    for _ in range(2):
+        ops.msda_fused(value, shapes, lsi, packed, refp)
 if which in ("all", "maskembed"):
     B, HW, Q, C = 8, 65536, 300, 256
     Fm = ops.split(torch.randn(B * HW, C, device=dev))
