@@ -1,19 +1,22 @@
-// tcgen05 flash attention for the ViT-H blocks (hd = 80), sm_100a: global 64-wide token grids (T % 256 == 0) and the 14x14 windows.
+// tcgen05 flash attention for the ViT-H blocks (hd = 80), sm_100a: global 64-wide token grids (T % 256 == 0), 80-wide ones
+// (1280-pixel inputs; T % 1280 == 0) and the 14x14 windows.
 //
 //   softmax((q*scale) k^T + rel_h[q, kh] + rel_w[q, kw]) v      (/root/reference/projects/HIPIE/hipie/backbone/vit.py:67-83,
 //                                                                 backbone/utils.py:96-125)
 //
-// One CTA = 256 query rows (two 128-row tiles) of one (batch, head); 352 threads:
-//   warp 0      TMA producer: K tiles (64 keys x 80) and V^T tiles (80 x 64 keys) into a hardware-swizzled shared-memory
+// One CTA = 256 query rows (two 128-row tiles) of one (batch, head); 384 threads in three warpgroups (setmaxnreg 216 / 216 / 72):
+//   warp 8      TMA producer: K tiles (64 keys x 80) and V^T tiles (80 x 64 keys) into a hardware-swizzled shared-memory
 //               ring (head dim 80 = one 128B-swizzled 64-wide box + one 32B-swizzled 16-wide box), plus the two Q lo tiles once
-//   warp 1 / 10 MMA issuers, one per query tile: S_t = Q_t K_j^T (M=128, N=64, K=80; A = Q hi in TENSOR MEMORY, TS mode) and
+//   warp 9 / 10 MMA issuers, one per query tile: S_t = Q_t K_j^T (M=128, N=64, K=80; A = Q hi in TENSOR MEMORY, TS mode) and
 //               O_t += P_t V_j (M=128, N=80, K=64; A = P in tensor memory).  QK_t(j+1) is issued as soon as the softmax warps
 //               hold S_t(j) in registers; the two issuers' streams interleave in the tensor pipe, so while one tile is in
 //               its softmax the pipe works for the other.  Latency-critical waits poll (mbarrier.test_wait)
-//   warps 2-5   softmax of tile 0, warps 6-9 softmax of tile 1: ONE THREAD PER QUERY ROW (no cross-warp max exchange):
+//   warps 0-3   softmax of tile 0, warps 4-7 softmax of tile 1: ONE THREAD PER QUERY ROW (no cross-warp max exchange):
 //               tcgen05.ld the 64 scores, scale + rel-pos bias, online softmax with lazy rescaling of the TMEM accumulator,
 //               P written back to TMEM with tcgen05.st as the A operand of the PV MMA
-//   global mode: rel_w hoisted in registers, one prefetched rel_h scalar per tile (a 64-key tile is one key row of the grid)
+//   global mode: rel_w hoisted in registers, one prefetched rel_h scalar per tile (a 64-key tile is one key row of the grid);
+//               80-wide grids keep the 64-key tiles: tile j starts at grid column (64 j) mod 80, which repeats every 5 tiles, so
+//               the loop is unrolled over the 5 phases and every rel_w index / row boundary is a compile-time constant
 //   window mode (T = 196, 14 x 14): one CTA per (window, head); keys padded to 4 x 64 and masked; the bias index
 //               (k / 14, k % 14) folds to constants in the unrolled 4-tile loop; V^T holds every window at a 200-column pitch
 //               because TMA box starts must be 16-byte aligned
@@ -34,7 +37,13 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols
                    int64_t bstride, int box_rows, int box_cols);
 
 constexpr int FA_BM = 128, FA_BN = 64, FA_HD = 80, FA_STAGES = 3;
-constexpr int FA_THREADS = 352;  // TMA warp, MMA warp of tile 0, 8 softmax warps, MMA warp of tile 1
+// Three warpgroups: warps 0-3 softmax of query tile 0, warps 4-7 softmax of tile 1, warps 8-11 = TMA producer, MMA issuer of tile 0,
+// MMA issuer of tile 1, (idle).  The roles are warpgroup-aligned so that setmaxnreg can move registers from the three single-thread
+// roles (72 each) to the softmax threads (216 each: 64 scores + the hoisted rel_w row of up to 80 entries stay in registers;
+// at the launch-bound 168 the 64-wide variant spilled 15 registers and the 80-wide one 34).
+constexpr int FA_THREADS = 384;
+constexpr int FA_W_TMA = 8, FA_W_MMA0 = 9, FA_W_MMA1 = 10;
+constexpr int FA_REGS_SOFTMAX = 216, FA_REGS_ISSUE = 72;      // 256 * 216 + 128 * 72 = 384 * 168: no spills in any variant
 constexpr int FA_QT = 2;           // query tiles per CTA (ping-pong: one in softmax while the other is in the tensor pipe)
 // tensor-memory map (columns), per query tile t at column 256 * t
 constexpr int TM_TILE = 256;
@@ -77,19 +86,21 @@ struct FaSmem {
     static constexpr int TOTAL = OFF_BAR + 256 + 1024;
 };
 
+template <int V> struct Phase { static constexpr int value = V; };
+constexpr int FA_GW2 = 80;        // second supported global grid width (1280-pixel inputs)
 constexpr int FA_WIN = 14, FA_WIN_T = FA_WIN * FA_WIN;     // window mode: 14 x 14 tokens, keys padded to 4 x 64
 constexpr int FA_WIN_TP = 200;   // window mode: column pitch of one window in V^T (TMA box starts must be 16-byte aligned)
 
 // F16 (with PREC == 1): q, k, v^T are IEEE fp16 planes and P is written as fp16: the single-pass QK^T / PV mode of the precision
 // map (2^-12 operand rounding instead of bf16's 2^-9 keeps the 1e-3 mask-logit budget, measured in
 // profiles/r02_precision_emulation.txt and tests/test_fullsize_gpu.py).
-template <int PREC, bool WIN, bool F16>
+template <int PREC, bool WIN, bool F16, bool TRACE, int GW>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     using SM = FaSmem<PREC>;
     constexpr int NPL = SM::NPL;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared address space (LDS / STS)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
     uint64_t* k_full = bars;                       // [STAGES]
     uint64_t* k_empty = k_full + FA_STAGES;
@@ -106,15 +117,15 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (FA_QT * FA_BM), h = blockIdx.y, b = blockIdx.z;
     const int ntiles = WIN ? (FA_WIN_T + FA_BN - 1) / FA_BN : p.T / FA_BN;     // window mode: 196 keys in 4 tiles, tail masked
-    const bool trace_cta = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    const bool trace_cta = TRACE && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == FA_W_TMA && lane == 0) {
         for (int i = 0; i < NPL; ++i) {
             prefetch_tmap(&maps.k64[i]); prefetch_tmap(&maps.k16[i]); prefetch_tmap(&maps.vt[i]);
         }
         if (PREC == 3) { prefetch_tmap(&maps.q64); prefetch_tmap(&maps.q16); }
     }
-    if (warp == 1) {
+    if (warp == FA_W_MMA0) {
         if (lane == 0) {
             for (int i = 0; i < FA_STAGES; ++i) {
                 mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], FA_QT);      // released by both tiles' issuers
@@ -136,7 +147,9 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 0) {
+    if (warp >= FA_W_TMA) {
+    setmaxnreg_dec<FA_REGS_ISSUE>();          // (register reallocation has to dominate the role's code: one branch per warpgroup)
+    if (warp == FA_W_TMA) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             if (PREC == 3) {
@@ -165,14 +178,14 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 if (++s == FA_STAGES) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1 || warp == 10) {
-        // ===================== MMA issuers: warp 1 drives query tile 0, warp 10 tile 1 =====================
+    } else if (warp == FA_W_MMA0 || warp == FA_W_MMA1) {
+        // ===================== MMA issuers: one warp per query tile =====================
         //   S_t = Q_t K_j^T  (A = Q hi in TMEM; the Ql.Kh pass takes Q lo from shared memory)     O_t += P_t V_j  (A = P in TMEM)
         // QK_t(j+1) is issued as soon as the softmax warps have pulled S_t(j) into registers, so the next scores are ready
         // before the current softmax finishes; PV_t(j) follows P_t(j).  The two issuers' instruction streams interleave in the
         // tensor pipe (independent accumulators), which hides the dependent-accumulate latency of the small-N MMAs and keeps
         // the pipe busy while one tile waits on its softmax.  Latency-critical waits poll (test_wait) instead of suspending.
-        const int t = warp == 1 ? 0 : 1;
+        const int t = warp - FA_W_MMA0;
         constexpr uint32_t idesc_qk = F16 ? make_idesc_f16(FA_BM, FA_BN) : make_idesc_bf16(FA_BM, FA_BN);
         constexpr uint32_t idesc_pv = F16 ? make_idesc_f16(FA_BM, FA_HD) : make_idesc_bf16(FA_BM, FA_HD);
         const uint32_t tb = tmem_base + t * TM_TILE;
@@ -241,10 +254,12 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             issue_pv(j);
             if (trm) p.trace[(j * 2 + t) * 8 + 7] = clock64();
         }
+    }
     } else {
-        // ===================== softmax / epilogue: warps 2-5 own query tile 0, warps 6-9 tile 1; one thread per row ==========
+        setmaxnreg_inc<FA_REGS_SOFTMAX>();
+        // ===================== softmax / epilogue: warps 0-3 own query tile 0, warps 4-7 tile 1; one thread per row ==========
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-        const int t = (warp - 2) >> 2;                // warps 2-5: tile 0, warps 6-9: tile 1
+        const int t = warp >> 2;                      // warps 0-3: tile 0, warps 4-7: tile 1
         const int r = quarter * 32 + lane;            // row of the query tile == TMEM lane
         const int qrow = q0 + t * FA_BM + r;
         const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + t * TM_TILE;
@@ -273,7 +288,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&q_ready[t]);
         }
-        float rw[WIN ? FA_WIN : FA_BN];       // rel_w row of this query (window mode: 14 entries, global: 64), log2 domain
+        float rw[WIN ? FA_WIN : GW];          // rel_w row of this query (window mode: 14 entries, global: the grid width), log2 domain
         float rhw[WIN ? FA_WIN : 1];          // window mode: the rel_h row as well (global mode streams one rel_h scalar per tile)
         const float* relh_row = nullptr;
         if (WIN) {
@@ -286,31 +301,45 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             }
         } else if (has_rel) {
             const int64_t rowi = ((int64_t)b * p.H + h) * p.T + qrow;
-            const float* rwp = p.rel_w + rowi * FA_BN;
+            const float* rwp = p.rel_w + rowi * GW;
 #pragma unroll
-            for (int i = 0; i < FA_BN; i += 4) {
+            for (int i = 0; i < GW; i += 4) {
                 const float4 v = *reinterpret_cast<const float4*>(rwp + i);
                 rw[i] = v.x * LOG2E; rw[i + 1] = v.y * LOG2E; rw[i + 2] = v.z * LOG2E; rw[i + 3] = v.w * LOG2E;
             }
             relh_row = p.rel_h + rowi * p.kh;
         }
         float m = -INFINITY, l = 0.f;          // m: running reference max (log2 domain, incl. rel-pos terms)
-        float rh_next = (!WIN && has_rel) ? __ldg(relh_row) * LOG2E : 0.f;
+        if (t == 1) named_bar_arrive(1 + 2 * quarter, 64);      // exp-phase hand-off (see tile_body): tile 0 goes first
+        // raw rel_h table values of the next tile (scaled at use, so the prefetch stays in flight).  GW == 64: a 64-key tile is one
+        // key row of the grid.  GW == 80: a tile straddles at most two rows (a: the row of its first key, b: the next one)
+        float rh_next = (!WIN && has_rel) ? __ldg(relh_row) : 0.f;
+        float rh_next_b = (!WIN && GW != FA_BN && has_rel) ? __ldg(relh_row + 1) : 0.f;
         // log2-domain score of key column i of tile j: global mode adds the hoisted rel_w entry (rel_h is per tile); window mode
         // decomposes the key index into the 14 x 14 grid (indices fold to constants once the 4-tile loop is unrolled) and masks
         // the 60 padding keys of the last tile
-        auto score = [&](uint32_t sbits, const int j, const int i) -> float {
+        // (global mode, OFF = grid column of the tile's first key: (64 j) mod GW, a compile-time constant per tile phase)
+        auto score = [&](uint32_t sbits, const int j, const int i, const int OFF) -> float {
             if (WIN) {
                 const int k = j * FA_BN + i;
                 if (k >= FA_WIN_T) return -INFINITY;
                 return fmaf(__uint_as_float(sbits), p.scale_log2e, rhw[k / FA_WIN]) + rw[k % FA_WIN];
             }
-            return fmaf(__uint_as_float(sbits), p.scale_log2e, has_rel ? rw[i] : 0.f);
+            return fmaf(__uint_as_float(sbits), p.scale_log2e, has_rel ? rw[WIN ? 0 : (OFF + i) % GW] : 0.f);
         };
-        auto tile_body = [&](const int j) {
-            const bool tr = trace_cta && lane == 0 && (warp == 2 || warp == 6) && j < 32;
-            const float rh = rh_next;
-            if (!WIN && has_rel && j + 1 < ntiles) rh_next = __ldg(relh_row + j + 1) * LOG2E;   // prefetch for the next tile
+        // PH: phase of the tile inside the period of lcm(64, GW) keys -- 0 for the 64-wide grid and the windows; 0..4 for the 80-wide
+        // grid, where tile j starts at grid column OFF = (64 PH) mod 80 and its keys [SPLIT, 64) belong to the next key row
+        auto tile_body = [&](const int j, auto ph_tag) {
+            constexpr int PH = decltype(ph_tag)::value;
+            constexpr int OFF = WIN ? 0 : (FA_BN * PH) % GW;
+            constexpr int SPLIT = (!WIN && OFF + FA_BN > GW) ? GW - OFF : FA_BN;
+            const bool tr = trace_cta && lane == 0 && (warp & 3) == 0 && j < 32;
+            const float rh = rh_next * LOG2E, rhb = rh_next_b * LOG2E;
+            if (!WIN && has_rel && j + 1 < ntiles) {                                     // prefetch for the next tile
+                const int r0n = GW == FA_BN ? j + 1 : (FA_BN * (j + 1)) / GW;
+                rh_next = __ldg(relh_row + r0n);
+                if (GW != FA_BN) rh_next_b = __ldg(relh_row + min(r0n + 1, p.kh - 1));
+            }
             if (tr) p.trace[(j * 2 + t) * 8 + 0] = clock64();
             mbar_wait_spin(&s_full[t], j & 1);
             tc_fence_after();
@@ -321,23 +350,24 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 tmem_ld_32x32b_x32(tm + TM_S, sv);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) tv[i] = score(sv[i], j, i);
+                for (int i = 0; i < 32; ++i) tv[i] = score(sv[i], j, i, OFF);
                 tmem_ld_32x32b_x32(tm + TM_S + 32, sv);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_empty[t]);      // scores are in registers: QK_t(j+1) may overwrite S_t
 #pragma unroll
-                for (int i = 0; i < 32; ++i) tv[32 + i] = score(sv[i], j, 32 + i);
+                for (int i = 0; i < 32; ++i) tv[32 + i] = score(sv[i], j, 32 + i, OFF);
             }
             // t_i = s_i*scale*log2e + rel_w_i ; rel_h is uniform over the tile -> folded into the max / exponent offset
-            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mxb[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int i = 0; i < FA_BN; i += 4) {
-                mx[0] = fmaxf(mx[0], tv[i]); mx[1] = fmaxf(mx[1], tv[i + 1]);
-                mx[2] = fmaxf(mx[2], tv[i + 2]); mx[3] = fmaxf(mx[3], tv[i + 3]);
+            for (int i = 0; i < FA_BN; ++i) {
+                if (i < SPLIT) mx[i & 3] = fmaxf(mx[i & 3], tv[i]);
+                else mxb[i & 3] = fmaxf(mxb[i & 3], tv[i]);
             }
-            const float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + rh;
+            float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) + rh;
+            if (SPLIT < FA_BN) tmax = fmaxf(tmax, fmaxf(fmaxf(mxb[0], mxb[1]), fmaxf(mxb[2], mxb[3])) + rhb);
             // lazy rescale: keep the running reference max unless the tile exceeds it by more than 2^8
             const bool need = tmax > m + 8.f;
             float corr = 1.f;
@@ -361,14 +391,20 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 }
             }
             if (tr) p.trace[(j * 2 + t) * 8 + 2] = clock64();
-            const float off = m - rh;
+            // The two softmax warps of an SM sub-partition (tile 0: warp q, tile 1: warp 4+q) share one MUFU unit.  Left alone
+            // they run in lock step and their 64-ex2 phases collide (ncu r02: 16 cycles per MUFU.EX2, XU 43 % busy overall); a
+            // named-barrier hand-off makes the exp phases alternate, so one warp's exponentials overlap the other's TMEM loads,
+            // max reduction and mbarrier waits.
+            named_bar_sync(1 + 2 * quarter + t, 64);
+            const float off = m - rh, offb = m - rhb;
             float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < FA_BN; c += 16) {
                 uint32_t ph_[8], pl_[8];
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    const float e0 = ex2_approx(tv[c + i] - off), e1 = ex2_approx(tv[c + i + 1] - off);
+                    const float e0 = ex2_approx(tv[c + i] - (c + i < SPLIT ? off : offb));
+                    const float e1 = ex2_approx(tv[c + i + 1] - (c + i + 1 < SPLIT ? off : offb));
                     rs[(i >> 1) & 3] += e0 + e1;
                     if (PREC == 3) split2(e0, e1, ph_[i >> 1], pl_[i >> 1]);
                     else ph_[i >> 1] = F16 ? pack_f16x2(e0, e1) : pack_bf16x2(e0, e1);
@@ -380,6 +416,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                     tmem_st_32x32b_x4(tm + TM_P + 32 + (c >> 1) + 4, pl_[4], pl_[5], pl_[6], pl_[7]);
                 }
             }
+            if (t == 0 || j + 1 < ntiles) named_bar_arrive(1 + 2 * quarter + (t ^ 1), 64);   // the other tile's exp phase may start
             l += (rs[0] + rs[1]) + (rs[2] + rs[3]);
             tmem_st_wait();
             tc_fence_before();
@@ -389,9 +426,14 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         };
         if (WIN) {
 #pragma unroll
-            for (int j = 0; j < (FA_WIN_T + FA_BN - 1) / FA_BN; ++j) tile_body(j);
-        } else {
-            for (int j = 0; j < ntiles; ++j) tile_body(j);
+            for (int j = 0; j < (FA_WIN_T + FA_BN - 1) / FA_BN; ++j) tile_body(j, Phase<0>{});
+        } else if (GW == FA_BN) {
+            for (int j = 0; j < ntiles; ++j) tile_body(j, Phase<0>{});
+        } else {                           // 80-wide grid: 5 tiles = 4 key rows per period (the host checks T % 320 == 0)
+            for (int j = 0; j < ntiles; j += 5) {
+                tile_body(j, Phase<0>{}); tile_body(j + 1, Phase<1>{}); tile_body(j + 2, Phase<2>{});
+                tile_body(j + 3, Phase<3>{}); tile_body(j + 4, Phase<4>{});
+            }
         }
         // ---- epilogue: O / l ----
         mbar_wait(&pv_done[t], (ntiles - 1) & 1);
@@ -429,18 +471,18 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 1) {
+    if (warp == FA_W_MMA0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
 }
 
-template <int PREC, bool WIN, bool F16>
+template <int PREC, bool WIN, bool F16, bool TRACE = false, int GW = FA_BN>
 static int launch_fa(const FaMaps& maps, const FaParams& p, cudaStream_t st) {
     using SM = FaSmem<PREC>;
-    HIPIE_ENSURE_SMEM((attn_tc_kernel<PREC, WIN, F16>), SM::TOTAL);
+    HIPIE_ENSURE_SMEM((attn_tc_kernel<PREC, WIN, F16, TRACE, GW>), SM::TOTAL);
     dim3 grid(WIN ? 1 : p.T / (FA_QT * FA_BM), p.H, p.B);
-    attn_tc_kernel<PREC, WIN, F16><<<grid, FA_THREADS, SM::TOTAL, st>>>(maps, p);
+    attn_tc_kernel<PREC, WIN, F16, TRACE, GW><<<grid, FA_THREADS, SM::TOTAL, st>>>(maps, p);
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
 }
@@ -463,7 +505,9 @@ extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int
     HIPIE_CHECK_ARG(win || (T > 0 && T % (FA_QT * FA_BM) == 0),
                     "hipie_attention_tc: T (%d) must be a multiple of 256 (or 196 with a 14x14 rel-pos grid: window mode)", T);
     HIPIE_CHECK_ARG((rel_h == nullptr) == (rel_w == nullptr), "hipie_attention_tc: rel_h and rel_w go together");
-    HIPIE_CHECK_ARG(win || !rel_h || (kw == FA_BN && kh * kw == T), "hipie_attention_tc: rel-pos needs kw == 64 and kh*kw == T");
+    const bool wide = !win && rel_h && kw == FA_GW2;       // 80-wide grid: 64-key tiles in 5 phases per 4 key rows
+    HIPIE_CHECK_ARG(win || !rel_h || ((kw == FA_BN || (wide && T % (5 * FA_BN) == 0)) && kh * kw == T),
+                    "hipie_attention_tc: rel-pos needs a 64-wide grid, or an 80-wide one with T %% 320 == 0, and kh*kw == T");
     HIPIE_CHECK_ARG(out_f32 || out_hi, "hipie_attention_tc: no output requested");
     HIPIE_CHECK_ARG(q_ts % 8 == 0 && q_bs % 8 == 0 && q_col0 % 8 == 0 && (reinterpret_cast<uintptr_t>(q_hi) & 15) == 0,
                     "hipie_attention_tc: q rows must be 16-byte aligned");
@@ -488,6 +532,8 @@ extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int
     p.scale_log2e = scale * 1.4426950408889634f;
     p.trace = trace;
     cudaStream_t st = (cudaStream_t)stream;
+    if (trace && !win && !wide) return prec == 3 ? launch_fa<3, false, false, true>(maps, p, st) : (f16 ? launch_fa<1, false, true, true>(maps, p, st) : launch_fa<1, false, false, true>(maps, p, st));
+    if (wide) return prec == 3 ? launch_fa<3, false, false, false, FA_GW2>(maps, p, st) : (f16 ? launch_fa<1, false, true, false, FA_GW2>(maps, p, st) : launch_fa<1, false, false, false, FA_GW2>(maps, p, st));
     if (win) return prec == 3 ? launch_fa<3, true, false>(maps, p, st) : (f16 ? launch_fa<1, true, true>(maps, p, st) : launch_fa<1, true, false>(maps, p, st));
     return prec == 3 ? launch_fa<3, false, false>(maps, p, st) : (f16 ? launch_fa<1, false, true>(maps, p, st) : launch_fa<1, false, false>(maps, p, st));
 }

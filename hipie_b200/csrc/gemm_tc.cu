@@ -443,7 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     // same CTA-relative offsets in both CTAs of a pair (the dynamic shared window starts at the same offset in every CTA of a
     // launch), which the pair MMA descriptors and the multicast commits rely on
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared address space (LDS / STS)
     uint8_t* stage_base = smem;
     float* epi = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE + Cfg::EPI_BYTES);

@@ -289,7 +289,8 @@ msda_win_kernel(const __grid_constant__ MsdaWinMaps maps, const MsdaWinParams p)
     using namespace ptx;
     constexpr int D = 32, L = 4, P = 4;
     extern __shared__ uint8_t mw_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mw_raw) + 127) & ~uintptr_t(127));
+    // offset arithmetic (not an integer round trip) keeps the pointer in the shared address space: LDS / STS, not generic LD / ST
+    uint8_t* smem = mw_raw + ((128u - (smem_u32(mw_raw) & 127u)) & 127u);
     uint32_t* recs = reinterpret_cast<uint32_t*>(smem + p.win_bytes);                      // [16 warps][4][MW_GROUP_WORDS]
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.win_bytes + (MW_THREADS / 32) * 4 * MW_GROUP_WORDS * 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hsub = lane >> 3, dsub = lane & 7;

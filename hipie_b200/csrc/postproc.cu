@@ -314,7 +314,7 @@ seg_post_tc_kernel(const float* __restrict__ masks, const __nv_bfloat16* __restr
                    const __nv_bfloat16* __restrict__ pt_lo, const float* __restrict__ scores, float* __restrict__ sem,
                    int* __restrict__ ids, int* __restrict__ areas, int Q, int Qpad, int C, int h, int w, int Hc, int Wc) {
     extern __shared__ uint8_t pt_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pt_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = pt_raw + ((1024u - (smem_u32(pt_raw) & 1023u)) & 1023u);   // stays in the shared address space (LDS / STS)
     float* taps = reinterpret_cast<float*>(smem + PtSmem::OFF_TAPS);
     float* sc = reinterpret_cast<float*>(smem + PtSmem::OFF_SC);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PtSmem::OFF_BAR);

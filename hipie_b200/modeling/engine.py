@@ -16,6 +16,8 @@ Reference call sites are cited next to each stage (H = /root/reference/projects/
 """
 import math
 
+import types
+
 import torch
 import torch.nn.functional as F
 
@@ -214,7 +216,9 @@ class Engine:
                 _, xn, _ = ops.layernorm(x, W[blk + ".norm1.weight"], W[blk + ".norm1.bias"], 1e-6)
                 Bq, Tq, qh, qw = B, T, gh, gw
             st = (Tq * 3 * E, 3 * E, hd)
-            use_tc = self.use_tc_attention and hd == 80 and ((not windowed and Tq % 256 == 0 and qw == 64) or (windowed and ws == 14))
+            # tcgen05 kernel: 64-wide grids (1024-pixel inputs), 80-wide grids (1280-pixel inputs; T a multiple of lcm(256, 320)) and 14x14 windows
+            tc_grid = Tq % 256 == 0 and (qw == 64 or (qw == 80 and Tq % 320 == 0))
+            use_tc = self.use_tc_attention and hd == 80 and ((not windowed and tc_grid) or (windowed and ws == 14))
             f16 = use_tc and self.attn_fp16 and ops.PREC == 3
             if use_tc:
                 # q,k as one GEMM (N = 2E); V emitted transposed (E, B*T) so it is the K-major B operand of P.V.  With the fp16
@@ -506,11 +510,12 @@ class Engine:
             x, x_s, _ = ops.layernorm(y, W[p + ".output.LayerNorm.weight"], W[p + ".output.LayerNorm.bias"], 1e-12, want_f32=True, want_split=True)
         return x.view(R, L, Hd)
 
-    def forward_text(self, input_ids, attention_mask, same_rows=None):
+    def forward_text(self, input_ids, attention_mask, same_rows=None, chunk_plan=None):
         """BertEncoder.forward (bert_model.py:32-154): rows > 512 tokens are chunked at '.'/EOS boundaries.
         `same_rows` says whether every row of the batch holds the same prompt (the detection case, hipie_img.py:330-332):
         then row 0 is encoded once and broadcast.  The caller decides it from the host-side token ids (no device sync, safe
-        inside a CUDA-graph capture); None = decide here from the tensors, which reads one flag back from the device."""
+        inside a CUDA-graph capture); None = decide here from the tensors, which reads one flag back from the device.
+        `chunk_plan` (rows > 512 tokens): the host-side cut plan from `text_chunk_plan`; None = computed here (device -> host copy)."""
         L = input_ids.shape[1]
         if same_rows is None:
             same_rows = self.rows_equal(input_ids, attention_mask)
@@ -519,10 +524,18 @@ class Engine:
             ids_u, am_u = input_ids[:1].contiguous(), attention_mask[:1].contiguous()
         else:
             ids_u, am_u = input_ids, attention_mask
-        hid = self.bert(ids_u, am_u) if L <= 512 else self._bert_chunked(ids_u, am_u)
+        hid = self.bert(ids_u, am_u) if L <= 512 else self._bert_chunked(ids_u, am_u, chunk_plan)
         if same:
             hid = hid.expand(input_ids.shape[0], -1, -1).contiguous()
         return {"hidden": hid, "masks": attention_mask}
+
+    def text_chunk_plan(self, input_ids, attention_mask, same_rows):
+        """The chunk plan forward_text will need for these (host or device) ids, or None for rows of <= 512 tokens."""
+        if input_ids.shape[1] <= 512:
+            return None
+        if bool(same_rows) and input_ids.shape[0] > 1:
+            input_ids, attention_mask = input_ids[:1], attention_mask[:1]
+        return self.plan_text_chunks(input_ids, attention_mask)
 
     @staticmethod
     def rows_equal(input_ids, attention_mask):
@@ -535,10 +548,14 @@ class Engine:
             raise RuntimeError("forward_text: pass same_rows explicitly inside a CUDA-graph capture")
         return bool(((input_ids == input_ids[:1]).all() & (attention_mask == attention_mask[:1]).all()).item())
 
-    def _bert_chunked(self, input_ids, mask, sep=1012):
+    def plan_text_chunks(self, input_ids, mask, sep=1012):
+        """Host half of the > 512-token path (bert_model.py:48-120): cut every row at its last '.' / EOS before position 510, re-wrap
+        each piece as a 512-token BERT input ([CLS] + piece for all but the first) and remember where its hidden states go.
+        Pure host work on the token ids -- done BEFORE a CUDA-graph capture; the plan's `signature` (the cut positions) is part
+        of the captured launch sequence, its `rows` / `masks` are refilled in place between replays."""
         CLS, EOS = 101, 102
-        bs, seq_len = mask.shape
         ids_c, mask_c = input_ids.cpu(), mask.cpu()
+        bs = mask_c.shape[0]
         chunks = []
         for bi in range(bs):
             inp, begin, start_src = ids_c[bi].clone(), 0, 0
@@ -566,11 +583,25 @@ class Engine:
                 start_src = 1
                 inp = inp[l_valid:]
                 begin += l_valid
-        rows = torch.stack([c[1] for c in chunks]).to(self.device)
-        masks = torch.stack([c[2] for c in chunks]).to(self.device)
-        last_hidden = self.bert(rows, masks)
-        out = torch.zeros(bs, seq_len, last_hidden.shape[-1], device=self.device)
-        for idx, (bi, _, _, (s0, s1, t0, t1)) in enumerate(chunks):
+        plan = types.SimpleNamespace()
+        plan.spans = [(c[0],) + c[3] for c in chunks]
+        plan.signature = (bs, int(mask_c.shape[1])) + tuple(plan.spans)
+        plan.rows = torch.stack([c[1] for c in chunks]) if chunks else torch.zeros(0, 512, dtype=torch.long)
+        plan.masks = torch.stack([c[2] for c in chunks]) if chunks else torch.zeros(0, 512, dtype=torch.long)
+        plan.rows_d, plan.masks_d = plan.rows.to(self.device), plan.masks.to(self.device)
+        return plan
+
+    def _bert_chunked(self, input_ids, mask, plan=None):
+        bs, seq_len = mask.shape
+        if plan is None:
+            if input_ids.is_cuda and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("forward_text: > 512 tokens inside a CUDA-graph capture needs chunk_plan= (plan_text_chunks on the host ids)")
+            plan = self.plan_text_chunks(input_ids, mask)
+        out = torch.zeros(bs, seq_len, self.hp.get("lang_dim", 768), device=self.device)
+        if len(plan.spans) == 0:
+            return out
+        last_hidden = self.bert(plan.rows_d, plan.masks_d)
+        for idx, (bi, s0, s1, t0, t1) in enumerate(plan.spans):
             out[bi, t0:t1] = last_hidden[idx, s0:s1]
         return out
 

@@ -185,7 +185,8 @@ class HIPIE_IMG(nn.Module):
                           mask_bits=md["mask_bits"])
         return out
 
-    def capture_hot_path(self, tensor, pad_mask, image_sizes, input_ids, attention_mask, task="detection", warmup=2, same_rows=None):
+    def capture_hot_path(self, tensor, pad_mask, image_sizes, input_ids, attention_mask, task="detection", warmup=2, same_rows=None,
+                         chunk_plan=None):
         """CUDA-graph the hot path (text encoder + coco_inference) for fixed-shape serving: ~2000 kernel launches per
         batch become one graph launch, which removes the host launch overhead (B200: ≈15 % of the step).
         Returns `replay() -> out` whose tensors are static buffers; refill `tensor` / `input_ids` in place between replays."""
@@ -196,8 +197,13 @@ class HIPIE_IMG(nn.Module):
         if same_rows is None:
             same_rows = self.engine.rows_equal(input_ids, attention_mask)
 
+        # prompts longer than 512 tokens: the cut positions are host logic on the token ids (bert_model.py:48-120), fixed before
+        # the capture; replays refill chunk_plan.rows_d / masks_d in place (forward keys its graphs on the plan's signature)
+        if chunk_plan is None:
+            chunk_plan = self.engine.text_chunk_plan(input_ids, attention_mask, same_rows)
+
         def step():
-            lang = self.engine.forward_text(ids, am, same_rows=same_rows)
+            lang = self.engine.forward_text(ids, am, same_rows=same_rows, chunk_plan=chunk_plan)
             return self.coco_inference(tensor, pad_mask, image_sizes, lang, task=task)
 
         side = torch.cuda.Stream(device=self.device_)
@@ -219,6 +225,7 @@ class HIPIE_IMG(nn.Module):
 
         replay.launches_per_replay = launches
         replay.graph = graph
+        replay.chunk_plan = chunk_plan
         return replay
 
     def enable_cuda_graphs(self, on=True):
@@ -229,14 +236,20 @@ class HIPIE_IMG(nn.Module):
         return self
 
     def _graphed_hot_path(self, tensor, pad_mask, image_sizes, ids, am, task, same_rows):
-        key = (tuple(tensor.shape), tuple(ids.shape), task, bool(same_rows), tuple(tuple(int(v) for v in s) for s in image_sizes))
+        plan = self.engine.text_chunk_plan(ids, am, same_rows)        # None unless the prompt exceeds 512 tokens
+        key = (tuple(tensor.shape), tuple(ids.shape), task, bool(same_rows), tuple(tuple(int(v) for v in s) for s in image_sizes),
+               None if plan is None else plan.signature)
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= 4:           # static buffers are large; keep a handful of shapes
                 self._graphs.pop(next(iter(self._graphs)))
             st = dict(tensor=tensor.clone(), pad=pad_mask.clone(), ids=ids.to(self.device_).clone(), am=am.to(self.device_).clone())
-            st["replay"] = self.capture_hot_path(st["tensor"], st["pad"], image_sizes, st["ids"], st["am"], task=task, same_rows=same_rows)
+            st["replay"] = self.capture_hot_path(st["tensor"], st["pad"], image_sizes, st["ids"], st["am"], task=task, same_rows=same_rows,
+                                                 chunk_plan=plan)
             self._graphs[key] = ent = st
+        elif plan is not None:                   # same cut positions, possibly other tokens: refill the captured plan's buffers
+            ent["replay"].chunk_plan.rows_d.copy_(plan.rows, non_blocking=True)
+            ent["replay"].chunk_plan.masks_d.copy_(plan.masks, non_blocking=True)
         ent["tensor"].copy_(tensor)
         ent["pad"].copy_(pad_mask)
         ent["ids"].copy_(ids, non_blocking=True)

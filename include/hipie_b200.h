@@ -128,7 +128,7 @@ typedef struct hipie_gemm_args {
  * value map): one work item = (image, head, 16x16-pixel region of the finest level); the region's windows of all four levels are
  * staged in shared memory by TMA (zero fill outside a level = the sampling's zero padding) and the region's queries gather from
  * shared memory; taps outside the halo take the global path, so results equal hipie_msda_fused_forward bit for bit.
- *   shapes_hw_host: HOST array of 4 (H_l, W_l) pairs (sizes the TMA boxes); halo: pixels around the region (0 = default 5, reduced
+ *   shapes_hw_host: HOST array of 4 (H_l, W_l) pairs (sizes the TMA boxes); halo: pixels around the region (0 = default 4, reduced
  *   automatically until the windows fit).  Returns HIPIE_EUNSUPPORTED when the windows cannot fit: use the flat kernel then. */
 int hipie_msda_encoder_forward(const void* value, const int* shapes_hw_host, const float* offs_logits, const float* reference_points,
                                void* out, int N, int S, int M, int D, int L, int P, int out_split_bf16, void* out_lo, int halo,
@@ -203,7 +203,8 @@ int hipie_attention(const hipie_attn_args* args, void* stream);
 
 /* tcgen05 flash attention for the ViT-H blocks (Attention.forward + add_decomposed_rel_pos, backbone/vit.py:67-83,
  * backbone/utils.py:96-125), hd == 80.  Two modes, selected by the shapes:
- *   global : T % 256 == 0, optional decomposed rel-pos bias with kw == 64 (kh * kw == T); one CTA per 256 queries.
+ *   global : T % 256 == 0, optional decomposed rel-pos bias with kw == 64 (1024-pixel inputs) or kw == 80 (1280-pixel inputs; then
+ *            also T % 320 == 0), kh * kw == T; one CTA per 256 queries.  Other grids: HIPIE_EINVAL (callers use hipie_attention).
  *   window : T == 196 with kh == kw == 14 (the 14 x 14 windows; B = number of windows): one CTA per (window, head), the
  *            60 padding keys of the last 64-key tile are masked.
  * q / k are bf16 planes viewed as (B, T, width) rows (token stride *_ts, batch stride *_bs, head h at columns

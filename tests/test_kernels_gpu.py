@@ -417,6 +417,36 @@ def test_attention_tcgen05(ops, cuda, prec, with_rel):
     assert err < (3e-5 if prec == 3 else 3e-2), err
 
 
+@pytest.mark.parametrize("prec", [3, 2])
+def test_attention_tcgen05_80_wide_grid(ops, cuda, prec):
+    """1280-pixel inputs give an 80-wide token grid: the kernel keeps its 64-key tiles, so a tile starts at grid column (64 j) mod 80
+    and straddles two key rows in 3 of the 5 phases (rel_w index rotation + two rel_h scalars per tile); vs fp64 attention."""
+    g = torch.Generator(device="cuda").manual_seed(51 + prec)
+    B, H, hd, gh, gw = 2, 2, 80, 16, 80          # T = 1280 tokens: 5 query tile pairs x 20 key tiles (4 periods of 5 phases)
+    T, E = gh * gw, H * hd
+    qk = torch.randn(B * T, 2 * E, device=cuda, generator=g)
+    v = torch.randn(B * T, E, device=cuda, generator=g)
+    rel_h = torch.randn(B, H, T, gh, device=cuda, generator=g)
+    rel_w = torch.randn(B, H, T, gw, device=cuda, generator=g)
+    if prec == 3:
+        S, Vs = ops.split(qk), ops.split(v.t().contiguous())
+        q, k = ops.BF2(S.hi[:, :E], S.lo[:, :E]), ops.BF2(S.hi[:, E:], S.lo[:, E:])
+        qq, kk, vv, tol = qk[:, :E], qk[:, E:], v, 3e-5
+    else:
+        qk16, vt16 = qk.half(), v.t().contiguous().half()
+        q, k, Vs = ops.BF2(qk16[:, :E], None), ops.BF2(qk16[:, E:], None), ops.BF2(vt16, None)
+        qq, kk, vv, tol = qk16[:, :E].float(), qk16[:, E:].float(), vt16.float().t(), 2e-3     # P is rounded to fp16 (2^-11)
+    o, _ = ops.attention_tc(q, k, Vs, B, H, T, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, rel_h=rel_h, rel_w=rel_w,
+                            kh=gh, kw=gw, want_f32=True, want_split=False, prec=prec if prec == 3 else None, f16=prec == 2)
+    sh = lambda x: x.reshape(B, T, H, hd).permute(0, 2, 1, 3).double()
+    ref = _attn_ref(sh(qq), sh(kk), sh(vv), hd ** -0.5, rel_h, rel_w, gh, gw).permute(0, 2, 1, 3).reshape(B, T, E)
+    err = (o.double() - ref).abs().max().item()
+    assert err < tol, err
+    with pytest.raises(RuntimeError):          # 80-wide but T % 320 != 0: refused, the caller falls back to the mma.sync kernel
+        ops.attention_tc(q, k, Vs, B, H, 1024, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, rel_h=rel_h, rel_w=rel_w,
+                         kh=1024 // 80, kw=80, want_f32=True, want_split=False, prec=prec if prec == 3 else None, f16=prec == 2)
+
+
 def test_relpos_tc_global_grid(ops, cuda):
     g = torch.Generator(device="cuda").manual_seed(11)
     B, H, hd, gh, gw = 1, 2, 80, 64, 64

@@ -351,6 +351,26 @@ def test_bert_chunk_path_over_512_tokens(cuda):
         so, sg = ro["sem_seg"], rg["sem_seg"].cpu()
         assert so.shape[0] == 230 and (so.argmax(0) == sg.argmax(0)).float().mean() > 0.9995
         assert [s["category_id"] for s in ro["panoptic_seg"][1]] == [s["category_id"] for s in rg["panoptic_seg"][1]]
+    # serving mode: the cut positions are planned on the host before the capture (the capture itself may not read the ids back);
+    # the replay with other tokens at the same cut positions refills the plan's buffers and must equal the eager result
+    eager = model(inputs)
+    ids2 = ids.clone()
+    word = (am[0] == 1) & (ids[0] != 1012) & (ids[0] != 101) & (ids[0] != 102)
+    ids2[0, word] = (ids[0, word] + 7) % 900 + 1100
+    inputs2 = [dict(x, input_ids=i) for x, i in zip(inputs, ids2)]
+    eager2 = model(inputs2)
+    model.enable_cuda_graphs(True)
+    try:
+        cap = model(inputs)
+        rep2 = model(inputs2)
+        assert len(model._graphs) == 1                    # same plan signature: one graph, refilled
+    finally:
+        model.enable_cuda_graphs(False)
+    for e, g in ((eager, cap), (eager2, rep2)):
+        for re_, rg in zip(e, g):
+            assert torch.equal(re_["instances"].pred_classes, rg["instances"].pred_classes)
+            assert (re_["sem_seg"] - rg["sem_seg"]).abs().max() < 1e-5
+    assert (eager[0]["sem_seg"] - eager2[0]["sem_seg"]).abs().max() > 1e-4          # the second prompt is a different prompt
 
 
 def test_pybind_shim_through_reference_style_function(cuda):
@@ -440,5 +460,5 @@ def test_predictor_and_registry_components(setup, cuda, tmp_path):
     with torch.no_grad():
         ref_md = setup["oracle"].detr.mask_dino(ref)
     out_md, _ = head(ref)
-    assert _err(out_md["pred_masks"], ref_md["pred_masks"]) < 1e-3 or not torch.equal(out_md["pred_masks"].argmax(1).cpu(), ref_md["pred_masks"].argmax(1)) is None
+    assert _err(out_md["pred_masks"], ref_md["pred_masks"]) < 1e-3
     assert out_md["pred_masks"].shape == ref_md["pred_masks"].shape and out_md["pred_logits"].shape == ref_md["pred_logits"].shape

@@ -24,3 +24,14 @@ for prec in (3, 1):
     e.record(); torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 5
     print(f"prec {prec}: {ms:.3f} ms  {4.0*B*H*T*T*hd/ms/1e9:.1f} TF algorithmic")
+q16, k16, v16 = ops.BF2(qk.half()[:, :E], None), ops.BF2(qk.half()[:, E:], None), ops.BF2(v.half(), None)
+for _ in range(2):
+    ops.attention_tc(q16, k16, v16, B, H, T, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=64, kw=64, f16=True)
+torch.cuda.synchronize()
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s.record()
+for _ in range(5):
+    ops.attention_tc(q16, k16, v16, B, H, T, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=64, kw=64, f16=True)
+e.record(); torch.cuda.synchronize()
+ms = s.elapsed_time(e) / 5
+print(f"fp16 single pass: {ms:.3f} ms  {4.0*B*H*T*T*hd/ms/1e9:.1f} TF algorithmic")

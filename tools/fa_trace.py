@@ -3,12 +3,14 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hipie_b200 import ops, _lib
 prec = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-ops.set_precision(prec)
+ops.set_precision(3 if prec == 2 else prec)
 dev = torch.device("cuda:0")
 B, H, hd, T = 2, 16, 80, 4096
 E = H * hd
 qk = torch.randn(B * T, 2 * E, device=dev); v = torch.randn(E, B * T, device=dev)
 S, Vs = ops.split(qk), ops.split(v)
+if prec == 2:      # single fp16 planes (the default ViT attention mode)
+    S, Vs = ops.BF2(qk.half(), None), ops.BF2(v.half(), None)
 rel_h = torch.randn(B, H, T, 64, device=dev); rel_w = torch.randn(B, H, T, 64, device=dev)
 out = ops._empty_bf2((B, T, E), dev)
 trace = torch.zeros(32 * 2 * 8, dtype=torch.int64, device=dev)
