@@ -41,7 +41,7 @@ class AttnArgs(ctypes.Structure):
         ("key_bias", c_void_p),
         ("out_f32", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p), ("o_bs", c_int64), ("o_ts", c_int64),
         ("B", c_int), ("H", c_int), ("Tq", c_int), ("Tk", c_int), ("hd", c_int),
-        ("scale", c_float), ("prec", c_int),
+        ("scale", c_float), ("prec", c_int), ("key_mask", c_void_p),
     ]
 
 

@@ -56,6 +56,7 @@ struct AttnParams {
     const float *rel_h, *rel_w;
     int kh, kw;
     const float* key_bias;
+    const uint32_t* key_mask;     // (B, Tq, ceil(Tk/32)) bit words: bit set = key masked out for that query, or null
     float* out_f32;
     __nv_bfloat16 *out_hi, *out_lo;
     int64_t o_bs, o_ts;
@@ -160,6 +161,12 @@ attention_kernel(const AttnParams p) {
         }
     }
     const float* kb = p.key_bias ? p.key_bias + (int64_t)b * p.Tk : nullptr;
+    const int mask_words = (p.Tk + 31) / 32;
+    const uint32_t* km_r[2] = {nullptr, nullptr};      // this thread's two query rows of the boolean attention mask
+    if (p.key_mask) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) km_r[i] = p.key_mask + ((int64_t)b * p.Tq + min(qrow[i], p.Tq - 1)) * mask_words;
+    }
     // one KV tile == one key row of the grid (kw == 64): rel_w terms are tile-invariant -> registers
     const bool hoist = has_rel && p.kw == ATT_BN;
     // otherwise (14x14 windows, 80-wide grids): the CTA's 64 x (kh + kw) table rows are staged in shared memory once,
@@ -227,6 +234,15 @@ attention_kernel(const AttnParams p) {
         float mx[2] = {-INFINITY, -INFINITY};
         float rh0 = 0.f, rh1 = 0.f;
         if (hoist) { rh0 = __ldg(relh_r[0] + t); rh1 = __ldg(relh_r[1] + t); }
+        uint32_t km0[2] = {0u, 0u}, km1[2] = {0u, 0u};       // mask words of this 64-key tile
+        if (km_r[0]) {
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int wi = t * 2 + w;
+                km0[w] = wi < mask_words ? __ldg(km_r[0] + wi) : 0u;
+                km1[w] = wi < mask_words ? __ldg(km_r[1] + wi) : 0u;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < ATT_BN / 8; ++j) {
             const int key = kv0 + j * 8 + (lane & 3) * 2;
@@ -246,8 +262,10 @@ attention_kernel(const AttnParams p) {
                     }
                     if (kb) { const float kbv = __ldg(kb + kk); add0 += kbv; add1 += kbv; }
                 }
-                s[j][e] = ok ? s[j][e] * p.scale + add0 : -INFINITY;
-                s[j][2 + e] = ok ? s[j][2 + e] * p.scale + add1 : -INFINITY;
+                const int kbit = (j * 8 + (lane & 3) * 2 + e) & 31, kw_ = j >> 2;       // key index inside the tile: word j / 4
+                const bool ok0 = ok && !((km0[kw_] >> kbit) & 1u), ok1 = ok && !((km1[kw_] >> kbit) & 1u);
+                s[j][e] = ok0 ? s[j][e] * p.scale + add0 : -INFINITY;
+                s[j][2 + e] = ok1 ? s[j][2 + e] * p.scale + add1 : -INFINITY;
                 mx[0] = fmaxf(mx[0], s[j][e]);
                 mx[1] = fmaxf(mx[1], s[j][2 + e]);
             }
@@ -529,6 +547,7 @@ extern "C" int hipie_attention(const hipie_attn_args* a, void* stream) {
     p.v_bs = a->v_bs; p.v_ts = a->v_ts; p.v_hs = a->v_hs;
     p.rel_h = a->rel_h; p.rel_w = a->rel_w; p.kh = a->kh; p.kw = a->kw;
     p.key_bias = a->key_bias;
+    p.key_mask = a->key_mask;
     p.out_f32 = a->out_f32; p.out_hi = (__nv_bfloat16*)a->out_hi; p.out_lo = (__nv_bfloat16*)a->out_lo;
     p.o_bs = a->o_bs; p.o_ts = a->o_ts;
     p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk; p.scale = a->scale;

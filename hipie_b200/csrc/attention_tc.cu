@@ -47,10 +47,19 @@ constexpr int FA_REGS_SOFTMAX = 216, FA_REGS_ISSUE = 72;      // 256 * 216 + 128
 constexpr int FA_QT = 2;           // query tiles per CTA (ping-pong: one in softmax while the other is in the tensor pipe)
 // tensor-memory map (columns), per query tile t at column 256 * t
 constexpr int TM_TILE = 256;
-constexpr int TM_S = 0;            // 64 fp32 score columns
-constexpr int TM_P = 64;           // P hi: 32 columns of packed bf16 pairs, P lo: next 32
-constexpr int TM_O = 128;          // 80 fp32 output columns
-constexpr int TM_Q = 208;          // Q hi: 40 columns of packed bf16 pairs (Q lo stays in shared memory)
+// Single-pass modes (PREC == 1: bf16 or fp16 operands) append a ROW OF ONES to every V^T tile, so the PV MMA (N = 96 instead of
+// 80) also accumulates the softmax denominator sum_k P[q, k] in output column 80: the 64 row-sum additions per tile leave the
+// exp phase, which is the serialised resource of the two softmax warps sharing a MUFU unit (see tile_body), and the denominator
+// is the sum of exactly the rounded probabilities the numerator used.  The 3-pass mode has no TMEM columns left for it.
+template <int PREC>
+struct FaTm {
+    static constexpr bool SUMCOL = PREC != 3;
+    static constexpr int S = 0;                        // 64 fp32 score columns
+    static constexpr int P = 64;                       // P hi: 32 columns of packed 16-bit pairs; (3-pass) P lo: next 32
+    static constexpr int Q = SUMCOL ? 96 : 208;        // Q hi: 40 columns of packed pairs (Q lo stays in shared memory)
+    static constexpr int O = SUMCOL ? 136 : 128;       // fp32 output columns: 80 (+ 16: column 80 = row sum, 81..95 zero)
+    static constexpr int ON = SUMCOL ? 96 : FA_HD;     // N of the PV MMA
+};
 
 struct FaMaps {
     CUtensorMap k64[2], k16[2], vt[2];   // [hi, lo]
@@ -75,7 +84,8 @@ template <int PREC>
 struct FaSmem {
     static constexpr int NPL = PREC == 3 ? 2 : 1;
     static constexpr int K64 = FA_BN * 128, K16 = FA_BN * 32;
-    static constexpr int VT = FA_HD * 128;
+    static constexpr int VT = FaTm<PREC>::ON * 128;   // (single-pass modes: + 16 rows, the first of them all ones)
+    static constexpr int V_TX = NPL * FA_HD * 128;    // bytes one stage receives by TMA
     static constexpr int K_STAGE = NPL * (K64 + K16);
     static constexpr int V_STAGE = NPL * VT;
     static constexpr int Q64 = FA_BM * 128, Q16 = FA_BM * 32;
@@ -98,6 +108,7 @@ template <int PREC, bool WIN, bool F16, bool TRACE, int GW>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     using SM = FaSmem<PREC>;
+    using TM = FaTm<PREC>;
     constexpr int NPL = SM::NPL;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared address space (LDS / STS)
@@ -142,6 +153,15 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         tmem_alloc(tmem_ptr, 512);
         tmem_relinquish();
     }
+    if (TM::SUMCOL) {
+        // rows 80..95 of every V^T stage: row 80 all ones (fp16 / bf16 1.0), the rest zero; TMA only ever rewrites rows 0..79
+        const uint32_t ones2 = F16 ? 0x3C003C00u : 0x3F803F80u;
+        for (int i = threadIdx.x; i < FA_STAGES * 512; i += FA_THREADS) {
+            const int st = i >> 9, w = i & 511;
+            reinterpret_cast<uint32_t*>(smem + SM::OFF_V + st * SM::V_STAGE + FA_HD * 128)[w] = w < 32 ? ones2 : 0u;
+        }
+        fence_proxy_async_smem();          // generic-proxy writes -> visible to the MMA's async-proxy reads
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -171,7 +191,7 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                     tma_load_3d(kb + pl * (SM::K64 + SM::K16) + SM::K64, &maps.k16[pl], &k_full[s], p.k_col0 + h * FA_HD + 64, j * FA_BN, b);
                 }
                 mbar_wait(&v_empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&v_full[s], SM::V_STAGE);
+                mbar_arrive_expect_tx(&v_full[s], SM::V_TX);
                 uint8_t* vb = smem + SM::OFF_V + s * SM::V_STAGE;
                 for (int pl = 0; pl < NPL; ++pl)
                     tma_load_3d(vb + pl * SM::VT, &maps.vt[pl], &v_full[s], b * (WIN ? FA_WIN_TP : p.T) + j * FA_BN, h * FA_HD, 0);
@@ -187,9 +207,9 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         // the pipe busy while one tile waits on its softmax.  Latency-critical waits poll (test_wait) instead of suspending.
         const int t = warp - FA_W_MMA0;
         constexpr uint32_t idesc_qk = F16 ? make_idesc_f16(FA_BM, FA_BN) : make_idesc_bf16(FA_BM, FA_BN);
-        constexpr uint32_t idesc_pv = F16 ? make_idesc_f16(FA_BM, FA_HD) : make_idesc_bf16(FA_BM, FA_HD);
+        constexpr uint32_t idesc_pv = F16 ? make_idesc_f16(FA_BM, TM::ON) : make_idesc_bf16(FA_BM, TM::ON);
         const uint32_t tb = tmem_base + t * TM_TILE;
-        const uint32_t dS = tb + TM_S, dO = tb + TM_O, tq = tb + TM_Q, tp_hi = tb + TM_P, tp_lo = tb + TM_P + 32;
+        const uint32_t dS = tb + TM::S, dO = tb + TM::O, tq = tb + TM::Q, tp_hi = tb + TM::P, tp_lo = tb + TM::P + 32;
         const uint32_t qb = smem_u32(smem + SM::OFF_Q + t * SM::Q_TILE);
         auto issue_qk = [&](int j) {
             const int st = j % FA_STAGES;
@@ -278,11 +298,11 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                             a3 = qok ? src[4 * c + 3] : zero4;
                 w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
                 w[8] = a2.x; w[9] = a2.y; w[10] = a2.z; w[11] = a2.w; w[12] = a3.x; w[13] = a3.y; w[14] = a3.z; w[15] = a3.w;
-                tmem_st_32x32b_x16(tm + TM_Q + 16 * c, w);
+                tmem_st_32x32b_x16(tm + TM::Q + 16 * c, w);
             }
             const uint4 a8 = qok ? src[8] : zero4, a9 = qok ? src[9] : zero4;
-            tmem_st_32x32b_x4(tm + TM_Q + 32, a8.x, a8.y, a8.z, a8.w);
-            tmem_st_32x32b_x4(tm + TM_Q + 36, a9.x, a9.y, a9.z, a9.w);
+            tmem_st_32x32b_x4(tm + TM::Q + 32, a8.x, a8.y, a8.z, a8.w);
+            tmem_st_32x32b_x4(tm + TM::Q + 36, a9.x, a9.y, a9.z, a9.w);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -347,11 +367,11 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             float tv[FA_BN];
             {
                 uint32_t sv[32];
-                tmem_ld_32x32b_x32(tm + TM_S, sv);
+                tmem_ld_32x32b_x32(tm + TM::S, sv);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) tv[i] = score(sv[i], j, i, OFF);
-                tmem_ld_32x32b_x32(tm + TM_S + 32, sv);
+                tmem_ld_32x32b_x32(tm + TM::S + 32, sv);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -380,13 +400,13 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 mbar_wait(&pv_done[t], (j - 1) & 1);           // PV_t(j-1) retired: P_t is free and O_t is current (long done normally)
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, need)) {           // warp-uniform: tcgen05.ld/st are warp-collective (rare once the max settles)
-                    for (int c = 0; c < FA_HD; c += 16) {
+                    for (int c = 0; c < TM::ON; c += 16) {       // (single-pass modes: incl. the row-sum column)
                         uint32_t o[16];
-                        tmem_ld_32x32b_x16(tm + TM_O + c, o);
+                        tmem_ld_32x32b_x16(tm + TM::O + c, o);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-                        tmem_st_32x32b_x16(tm + TM_O + c, o);
+                        tmem_st_32x32b_x16(tm + TM::O + c, o);
                     }
                 }
             }
@@ -395,29 +415,33 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
             // they run in lock step and their 64-ex2 phases collide (ncu r02: 16 cycles per MUFU.EX2, XU 43 % busy overall); a
             // named-barrier hand-off makes the exp phases alternate, so one warp's exponentials overlap the other's TMEM loads,
             // max reduction and mbarrier waits.
+            // exponent arguments now, outside the hand-off: the exp phase below is only ex2 + pack + tcgen05.st
+            {
+                const float off = m - rh, offb = m - rhb;
+#pragma unroll
+                for (int i = 0; i < FA_BN; ++i) tv[i] -= (i < SPLIT ? off : offb);
+            }
             named_bar_sync(1 + 2 * quarter + t, 64);
-            const float off = m - rh, offb = m - rhb;
             float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < FA_BN; c += 16) {
                 uint32_t ph_[8], pl_[8];
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    const float e0 = ex2_approx(tv[c + i] - (c + i < SPLIT ? off : offb));
-                    const float e1 = ex2_approx(tv[c + i + 1] - (c + i + 1 < SPLIT ? off : offb));
-                    rs[(i >> 1) & 3] += e0 + e1;
+                    const float e0 = ex2_approx(tv[c + i]), e1 = ex2_approx(tv[c + i + 1]);
+                    if (!TM::SUMCOL) rs[(i >> 1) & 3] += e0 + e1;
                     if (PREC == 3) split2(e0, e1, ph_[i >> 1], pl_[i >> 1]);
                     else ph_[i >> 1] = F16 ? pack_f16x2(e0, e1) : pack_bf16x2(e0, e1);
                 }
-                tmem_st_32x32b_x4(tm + TM_P + (c >> 1), ph_[0], ph_[1], ph_[2], ph_[3]);
-                tmem_st_32x32b_x4(tm + TM_P + (c >> 1) + 4, ph_[4], ph_[5], ph_[6], ph_[7]);
+                tmem_st_32x32b_x4(tm + TM::P + (c >> 1), ph_[0], ph_[1], ph_[2], ph_[3]);
+                tmem_st_32x32b_x4(tm + TM::P + (c >> 1) + 4, ph_[4], ph_[5], ph_[6], ph_[7]);
                 if (PREC == 3) {
-                    tmem_st_32x32b_x4(tm + TM_P + 32 + (c >> 1), pl_[0], pl_[1], pl_[2], pl_[3]);
-                    tmem_st_32x32b_x4(tm + TM_P + 32 + (c >> 1) + 4, pl_[4], pl_[5], pl_[6], pl_[7]);
+                    tmem_st_32x32b_x4(tm + TM::P + 32 + (c >> 1), pl_[0], pl_[1], pl_[2], pl_[3]);
+                    tmem_st_32x32b_x4(tm + TM::P + 32 + (c >> 1) + 4, pl_[4], pl_[5], pl_[6], pl_[7]);
                 }
             }
             if (t == 0 || j + 1 < ntiles) named_bar_arrive(1 + 2 * quarter + (t ^ 1), 64);   // the other tile's exp phase may start
-            l += (rs[0] + rs[1]) + (rs[2] + rs[3]);
+            if (!TM::SUMCOL) l += (rs[0] + rs[1]) + (rs[2] + rs[3]);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -438,12 +462,18 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         // ---- epilogue: O / l ----
         mbar_wait(&pv_done[t], (ntiles - 1) & 1);
         tc_fence_after();
+        if (TM::SUMCOL) {                 // the denominator came out of the PV MMA: output column 80
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tm + TM::O + FA_HD, o);
+            tmem_ld_wait();
+            l = __uint_as_float(o[0]);
+        }
         const float inv = 1.f / l;
         const int64_t obase = (int64_t)b * p.o_bs + (int64_t)qrow * p.o_ts + (int64_t)h * FA_HD;
         const bool row_ok = !WIN || qrow < p.T;
         for (int c = 0; c < FA_HD; c += 16) {
             uint32_t o[16];
-            tmem_ld_32x32b_x16(tm + TM_O + c, o);
+            tmem_ld_32x32b_x16(tm + TM::O + c, o);
             tmem_ld_wait();
             float f[16];
 #pragma unroll

@@ -86,15 +86,17 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == HIPIE_ACT_RELU) return fmaxf(v, 0.f);
     if (act == HIPIE_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
     if (act == HIPIE_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    if (act == HIPIE_ACT_QUICK_GELU) return v / (1.f + expf(-1.702f * v));
     return v;
 }
 
-
+// QuickGELU (x * sigmoid(1.702 x): OpenAI CLIP's activation, open_clip model.py QuickGELU) shares the SIGMOID instantiation of
+// the epilogues -- one uniform flag instead of a fourth copy of every epilogue
 template <int ACT>
-__device__ __forceinline__ float act_apply_t(float v) {
+__device__ __forceinline__ float act_apply_t(float v, bool quick) {
     if (ACT == HIPIE_ACT_RELU) return fmaxf(v, 0.f);
     if (ACT == HIPIE_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-    if (ACT == HIPIE_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    if (ACT == HIPIE_ACT_SIGMOID) return quick ? v / (1.f + expf(-1.702f * v)) : 1.f / (1.f + expf(-v));
     return v;
 }
 
@@ -157,10 +159,10 @@ __device__ __forceinline__ void epilogue_rows_fast(const GemmParams& p, uint32_t
         for (int it = 0; it < 4; ++it) {
             const int rr = it * 8 + rsub;
             float4 x = lds128(es + rr * (EPI_LD * 4) + (((lane & 3) ^ ((rr >> 1) & 3)) << 4));
-            x.x = act_apply_t<ACT>(fmaf(x.x, alpha, bias.x));
-            x.y = act_apply_t<ACT>(fmaf(x.y, alpha, bias.y));
-            x.z = act_apply_t<ACT>(fmaf(x.z, alpha, bias.z));
-            x.w = act_apply_t<ACT>(fmaf(x.w, alpha, bias.w));
+            x.x = act_apply_t<ACT>(fmaf(x.x, alpha, bias.x), p.act == HIPIE_ACT_QUICK_GELU);
+            x.y = act_apply_t<ACT>(fmaf(x.y, alpha, bias.y), p.act == HIPIE_ACT_QUICK_GELU);
+            x.z = act_apply_t<ACT>(fmaf(x.z, alpha, bias.z), p.act == HIPIE_ACT_QUICK_GELU);
+            x.w = act_apply_t<ACT>(fmaf(x.w, alpha, bias.w), p.act == HIPIE_ACT_QUICK_GELU);
             if (cs_t) { x.x *= cs.x; x.y *= cs.y; x.z *= cs.z; x.w *= cs.w; }
             if (res_t) {
                 const float4 rv = *reinterpret_cast<const float4*>(res_t + rr * ldr + cb);
@@ -235,10 +237,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
             const int rr = it * 8 + rsub;
             if (rr >= rmax || col >= p.N) continue;
             float4 x = *reinterpret_cast<const float4*>(my_epi + rr * EPI_LD + (((lane & 3) ^ ((rr >> 1) & 3)) << 2));
-            x.x = act_apply_t<ACT>(x.x * p.alpha + bias.x) * cs.x;
-            x.y = act_apply_t<ACT>(x.y * p.alpha + bias.y) * cs.y;
-            x.z = act_apply_t<ACT>(x.z * p.alpha + bias.z) * cs.z;
-            x.w = act_apply_t<ACT>(x.w * p.alpha + bias.w) * cs.w;
+            x.x = act_apply_t<ACT>(x.x * p.alpha + bias.x, p.act == HIPIE_ACT_QUICK_GELU) * cs.x;
+            x.y = act_apply_t<ACT>(x.y * p.alpha + bias.y, p.act == HIPIE_ACT_QUICK_GELU) * cs.y;
+            x.z = act_apply_t<ACT>(x.z * p.alpha + bias.z, p.act == HIPIE_ACT_QUICK_GELU) * cs.z;
+            x.w = act_apply_t<ACT>(x.w * p.alpha + bias.w, p.act == HIPIE_ACT_QUICK_GELU) * cs.w;
             int64_t row = m0 + rr;
             if (p.row_map) {
                 row = p.row_map[(int64_t)b * p.M + row];
@@ -328,10 +330,10 @@ __device__ __forceinline__ void epilogue_rows_tma(const GemmParams& p, const CUt
                                        __uint_as_float(v[4 * g + 3]));
                 float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias) bias = load4_guard(p.bias, col, p.N, 0.f);
-                x.x = act_apply_t<ACT>(fmaf(x.x, alpha, bias.x));
-                x.y = act_apply_t<ACT>(fmaf(x.y, alpha, bias.y));
-                x.z = act_apply_t<ACT>(fmaf(x.z, alpha, bias.z));
-                x.w = act_apply_t<ACT>(fmaf(x.w, alpha, bias.w));
+                x.x = act_apply_t<ACT>(fmaf(x.x, alpha, bias.x), p.act == HIPIE_ACT_QUICK_GELU);
+                x.y = act_apply_t<ACT>(fmaf(x.y, alpha, bias.y), p.act == HIPIE_ACT_QUICK_GELU);
+                x.z = act_apply_t<ACT>(fmaf(x.z, alpha, bias.z), p.act == HIPIE_ACT_QUICK_GELU);
+                x.w = act_apply_t<ACT>(fmaf(x.w, alpha, bias.w), p.act == HIPIE_ACT_QUICK_GELU);
                 if (p.colscale) {
                     const float4 cs = load4_guard(p.colscale, col, p.N, 1.f);
                     x.x *= cs.x; x.y *= cs.y; x.z *= cs.z; x.w *= cs.w;
@@ -621,6 +623,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     switch (p.act) {
                         case HIPIE_ACT_RELU: epilogue_rows_tma<HIPIE_ACT_RELU>(p, &tm_c_f32, &tm_c_hi, &tm_c_lo, taddr, my_sbuf, b, m0, n0, cbeg, cend, lane); break;
                         case HIPIE_ACT_GELU: epilogue_rows_tma<HIPIE_ACT_GELU>(p, &tm_c_f32, &tm_c_hi, &tm_c_lo, taddr, my_sbuf, b, m0, n0, cbeg, cend, lane); break;
+                        case HIPIE_ACT_QUICK_GELU:
                         case HIPIE_ACT_SIGMOID: epilogue_rows_tma<HIPIE_ACT_SIGMOID>(p, &tm_c_f32, &tm_c_hi, &tm_c_lo, taddr, my_sbuf, b, m0, n0, cbeg, cend, lane); break;
                         default: epilogue_rows_tma<HIPIE_ACT_NONE>(p, &tm_c_f32, &tm_c_hi, &tm_c_lo, taddr, my_sbuf, b, m0, n0, cbeg, cend, lane); break;
                     }
@@ -628,6 +631,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                     switch (p.act) {
                         case HIPIE_ACT_RELU: epilogue_rows<HIPIE_ACT_RELU>(p, taddr, my_epi, b, m0, n0, cbeg, cend, lane); break;
                         case HIPIE_ACT_GELU: epilogue_rows<HIPIE_ACT_GELU>(p, taddr, my_epi, b, m0, n0, cbeg, cend, lane); break;
+                        case HIPIE_ACT_QUICK_GELU:
                         case HIPIE_ACT_SIGMOID: epilogue_rows<HIPIE_ACT_SIGMOID>(p, taddr, my_epi, b, m0, n0, cbeg, cend, lane); break;
                         default: epilogue_rows<HIPIE_ACT_NONE>(p, taddr, my_epi, b, m0, n0, cbeg, cend, lane); break;
                     }

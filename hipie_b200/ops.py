@@ -15,7 +15,7 @@ from . import _lib
 # 1 = plain bf16 (fast mode).
 PREC = 3
 
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SIGMOID, ACT_QUICK_GELU = 0, 1, 2, 3, 4
 
 
 def set_precision(prec: int):
@@ -351,8 +351,9 @@ def row_softmax(x, colbias=None, rows_per_batch=None, clampv=50000.0, sub_rowmax
 
 
 def attention(q: BF2, k: BF2, v: BF2, B, H, Tq, Tk, hd, q_strides, k_strides, v_strides, scale, rel_h=None, rel_w=None,
-              kh=0, kw=0, key_bias=None, want_f32=False, want_split=True, prec=None):
-    """q/k/v: planes with explicit (batch, token, head) element strides; output (B, Tq, H*hd)."""
+              kh=0, kw=0, key_bias=None, want_f32=False, want_split=True, prec=None, key_mask=None):
+    """q/k/v: planes with explicit (batch, token, head) element strides; output (B, Tq, H*hd).
+    key_mask: (B, Tq, ceil(Tk/32)) int32 bit words, bit set = key masked out for that query (boolean attn_mask, all heads)."""
     prec = PREC if prec is None else prec
     dev = q.hi.device
     o = torch.empty((B, Tq, H * hd), dtype=torch.float32, device=dev) if want_f32 else None
@@ -367,7 +368,7 @@ def attention(q: BF2, k: BF2, v: BF2, B, H, Tq, Tk, hd, q_strides, k_strides, v_
         kh=kh, kw=kw, key_bias=key_bias.data_ptr() if key_bias is not None else None,
         out_f32=o.data_ptr() if o is not None else None, out_hi=s.hi.data_ptr() if s else None,
         out_lo=s.lo.data_ptr() if (s and s.lo is not None) else None, o_bs=Tq * H * hd, o_ts=H * hd,
-        B=B, H=H, Tq=Tq, Tk=Tk, hd=hd, scale=float(scale), prec=prec)
+        B=B, H=H, Tq=Tq, Tk=Tk, hd=hd, scale=float(scale), prec=prec, key_mask=key_mask.data_ptr() if key_mask is not None else None)
     with _timed(f"attention[p{prec}]" + (":global" if Tq >= 1024 else ":small"), 4.0 * B * H * Tq * Tk * hd):
         _lib.check(_lib.load().hipie_attention(ctypes.byref(args), _stream()), "attention")
     return o, s

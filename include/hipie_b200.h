@@ -51,6 +51,7 @@ extern "C" {
 #define HIPIE_ACT_RELU 1
 #define HIPIE_ACT_GELU 2      /* exact erf GELU (timm Mlp / nn.GELU default) */
 #define HIPIE_ACT_SIGMOID 3
+#define HIPIE_ACT_QUICK_GELU 4 /* x * sigmoid(1.702 x): OpenAI CLIP (open_clip model.py, QuickGELU) */
 
 const char* hipie_last_error(void);
 int hipie_abi_version(void);
@@ -181,7 +182,7 @@ int hipie_row_softmax(const float* x, const float* colbias, int64_t rows, int64_
  *   q, k, v : bf16 split planes (hi, lo), logical shape (B, T, H, hd) with element strides
  *             given explicitly so the packed qkv GEMM output can be consumed in place.
  *   rel_h   : (B, H, Tq, kh) fp32 or NULL ; rel_w : (B, H, Tq, kw) fp32 or NULL ; Tk = kh*kw
- *   key_bias: (B, Tk) fp32 additive (0 / -inf style) or NULL
+ *   key_bias: (B, Tk) fp32 additive (0 / -inf style) or NULL ; key_mask: per-(batch, query) bit mask over the keys or NULL
  *   out     : (B, Tq, H*hd) fp32 and/or bf16 split.
  * scale is applied to q.k^T before the bias (reference: (q*scale) @ k^T + rel).
  * ------------------------------------------------------------------------------------------ */
@@ -197,6 +198,9 @@ typedef struct hipie_attn_args {
     int B, H, Tq, Tk, hd;
     float scale;
     int prec;
+    const uint32_t* key_mask;   /* optional (B, Tq, ceil(Tk / 32)) bit words shared by all heads: bit k of a query's row set = key k is
+                                 * masked OUT for that query (nn.MultiheadAttention's boolean attn_mask; MaskCLIP's per-query patch
+                                 * masks open_vocab/clip.py:288-332, the causal mask of the CLIP text transformer) */
 } hipie_attn_args;
 
 int hipie_attention(const hipie_attn_args* args, void* stream);

@@ -19,6 +19,9 @@ same outputs, which pins these rows of SURVEY.md §8a to the reference itself:
   ref_bert_chunk.pt   a7      bert_model.py BertEncoder.forward incl. the > 512-token chunk path (random-init HF BertModel)
   ref_postproc.pt     a20-a23 hipie_img.py convert_grounding_to_od_logits / semantic_inference / panoptic_inference,
                               ddetrs.py segmentation_postprocess
+  ref_maskclip.pt     a22/f2  open_vocab/clip.py MaskCLIP (mask tokens, per-query attention masks, logit ensembling) and ClipAdapter._encode_text
+                              on top of the restated open_clip 2.0.2 model (absent third-party dependency: hipie_oracle/clip.py), and
+                              hipie_img.py HIPIE_IMG.get_clip_logits (MUL and ADD fusion, seen / unseen weights)
 """
 import copy
 import os
@@ -333,8 +336,62 @@ def gen_r50():
     print("ref_r50.pt", {k: tuple(v.shape) for k, v in out.items()})
 
 
+def gen_maskclip():
+    """open_vocab/clip.py: the UNMODIFIED MaskCLIP / ClipAdapter classes, constructed through a stub `open_clip` whose
+    create_model_and_transforms returns hipie_oracle.clip.CLIP (the restated open_clip 2.0.2 model, tiny configuration) -- so the mask-token
+    construction, the attention-mask layout, ln_post / proj on the mask tokens, the logit scale clamp and the synonym ensembling that run
+    here are the reference's own lines.  get_clip_logits is the reference's HIPIE_IMG method, called on a stand-in `self`."""
+    import torchvision.transforms as T
+    from hipie_oracle import clip as oc
+    ref_import.install()
+    cfg = dict(oc.TINY)
+    model = oc.init_clip_(oc.CLIP(cfg), seed=31)
+    import open_clip                                   # the stub module
+    size = cfg["image_size"]
+    preprocess = T.Compose([T.Resize(size, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(size), (lambda im: im), (lambda im: im),
+                            T.Normalize(oc.OPENAI_MEAN, oc.OPENAI_STD)])      # open_clip transform.py image_transform(is_train=False)
+    open_clip.create_model_and_transforms = lambda *a, **k: (model, None, preprocess)
+    open_clip.tokenize = lambda texts: oc.synth_clip_tokenize(texts, cfg["text_ctx"], cfg["vocab"])
+    import detectron2.utils.comm as comm
+    comm.get_local_rank, comm.synchronize = (lambda: 0), (lambda: None)
+    rc = ref_import.ref("open_vocab.clip")
+    hi = ref_import.ref("hipie_img")
+    mc = rc.MaskCLIP(name="tiny")
+    g = torch.Generator().manual_seed(32)
+    Q, H, W = 7, 40, 60
+    image = torch.rand(1, 3, H, W, generator=g)
+    mask = torch.full((1, Q, H // 4, W // 4), -5.0)
+    for q in range(Q):                                   # blob-like mask logits: most patches are masked out, different ones per query
+        y0, x0 = int(torch.randint(0, H // 4 - 4, (1,), generator=g)), int(torch.randint(0, W // 4 - 5, (1,), generator=g))
+        mask[0, q, y0:y0 + 4, x0:x0 + 5] = 5.0
+    mask = mask + torch.randn(mask.shape, generator=g)
+    test_labels = [{"id": 1, "name": "person,child,girl"}, {"id": 2, "name": "wall"}, {"id": 3, "name": "zebra,okapi"}, {"id": 4, "name": "sky"},
+                   {"id": 5, "name": "traffic light,signal"}]
+    train_labels = [{"id": 1, "name": "person,people"}, {"id": 2, "name": "sky,clouds"}, {"id": 3, "name": "traffic light"}]
+    names = [x["name"].split(",") for x in test_labels]
+    labels = hi.prompt_labels(names, "photo")                           # helper.py:112-130 (imported by hipie_img.py)
+    flat = [t for ls in labels for t in ls]
+    ids = open_clip.tokenize(flat)
+    with torch.no_grad():
+        text_embed, text_enc = mc._encode_text(ids)                      # ClipAdapter._encode_text :152-166
+        text_embed2 = mc.build_text_embed(labels, always_cache=True)    # clip.py:29-73 through the stub tokenizer
+        out = mc(image, mask, text_embed, labels)
+        pred_open_prob = torch.softmax(torch.randn(Q, len(test_labels), generator=g) * 2, -1)
+        fused = {}
+        for mode in ("MUL", "ADD"):
+            fake = types.SimpleNamespace(train_labels=train_labels, clip=mc, clip_agg_mode=mode)
+            fused[mode] = hi.HIPIE_IMG.get_clip_logits(fake, 0, [test_labels], mask, types.SimpleNamespace(tensor=image), pred_open_prob,
+                                                       alpha=0.35, beta=0.7)
+        single = rc.MaskCLIP.pred_logits(mc, out["mask_embed"], text_embed[:1], [labels[0][:1]])       # one prompt: the sigmoid branch input
+    assert torch.equal(text_embed, text_embed2)
+    torch.save(dict(cfg=cfg, seed=31, image=image, mask=mask, ids=ids, labels=labels, test_labels=test_labels, train_labels=train_labels,
+                    text_embed=text_embed, mask_embed=out["mask_embed"], logits=out["mask_pred_open_logits"], pred_open_prob=pred_open_prob,
+                    fused=fused, single_logits=single, logit_scale=float(mc.logit_scale)), os.path.join(OUT, "ref_maskclip.pt"))
+    print("ref_maskclip.pt", tuple(out["mask_embed"].shape), tuple(out["mask_pred_open_logits"].shape), {k: tuple(v.shape) for k, v in fused.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["vit", "transformer", "maskdino", "condinst", "bert", "postproc", "prompts", "r50"]
+    which = sys.argv[1:] or ["vit", "transformer", "maskdino", "condinst", "bert", "postproc", "prompts", "r50", "maskclip"]
     for w in which:
         globals()["gen_" + w]()

@@ -160,6 +160,14 @@ class HipieOracle(nn.Module):
         self.mask_stride, self.mask_thres = 4, 0.5
         self.pano_temp, self.object_mask_threshold, self.overlap_threshold = 0.06, 0.25, 0.8
         self.max_pool, self.use_bg_for_pano, self.bg_cls_agnostic = hp.get("max_pool", False), False, hp.get("bg_cls_agnostic", False)
+        self.clip = None                 # MaskCLIP re-scoring (MODEL.CLIP.ENABLED, hipie_img.py:249-262): attach_clip()
+
+    def attach_clip(self, maskclip, train_labels, alpha=0.35, beta=0.7, fg_a=0.3, fg_b=1.7, agg_mode="MUL", pano_temp_fg=0.06):
+        """hipie_img.py:249-262: `maskclip` = hipie_oracle.clip.MaskCLIPOracle; `train_labels` = the COCO-panoptic prompt-engineered
+        label list the reference reads at :72 (list of {id, name})."""
+        object.__setattr__(self, "clip", maskclip)          # not a submodule: CLIP is never part of the state_dict (clip.py:125)
+        self.train_labels, self.clip_alpha, self.clip_beta = train_labels, alpha, beta
+        self.clip_fg_a, self.clip_fg_b, self.clip_agg_mode, self.pano_temp_fg = fg_a, fg_b, agg_mode, pano_temp_fg
 
     # ---------------------------------------------------------------- stages
     def preprocess(self, images):
@@ -296,8 +304,11 @@ class HipieOracle(nn.Module):
         return panoptic_seg, segments_info
 
     @torch.no_grad()
-    def inference(self, out, image_sizes, positive_map, num_classes, task, is_thing, sizes):
-        """hipie_img.py:537-766 (OTA path, CLIP off, demo_only False, decoupled MaskDINO decoder)."""
+    def inference(self, out, image_sizes, positive_map, num_classes, task, is_thing, sizes, clip_inputs=None):
+        """hipie_img.py:537-766 (OTA path, demo_only False, decoupled MaskDINO decoder).  With MaskCLIP attached, `clip_inputs[i]` =
+        dict(image=(3,H,W) in 0..1, test_labels=[{id,name}], text_embed=(n_prompts, D)) drives the two re-scoring sites :592-609
+        and :735-747."""
+        from .clip import get_clip_logits
         max_num_inst = 100 if task == "detection" else 1
         fg = self.num_bg
         box_cls, box_pred = out["pred_logits"][:, fg:], out["pred_boxes"][:, fg:]
@@ -310,7 +321,15 @@ class HipieOracle(nn.Module):
             has_thing = any(is_thing[i].values())
             logits_per_image = self.convert_grounding_to_od_logits(box_cls[i].unsqueeze(0), num_classes, positive_map, is_thing[i],
                                                                    mode="FG" if has_thing else None, max_pool=self.max_pool)[0]
-            prob = torch.sqrt(logits_per_image.sigmoid() * iou_pred[i].sigmoid())
+            if self.clip is not None:
+                ci = clip_inputs[i]
+                is_thing_mask = ~(logits_per_image[:1] == -9999.0)
+                p_model = F.softmax(logits_per_image.sigmoid() / self.pano_temp_fg, dim=-1) if logits_per_image.shape[-1] > 1 else logits_per_image.sigmoid()
+                prob = get_clip_logits(self.clip, ci["test_labels"], self.train_labels, mask_pred[i][None, :, 0], ci["image"][None], p_model,
+                                       ci["text_embed"], self.clip_alpha, self.clip_beta, self.clip_agg_mode).sigmoid() * is_thing_mask.float()
+                prob = torch.sqrt((prob ** self.clip_fg_a) * (iou_pred[i].sigmoid() ** self.clip_fg_b))
+            else:
+                prob = torch.sqrt(logits_per_image.sigmoid() * iou_pred[i].sigmoid())
             nms_scores, idxs = torch.max(prob, 1)
             boxes_before_nms = box_cxcywh_to_xyxy(box_pred[i])
             keep_indices = tvops.batched_nms(boxes_before_nms, nms_scores, idxs, 0.7)
@@ -339,6 +358,11 @@ class HipieOracle(nn.Module):
                 logits_all = F.softmax(logits_all.sigmoid() / self.pano_temp, dim=-1)
                 mask_all = F.interpolate(mask_all, size=(H * self.mask_stride, W * self.mask_stride), mode="bilinear", align_corners=False)
                 mask_all = mask_all[:, :, :image_size[0], :image_size[1]]
+                if self.clip is not None:
+                    ci = clip_inputs[i]
+                    clip_logits = get_clip_logits(self.clip, ci["test_labels"], self.train_labels, mask_all[None, :, 0], ci["image"][None],
+                                                  logits_all, ci["text_embed"], self.clip_alpha, self.clip_beta, self.clip_agg_mode)
+                    logits_all = clip_logits.softmax(-1)
                 mask_up = F.interpolate(mask_all, size=sizes[i], mode="bilinear", align_corners=False)[:, 0]
                 sem = self.semantic_inference(logits_all, mask_up)
                 pano = self.panoptic_inference(logits_all, mask_up, is_thing[i])
@@ -372,7 +396,11 @@ class HipieOracle(nn.Module):
         out = self.coco_inference(tensor, mask, image_sizes, lang, task=task, forced=forced)
         is_thing = [x["is_thing"] for x in batched_inputs]
         sizes = [(x.get("height", s[0]), x.get("width", s[1])) for x, s in zip(batched_inputs, image_sizes)]
-        results = self.inference(out, image_sizes, positive_map, num_classes, task, is_thing, sizes)
+        clip_inputs = None
+        if self.clip is not None:          # hipie_img.py:348-352: the un-normalised image / 255, open_seg_labels of every input
+            clip_inputs = [dict(image=x["image"] / 255.0, test_labels=x["open_seg_labels"],
+                                text_embed=self.clip.build_text_embed(x["clip_prompt_ids"])) for x in batched_inputs]
+        results = self.inference(out, image_sizes, positive_map, num_classes, task, is_thing, sizes, clip_inputs=clip_inputs)
         for r, x, s in zip(results, batched_inputs, image_sizes):
             r["instances_post"] = self.segmentation_postprocess(r["instances"], s, x.get("height", s[0]), x.get("width", s[1]))
         return results, out

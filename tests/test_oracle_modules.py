@@ -151,7 +151,7 @@ def test_postprocessing_matches_reference_inference(golden_dir):
                        pool["max_bg"])
     for tag, v in g["variants"].items():
         fake = types.SimpleNamespace(num_bg=g["nbg"], num_fg=g["nfg"], mask_stride=4, mask_thres=0.5, pano_temp=0.06, object_mask_threshold=0.25,
-                                     overlap_threshold=0.8, max_pool=v["max_pool"], use_bg_for_pano=False, bg_cls_agnostic=v["bg_cls_agnostic"])
+                                     overlap_threshold=0.8, max_pool=v["max_pool"], use_bg_for_pano=False, bg_cls_agnostic=v["bg_cls_agnostic"], clip=None)
         fake.convert_grounding_to_od_logits = HipieOracle.convert_grounding_to_od_logits
         fake.semantic_inference = lambda *a, f=fake: HipieOracle.semantic_inference(f, *a)
         fake.panoptic_inference = lambda *a, f=fake: HipieOracle.panoptic_inference(f, *a)
@@ -184,3 +184,37 @@ def test_resnet50_matches_reference(golden_dir):
         ref = g["out"][k]
         got = out[k][:, ::8]
         assert (got - ref).abs().max() < 1e-5 * ref.abs().max() + 1e-5, (k, (got - ref).abs().max())
+
+
+def test_maskclip_matches_reference(golden_dir):
+    """open_vocab/clip.py MaskCLIP + ClipAdapter._encode_text and hipie_img.py get_clip_logits, run unmodified on the restated
+    open_clip model (tiny configuration), against hipie_oracle.clip: mask embeddings, per-class logits (max over synonyms,
+    clamped logit scale) and the fused log-probabilities in both aggregation modes."""
+    from hipie_oracle import clip as oc
+    g = _load(golden_dir, "ref_maskclip.pt")
+    mc = oc.MaskCLIPOracle(oc.init_clip_(oc.CLIP(g["cfg"]), g["seed"]))
+    assert abs(float(mc.logit_scale) - g["logit_scale"]) < 1e-6
+    with torch.no_grad():
+        te = mc.build_text_embed(g["ids"])
+        out = mc(g["image"], g["mask"], te, g["labels"])
+    tol = lambda ref: 2e-5 * float(ref.abs().max()) + 2e-6
+    assert (te - g["text_embed"]).abs().max() < tol(g["text_embed"])
+    assert (out["mask_embed"] - g["mask_embed"]).abs().max() < tol(g["mask_embed"])
+    assert (out["mask_pred_open_logits"] - g["logits"]).abs().max() < tol(g["logits"])
+    assert torch.equal(oc.synth_clip_tokenize([t for ls in g["labels"] for t in ls], g["cfg"]["text_ctx"], g["cfg"]["vocab"]), g["ids"])
+    assert oc.prompt_labels([x["name"].split(",") for x in g["test_labels"]], "photo") == g["labels"]
+    assert oc.category_overlapping_mask(g["test_labels"], g["train_labels"]).tolist() == [1, 0, 0, 1, 1]
+    for mode, ref in g["fused"].items():
+        with torch.no_grad():
+            got = oc.get_clip_logits(mc, g["test_labels"], g["train_labels"], g["mask"], g["image"], g["pred_open_prob"], te, 0.35, 0.7, mode)
+        assert (got - ref).abs().max() < 2e-5 * float(ref.abs().max()) + 1e-5, mode
+    with torch.no_grad():
+        single = mc.pred_logits(out["mask_embed"], te[:1], [g["labels"][0][:1]])
+    assert (single - g["single_logits"]).abs().max() < tol(g["single_logits"])
+    # the attention mask the oracle builds is the reference's layout: nobody attends to mask tokens, CLS always visible
+    import torch.nn.functional as F
+    m336 = F.interpolate(g["mask"], size=(g["cfg"]["image_size"],) * 2, mode="bilinear", align_corners=False)
+    a = mc.attention_mask(m336)
+    Q = g["mask"].shape[1]
+    assert a.shape == (1, Q + 17, Q + 17) and bool(a[:, :, :Q].all()) and not bool(a[:, :, Q].any()) and not bool(a[:, Q:, Q:].any())
+    assert 0 < int(a[:, :Q, Q + 1:].sum()) < Q * 16
