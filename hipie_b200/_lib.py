@@ -85,6 +85,10 @@ SYMBOLS = {
     "hipie_class_scores": (c_int, [c_void_p] * 9 + [c_int] * 5 + [c_void_p]),
     "hipie_batched_nms": (c_int, [c_void_p] * 5 + [c_int, c_int, c_float, c_void_p]),
     "hipie_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "hipie_maskclip_patch_mask": (c_int, [c_void_p] + [c_int] * 8 + [c_void_p, c_int, c_int, c_void_p]),
+    "hipie_clip_patches": (c_int, [c_void_p] + [c_int] * 4 + [c_void_p] * 4 + [c_int, c_void_p]),
+    "hipie_clip_fuse": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_float, c_void_p, c_float, c_float, c_int,
+                                c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
 

@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhipie_b200.so")
 STAMP = os.path.join(HERE, ".libhipie_b200.stamp")
 
-SOURCES = ["core.cu", "msda.cu", "gemm_tc.cu", "norm.cu", "attention.cu", "attention_tc.cu", "misc.cu", "postproc.cu", "select.cu"]
+SOURCES = ["core.cu", "msda.cu", "gemm_tc.cu", "norm.cu", "attention.cu", "attention_tc.cu", "misc.cu", "postproc.cu", "select.cu", "maskclip.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",

@@ -60,6 +60,10 @@ def hp_from_cfg(cfg):
     hp.update(mask_stride=m.DDETRS.MASK_STRIDE, mask_thres=float(m.DDETRS.MASK_THRES), pano_temp=float(m.PANO_TEMPERATURE),
               object_mask_threshold=float(m.OBJECT_MASK_THRESHOLD), overlap_threshold=float(m.OVERLAP_THRESHOLD),
               pad_max=bool(m.LANGUAGE_BACKBONE.PAD_MAX), clip_enabled=bool(getattr(getattr(m, "CLIP", None), "ENABLED", False)))
+    if hp["clip_enabled"]:               # hipie_img.py:249-262
+        cl = m.CLIP
+        hp.update(clip_name=str(cl.NAME), clip_alpha=float(cl.ALPHA), clip_beta=float(cl.BETA), clip_fg_a=float(cl.FG_IOU_A),
+                  clip_fg_b=float(cl.FG_IOU_B), clip_agg_mode=str(cl.AGG_MODE), pano_temp_fg=float(m.PANO_TEMPERATURE_CLIP_FG))
     md = getattr(cfg, "_maskdino_cfg", None)
     if md is not None:
         hp.update(md_queries=md.MODEL.MaskDINO.NUM_OBJECT_QUERIES, md_dec_layers=md.MODEL.MaskDINO.DEC_LAYERS,
@@ -91,6 +95,13 @@ class HIPIE_IMG(nn.Module):
         self.use_cuda_graphs = False       # see enable_cuda_graphs()
         self._graphs = {}
         self.max_pool, self.bg_cls_agnostic, self.use_bg_for_pano = hp.get("max_pool", False), hp.get("bg_cls_agnostic", False), False
+        # MaskCLIP re-scoring (MODEL.CLIP.ENABLED; hipie_img.py:249-262).  CLIP weights are never part of the HIPIE checkpoint
+        # (open_vocab/clip.py:125-126): attach them with attach_clip(); until then an enabled config refuses to run.
+        self.enable_clip = bool(hp.get("clip_enabled", False))
+        self.clip, self.train_labels, self.clip_tokenize = None, None, None
+        self.clip_alpha, self.clip_beta = hp.get("clip_alpha", 0.35), hp.get("clip_beta", 0.7)
+        self.clip_fg_a, self.clip_fg_b = hp.get("clip_fg_a", 0.3), hp.get("clip_fg_b", 1.7)
+        self.clip_agg_mode, self.pano_temp_fg = hp.get("clip_agg_mode", "MUL"), hp.get("pano_temp_fg", 0.06)
         self._sd = OrderedDict()
         self.engine = None
         if state_dict is None:
@@ -283,6 +294,50 @@ class HIPIE_IMG(nn.Module):
             cache[key] = (tok.to(device), cnt.to(device), fg.to(device), bg.to(device))
         return cache[key]
 
+    # ---- MaskCLIP re-scoring (hipie_img.py:592-609, 735-747, 811-868; open_vocab/clip.py:243-383)
+    def attach_clip(self, clip, train_labels, tokenize=None):
+        """clip: a hipie_b200.modeling.maskclip.MaskCLIP or an open_clip state_dict; train_labels: the COCO-panoptic prompt-engineered
+        label list the reference reads at hipie_img.py:72 (data.load_openseg_labels); tokenize: callable(list[str]) -> (N, ctx) int64
+        CLIP token ids (open_clip.tokenize), needed unless the inputs carry `clip_prompt_ids`."""
+        from .maskclip import MaskCLIP
+        self.clip = clip if isinstance(clip, MaskCLIP) else MaskCLIP(clip, device=self.device_)
+        self.train_labels, self.clip_tokenize = train_labels, tokenize
+        self.enable_clip = True
+        return self
+
+    def _clip_tables(self, x):
+        """prompt embeddings, prompt offsets per class and seen-class flags of one input's `open_seg_labels` (cached per label set)."""
+        from .maskclip import class_tables
+        if self.clip is None:
+            raise RuntimeError("MODEL.CLIP.ENABLED is set but no CLIP weights are attached: call model.attach_clip(state_dict, train_labels)")
+        test_labels = x.get("open_seg_labels")
+        if test_labels is None:
+            raise ValueError("MaskCLIP re-scoring needs `open_seg_labels` (list of {id, name}) in every input (hipie_img.py:347)")
+        key = str(test_labels)
+        prompts, seg, overlap = class_tables(test_labels, self.train_labels, self.device_)
+        flat = [t for ls in prompts for t in ls]
+        if key not in self.clip.cache_text:
+            ids = x.get("clip_prompt_ids")
+            if ids is None:
+                if self.clip_tokenize is None:
+                    raise RuntimeError("no CLIP tokenizer: pass tokenize= to attach_clip or put `clip_prompt_ids` into the inputs")
+                ids = self.clip_tokenize(flat)
+            if ids.shape[0] != len(flat):
+                raise ValueError(f"clip_prompt_ids has {ids.shape[0]} rows for {len(flat)} prompts")
+        else:
+            ids = None
+        text_unit, _ = self.clip.build_text_embed(ids, cache_key=key)
+        return text_unit, seg, overlap
+
+    def _clip_scores(self, x, masks, scores, temp, mode, iou=None, up=1, crop=None):
+        """get_clip_logits (hipie_img.py:811-868) for one image: masks (Q, h, w) logits, scores (Q, C) class scores."""
+        text_unit, seg, overlap = self._clip_tables(x)
+        image01 = (x["image"].to(self.device_, torch.float32) / 255.0).contiguous()            # hipie_img.py:350-352
+        emb = self.clip.get_mask_embed(image01, masks, up=up, crop=crop)
+        raw = self.clip.raw_logits(emb, text_unit)
+        return ops.clip_fuse(raw, emb, self.clip.logit_scale, seg, scores, temp, overlap, self.clip_alpha, self.clip_beta,
+                             self.clip_agg_mode == "ADD", mode, iou=iou, fg_a=self.clip_fg_a, fg_b=self.clip_fg_b)
+
     def convert_grounding_to_od_logits(self, logits, num_classes, positive_map, is_thing, mode=None, max_pool=False, iou=None):
         """logits (bs, Q, Lt) -> scores (bs, Q, C): per-class mean (or max) over its token span, -9999 for masked classes; one kernel
         (ops.class_scores).  With `iou` (bs, Q, 1) also returns prob = sqrt(sigmoid(score) * sigmoid(iou)), its row max and argmax."""
@@ -373,7 +428,7 @@ class HIPIE_IMG(nn.Module):
         return pend["sem"], (panoptic_seg, segments_info)
 
     @torch.no_grad()
-    def inference(self, out, image_sizes, positive_map, num_classes, task, is_thing, sizes):
+    def inference(self, out, image_sizes, positive_map, num_classes, task, is_thing, sizes, batched_inputs=None):
         """HIPIE_IMG.inference (hipie_img.py:537-766, OTA path): class pooling, sqrt(cls x iou), class-aware NMS and the flat
         top-100 run as kernels for the whole batch (ops.class_scores / batched_nms / topk); one device->host read of the kept
         counts sizes the per-image tensors."""
@@ -396,6 +451,12 @@ class HIPIE_IMG(nn.Module):
                                                                  iou=iou_pred[grp[0]:grp[-1] + 1])
             for j, i in enumerate(grp):
                 logits_fg[i], prob_all[i], nms_scores[i], idxs[i] = sc[j], pr[j], rm[j], ra[j]
+                if self.enable_clip:
+                    # hipie_img.py:592-609: the foreground scores become sqrt(sigmoid(fused)^a * sigmoid(iou)^b) on thing classes, fused =
+                    # MaskCLIP's class probabilities of the 1/4-resolution masks ensembled with softmax(sigmoid(score) / T_fg)
+                    temp = self.pano_temp_fg if num_classes > 1 else 0.0
+                    prob_all[i], nms_scores[i], idxs[i] = self._clip_scores(batched_inputs[i], mask_pred[i][:, 0], sc[j], temp, 1,
+                                                                            iou=iou_pred[i].reshape(-1))
         keep_all, nkeep = ops.batched_nms(box_pred, torch.stack(nms_scores), torch.stack(idxs), 0.7)
         nk_host = nkeep.tolist()                       # the one host read of the selection stage
         results = []
@@ -431,7 +492,13 @@ class HIPIE_IMG(nn.Module):
                 logits_all = torch.cat([logits_per_image[keep_indices], logits_bg], dim=0)
                 mask_all = torch.cat([mask_pred[i][keep_indices], mask_pred_bg[i]], dim=0)
                 N, C, H, Wd = mask_all.shape
-                logits_all = F.softmax(logits_all.sigmoid() / self.pano_temp, dim=-1)
+                if self.enable_clip:
+                    # hipie_img.py:735-747: class probabilities = softmax of the fused log-probabilities; MaskCLIP sees the x4-upsampled,
+                    # cropped masks (evaluated on the fly by the patch-mask kernel)
+                    logits_all = self._clip_scores(batched_inputs[i], mask_all[:, 0], logits_all, self.pano_temp, 2, up=self.mask_stride,
+                                                   crop=image_size)
+                else:
+                    logits_all = F.softmax(logits_all.sigmoid() / self.pano_temp, dim=-1)
                 if (self.fused_postprocess and self.mask_stride == 4 and N <= 8192 and tuple(sizes[i]) == tuple(image_size)):
                     pend = self.fused_sem_pano_launch(logits_all, mask_all[:, 0], image_size)
                     results.append(dict(instances=result, panoptic_seg=None, sem_seg=None, _pending=pend))
@@ -511,7 +578,9 @@ class HIPIE_IMG(nn.Module):
             out = self.coco_inference(tensor, pad_mask, image_sizes, lang, task=task, forced=forced)
         is_thing = [x["is_thing"] for x in batched_inputs]
         sizes = [(x.get("height", s[0]), x.get("width", s[1])) for x, s in zip(batched_inputs, image_sizes)]
-        results = self.inference(out, image_sizes, positive_map, num_classes, task, is_thing, sizes)
+        if self.enable_clip and self.clip is None:
+            raise RuntimeError("MODEL.CLIP.ENABLED is set but no CLIP weights are attached: call model.attach_clip(state_dict, train_labels)")
+        results = self.inference(out, image_sizes, positive_map, num_classes, task, is_thing, sizes, batched_inputs=batched_inputs)
         if do_postprocess:
             for r, x, s in zip(results, batched_inputs, image_sizes):
                 r["instances"] = self.segmentation_postprocess(r["instances"], x.get("height", s[0]), x.get("width", s[1]))

@@ -597,3 +597,48 @@ def topk(values, k, n_rows=None, n_cols_per_row=0):
     with _timed("topk"):
         _lib.check(_lib.load().hipie_topk(_p(values), values.stride(0), _p(n_rows), n_cols_per_row, R, n, k, _p(ov), _p(oi), _stream()), "topk")
     return ov, oi
+
+
+# ---------------------------------------------------------------------------- MaskCLIP support (open_vocab/clip.py, hipie_img.py:811-868)
+def maskclip_patch_mask(masks, S, P, bits, key_offset=1, up=1, crop=None):
+    """Per-query patch masks into `bits` (Q, row_words) int32 (zeroed first): bit key_offset + patch set = patch masked OUT.
+    masks (Q, h, w) f32 logits; up = 4 with crop = (Hc, Wc): the x4-upsampled, cropped maps are the source of the resize to S x S."""
+    masks = masks.contiguous()
+    Q, h, w = masks.shape
+    Hc, Wc = (h, w) if up == 1 else (int(crop[0]), int(crop[1]))
+    assert bits.dtype == torch.int32 and bits.is_contiguous() and bits.shape[0] >= Q
+    with _timed("maskclip_patch_mask"):
+        _lib.check(_lib.load().hipie_maskclip_patch_mask(_p(masks), Q, h, w, up, Hc, Wc, S, P, _p(bits), bits.shape[1], key_offset, _stream()),
+                   "maskclip_patch_mask")
+    return bits
+
+
+def clip_patches(image01, S, P, mean, std):
+    """(3, H, W) f32 image in 0..1 -> BF2 ((S/P)^2, 3*P*P padded to a multiple of 8) normalised patch rows of the S x S resize."""
+    image01 = image01.contiguous()
+    _, H, W = image01.shape
+    G, K = S // P, 3 * P * P
+    ld = (K + 7) // 8 * 8
+    out = BF2(torch.zeros((G * G, ld), dtype=torch.bfloat16, device=image01.device),
+              torch.zeros((G * G, ld), dtype=torch.bfloat16, device=image01.device) if PREC == 3 else None)
+    m3, s3 = (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std)
+    with _timed("clip_patches"):
+        _lib.check(_lib.load().hipie_clip_patches(_p(image01), H, W, S, P, ctypes.cast(m3, ctypes.c_void_p), ctypes.cast(s3, ctypes.c_void_p),
+                                                  _p(out.hi), _p(out.lo) if out.lo is not None else None, ld, _stream()), "clip_patches")
+    return out
+
+
+def clip_fuse(raw, mask_embed, logit_scale, seg, scores, temp, overlap, alpha, beta, agg_add, mode, iou=None, fg_a=1.0, fg_b=1.0):
+    """hipie_clip_fuse: CLIP logits (norm, scale, max over synonyms, softmax) fused with the model's class probabilities.
+    mode 0 -> fused log-probs (R, C); mode 1 -> (prob, row_max, row_arg); mode 2 -> softmax(fused)."""
+    raw, mask_embed, scores = raw.contiguous(), mask_embed.contiguous(), scores.contiguous()
+    R, C = scores.shape
+    out = torch.empty((R, C), dtype=torch.float32, device=scores.device)
+    rmax = torch.empty((R,), dtype=torch.float32, device=scores.device) if mode == 1 else None
+    rarg = torch.empty((R,), dtype=torch.int32, device=scores.device) if mode == 1 else None
+    with _timed("clip_fuse"):
+        _lib.check(_lib.load().hipie_clip_fuse(_p(raw), raw.shape[1], _p(mask_embed), mask_embed.shape[1], float(logit_scale), _p(seg), _p(scores),
+                                               float(temp), _p(overlap), float(alpha), float(beta), 1 if agg_add else 0,
+                                               _p(iou.contiguous()) if iou is not None else None, float(fg_a), float(fg_b), mode, _p(out), _p(rmax),
+                                               _p(rarg), R, C, _stream()), "clip_fuse")
+    return (out, rmax, rarg) if mode == 1 else out

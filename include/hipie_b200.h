@@ -301,6 +301,28 @@ int hipie_batched_nms(const float* boxes_cxcywh, const float* scores, const int*
 int hipie_topk(const float* values, int64_t row_stride, const int* n_rows, int n_cols_per_row, int R, int n, int k,
                float* out_val, int* out_idx, void* stream);
 
+/* ---- MaskCLIP re-scoring (projects/HIPIE/hipie/open_vocab/clip.py:243-383, hipie_img.py:592-609,735-747,811-868) ----
+ * The ViT-L/14 forward itself runs on hipie_gemm (QuickGELU epilogue) / hipie_layernorm / hipie_attention (key_mask); these cover
+ * the steps around it.
+ * hipie_maskclip_patch_mask: per-query patch masks of the mask tokens (clip.py:288-324).  masks (Q, h, w) f32 logits; up = 1: the
+ *   maps are resized to S x S directly (hipie_img.py:599-602 passes the 1/4-resolution maps); up = 4: they are first upsampled x4 and
+ *   cropped to (Hc, Wc) (hipie_img.py:733-741), evaluated on the fly.  For key = key_offset + patch: bit set in
+ *   bits[q * row_words + key / 32] when max_pool_PxP(sigmoid(resized)) < 0.5, i.e. the patch is masked OUT; the rows are zeroed first.
+ * hipie_clip_patches: image (3, H, W) f32 in 0..1 -> bilinear resize to S x S, (x - mean) / std, patch rows (S/P)^2 x (3 P P) in
+ *   Conv2d weight order as bf16 hi/lo planes with row stride ld (the A operand of the patch-embedding GEMM).
+ * hipie_clip_fuse: raw (R, Np) = mask_embed . unit(text_embed)^T; seg (C + 1) prompt offsets per class; scores (R, C) the model's
+ *   class scores (-9999 = masked class), temp > 0: softmax(sigmoid(score) / temp), 0: sigmoid(score); overlap (C) i8 1 = class seen
+ *   in training (weight alpha, else beta); agg_add 0 = geometric 'MUL', 1 = arithmetic 'ADD' (hipie_img.py:845-866).
+ *   mode 0: out = fused log-probabilities; mode 1: out = sqrt(sigmoid(fused)^fg_a * sigmoid(iou)^fg_b) * [scores[0, c] != -9999]
+ *   and its row max / first argmax; mode 2: out = softmax(fused) over the classes. */
+int hipie_maskclip_patch_mask(const float* masks, int Q, int h, int w, int up, int Hc, int Wc, int S, int P, uint32_t* bits,
+                              int row_words, int key_offset, void* stream);
+int hipie_clip_patches(const float* image, int H, int W, int S, int P, const float* mean3, const float* std3, void* hi, void* lo,
+                       int ld, void* stream);
+int hipie_clip_fuse(const float* raw, int ld_raw, const float* mask_embed, int D, float logit_scale, const int* seg,
+                    const float* scores, float temp, const int8_t* overlap, float alpha, float beta, int agg_add, const float* iou,
+                    float fg_a, float fg_b, int mode, float* out, float* row_max, int* row_arg, int R, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
