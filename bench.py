@@ -275,15 +275,21 @@ def run_product(args, cfg):
                         input_ids=ids[b], attention_mask=am[b]) for b, im in enumerate(host_imgs)]
         res = model(batched)
         host = []
+
+        def to_host(t):        # results land in pinned host memory, all copies queued before the one synchronize
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            return buf
         for r in res:
             inst = r["instances"]
-            item = [inst.pred_boxes.tensor.cpu(), inst.scores.cpu(), inst.pred_classes.cpu()]
+            item = [to_host(inst.pred_boxes.tensor), to_host(inst.scores), to_host(inst.pred_classes)]
             if task == "detection":
                 sem = r["sem_seg"].argmax(0)
-                item += [r["panoptic_seg"][0].cpu(), sem.to(torch.uint8 if r["sem_seg"].shape[0] <= 256 else torch.int16).cpu()]
+                item += [to_host(r["panoptic_seg"][0]), to_host(sem.to(torch.uint8 if r["sem_seg"].shape[0] <= 256 else torch.int16))]
             else:
-                item.append(inst.pred_masks.cpu())
+                item.append(to_host(inst.pred_masks))
             host.append(tuple(item))
+        torch.cuda.synchronize()
         return host
 
     def barrier():

@@ -535,7 +535,8 @@ class HIPIE_IMG(nn.Module):
         keep = boxes.nonempty()
         out.pred_boxes = Boxes(boxes.tensor[keep])
         if tuple(results.pred_masks.shape[-2:]) == (output_height, output_width):
-            masks = results.pred_masks[:, 0].to(torch.uint8)            # nearest resize to the same size is the identity
+            m0 = results.pred_masks[:, 0]                                # nearest resize to the same size is the identity;
+            masks = m0.view(torch.uint8) if m0.dtype == torch.bool and m0.is_contiguous() else m0.to(torch.uint8)   # bool bytes ARE uint8 0/1
         else:
             masks = F.interpolate(results.pred_masks.float(), size=(output_height, output_width), mode="nearest")[:, 0].to(torch.uint8)
         out.pred_masks = masks[keep]
