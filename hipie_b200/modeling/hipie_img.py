@@ -93,6 +93,8 @@ class HIPIE_IMG(nn.Module):
         self.tokenizer = None              # attached by the predictor, or loaded lazily from projects/HIPIE/bert-base-uncased
         self.fused_postprocess = True      # semantic/panoptic tensor work in one kernel (ops.seg_postprocess)
         self.use_cuda_graphs = False       # see enable_cuda_graphs()
+        self.overlap_branches = True       # DETR and MaskDINO branches on two streams (coco_inference)
+        self._side_stream = None
         self._graphs = {}
         self.max_pool, self.bg_cls_agnostic, self.use_bg_for_pano = hp.get("max_pool", False), hp.get("bg_cls_agnostic", False), False
         # MaskCLIP re-scoring (MODEL.CLIP.ENABLED; hipie_img.py:249-262).  CLIP weights are never part of the HIPIE checkpoint
@@ -170,9 +172,23 @@ class HIPIE_IMG(nn.Module):
             lm = lang["masks"].float()
             lang_feat_pool = ((lang["hidden"] * lm.unsqueeze(-1)).sum(1) / lm.sum(-1, keepdim=True)).unsqueeze(1)   # pre-fusion (:809-811)
         any_pad = any(tuple(s) != tuple(tensor.shape[-2:]) for s in image_sizes)      # host-side: no device sync
-        di = eng.detr_inputs(feats, pad_mask, B, any_pad=any_pad)
-        tr = eng.detr_transformer(di, lang, B, forced_topk=forced.get("topk_fg"))
-        md = eng.maskdino(feats, B, forced_topk=forced.get("topk_md"))
+        # The MaskDINO branch (pixel decoder + 9 decoder layers + mask-embed) and the DETR branch (VL fusion, encoder, decoder, heads,
+        # CondInst) only share the backbone features: they run on two streams, so the many small launches of the two decoders fill
+        # each other's gaps (inside a CUDA-graph capture the fork / join becomes graph dependencies).
+        if self.overlap_branches:
+            cur = torch.cuda.current_stream(self.device_)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.device_)
+            side = self._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                md = eng.maskdino(feats, B, forced_topk=forced.get("topk_md"))
+            di = eng.detr_inputs(feats, pad_mask, B, any_pad=any_pad)
+            tr = eng.detr_transformer(di, lang, B, forced_topk=forced.get("topk_fg"))
+        else:
+            di = eng.detr_inputs(feats, pad_mask, B, any_pad=any_pad)
+            tr = eng.detr_transformer(di, lang, B, forced_topk=forced.get("topk_fg"))
+            md = eng.maskdino(feats, B, forced_topk=forced.get("topk_md"))
         nd = hp.get("dec_layers", 6)
         lvl = nd - 1
         hs, hs_s = tr["hs"][lvl]
@@ -185,6 +201,8 @@ class HIPIE_IMG(nn.Module):
         out["pred_boxious"] = ops.gemm(hs_s.view(B * Q, 256), wi, bias=bi)[0].view(B, Q, 1)
         masks, mh_feats, params, ref_px = eng.condinst(tr["memory"], tr, di, image_sizes, B)
         out["pred_masks"] = masks.unsqueeze(2)
+        if self.overlap_branches:
+            torch.cuda.current_stream(self.device_).wait_stream(self._side_stream)      # join: everything below reads the MaskDINO outputs
         nqm = md["pred_logits_emb"].shape[1]
         ncls = hp.get("md_dec_layers", 9) + 2
         out["pred_logits_maskdino"] = eng.vl_align(f"detr.mask_dino_cls_embed.{ncls - 1}", md["pred_logits_emb_s"], lang_for_cls, B, nqm)

@@ -261,10 +261,11 @@ def groupnorm_nhwc(x, gamma, beta, eps=1e-5, groups=32, relu=False, post_add=Non
     """x: (N, HW, C) fp32 contiguous."""
     N, HW, C = x.shape
     dev = x.device
-    ws = _gn_ws.get((dev, N * groups))
+    key = (dev, N * groups, torch.cuda.current_stream(dev).cuda_stream)       # one workspace per stream: branches of the forward overlap
+    ws = _gn_ws.get(key)
     if ws is None:
         ws = torch.empty(2 * N * groups, dtype=torch.float64, device=dev)
-        _gn_ws[(dev, N * groups)] = ws
+        _gn_ws[key] = ws
     y = out_f32 if out_f32 is not None else (torch.empty_like(x) if want_f32 else None)
     s = _empty_bf2(x.shape, dev) if want_split else None
     yb = HW * C if y_bstride is None else y_bstride
