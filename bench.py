@@ -264,7 +264,7 @@ def run_product(args, cfg):
         if graphed is not None:
             out = graphed()
         else:
-            lang = model.engine.forward_text(ids_d, am_d, same_rows=same_rows)
+            lang = model.forward_text_async(ids_d, am_d, same_rows=same_rows)
             out = model.coco_inference(dev_imgs, pad_mask, sizes, lang, task=task)
         if gather is not None:     # the only collective of the data-parallel path: ONE all-gather of the packed fixed-shape outputs
             gather(out, gather_keys)
@@ -277,6 +277,8 @@ def run_product(args, cfg):
         host = []
 
         def to_host(t):        # results land in pinned host memory, all copies queued before the one synchronize
+            if os.environ.get("HIPIE_BENCH_PAGEABLE_D2H") == "1":
+                return t.cpu()
             buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             buf.copy_(t, non_blocking=True)
             return buf

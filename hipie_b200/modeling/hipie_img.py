@@ -7,6 +7,8 @@ The forward path has no CPU fallback: the CUDA extension must be built and a CUD
 """
 from collections import OrderedDict
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -93,8 +95,10 @@ class HIPIE_IMG(nn.Module):
         self.tokenizer = None              # attached by the predictor, or loaded lazily from projects/HIPIE/bert-base-uncased
         self.fused_postprocess = True      # semantic/panoptic tensor work in one kernel (ops.seg_postprocess)
         self.use_cuda_graphs = False       # see enable_cuda_graphs()
-        self.overlap_branches = True       # DETR and MaskDINO branches on two streams (coco_inference)
+        self.overlap_branches = os.environ.get("HIPIE_OVERLAP_BRANCHES", "1") != "0"   # DETR and MaskDINO branches on two streams (coco_inference)
         self._side_stream = None
+        self._text_stream = None
+        self.overlap_text = os.environ.get("HIPIE_OVERLAP_TEXT", "1") != "0"          # text encoder beside the backbone (forward_text_async)
         self._graphs = {}
         self.max_pool, self.bg_cls_agnostic, self.use_bg_for_pano = hp.get("max_pool", False), hp.get("bg_cls_agnostic", False), False
         # MaskCLIP re-scoring (MODEL.CLIP.ENABLED; hipie_img.py:249-262).  CLIP weights are never part of the HIPIE checkpoint
@@ -168,6 +172,8 @@ class HIPIE_IMG(nn.Module):
         eng, hp = self.engine, self.hp
         B = tensor.shape[0]
         feats = eng.vit(tensor) if hp["backbone"] == "vit" else eng.resnet50(tensor)
+        if callable(lang):                 # text encoder launched on its own stream (forward_text_async): join here, after the backbone
+            lang = lang()
         if task == "grounding":
             lm = lang["masks"].float()
             lang_feat_pool = ((lang["hidden"] * lm.unsqueeze(-1)).sum(1) / lm.sum(-1, keepdim=True)).unsqueeze(1)   # pre-fusion (:809-811)
@@ -232,7 +238,7 @@ class HIPIE_IMG(nn.Module):
             chunk_plan = self.engine.text_chunk_plan(input_ids, attention_mask, same_rows)
 
         def step():
-            lang = self.engine.forward_text(ids, am, same_rows=same_rows, chunk_plan=chunk_plan)
+            lang = self.forward_text_async(ids, am, same_rows=same_rows, chunk_plan=chunk_plan)
             return self.coco_inference(tensor, pad_mask, image_sizes, lang, task=task)
 
         side = torch.cuda.Stream(device=self.device_)
@@ -562,6 +568,28 @@ class HIPIE_IMG(nn.Module):
         out.pred_classes = results.pred_classes[keep]
         return out
 
+    def forward_text_async(self, input_ids, attention_mask, same_rows=None, chunk_plan=None):
+        """The text encoder does not depend on the image: launch it on a second stream so that its ~100 small kernels run beside the
+        backbone, and hand back a join() that makes the current stream wait for it and returns the features (coco_inference calls
+        it after the backbone).  With overlap_branches off this is the plain synchronous call."""
+        if same_rows is None:
+            same_rows = self.engine.rows_equal(input_ids, attention_mask)
+        ids, am = input_ids.to(self.device_), attention_mask.to(self.device_)
+        if not (self.overlap_branches and self.overlap_text):
+            return self.engine.forward_text(ids, am, same_rows=same_rows, chunk_plan=chunk_plan)
+        cur = torch.cuda.current_stream(self.device_)
+        if self._text_stream is None:
+            self._text_stream = torch.cuda.Stream(device=self.device_)
+        side = self._text_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            lang = self.engine.forward_text(ids, am, same_rows=same_rows, chunk_plan=chunk_plan)
+
+        def join():
+            torch.cuda.current_stream(self.device_).wait_stream(side)
+            return lang
+        return join
+
     def forward_text(self, input_ids, attention_mask, same_rows=None):
         if same_rows is None:
             same_rows = self.engine.rows_equal(input_ids, attention_mask)     # host tensors: compared on the host
@@ -593,7 +621,7 @@ class HIPIE_IMG(nn.Module):
         if self.use_cuda_graphs and forced is None:
             out = self._graphed_hot_path(tensor, pad_mask, image_sizes, ids, am, task, same_rows)
         else:
-            lang = self.forward_text(ids, am, same_rows=same_rows)
+            lang = self.forward_text_async(ids, am, same_rows=same_rows)
             out = self.coco_inference(tensor, pad_mask, image_sizes, lang, task=task, forced=forced)
         is_thing = [x["is_thing"] for x in batched_inputs]
         sizes = [(x.get("height", s[0]), x.get("width", s[1])) for x, s in zip(batched_inputs, image_sizes)]
