@@ -57,6 +57,7 @@ SYMBOLS = {
     "hipie_gemm": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     "hipie_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "hipie_layernorm": (c_int, [c_void_p] * 4 + [c_float] + [c_void_p] * 4 + [c_int64, c_int, c_void_p, c_void_p]),
+    "hipie_layernorm_f16": (c_int, [c_void_p] * 4 + [c_float] + [c_void_p] * 3 + [c_int64, c_int, c_void_p, c_void_p]),
     "hipie_groupnorm_nhwc": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 5 + [c_int] * 5 + [c_int64] * 3 + [c_void_p]),
     "hipie_add_split": (c_int, [c_void_p] * 5 + [c_int64, c_void_p]),
     "hipie_patchify": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p] * 3),

@@ -20,6 +20,9 @@
 // Precision: operands are bf16 "split" planes.  prec==1 uses hi only; prec==3 computes
 // Ahi.Whi + Ahi.Wlo + Alo.Whi in the same fp32 TMEM accumulator (error ~2^-16 relative, i.e.
 // fp32-class results from the bf16 tensor pipe), loading 4 tiles per 3 MMAs per k-block.
+// prec==4 is the two-pass fp16 mode of the precision map: A is ONE IEEE fp16 plane (an activation that is
+// rounded to fp16 downstream anyway: the LayerNorm output feeding qkv), W is fp16 hi + lo, A.Whi + A.Wlo -- the weight is exact
+// to ~2^-22, the only rounding is the 2^-12 of the activation plane; 3 tiles per 2 MMAs per k-block.
 #include "common.cuh"
 #include "ptx.cuh"
 #include <mutex>
@@ -49,7 +52,7 @@ struct GemmParams {
     int M, N, K, batch;
     int act;
     float alpha;
-    int transposed;  // 1: C stored as [N, ldc] (column-major output), lanes = rows
+    int transposed;  // 1: C stored as [N, ldc] (column-major output), lanes = rows; 2 / 3: the vectorised fp16-plane variant (8 / 4 rows per store)
     int tiles_m, tiles_n;
     int f16_ops;     // operands are IEEE fp16 planes (single pass): fp16 instruction descriptor
     int relu_post;   // ReLU after the residual add
@@ -66,13 +69,14 @@ struct GemmParams {
 // traffic per k-block from 120 KB (over the 128 B/clk port budget: tensor pipe 76 % in round 1) to 80 KB.
 template <int PREC, int BN, int CTAS>
 struct GemmCfg {
-    static constexpr int BK = PREC == 3 ? 32 : 64;          // elements; BK*2 bytes == swizzle span
+    static constexpr bool P4 = PREC == 4 || PREC == 5;      // 5 = prec 4 with 32-element k-blocks on CTA pairs (A/B variant)
+    static constexpr int BK = (PREC == 3 || PREC == 5 || (PREC == 4 && CTAS == 1)) ? 32 : 64;   // elements; BK*2 bytes == swizzle span
     static constexpr int SWZ = BK * 2;
     static constexpr int A_TILE = GEMM_BM * BK * 2;          // bytes
     static constexpr int W_ROWS = BN / CTAS;                 // W rows staged by one CTA
     static constexpr int W_TILE = W_ROWS * BK * 2;
-    static constexpr int NPLANES = PREC == 3 ? 2 : 1;
-    static constexpr int STAGE = NPLANES * (A_TILE + W_TILE);
+    static constexpr int A_PLANES = PREC == 3 ? 2 : 1, W_PLANES = (PREC == 3 || P4) ? 2 : 1;
+    static constexpr int STAGE = A_PLANES * A_TILE + W_PLANES * W_TILE;     // layout: A_hi | W_hi | (A_lo) | W_lo
     static constexpr int EPI_BYTES = GEMM_EPI_WARPS * EPI_WARP_BYTES;
     static constexpr int SMEM_BUDGET = 232448 - 1024 - 256 - EPI_BYTES;                  // 227 KB per CTA
     static constexpr int MAX_STAGES = CTAS == 2 ? 6 : 4;
@@ -377,6 +381,56 @@ __device__ __forceinline__ void epilogue_rows_tma(const GemmParams& p, const CUt
     }
 }
 
+// Transposed fp16-plane epilogue (the V^T operand of the attention: C^T stored [col * ldc + row], one IEEE fp16 plane, bias only).
+// A lane owns ONE row of the accumulator, so the scalar path below stores 2 bytes per lane and instruction (64-byte segments, 32
+// store instructions per 32-column chunk: the V^T GEMM took the same 0.21 ms in one, two or three MMA passes).  Here the warp's
+// 32 x 32 chunk goes through its shared-memory staging buffer as [col][row] halves, and leaves as VEC consecutive rows per lane:
+// VEC = 8 (16-byte stores) for plain outputs, VEC = 4 (8-byte stores) when rows are re-spaced per window (t_row_group / t_row_pad
+// multiples of 4 keep every 4-row run contiguous and 8-byte aligned).  Requires M % VEC == 0 and ldc % VEC == 0 (host-checked).
+template <int VEC>
+__device__ __forceinline__ void epilogue_transposed_f16(const GemmParams& p, uint32_t taddr, uint32_t sbuf, int b, int m0, int n0,
+                                                        int col_begin, int col_end, int lane) {
+    __half* c_b = reinterpret_cast<__half*>(p.c_hi) + (int64_t)b * p.c_bstride;
+    constexpr int SEGS = 32 / VEC;                  // row segments per column
+    constexpr int ITER = 32 * SEGS / 32;            // (column, segment) items per lane
+#pragma unroll 1
+    for (int cb = col_begin; cb < col_end; cb += 32) {
+        const int nbase = n0 + cb;
+        if (nbase >= p.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + cb, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) * p.alpha;
+            if (p.bias && nbase + j < p.N) x += __ldg(p.bias + nbase + j);
+            const __half h = __float2half_rn(x);
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(sbuf + (uint32_t)(j * 64 + lane * 2)), "h"(*reinterpret_cast<const unsigned short*>(&h)) : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+            const int idx = i * 32 + lane;
+            const int cj = idx / SEGS, seg = idx - cj * SEGS;
+            const int r = m0 + seg * VEC;
+            const int col = nbase + cj;
+            if (col < p.N && r < p.M) {
+                const int row = p.t_row_group > 0 ? r + (r / p.t_row_group) * p.t_row_pad : r;
+                __half* dst = c_b + (int64_t)col * p.ldc + row;
+                if (VEC == 8) {
+                    const float4 q = lds128(sbuf + (uint32_t)(cj * 64 + seg * 16));
+                    *reinterpret_cast<float4*>(dst) = q;
+                } else {
+                    float2 q;
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(q.x), "=f"(q.y) : "r"(sbuf + (uint32_t)(cj * 64 + seg * 8)) : "memory");
+                    *reinterpret_cast<float2*>(dst) = q;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Transposed epilogue (C stored [col * ldc + row]): lanes hold 32 consecutive rows, so each register j is a
 // coalesced 128-byte store along M; optional bit-packed (x > threshold) output packed along M.
 __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, uint32_t taddr, int b, int m0, int n0,
@@ -468,10 +522,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_a_hi);
         prefetch_tmap(&tm_w_hi);
-        if (PREC == 3) {
-            prefetch_tmap(&tm_a_lo);
-            prefetch_tmap(&tm_w_lo);
-        }
+        if (PREC == 3) prefetch_tmap(&tm_a_lo);
+        if (PREC == 3 || Cfg::P4) prefetch_tmap(&tm_w_lo);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -521,6 +573,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                             tma_load_3d(st + Cfg::A_TILE + Cfg::W_TILE, &tm_a_lo, &full_bar[s], k0, m0, b);
                             tma_load_3d(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tm_w_lo, &full_bar[s], k0, n0, b);
                         }
+                        if (Cfg::P4) tma_load_3d(st + Cfg::A_TILE + Cfg::W_TILE, &tm_w_lo, &full_bar[s], k0, n0, b);
                     } else {
                         // both CTAs' loads report to the LEADER's barrier, which expects the bytes of the whole pair; the peer's
                         // loads of this stage cannot run ahead of the phase (its empty barrier is released by the same commit)
@@ -531,6 +584,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                             tma_load_3d_2sm(st + Cfg::A_TILE + Cfg::W_TILE, &tm_a_lo, &full_bar[s], k0, m0, b);
                             tma_load_3d_2sm(st + 2 * Cfg::A_TILE + Cfg::W_TILE, &tm_w_lo, &full_bar[s], k0, n0, b);
                         }
+                        if (Cfg::P4) tma_load_3d_2sm(st + Cfg::A_TILE + Cfg::W_TILE, &tm_w_lo, &full_bar[s], k0, n0, b);
                     }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -560,6 +614,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                             // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in addr>>4 units
                             if (CTAS == 2) umma_f16_2sm(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
                             else umma_f16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        if (Cfg::P4) {
+                            const uint64_t w_lo = make_kmajor_desc<Cfg::SWZ>(st + Cfg::A_TILE + Cfg::W_TILE);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                if (CTAS == 2) umma_f16_2sm(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1);
+                                else umma_f16(d_tmem, a_hi + 2 * k, w_lo + 2 * k, idesc, 1);
+                            }
                         }
                         if (PREC == 3) {
                             const uint64_t a_lo = make_kmajor_desc<Cfg::SWZ>(st + Cfg::A_TILE + Cfg::W_TILE);
@@ -617,7 +679,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
             if (active && m0 - quarter * 32 < p.M) {
-                if (p.transposed)
+                if (p.transposed == 2)
+                    epilogue_transposed_f16<8>(p, taddr, my_sbuf, b, m0, n0, cbeg, cend, lane);
+                else if (p.transposed == 3)
+                    epilogue_transposed_f16<4>(p, taddr, my_sbuf, b, m0, n0, cbeg, cend, lane);
+                else if (p.transposed)
                     epilogue_transposed(p, taddr, b, m0, n0, cbeg, cend, lane);
                 else if (p.tma_out)
                     switch (p.act) {
@@ -746,6 +812,8 @@ int make_tmap(CUtensorMap* out, const void* ptr, int esize, int64_t rows, int64_
 // hipie_set_option switches (A/B measurements, fallbacks): CTA-pair (cta_group::2) tiles, TMA-store epilogue
 int g_gemm_cta_pairs = 1;
 int g_gemm_tma_store = 1;
+int g_gemm_fast_transposed = 1;   // vectorised fp16-plane transposed epilogue (A/B switch)
+int g_gemm_p4_bk32 = 0;       // prec 4 on CTA pairs: 32-element k-blocks (6 stages of 24 KB) instead of 64 (3 stages of 48 KB)
 
 // fp32 tensor of rank 5 (dims / strides innermost first, strides in BYTES for dims 1..4), dense unswizzled boxes: the value-map
 // windows of the shared-memory MSDeformAttn kernel (msda.cu).  Not cached: built once per launch from host-side geometry.
@@ -778,13 +846,11 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     int rc;
     if ((rc = make_tmap_bf16(&ta_hi, a->a_hi, a->M, a->K, a->lda, a->batch, a->a_bstride, GEMM_BM, Cfg::BK))) return rc;
     if ((rc = make_tmap_bf16(&tw_hi, a->w_hi, a->N, a->K, a->ldw, a->batch, a->w_bstride, Cfg::W_ROWS, Cfg::BK))) return rc;
-    if (PREC == 3) {
-        if ((rc = make_tmap_bf16(&ta_lo, a->a_lo, a->M, a->K, a->lda, a->batch, a->a_bstride, GEMM_BM, Cfg::BK))) return rc;
-        if ((rc = make_tmap_bf16(&tw_lo, a->w_lo, a->N, a->K, a->ldw, a->batch, a->w_bstride, Cfg::W_ROWS, Cfg::BK))) return rc;
-    } else {
-        ta_lo = ta_hi;
-        tw_lo = tw_hi;
-    }
+    ta_lo = ta_hi;
+    tw_lo = tw_hi;
+    if (PREC == 3 && (rc = make_tmap_bf16(&ta_lo, a->a_lo, a->M, a->K, a->lda, a->batch, a->a_bstride, GEMM_BM, Cfg::BK))) return rc;
+    if ((PREC == 3 || Cfg::P4) &&
+        (rc = make_tmap_bf16(&tw_lo, a->w_lo, a->N, a->K, a->ldw, a->batch, a->w_bstride, Cfg::W_ROWS, Cfg::BK))) return rc;
     // row-major outputs through TMA stores when nothing needs per-element addressing (residual / row map / transposed stay on the
     // register path) and the output rows satisfy TMA's 16-byte rules
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -804,7 +870,7 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     p.tma_out = tma_out ? 1 : 0;
     p.c_fp16 = a->c_fp16 ? 1 : 0;
     p.relu_post = a->relu_after_residual ? 1 : 0;
-    p.f16_ops = a->prec == 2 ? 1 : 0;
+    p.f16_ops = (a->prec == 2 || a->prec == 4) ? 1 : 0;
     p.bias = a->bias; p.colscale = a->colscale; p.residual = a->residual;
     p.ldr = a->ldr; p.r_bstride = a->r_bstride;
     p.c_f32 = a->c_f32; p.c_hi = (__nv_bfloat16*)a->c_hi; p.c_lo = (__nv_bfloat16*)a->c_lo;
@@ -813,6 +879,13 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
     p.act = a->act; p.alpha = a->alpha;
     p.transposed = a->transposed;
+    if (a->transposed && a->c_fp16 && a->c_hi && !a->c_f32 && !a->c_lo && !a->c_bits && !a->residual && !a->colscale && a->act == HIPIE_ACT_NONE &&
+        g_gemm_fast_transposed && (reinterpret_cast<uintptr_t>(a->c_hi) & 15) == 0) {
+        // vectorised V^T epilogue: whole 8-row (or, with per-window row padding, 4-row) runs must exist and stay aligned
+        const bool grp4 = a->t_row_group > 0 && a->t_row_group % 4 == 0 && a->t_row_pad % 4 == 0;
+        if (a->t_row_group == 0 && a->M % 8 == 0 && a->ldc % 8 == 0 && (a->batch == 1 || a->c_bstride % 8 == 0)) p.transposed = 2;
+        else if ((grp4 || a->t_row_group == 0) && a->M % 4 == 0 && a->ldc % 4 == 0 && (a->batch == 1 || a->c_bstride % 4 == 0)) p.transposed = 3;
+    }
     p.row_map = a->c_row_map;
     p.t_row_group = a->transposed ? a->t_row_group : 0;
     p.t_row_pad = a->transposed ? a->t_row_pad : 0;
@@ -849,8 +922,9 @@ using namespace hipie;
 extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     HIPIE_CHECK_ARG(a != nullptr, "hipie_gemm: null args");
     HIPIE_CHECK_ARG(a->a_hi && a->w_hi, "hipie_gemm: a_hi / w_hi required");
-    HIPIE_CHECK_ARG(a->prec == 1 || a->prec == 2 || a->prec == 3, "hipie_gemm: prec must be 1, 2 or 3 (got %d)", a->prec);
+    HIPIE_CHECK_ARG(a->prec >= 1 && a->prec <= 4, "hipie_gemm: prec must be 1, 2, 3 or 4 (got %d)", a->prec);
     HIPIE_CHECK_ARG(a->prec != 3 || (a->a_lo && a->w_lo), "hipie_gemm: prec 3 needs a_lo and w_lo");
+    HIPIE_CHECK_ARG(a->prec != 4 || a->w_lo, "hipie_gemm: prec 4 (A fp16, W fp16 hi + lo) needs w_lo");
     HIPIE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "hipie_gemm: bad sizes M=%d N=%d K=%d batch=%d",
                     a->M, a->N, a->K, a->batch);
     HIPIE_CHECK_ARG(a->K % 8 == 0, "hipie_gemm: K (%d) must be a multiple of 8", a->K);
@@ -865,7 +939,12 @@ extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     // CTA pairs where the mainloop dominates: big row counts, K >= 512, 3-pass operands (ViT / BERT / VL linears).  Measured on
     // B200 (tools/gemm_check.py, profiles/r02_gemm_pairs.txt): fc1 32768x5120x1280 0.944 -> 0.844 ms, qk 0.489 -> 0.454 ms;
     // K = 256 problems are epilogue/store-bound and lose 8-10 % with pairs, single-pass operands gain nothing.
-    const bool pairs = g_gemm_cta_pairs && a->M >= 1024 && a->N > 64 && a->K >= 512 && a->prec == 3;
+    const bool pairs = g_gemm_cta_pairs && a->M >= 1024 && a->N > 64 && a->K >= 512 && (a->prec == 3 || a->prec == 4);
+    if (a->prec == 4) {                    // two-pass fp16 (the qkv linears): wide outputs only
+        if (a->N <= 128) return pairs ? launch_gemm<4, 128, 2>(a, st) : launch_gemm<4, 128, 1>(a, st);
+        if (pairs && g_gemm_p4_bk32) return launch_gemm<5, 256, 2>(a, st);
+        return pairs ? launch_gemm<4, 256, 2>(a, st) : launch_gemm<4, 256, 1>(a, st);
+    }
     const bool p3 = a->prec == 3;          // prec 1 (bf16) and prec 2 (fp16) share the single-plane kernels; the MMA kind differs
     if (a->N <= 64) return p3 ? launch_gemm<3, 64, 1>(a, st) : launch_gemm<1, 64, 1>(a, st);
     if (a->N <= 128) {
@@ -880,6 +959,8 @@ extern "C" int hipie_set_option(const char* name, int value) {
     HIPIE_CHECK_ARG(name != nullptr, "hipie_set_option: null name");
     if (strcmp(name, "gemm_cta_pairs") == 0) { g_gemm_cta_pairs = value ? 1 : 0; return HIPIE_OK; }
     if (strcmp(name, "gemm_tma_store") == 0) { g_gemm_tma_store = value ? 1 : 0; return HIPIE_OK; }
+    if (strcmp(name, "gemm_p4_bk32") == 0) { g_gemm_p4_bk32 = value ? 1 : 0; return HIPIE_OK; }
+    if (strcmp(name, "gemm_fast_transposed") == 0) { g_gemm_fast_transposed = value ? 1 : 0; return HIPIE_OK; }
     set_error("hipie_set_option: unknown option '%s'", name);
     return HIPIE_EINVAL;
 }

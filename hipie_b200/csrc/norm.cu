@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, float* __restrict__ sum_out,
                  float* __restrict__ y_f32, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
-                 int64_t rows, int C, const int* __restrict__ omap) {
+                 int64_t rows, int C, const int* __restrict__ omap, int y_fp16) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= rows) return;
@@ -58,8 +58,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, con
             if (y_f32) *reinterpret_cast<float4*>(y_f32 + orow * C + c0) = o;
             if (y_hi) {
                 uint2 hi, lo;
-                split2(o.x, o.y, hi.x, lo.x);
-                split2(o.z, o.w, hi.y, lo.y);
+                split2m(o.x, o.y, hi.x, lo.x, y_fp16);       // y_fp16: y_hi is ONE IEEE fp16 plane (y_lo NULL)
+                split2m(o.z, o.w, hi.y, lo.y, y_fp16);
                 *reinterpret_cast<uint2*>(y_hi + orow * C + c0) = hi;
                 if (y_lo) *reinterpret_cast<uint2*>(y_lo + orow * C + c0) = lo;
             }
@@ -73,7 +73,7 @@ layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ 
                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                          float* __restrict__ sum_out, float* __restrict__ y_f32,
                          __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, int64_t rows, int C,
-                         const int* __restrict__ omap) {
+                         const int* __restrict__ omap, int y_fp16) {
     __shared__ float red[4];
     __shared__ float bc;
     const int64_t row = blockIdx.x;
@@ -107,7 +107,9 @@ layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ 
         const float v = xr[c] + (ar ? ar[c] : 0.f);
         const float o = (v - mean) * rstd * gamma[c] + beta[c];
         if (y_f32) y_f32[orow * C + c] = o;
-        if (y_hi) {
+        if (y_hi && y_fp16) {
+            reinterpret_cast<__half*>(y_hi)[orow * C + c] = __float2half_rn(o);
+        } else if (y_hi) {
             const __nv_bfloat16 h = __float2bfloat16_rn(o);
             y_hi[orow * C + c] = h;
             if (y_lo) y_lo[orow * C + c] = __float2bfloat16_rn(o - __bfloat162float(h));
@@ -195,34 +197,43 @@ groupnorm_apply_kernel(const float* __restrict__ x, const double* __restrict__ s
 
 using namespace hipie;
 
-extern "C" int hipie_layernorm(const float* x, const float* add, const float* gamma, const float* beta, float eps,
-                               float* sum_out, float* y_f32, void* y_hi, void* y_lo, int64_t rows, int C,
-                               const int32_t* out_row_map, void* stream) {
+static int layernorm_launch(const float* x, const float* add, const float* gamma, const float* beta, float eps,
+                            float* sum_out, float* y_f32, void* y_hi, void* y_lo, int y_fp16, int64_t rows, int C,
+                            const int32_t* out_row_map, void* stream) {
     HIPIE_CHECK_ARG(x && gamma && beta, "hipie_layernorm: null input");
     HIPIE_CHECK_ARG(y_f32 || y_hi, "hipie_layernorm: no output requested");
     HIPIE_CHECK_ARG(rows >= 0 && C > 0, "hipie_layernorm: bad sizes");
     if (rows == 0) return HIPIE_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16 *hi = (__nv_bfloat16*)y_hi, *lo = (__nv_bfloat16*)y_lo;
     if (C % 128 == 0 && C <= 128 * 16) {
         const int64_t blocks = (rows + 7) / 8;
         if (C <= 128 * 2)
-            layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32,
-                                                                  (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, rows, C, out_row_map);
+            layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16);
         else if (C <= 128 * 6)
-            layernorm_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32,
-                                                                  (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, rows, C, out_row_map);
+            layernorm_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16);
         else if (C <= 128 * 10)
-            layernorm_kernel<10><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32,
-                                                                   (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, rows, C, out_row_map);
+            layernorm_kernel<10><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16);
         else
-            layernorm_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32,
-                                                                   (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, rows, C, out_row_map);
+            layernorm_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16);
     } else {
-        layernorm_generic_kernel<<<(unsigned)rows, 128, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32,
-                                                                 (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, rows, C, out_row_map);
+        layernorm_generic_kernel<<<(unsigned)rows, 128, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16);
     }
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
+}
+
+extern "C" int hipie_layernorm(const float* x, const float* add, const float* gamma, const float* beta, float eps,
+                               float* sum_out, float* y_f32, void* y_hi, void* y_lo, int64_t rows, int C,
+                               const int32_t* out_row_map, void* stream) {
+    return layernorm_launch(x, add, gamma, beta, eps, sum_out, y_f32, y_hi, y_lo, 0, rows, C, out_row_map, stream);
+}
+
+extern "C" int hipie_layernorm_f16(const float* x, const float* add, const float* gamma, const float* beta, float eps,
+                                   float* sum_out, float* y_f32, void* y_f16, int64_t rows, int C,
+                                   const int32_t* out_row_map, void* stream) {
+    HIPIE_CHECK_ARG(y_f16 != nullptr, "hipie_layernorm_f16: y_f16 required");
+    return layernorm_launch(x, add, gamma, beta, eps, sum_out, y_f32, y_f16, nullptr, 1, rows, C, out_row_map, stream);
 }
 
 extern "C" int hipie_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float eps,

@@ -149,6 +149,7 @@ class Engine:
         self.bf16_value_map = False     # fast mode: MSDeformAttn value map stored as bf16
         self.use_tc_attention = True    # tcgen05 flash attention for the global ViT blocks
         self.attn_fp16 = True           # precision map: QK^T / PV / rel-pos of the ViT attention run as ONE fp16 MMA pass
+        self.qkv_f16x2 = True           # ... and the qkv linears feeding it as TWO fp16 passes (LN output one fp16 plane, W fp16 hi + lo)
         self.taps = None                # parity harness: {"blocks": (7, 15, 31)} -> residual stream copies "vit.block<i>"
 
     # ------------------------------------------------------------ helpers
@@ -208,26 +209,39 @@ class Engine:
             wproj, bproj = W.lin(blk + ".attn.proj")
             if windowed:
                 tok2win, win2tok, nW = self._window_maps(B, gh, gw, ws)
-                rows_w = B * nW * ws * ws
-                xn = self._zero_bf2(("winln", rows_w, E), (rows_w, E))        # pad rows stay exactly zero
-                ops.layernorm(x, W[blk + ".norm1.weight"], W[blk + ".norm1.bias"], 1e-6, row_map=tok2win, out_split=xn)
                 Bq, Tq, qh, qw = B * nW, ws * ws, ws, ws
             else:
-                _, xn, _ = ops.layernorm(x, W[blk + ".norm1.weight"], W[blk + ".norm1.bias"], 1e-6)
                 Bq, Tq, qh, qw = B, T, gh, gw
-            st = (Tq * 3 * E, 3 * E, hd)
             # tcgen05 kernel: 64-wide grids (1024-pixel inputs), 80-wide grids (1280-pixel inputs; T a multiple of lcm(256, 320)) and 14x14 windows
             tc_grid = Tq % 256 == 0 and (qw == 64 or (qw == 80 and Tq % 320 == 0))
             use_tc = self.use_tc_attention and hd == 80 and ((not windowed and tc_grid) or (windowed and ws == 14))
             f16 = use_tc and self.attn_fp16 and ops.PREC == 3
+            # q, k, v are rounded to fp16 by the attention: the linears that produce them take the LayerNorm output as ONE fp16 plane
+            # against fp16 hi + lo weights (two MMA passes; tools/prec_map_emulate.py: +3e-5 on the mask logits, 1-pass would cost 7e-4)
+            qkv2 = f16 and self.qkv_f16x2
+            if windowed:
+                rows_w = B * nW * ws * ws
+                if qkv2:
+                    key = ("winln16", rows_w, E)
+                    if key not in self._bufs:
+                        self._bufs[key] = BF2(torch.zeros((rows_w, E), dtype=torch.float16, device=self.device), None)
+                    xn = self._bufs[key]                                      # pad rows stay exactly zero
+                else:
+                    xn = self._zero_bf2(("winln", rows_w, E), (rows_w, E))
+                ops.layernorm(x, W[blk + ".norm1.weight"], W[blk + ".norm1.bias"], 1e-6, row_map=tok2win, out_split=xn, out_fp16=qkv2)
+            else:
+                _, xn, _ = ops.layernorm(x, W[blk + ".norm1.weight"], W[blk + ".norm1.bias"], 1e-6, out_fp16=qkv2)
+            st = (Tq * 3 * E, 3 * E, hd)
             if use_tc:
                 # q,k as one GEMM (N = 2E); V emitted transposed (E, B*T) so it is the K-major B operand of P.V.  With the fp16
                 # attention mode both epilogues write ONE fp16 plane instead of bf16 hi/lo (half the bytes of the qkv output).
-                wqk, bqk, wv, bv = W.cached(("qk_v", blk), lambda: (ops.split_weight(W[blk + ".attn.qkv.weight"][:2 * E]),
-                                                                     W[blk + ".attn.qkv.bias"][:2 * E].contiguous(),
-                                                                     ops.split_weight(W[blk + ".attn.qkv.weight"][2 * E:]),
-                                                                     W[blk + ".attn.qkv.bias"][2 * E:].contiguous()))
-                _, qk, _ = ops.gemm(xn, wqk, bias=bqk, want_f32=False, want_split=True, out_fp16=f16)   # (B*T, 2E)
+                wsplit = ops.split_weight_f16 if qkv2 else ops.split_weight
+                qprec = 4 if qkv2 else None
+                wqk, bqk, wv, bv = W.cached(("qk_v", blk, qkv2), lambda: (wsplit(W[blk + ".attn.qkv.weight"][:2 * E]),
+                                                                           W[blk + ".attn.qkv.bias"][:2 * E].contiguous(),
+                                                                           wsplit(W[blk + ".attn.qkv.weight"][2 * E:]),
+                                                                           W[blk + ".attn.qkv.bias"][2 * E:].contiguous()))
+                _, qk, _ = ops.gemm(xn, wqk, bias=bqk, want_f32=False, want_split=True, out_fp16=f16, prec=qprec)   # (B*T, 2E)
                 if windowed:
                     # V^T per window at a 200-column pitch (TMA box starts must be 16-byte aligned; 196 is not a multiple of 8);
                     # the 4 pad columns of every window stay zero in this cached buffer
@@ -239,9 +253,9 @@ class Engine:
                     else:
                         vt = self._zero_bf2(("vtwin", E, Bq), (E, Bq * 200))
                     ops.gemm(xn, wv, bias=bv, want_f32=False, transposed=True, ldc=Bq * 200, out_split=vt, t_row_group=Tq, t_row_pad=200 - Tq,
-                             out_fp16=f16)
+                             out_fp16=f16, prec=qprec)
                 else:
-                    _, vt, _ = ops.gemm(xn, wv, bias=bv, want_f32=False, want_split=True, transposed=True, out_fp16=f16)  # (E, B*T)
+                    _, vt, _ = ops.gemm(xn, wv, bias=bv, want_f32=False, want_split=True, transposed=True, out_fp16=f16, prec=qprec)  # (E, B*T)
                 q = BF2(qk.hi[:, 0:E], None if qk.lo is None else qk.lo[:, 0:E])
                 k = BF2(qk.hi[:, E:], None if qk.lo is None else qk.lo[:, E:])
                 st = (Tq * 2 * E, 2 * E, hd)

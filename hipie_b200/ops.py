@@ -155,8 +155,10 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
     prec = PREC if prec is None else prec
     if prec == 3 and (a.lo is None or w.lo is None):
         raise RuntimeError("gemm: prec=3 needs lo planes")
-    if prec == 2 and not (a.hi.dtype == torch.float16 and w.hi.dtype == torch.float16):
-        raise RuntimeError("gemm: prec=2 takes fp16 planes (gemm(out_fp16=True) / row_softmax(out_fp16=True) / split_weight_f16)")
+    if prec in (2, 4) and not (a.hi.dtype == torch.float16 and w.hi.dtype == torch.float16):
+        raise RuntimeError("gemm: prec=2 / 4 take fp16 planes (gemm(out_fp16=True) / layernorm(out_fp16=True) / row_softmax(out_fp16=True) / split_weight_f16)")
+    if prec == 4 and (w.lo is None or w.lo.dtype != torch.float16):
+        raise RuntimeError("gemm: prec=4 (A one fp16 plane, W fp16 hi + lo) needs the weight's fp16 lo plane (split_weight_f16)")
     dev = a.hi.device
     if M is None:
         assert a.hi.dim() == 2 and w.hi.dim() == 2
@@ -191,7 +193,7 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
         ldr = residual.stride(-2) if not transposed else residual.stride(-2)
     args = _lib.GemmArgs(
         a_hi=a.hi.data_ptr(), a_lo=a.lo.data_ptr() if (a.lo is not None and prec == 3) else None, lda=lda, a_bstride=a_bstride,
-        w_hi=w.hi.data_ptr(), w_lo=w.lo.data_ptr() if (w.lo is not None and prec == 3) else None, ldw=ldw, w_bstride=w_bstride,
+        w_hi=w.hi.data_ptr(), w_lo=w.lo.data_ptr() if (w.lo is not None and prec in (3, 4)) else None, ldw=ldw, w_bstride=w_bstride,
         bias=bias.data_ptr() if bias is not None else None,
         colscale=colscale.data_ptr() if colscale is not None else None,
         residual=residual.data_ptr() if residual is not None else None,
@@ -205,7 +207,7 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
         M=M, N=N, K=K, batch=batch, act=act, prec=prec, alpha=float(alpha), transposed=1 if transposed else 0,
         c_row_map=row_map.data_ptr() if row_map is not None else None, t_row_group=t_row_group, t_row_pad=t_row_pad,
         relu_after_residual=1 if relu_after_residual else 0, c_fp16=1 if out_fp16 else 0)
-    tag = ("gemm_tc[f16x1]" if prec == 2 else f"gemm_tc[p{prec}]") + (":mask_embed" if c_bits is not None else "")
+    tag = ("gemm_tc[f16x1]" if prec == 2 else ("gemm_tc[f16x2]" if prec == 4 else f"gemm_tc[p{prec}]")) + (":mask_embed" if c_bits is not None else "")
     if profiler.enabled and profiler.shapes:
         tag += f" {M}x{N}x{K}" + (f"x{batch}" if batch > 1 else "") + ("T" if transposed else "")
     work = 2.0 * M * N * K * batch
@@ -235,7 +237,8 @@ def linear(x: BF2, w: BF2, bias=None, **kw):
 
 
 def layernorm(x, gamma, beta, eps, add=None, want_f32=False, want_split=True, want_sum=False, row_map=None,
-              out_rows=None, out_split: Optional[BF2] = None):
+              out_rows=None, out_split: Optional[BF2] = None, out_fp16=False):
+    """out_fp16: the normalised rows leave as ONE IEEE fp16 plane (BF2(hi=fp16, lo=None)), the A operand of a prec-4 GEMM."""
     x = x.contiguous()
     C = x.shape[-1]
     rows = x.numel() // C
@@ -243,13 +246,22 @@ def layernorm(x, gamma, beta, eps, add=None, want_f32=False, want_split=True, wa
         add = add.contiguous()
     oshape = x.shape if out_rows is None else (out_rows, C)
     y = torch.empty(oshape, dtype=torch.float32, device=x.device) if want_f32 else None
-    s = out_split if out_split is not None else (_empty_bf2(oshape, x.device) if want_split else None)
+    if out_fp16:
+        s = out_split if out_split is not None else BF2(torch.empty(oshape, dtype=torch.float16, device=x.device), None)
+        assert s.hi.dtype == torch.float16 and s.lo is None
+    else:
+        s = out_split if out_split is not None else (_empty_bf2(oshape, x.device) if want_split else None)
     ssum = torch.empty_like(x) if (want_sum and add is not None) else None
-    nbytes = x.numel() * 4.0 * (1 + (add is not None) + (ssum is not None) + (y is not None)) + (x.numel() * 2.0 * (2 if PREC == 3 else 1) if s else 0.0)
+    planes = 1 if (out_fp16 or PREC != 3) else 2
+    nbytes = x.numel() * 4.0 * (1 + (add is not None) + (ssum is not None) + (y is not None)) + (x.numel() * 2.0 * planes if s else 0.0)
     with _timed("layernorm", nbytes):
-        _lib.check(_lib.load().hipie_layernorm(_p(x), _p(add), _p(gamma), _p(beta), float(eps), _p(ssum), _p(y),
-                                               _p(s.hi) if s else None, _p(s.lo) if (s and s.lo is not None) else None,
-                                               rows, C, _p(row_map), _stream()), "layernorm")
+        if out_fp16:
+            _lib.check(_lib.load().hipie_layernorm_f16(_p(x), _p(add), _p(gamma), _p(beta), float(eps), _p(ssum), _p(y), _p(s.hi),
+                                                       rows, C, _p(row_map), _stream()), "layernorm_f16")
+        else:
+            _lib.check(_lib.load().hipie_layernorm(_p(x), _p(add), _p(gamma), _p(beta), float(eps), _p(ssum), _p(y),
+                                                   _p(s.hi) if s else None, _p(s.lo) if (s and s.lo is not None) else None,
+                                                   rows, C, _p(row_map), _stream()), "layernorm")
     return y, s, ssum
 
 

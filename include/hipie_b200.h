@@ -93,6 +93,9 @@ int hipie_msda_fused_forward(const void* value, const int64_t* spatial_shapes,
  * A and W are bf16 "split" operands: a_hi/a_lo and w_hi/w_lo (lo may be NULL when prec == 1).
  *   prec == 1 : C = Ahi.Whi                      (plain bf16, fp32 accumulate)
  *   prec == 3 : C = Ahi.Whi + Ahi.Wlo + Alo.Whi  (bf16x3 split, ~fp32 accuracy)
+ *   prec == 2 : C = A.W, both ONE IEEE fp16 plane  (contractions normalised by a softmax)
+ *   prec == 4 : C = A.Whi + A.Wlo, A ONE fp16 plane, W fp16 hi + lo (a_lo NULL): the weight exact to ~2^-22, the activation
+ *               rounded to fp16 once -- the qkv linears, whose outputs the fp16 attention rounds to fp16 anyway
  * Row strides (in elements) lda / ldw / ldc allow strided sub-matrices; K % 8 == 0,
  * all base pointers 16-byte aligned.  Outputs (any subset, NULL to skip):
  *   c_f32 (fp32), c_hi / c_lo (bf16 split of the fp32 result, for feeding the next GEMM),
@@ -112,7 +115,8 @@ typedef struct hipie_gemm_args {
     int M, N, K, batch;
     int act;                  /* HIPIE_ACT_* */
     int prec;                 /* 3: bf16 hi/lo planes, Ah.Wh + Ah.Wl + Al.Wh (fp32-class); 1: bf16 hi planes, one pass;
-                                 2: a_hi / w_hi are IEEE fp16 planes, one pass (the parity-grade single-pass mode) */
+                                 2: a_hi / w_hi are IEEE fp16 planes, one pass (the parity-grade single-pass mode);
+                                 4: a_hi one fp16 plane, w_hi / w_lo fp16 hi + lo planes, two passes */
     float alpha;              /* scales the accumulator before bias (1.0f default) */
     int transposed;           /* 1: C (and residual, c_hi/lo) addressed as [col * ld + row]; c_bits is then packed along M:
                                  bits[b][col][row/32].  0: c_bits (needs N % 16 == 0) is packed along N: bits[b][row][col/32] */
@@ -146,6 +150,11 @@ int hipie_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream
 int hipie_layernorm(const float* x, const float* add, const float* gamma, const float* beta,
                     float eps, float* sum_out, float* y_f32, void* y_hi, void* y_lo,
                     int64_t rows, int C, const int32_t* out_row_map, void* stream);
+/* Same LayerNorm with the normalised rows written as ONE IEEE fp16 plane: the A operand of a prec-4 (two-pass fp16) hipie_gemm
+ * -- the qkv linears of the ViT blocks (H:backbone/vit.py:67-70), whose outputs are rounded to fp16 for the attention anyway. */
+int hipie_layernorm_f16(const float* x, const float* add, const float* gamma, const float* beta,
+                        float eps, float* sum_out, float* y_f32, void* y_f16,
+                        int64_t rows, int C, const int32_t* out_row_map, void* stream);
 
 /* GroupNorm(G) over NHWC fp32 (N, HW, C) with per-sample strides, optional fused ReLU and a
  * tensor added after the normalisation; stats_ws: 2*N*G doubles of scratch. */

@@ -147,8 +147,10 @@ def _check_unforced(r, detection=True):
     (deformable_transformer_dino.py:228-248), so the RANK ORDER inside the top-k matters, and with seeded random weights the
     encoder scores contain (a) hundreds of EXACT ties -- every border position whose proposal is invalid gets the same
     score, utils: (op > 0.01) & (op < 0.99) -- which torch.topk breaks differently on CPU and CUDA (the reference's own CUDA
-    top-k is not deterministic there), and (b) neighbours closer than fp32 rounding.  Asserted here: the engine's selection is a
-    valid top-k OF THE ORACLE'S SCORES up to 5e-5 ties, every rank swap is between scores closer than 5e-5, and the final
+    top-k is not deterministic there), and (b) neighbours closer than fp32 rounding.  Two scores can change order only when they are
+    closer than twice the largest score error eps = max|s_engine - s_oracle| (asserted < 2e-4 on logits of magnitude ~5, i.e. well
+    inside the 2e-3 class-logit tolerance), so the tie width is 2 eps (at least 5e-5).  Asserted here: the engine's selection is a
+    valid top-k OF THE ORACLE'S SCORES up to such ties, every rank swap is between scores closer than the tie width, and the final
     discrete outputs agree except where such a swap re-paired a query (>= 90 % of the instances one-to-one with identical class,
     score within 1e-4 and box within 0.05 px; semantic argmax >= 99.5 % of the pixels).  The forced variant of the same case
     (proposal ranks pinned, everything downstream unforced) must match completely."""
@@ -158,16 +160,20 @@ def _check_unforced(r, detection=True):
     same_sets = [len(set(a.tolist()) & set(b.tolist())) / a.numel() for a, b in zip(tk_o, tk_u)]
     kth = torch.gather(s_o, 1, tk_o).min(1)[0]
     sel = torch.gather(s_o, 1, tk_u)                       # the oracle's scores of the engine's picks
-    valid_topk = bool((sel >= kth[:, None] - 5e-5).all())
+    eps = (s_o - s_u).abs().max().item()
+    tie = max(5e-5, 2.0 * eps + 1e-6)
+    valid_topk = bool((sel >= kth[:, None] - tie).all())
     rank_gap = (torch.gather(s_o, 1, tk_o) - sel).abs().max().item()      # same rank -> (almost) the same score
-    stats = {"enc_scores_max_abs_err": (s_o - s_u).abs().max().item(), "proposal_topk_overlap": same_sets,
+    stats = {"enc_scores_max_abs_err": eps, "tie_width": tie, "proposal_topk_overlap": same_sets,
              "proposal_topk_identical_order": bool(torch.equal(tk_o, tk_u)), "engine_topk_valid_for_oracle_scores": valid_topk,
              "max_score_gap_at_equal_rank": rank_gap}
     fails = []
+    if eps > 2e-4:
+        fails.append(f"proposal scores differ by {eps}")
     if not valid_topk:
         fails.append("engine proposal top-k is not a top-k of the oracle's scores")
-    if rank_gap > 5e-5:
-        fails.append(f"rank swap between scores {rank_gap} apart")
+    if rank_gap > tie:
+        fails.append(f"rank swap between scores {rank_gap} apart (tie width {tie})")
     for n, (ro, ru) in enumerate(zip(r["res_o"], r["res_u"])):
         io, iu = ro["instances_post"], ru["instances"]
         m = _match_instances(io, iu)

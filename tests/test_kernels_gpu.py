@@ -738,6 +738,72 @@ def _lib_set(name, v):
     _lib.set_option(name, v)
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (4096, 2560, 1280), (2048, 1280, 1280), (1000, 100, 512), (3000, 384, 256), (130, 40, 64)])
+def test_gemm_two_pass_fp16(ops, cuda, M, N, K):
+    """prec 4 (the qkv linears): A is ONE fp16 plane, W is fp16 hi + lo, two MMA passes.  Against fp64 on the SAME
+    fp16-rounded activation the result is fp32-class (the weight is exact to ~2^-22); all tile variants (CTA pairs / single, BN 256 / 128)."""
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + K)
+    a = torch.randn(M, K, device=cuda, generator=g)
+    w = torch.randn(N, K, device=cuda, generator=g) * 0.05
+    b = torch.randn(N, device=cuda, generator=g)
+    A = ops.BF2(a.half(), None)
+    W = ops.split_weight_f16(w)
+    c, s16, _ = ops.gemm(A, W, bias=b, prec=4, want_split=True, out_fp16=True)
+    ref = _gemm_ref(A.hi.float(), w, bias=b)
+    tol = 3e-5 * math.sqrt(K) * 0.05 * 4 + 1e-5
+    err = (c.double() - ref).abs().max().item()
+    assert err < tol, f"max err {err} (tol {tol})"
+    assert torch.equal(s16.hi, c.half())
+    ct, _, _ = ops.gemm(A, W, bias=b, prec=4, transposed=True)
+    assert (ct.t().double() - ref).abs().max().item() < tol
+    with pytest.raises(RuntimeError):
+        ops.gemm(A, ops.BF2(W.hi, None), prec=4)
+
+
+def test_gemm_transposed_fp16_vectorised_epilogue(ops, cuda):
+    """The V^T epilogue (transposed fp16 plane) stores 8 (plain) or 4 (per-window row padding) rows per lane through shared memory: it
+    must write exactly what the scalar epilogue writes, including the untouched pad columns, ragged N and prec 3 / 4 operands."""
+    g = torch.Generator(device="cuda").manual_seed(77)
+    for (M, N, K, grp, pad) in ((2048, 320, 256, 0, 0), (8 * 196, 200, 128, 196, 4), (4096, 1280, 1280, 0, 0), (25 * 196, 1280, 256, 196, 4)):
+        a, w, b = torch.randn(M, K, device=cuda, generator=g), torch.randn(N, K, device=cuda, generator=g) * 0.1, torch.randn(N, device=cuda, generator=g)
+        ld = M if grp == 0 else (M // grp) * (grp + pad)
+        for prec, A, W in ((3, ops.split(a), ops.split_weight(w)), (4, ops.BF2(a.half(), None), ops.split_weight_f16(w))):
+            outs = []
+            for fast in (0, 1):
+                _lib_set("gemm_fast_transposed", fast)
+                buf = ops.BF2(torch.full((N, ld), 7.0, dtype=torch.float16, device=cuda), None)
+                ops.gemm(A, W, bias=b, want_f32=False, transposed=True, ldc=ld, out_split=buf, t_row_group=grp, t_row_pad=pad if grp else 0,
+                         out_fp16=True, prec=prec)
+                outs.append(buf.hi.clone())
+            _lib_set("gemm_fast_transposed", 1)
+            assert torch.equal(outs[0], outs[1])
+            ref = (A.float() if prec == 3 else A.hi.float()) @ w.t() + b
+            got = outs[1].float().view(N, -1, grp + pad)[:, :, :grp].reshape(N, M) if grp else outs[1].float()
+            assert (got.t() - ref).abs().max() < 2e-2
+            if grp:
+                assert (outs[1].view(N, -1, grp + pad)[:, :, grp:] == 7.0).all()
+
+
+def test_layernorm_fp16_plane(ops, cuda):
+    """hipie_layernorm_f16: the same statistics, the normalised rows rounded once to IEEE fp16 (with and without a row map)."""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for C in (1280, 256, 200):
+        x = torch.randn(300, C, device=cuda, generator=g) * 2 + 0.3
+        gm, bt = torch.randn(C, device=cuda, generator=g), torch.randn(C, device=cuda, generator=g)
+        y32, s, _ = ops.layernorm(x, gm, bt, 1e-6, want_f32=True, out_fp16=True)
+        assert s.hi.dtype == torch.float16 and s.lo is None
+        assert torch.equal(s.hi, y32.half())
+        assert (y32 - F.layer_norm(x, (C,), gm, bt, 1e-6)).abs().max() < 2e-5
+    rmap = torch.randperm(300, device=cuda).int()
+    out = ops.BF2(torch.zeros(320, 1280, dtype=torch.float16, device=cuda), None)
+    x = torch.randn(300, 1280, device=cuda, generator=g)
+    gm, bt = torch.randn(1280, device=cuda, generator=g), torch.randn(1280, device=cuda, generator=g)
+    ops.layernorm(x, gm, bt, 1e-6, row_map=rmap, out_split=out, out_fp16=True)
+    assert torch.equal(out.hi[rmap.long()], F.layer_norm(x, (1280,), gm, bt, 1e-6).half()) or \
+        (out.hi[rmap.long()].float() - F.layer_norm(x, (1280,), gm, bt, 1e-6)).abs().max() < 4e-3
+    assert (out.hi[300:] == 0).all()
+
+
 @pytest.mark.parametrize("win", [False, True])
 def test_attention_tcgen05_fp16_single_pass(ops, cuda, win):
     """prec 2: q / k / v^T as single fp16 planes, P as fp16, one MMA pass -- against fp64 attention on the SAME fp16-rounded
