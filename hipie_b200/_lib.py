@@ -27,6 +27,7 @@ class GemmArgs(ctypes.Structure):
         ("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int),
         ("act", c_int), ("prec", c_int), ("alpha", c_float), ("transposed", c_int), ("c_row_map", c_void_p),
         ("t_row_group", c_int), ("t_row_pad", c_int), ("relu_after_residual", c_int), ("c_fp16", c_int),
+        ("a8", c_void_p), ("lda8", c_int64), ("w8", c_void_p), ("ldw8", c_int64), ("c8", c_void_p), ("ldc8", c_int64),
     ]
 
 
@@ -57,7 +58,8 @@ SYMBOLS = {
     "hipie_gemm": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     "hipie_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "hipie_layernorm": (c_int, [c_void_p] * 4 + [c_float] + [c_void_p] * 4 + [c_int64, c_int, c_void_p, c_void_p]),
-    "hipie_layernorm_f16": (c_int, [c_void_p] * 4 + [c_float] + [c_void_p] * 3 + [c_int64, c_int, c_void_p, c_void_p]),
+    "hipie_layernorm_f16": (c_int, [c_void_p] * 4 + [c_float] + [c_void_p] * 4 + [c_int64, c_int, c_void_p, c_void_p]),
+    "hipie_split_f16_e4m3": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "hipie_groupnorm_nhwc": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 5 + [c_int] * 5 + [c_int64] * 3 + [c_void_p]),
     "hipie_add_split": (c_int, [c_void_p] * 5 + [c_int64, c_void_p]),
     "hipie_patchify": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p] * 3),

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -103,6 +104,21 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 // hi/lo planes of a pair: bf16 split, or (fp16 != 0) one IEEE fp16 plane
+// ---- fp16 + e4m3 split (prec 6 of hipie_gemm): x = h + l, h = fp16(x); planes fp16(h), e4m3(h), e4m3(2^10 l) -----------------
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+    return lo | (hi << 16);
+}
+__device__ __forceinline__ void split4_f16_e4m3(const float4& x, uint2& h16, uint32_t& hi8, uint32_t& lo8) {
+    const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+    h16.x = *reinterpret_cast<const uint32_t*>(&h0);
+    h16.y = *reinterpret_cast<const uint32_t*>(&h1);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    hi8 = pack_e4m3x4(f0.x, f0.y, f1.x, f1.y);
+    lo8 = pack_e4m3x4((x.x - f0.x) * 1024.f, (x.y - f0.y) * 1024.f, (x.z - f1.x) * 1024.f, (x.w - f1.y) * 1024.f);
+}
+
 __device__ __forceinline__ void split2m(float a, float b, uint32_t& hi, uint32_t& lo, int fp16) {
     if (fp16) { hi = pack_f16x2(a, b); lo = 0u; }
     else split2(a, b, hi, lo);

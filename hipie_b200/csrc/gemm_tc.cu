@@ -23,6 +23,14 @@
 // prec==4 is the two-pass fp16 mode of the precision map: A is ONE IEEE fp16 plane (an activation that is
 // rounded to fp16 downstream anyway: the LayerNorm output feeding qkv), W is fp16 hi + lo, A.Whi + A.Wlo -- the weight is exact
 // to ~2^-22, the only rounding is the 2^-12 of the activation plane; 3 tiles per 2 MMAs per k-block.
+// prec==6 is the fp16 + e4m3 split (the large ViT linears): with A = Ah + Al, W = Wh + Wl (fp16 hi, exact remainders)
+//     A.W = Ah.Wh  +  2^-14 * ( e4m3(Ah) . e4m3(2^14 Wl)  +  e4m3(2^10 Al) . e4m3(2^4 Wh) )  +  O(2^-16 |A||W|)
+// The cross terms are 2^-11 of the product, so the 2^-4 relative rounding of their e4m3 factors lands at 2^-15..2^-16 -- the
+// class of the bf16x3 scheme (tools/prec_map_emulate.py: mask logits unchanged at 1.4e-4) -- and both of them are ONE fp8
+// contraction over 2K: operand planes A8 = [e4m3(Ah) | e4m3(2^10 Al)] (M x 2K) and W8 = [e4m3(2^14 Wl) | e4m3(2^4 Wh)]
+// (N x 2K).  Per tile the MMA warp first sweeps the fp8 planes (kind::f8f6f4, K = 32 per instruction: twice the rate of the
+// 16-bit kinds), accumulating 2^14 x the cross terms, then the fp16 planes, whose first MMA rescales the accumulator with the
+// instruction's scale-input-d immediate (D = A.B + D * 2^-14).  Two pass-equivalents instead of three, same operand bytes.
 #include "common.cuh"
 #include "ptx.cuh"
 #include <mutex>
@@ -57,6 +65,7 @@ struct GemmParams {
     int f16_ops;     // operands are IEEE fp16 planes (single pass): fp16 instruction descriptor
     int relu_post;   // ReLU after the residual add
     int c_fp16;      // c_hi is one IEEE fp16 plane instead of bf16 hi/lo
+    int c_e4m3;      // ... plus the e4m3 planes [e4m3(h) | e4m3(2^10 (x - h))] of the result (M x 2N, TMA-store path, map tm_c_lo)
     int tma_out;     // row-major outputs leave through TMA stores (32 x 32 boxes staged in swizzled shared memory)
     int m_fastest;   // tile order: 1 = the few M tiles of one N tile run back to back (concurrently on neighbouring SMs), so the
                      // big streamed W operand is fetched from HBM once and re-read from L2 (short, wide problems)
@@ -69,13 +78,17 @@ struct GemmParams {
 // traffic per k-block from 120 KB (over the 128 B/clk port budget: tensor pipe 76 % in round 1) to 80 KB.
 template <int PREC, int BN, int CTAS>
 struct GemmCfg {
-    static constexpr bool P4 = PREC == 4 || PREC == 5;      // 5 = prec 4 with 32-element k-blocks on CTA pairs (A/B variant)
-    static constexpr int BK = (PREC == 3 || PREC == 5 || (PREC == 4 && CTAS == 1)) ? 32 : 64;   // elements; BK*2 bytes == swizzle span
+    static constexpr bool P4 = PREC == 4;
+    static constexpr bool P6 = PREC == 6;                    // fp16 hi.hi sweep + e4m3 sweep for the two cross terms (see the header comment)
+    // elements per k-block of the 16-bit operands; BK*2 bytes == swizzle span.  (prec 4 on CTA pairs: 64-element blocks in 3 stages
+    // measured 4 % faster than 32-element blocks in 6 stages, tools/gemm_p4_micro.py)
+    static constexpr int BK = (PREC == 3 || (PREC == 4 && CTAS == 1)) ? 32 : 64;
+    static constexpr int BK8 = 128;                          // elements (= bytes) per k-block of the e4m3 sweep
     static constexpr int SWZ = BK * 2;
     static constexpr int A_TILE = GEMM_BM * BK * 2;          // bytes
     static constexpr int W_ROWS = BN / CTAS;                 // W rows staged by one CTA
     static constexpr int W_TILE = W_ROWS * BK * 2;
-    static constexpr int A_PLANES = PREC == 3 ? 2 : 1, W_PLANES = (PREC == 3 || P4) ? 2 : 1;
+    static constexpr int A_PLANES = PREC == 3 ? 2 : 1, W_PLANES = (PREC == 3 || P4) ? 2 : 1;     // prec 6: one plane per sweep, same tile bytes
     static constexpr int STAGE = A_PLANES * A_TILE + W_PLANES * W_TILE;     // layout: A_hi | W_hi | (A_lo) | W_lo
     static constexpr int EPI_BYTES = GEMM_EPI_WARPS * EPI_WARP_BYTES;
     static constexpr int SMEM_BUDGET = 232448 - 1024 - 256 - EPI_BYTES;                  // 227 KB per CTA
@@ -327,6 +340,7 @@ __device__ __forceinline__ void epilogue_rows_tma(const GemmParams& p, const CUt
             if (lane == 0) bulk_wait_read0();
             __syncwarp();
             uint32_t word = 0;
+            uint32_t h8[8], l8[8];
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const int col = nbase + 4 * g;
@@ -352,6 +366,12 @@ __device__ __forceinline__ void epilogue_rows_tma(const GemmParams& p, const CUt
                     // fp32 box: 128-byte rows, 16-byte group g of row r at g ^ (r & 7)  (CU_TENSOR_MAP_SWIZZLE_128B)
                     sts128(sbuf + lane * 128 + ((g ^ (lane & 7)) << 4), __float_as_uint(x.x), __float_as_uint(x.y), __float_as_uint(x.z),
                            __float_as_uint(x.w));
+                } else if (p.c_e4m3) {
+                    // fp16 box as below + the two e4m3 boxes (32-byte rows, unswizzled) collected in registers
+                    uint2 hi;
+                    split4_f16_e4m3(x, hi, h8[g], l8[g]);
+                    const uint32_t off = lane * 64 + (((g >> 1) ^ ((lane >> 1) & 3)) << 4) + ((g & 1) << 3);
+                    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sbuf + off), "r"(hi.x), "r"(hi.y) : "memory");
                 } else {
                     // bf16 boxes: 64-byte rows, 16-byte group c of row r at c ^ ((r >> 1) & 3)  (CU_TENSOR_MAP_SWIZZLE_64B)
                     uint2 hi, lo;
@@ -362,6 +382,12 @@ __device__ __forceinline__ void epilogue_rows_tma(const GemmParams& p, const CUt
                     if (p.c_lo) asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sbuf + 2048 + off), "r"(lo.x), "r"(lo.y) : "memory");
                 }
             }
+            if (planes && p.c_e4m3) {
+                sts128(sbuf + 2048 + lane * 32, h8[0], h8[1], h8[2], h8[3]);
+                sts128(sbuf + 2048 + lane * 32 + 16, h8[4], h8[5], h8[6], h8[7]);
+                sts128(sbuf + 3072 + lane * 32, l8[0], l8[1], l8[2], l8[3]);
+                sts128(sbuf + 3072 + lane * 32 + 16, l8[4], l8[5], l8[6], l8[7]);
+            }
             fence_proxy_async_smem();      // generic-proxy writes -> visible to the TMA (async proxy)
             __syncwarp();
             if (lane == 0) {
@@ -369,7 +395,10 @@ __device__ __forceinline__ void epilogue_rows_tma(const GemmParams& p, const CUt
                     tma_store_3d(tm_f32, sbuf, nbase, m0, b);
                 } else {
                     tma_store_3d(tm_hi, sbuf, nbase, m0, b);
-                    if (p.c_lo) tma_store_3d(tm_lo, sbuf + 2048, nbase, m0, b);
+                    if (p.c_e4m3) {
+                        tma_store_3d(tm_lo, sbuf + 2048, nbase, m0, b);             // e4m3(h)          -> columns [0, N)
+                        tma_store_3d(tm_lo, sbuf + 3072, p.N + nbase, m0, b);       // e4m3(2^10 (x-h)) -> columns [N, 2N)
+                    } else if (p.c_lo) tma_store_3d(tm_lo, sbuf + 2048, nbase, m0, b);
                 }
                 bulk_commit();
             }
@@ -513,7 +542,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int lane = threadIdx.x & 31;
     const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
-    const int num_kb = (p.K + BK - 1) / BK;
+    const int num_kb8 = Cfg::P6 ? (2 * p.K + Cfg::BK8 - 1) / Cfg::BK8 : 0;     // k-blocks of the e4m3 sweep (planes are 2K wide)
+    const int num_kb = num_kb8 + (p.K + BK - 1) / BK;
     const int tiles_per_batch = p.tiles_m * p.tiles_n;      // tiles_m counts (128 * CTAS)-row tiles
     const int total_tiles = tiles_per_batch * p.batch;
     const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
@@ -564,6 +594,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* st = stage_base + s * Cfg::STAGE;
+                    if (Cfg::P6) {
+                        // sweep 1: e4m3 planes (maps tm_a_lo / tm_w_lo, 128-byte k-blocks); sweep 2: fp16 planes (64-element k-blocks)
+                        const bool f8 = kb < num_kb8;
+                        const int k0 = f8 ? kb * Cfg::BK8 : (kb - num_kb8) * BK;
+                        const CUtensorMap* ma = f8 ? &tm_a_lo : &tm_a_hi;
+                        const CUtensorMap* mw = f8 ? &tm_w_lo : &tm_w_hi;
+                        if (CTAS == 1) {
+                            mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
+                            tma_load_3d(st, ma, &full_bar[s], k0, m0, b);
+                            tma_load_3d(st + Cfg::A_TILE, mw, &full_bar[s], k0, n0, b);
+                        } else {
+                            if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE);
+                            tma_load_3d_2sm(st, ma, &full_bar[s], k0, m0, b);
+                            tma_load_3d_2sm(st + Cfg::A_TILE, mw, &full_bar[s], k0, n0, b);
+                        }
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                        continue;
+                    }
                     const int k0 = kb * BK;
                     if (CTAS == 1) {
                         mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE);
@@ -609,11 +657,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         const uint32_t st = smem_u32(stage_base + s * Cfg::STAGE);
                         const uint64_t a_hi = make_kmajor_desc<Cfg::SWZ>(st);
                         const uint64_t w_hi = make_kmajor_desc<Cfg::SWZ>(st + Cfg::A_TILE);
+                        if (Cfg::P6) {
+                            // 32 bytes along K per MMA in both sweeps (32 e4m3 or 16 fp16 elements): +2 in addr>>4 units
+                            if (kb < num_kb8) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in addr>>4 units
-                            if (CTAS == 2) umma_f16_2sm(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
-                            else umma_f16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
+                                for (int k = 0; k < 4; ++k) {
+                                    if (CTAS == 2) umma_f8_2sm(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
+                                    else umma_f8(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (kb == num_kb8 && k == 0) {     // first fp16 MMA: D = A.B + D * 2^-14
+                                        if (CTAS == 2) umma_f16_2sm_scale14(d_tmem, a_hi, w_hi, idesc);
+                                        else umma_f16_scale14(d_tmem, a_hi, w_hi, idesc);
+                                    } else {
+                                        if (CTAS == 2) umma_f16_2sm(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, 1);
+                                        else umma_f16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, 1);
+                                    }
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in addr>>4 units
+                                if (CTAS == 2) umma_f16_2sm(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
+                                else umma_f16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
+                            }
                         }
                         if (Cfg::P4) {
                             const uint64_t w_lo = make_kmajor_desc<Cfg::SWZ>(st + Cfg::A_TILE + Cfg::W_TILE);
@@ -663,7 +733,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if (p.tma_out && lane == 0) {
             if (p.c_f32) prefetch_tmap(&tm_c_f32);
             if (p.c_hi) prefetch_tmap(&tm_c_hi);
-            if (p.c_lo) prefetch_tmap(&tm_c_lo);
+            if (p.c_lo || p.c_e4m3) prefetch_tmap(&tm_c_lo);
         }
         constexpr int COLS_PER = BN / 4 >= 32 ? BN / 4 : 32;   // columns per warp (multiple of the 32-column transposed chunk)
         const bool active = cgroup * COLS_PER < BN;
@@ -768,7 +838,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols
     return make_tmap(out, ptr, 2, rows, cols, ld, batch, bstride, box_rows, box_cols);
 }
 
-// matrix (batch, rows, cols) of 2-byte (bf16) or 4-byte (fp32) elements; swizzle span == box_cols * esize bytes (32 / 64 / 128)
+// matrix (batch, rows, cols) of 1-byte (e4m3), 2-byte (bf16 / fp16) or 4-byte (fp32) elements; swizzle span == box_cols * esize bytes (32 / 64 / 128)
 int make_tmap(CUtensorMap* out, const void* ptr, int esize, int64_t rows, int64_t cols, int64_t ld, int batch, int64_t bstride,
               int box_rows, int box_cols) {
     static std::mutex mu;
@@ -793,7 +863,9 @@ int make_tmap(CUtensorMap* out, const void* ptr, int esize, int64_t rows, int64_
     cuuint32_t estr[3] = {1, 1, 1};
     CUtensorMapSwizzle swz = box_cols * esize == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                              : (box_cols * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    CUresult r = enc(out, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+    if (esize == 1 && box_cols == 32) swz = CU_TENSOR_MAP_SWIZZLE_NONE;        // e4m3 output boxes: plain 32-byte rows
+    const CUtensorMapDataType dt = esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    CUresult r = enc(out, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -813,7 +885,6 @@ int make_tmap(CUtensorMap* out, const void* ptr, int esize, int64_t rows, int64_
 int g_gemm_cta_pairs = 1;
 int g_gemm_tma_store = 1;
 int g_gemm_fast_transposed = 1;   // vectorised fp16-plane transposed epilogue (A/B switch)
-int g_gemm_p4_bk32 = 0;       // prec 4 on CTA pairs: 32-element k-blocks (6 stages of 24 KB) instead of 64 (3 stages of 48 KB)
 
 // fp32 tensor of rank 5 (dims / strides innermost first, strides in BYTES for dims 1..4), dense unswizzled boxes: the value-map
 // windows of the shared-memory MSDeformAttn kernel (msda.cu).  Not cached: built once per launch from host-side geometry.
@@ -848,6 +919,10 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     if ((rc = make_tmap_bf16(&tw_hi, a->w_hi, a->N, a->K, a->ldw, a->batch, a->w_bstride, Cfg::W_ROWS, Cfg::BK))) return rc;
     ta_lo = ta_hi;
     tw_lo = tw_hi;
+    if (Cfg::P6) {       // e4m3 planes, 2K wide, 128-byte k-blocks
+        if ((rc = make_tmap(&ta_lo, a->a8, 1, a->M, 2 * (int64_t)a->K, a->lda8, 1, 0, GEMM_BM, Cfg::BK8))) return rc;
+        if ((rc = make_tmap(&tw_lo, a->w8, 1, a->N, 2 * (int64_t)a->K, a->ldw8, 1, 0, Cfg::W_ROWS, Cfg::BK8))) return rc;
+    }
     if (PREC == 3 && (rc = make_tmap_bf16(&ta_lo, a->a_lo, a->M, a->K, a->lda, a->batch, a->a_bstride, GEMM_BM, Cfg::BK))) return rc;
     if ((PREC == 3 || Cfg::P4) &&
         (rc = make_tmap_bf16(&tw_lo, a->w_lo, a->N, a->K, a->ldw, a->batch, a->w_bstride, Cfg::W_ROWS, Cfg::BK))) return rc;
@@ -859,18 +934,21 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
     if (a->c_hi) tma_out = tma_out && al16(a->c_hi) && (!a->c_lo || al16(a->c_lo)) && (a->ldc * 2) % 16 == 0 &&
                            (a->batch == 1 || (a->c_bstride * 2) % 16 == 0);
     if (!a->c_f32 && !a->c_hi) tma_out = false;
+    HIPIE_CHECK_ARG(!a->c8 || tma_out, "hipie_gemm: the e4m3 output planes (c8) need the TMA-store epilogue (row-major, no residual / row map, aligned)");
     CUtensorMap tc_f32 = ta_hi, tc_hi = ta_hi, tc_lo = ta_hi;
     if (tma_out) {
         const int64_t cbs = a->batch > 1 ? a->c_bstride : (int64_t)a->M * a->ldc;
         if (a->c_f32 && (rc = make_tmap(&tc_f32, a->c_f32, 4, a->M, a->N, a->ldc, a->batch, cbs, 32, 32))) return rc;
         if (a->c_hi && (rc = make_tmap(&tc_hi, a->c_hi, 2, a->M, a->N, a->ldc, a->batch, cbs, 32, 32))) return rc;
         if (a->c_lo && (rc = make_tmap(&tc_lo, a->c_lo, 2, a->M, a->N, a->ldc, a->batch, cbs, 32, 32))) return rc;
+        if (a->c8 && (rc = make_tmap(&tc_lo, a->c8, 1, a->M, 2 * (int64_t)a->N, a->ldc8, 1, 0, 32, 32))) return rc;
     }
     GemmParams p;
     p.tma_out = tma_out ? 1 : 0;
     p.c_fp16 = a->c_fp16 ? 1 : 0;
+    p.c_e4m3 = a->c8 ? 1 : 0;
     p.relu_post = a->relu_after_residual ? 1 : 0;
-    p.f16_ops = (a->prec == 2 || a->prec == 4) ? 1 : 0;
+    p.f16_ops = (a->prec == 2 || a->prec == 4 || a->prec == 6) ? 1 : 0;
     p.bias = a->bias; p.colscale = a->colscale; p.residual = a->residual;
     p.ldr = a->ldr; p.r_bstride = a->r_bstride;
     p.c_f32 = a->c_f32; p.c_hi = (__nv_bfloat16*)a->c_hi; p.c_lo = (__nv_bfloat16*)a->c_lo;
@@ -922,7 +1000,12 @@ using namespace hipie;
 extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     HIPIE_CHECK_ARG(a != nullptr, "hipie_gemm: null args");
     HIPIE_CHECK_ARG(a->a_hi && a->w_hi, "hipie_gemm: a_hi / w_hi required");
-    HIPIE_CHECK_ARG(a->prec >= 1 && a->prec <= 4, "hipie_gemm: prec must be 1, 2, 3 or 4 (got %d)", a->prec);
+    HIPIE_CHECK_ARG((a->prec >= 1 && a->prec <= 4) || a->prec == 6, "hipie_gemm: prec must be 1, 2, 3, 4 or 6 (got %d)", a->prec);
+    HIPIE_CHECK_ARG(a->prec != 6 || (a->a8 && a->w8 && a->batch == 1 && a->lda8 % 16 == 0 && a->ldw8 % 16 == 0 && a->lda8 >= 2 * (int64_t)a->K &&
+                                     a->ldw8 >= 2 * (int64_t)a->K),
+                    "hipie_gemm: prec 6 needs the e4m3 planes a8 (M x 2K) / w8 (N x 2K) with 16-byte aligned row strides, batch 1");
+    HIPIE_CHECK_ARG(!a->c8 || (a->c_fp16 && a->c_hi && !a->c_lo && a->N % 32 == 0 && a->batch == 1 && a->ldc8 % 16 == 0 && a->ldc8 >= 2 * (int64_t)a->N),
+                    "hipie_gemm: c8 (e4m3 planes of the result) goes with c_fp16, N %% 32 == 0, batch 1 and a 16-byte aligned ldc8 >= 2N");
     HIPIE_CHECK_ARG(a->prec != 3 || (a->a_lo && a->w_lo), "hipie_gemm: prec 3 needs a_lo and w_lo");
     HIPIE_CHECK_ARG(a->prec != 4 || a->w_lo, "hipie_gemm: prec 4 (A fp16, W fp16 hi + lo) needs w_lo");
     HIPIE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "hipie_gemm: bad sizes M=%d N=%d K=%d batch=%d",
@@ -939,10 +1022,13 @@ extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     // CTA pairs where the mainloop dominates: big row counts, K >= 512, 3-pass operands (ViT / BERT / VL linears).  Measured on
     // B200 (tools/gemm_check.py, profiles/r02_gemm_pairs.txt): fc1 32768x5120x1280 0.944 -> 0.844 ms, qk 0.489 -> 0.454 ms;
     // K = 256 problems are epilogue/store-bound and lose 8-10 % with pairs, single-pass operands gain nothing.
-    const bool pairs = g_gemm_cta_pairs && a->M >= 1024 && a->N > 64 && a->K >= 512 && (a->prec == 3 || a->prec == 4);
+    const bool pairs = g_gemm_cta_pairs && a->M >= 1024 && a->N > 64 && a->K >= 512 && (a->prec == 3 || a->prec == 4 || a->prec == 6);
+    if (a->prec == 6) {                    // fp16 + e4m3 split (the large ViT linears)
+        if (a->N <= 128) return pairs ? launch_gemm<6, 128, 2>(a, st) : launch_gemm<6, 128, 1>(a, st);
+        return pairs ? launch_gemm<6, 256, 2>(a, st) : launch_gemm<6, 256, 1>(a, st);
+    }
     if (a->prec == 4) {                    // two-pass fp16 (the qkv linears): wide outputs only
         if (a->N <= 128) return pairs ? launch_gemm<4, 128, 2>(a, st) : launch_gemm<4, 128, 1>(a, st);
-        if (pairs && g_gemm_p4_bk32) return launch_gemm<5, 256, 2>(a, st);
         return pairs ? launch_gemm<4, 256, 2>(a, st) : launch_gemm<4, 256, 1>(a, st);
     }
     const bool p3 = a->prec == 3;          // prec 1 (bf16) and prec 2 (fp16) share the single-plane kernels; the MMA kind differs
@@ -959,7 +1045,6 @@ extern "C" int hipie_set_option(const char* name, int value) {
     HIPIE_CHECK_ARG(name != nullptr, "hipie_set_option: null name");
     if (strcmp(name, "gemm_cta_pairs") == 0) { g_gemm_cta_pairs = value ? 1 : 0; return HIPIE_OK; }
     if (strcmp(name, "gemm_tma_store") == 0) { g_gemm_tma_store = value ? 1 : 0; return HIPIE_OK; }
-    if (strcmp(name, "gemm_p4_bk32") == 0) { g_gemm_p4_bk32 = value ? 1 : 0; return HIPIE_OK; }
     if (strcmp(name, "gemm_fast_transposed") == 0) { g_gemm_fast_transposed = value ? 1 : 0; return HIPIE_OK; }
     set_error("hipie_set_option: unknown option '%s'", name);
     return HIPIE_EINVAL;

@@ -515,6 +515,45 @@ static inline int grid_for(int64_t n, int threads = 256) {
 
 using namespace hipie;
 
+// fp32 (rows, cols) -> fp16 plane + e4m3 planes of a prec-6 GEMM operand (gemm_tc.cu); thread = 4 consecutive columns
+__global__ void __launch_bounds__(256)
+split_f16_e4m3_kernel(const float* __restrict__ x, __half* __restrict__ h16, uint8_t* __restrict__ p8, int64_t rows, int cols, int weight) {
+    const int c4 = cols >> 2;
+    const int64_t total = rows * c4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / c4;
+        const int c = (int)(i - r * c4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + r * cols + c);
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        uint2 h;
+        h.x = *reinterpret_cast<const uint32_t*>(&h0);
+        h.y = *reinterpret_cast<const uint32_t*>(&h1);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        uint32_t first, second;
+        if (weight) {      // [e4m3(2^14 (w - h)) | e4m3(2^4 h)]
+            first = pack_e4m3x4((v.x - f0.x) * 16384.f, (v.y - f0.y) * 16384.f, (v.z - f1.x) * 16384.f, (v.w - f1.y) * 16384.f);
+            second = pack_e4m3x4(f0.x * 16.f, f0.y * 16.f, f1.x * 16.f, f1.y * 16.f);
+        } else {           // [e4m3(h) | e4m3(2^10 (a - h))]
+            first = pack_e4m3x4(f0.x, f0.y, f1.x, f1.y);
+            second = pack_e4m3x4((v.x - f0.x) * 1024.f, (v.y - f0.y) * 1024.f, (v.z - f1.x) * 1024.f, (v.w - f1.y) * 1024.f);
+        }
+        *reinterpret_cast<uint2*>(h16 + r * cols + c) = h;
+        *reinterpret_cast<uint32_t*>(p8 + r * 2 * cols + c) = first;
+        *reinterpret_cast<uint32_t*>(p8 + r * 2 * cols + cols + c) = second;
+    }
+}
+
+extern "C" int hipie_split_f16_e4m3(const float* x, void* h16, void* p8, int64_t rows, int cols, int weight, void* stream) {
+    HIPIE_CHECK_ARG(x && h16 && p8, "hipie_split_f16_e4m3: null pointer");
+    HIPIE_CHECK_ARG(rows >= 0 && cols > 0 && cols % 4 == 0, "hipie_split_f16_e4m3: cols must be a positive multiple of 4");
+    if (rows == 0) return HIPIE_OK;
+    const int64_t total = rows * (cols / 4);
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+    split_f16_e4m3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__half*)h16, (uint8_t*)p8, rows, cols, weight);
+    HIPIE_CHECK_LAUNCH();
+    return HIPIE_OK;
+}
+
 extern "C" int hipie_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
     HIPIE_CHECK_ARG(x && hi, "hipie_split_bf16: null pointer");
     HIPIE_CHECK_ARG(n % 4 == 0, "hipie_split_bf16: n must be a multiple of 4");

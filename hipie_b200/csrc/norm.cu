@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, float* __restrict__ sum_out,
                  float* __restrict__ y_f32, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
-                 int64_t rows, int C, const int* __restrict__ omap, int y_fp16) {
+                 int64_t rows, int C, const int* __restrict__ omap, int y_fp16, uint8_t* __restrict__ y8) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= rows) return;
@@ -56,7 +56,14 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, con
             o.z = (v[i].z - mean) * rstd * g.z + b.z;
             o.w = (v[i].w - mean) * rstd * g.w + b.w;
             if (y_f32) *reinterpret_cast<float4*>(y_f32 + orow * C + c0) = o;
-            if (y_hi) {
+            if (y_hi && y8) {                                // fp16 plane + e4m3 planes [e4m3(h) | e4m3(2^10 (o - h))] (prec-6 GEMM operand)
+                uint2 h16;
+                uint32_t a8, b8;
+                split4_f16_e4m3(o, h16, a8, b8);
+                *reinterpret_cast<uint2*>(y_hi + orow * C + c0) = h16;
+                *reinterpret_cast<uint32_t*>(y8 + orow * 2 * C + c0) = a8;
+                *reinterpret_cast<uint32_t*>(y8 + orow * 2 * C + C + c0) = b8;
+            } else if (y_hi) {
                 uint2 hi, lo;
                 split2m(o.x, o.y, hi.x, lo.x, y_fp16);       // y_fp16: y_hi is ONE IEEE fp16 plane (y_lo NULL)
                 split2m(o.z, o.w, hi.y, lo.y, y_fp16);
@@ -73,7 +80,7 @@ layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ 
                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                          float* __restrict__ sum_out, float* __restrict__ y_f32,
                          __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, int64_t rows, int C,
-                         const int* __restrict__ omap, int y_fp16) {
+                         const int* __restrict__ omap, int y_fp16, uint8_t* __restrict__ y8) {
     __shared__ float red[4];
     __shared__ float bc;
     const int64_t row = blockIdx.x;
@@ -108,7 +115,12 @@ layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ 
         const float o = (v - mean) * rstd * gamma[c] + beta[c];
         if (y_f32) y_f32[orow * C + c] = o;
         if (y_hi && y_fp16) {
-            reinterpret_cast<__half*>(y_hi)[orow * C + c] = __float2half_rn(o);
+            const __half h = __float2half_rn(o);
+            reinterpret_cast<__half*>(y_hi)[orow * C + c] = h;
+            if (y8) {
+                y8[orow * 2 * C + c] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(h), __NV_SATFINITE, __NV_E4M3);
+                y8[orow * 2 * C + C + c] = (uint8_t)__nv_cvt_float_to_fp8((o - __half2float(h)) * 1024.f, __NV_SATFINITE, __NV_E4M3);
+            }
         } else if (y_hi) {
             const __nv_bfloat16 h = __float2bfloat16_rn(o);
             y_hi[orow * C + c] = h;
@@ -199,7 +211,7 @@ using namespace hipie;
 
 static int layernorm_launch(const float* x, const float* add, const float* gamma, const float* beta, float eps,
                             float* sum_out, float* y_f32, void* y_hi, void* y_lo, int y_fp16, int64_t rows, int C,
-                            const int32_t* out_row_map, void* stream) {
+                            const int32_t* out_row_map, void* stream, uint8_t* y8 = nullptr) {
     HIPIE_CHECK_ARG(x && gamma && beta, "hipie_layernorm: null input");
     HIPIE_CHECK_ARG(y_f32 || y_hi, "hipie_layernorm: no output requested");
     HIPIE_CHECK_ARG(rows >= 0 && C > 0, "hipie_layernorm: bad sizes");
@@ -209,15 +221,15 @@ static int layernorm_launch(const float* x, const float* add, const float* gamma
     if (C % 128 == 0 && C <= 128 * 16) {
         const int64_t blocks = (rows + 7) / 8;
         if (C <= 128 * 2)
-            layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16);
+            layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
         else if (C <= 128 * 6)
-            layernorm_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16);
+            layernorm_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
         else if (C <= 128 * 10)
-            layernorm_kernel<10><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16);
+            layernorm_kernel<10><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
         else
-            layernorm_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16);
+            layernorm_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
     } else {
-        layernorm_generic_kernel<<<(unsigned)rows, 128, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16);
+        layernorm_generic_kernel<<<(unsigned)rows, 128, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
     }
     HIPIE_CHECK_LAUNCH();
     return HIPIE_OK;
@@ -230,10 +242,11 @@ extern "C" int hipie_layernorm(const float* x, const float* add, const float* ga
 }
 
 extern "C" int hipie_layernorm_f16(const float* x, const float* add, const float* gamma, const float* beta, float eps,
-                                   float* sum_out, float* y_f32, void* y_f16, int64_t rows, int C,
+                                   float* sum_out, float* y_f32, void* y_f16, void* y_e4m3, int64_t rows, int C,
                                    const int32_t* out_row_map, void* stream) {
     HIPIE_CHECK_ARG(y_f16 != nullptr, "hipie_layernorm_f16: y_f16 required");
-    return layernorm_launch(x, add, gamma, beta, eps, sum_out, y_f32, y_f16, nullptr, 1, rows, C, out_row_map, stream);
+    HIPIE_CHECK_ARG(!y_e4m3 || C % 4 == 0, "hipie_layernorm_f16: the e4m3 planes need C %% 4 == 0");
+    return layernorm_launch(x, add, gamma, beta, eps, sum_out, y_f32, y_f16, nullptr, 1, rows, C, out_row_map, stream, (uint8_t*)y_e4m3);
 }
 
 extern "C" int hipie_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float eps,

@@ -103,6 +103,9 @@ class BF2:
 
     def float(self):
         f = self.hi.float()
+        if self.lo is not None and self.lo.dtype == torch.uint8:      # fp16 + e4m3 planes of an ACTIVATION (split_f16_e4m3): [e4m3(h) | e4m3(2^10 l)]
+            K = self.hi.shape[-1]
+            return f + self.lo[..., K:].view(torch.float8_e4m3fn).float() / 1024.0
         return f if self.lo is None else f + self.lo.float()
 
 
@@ -129,6 +132,18 @@ def split_weight(w: torch.Tensor) -> BF2:
     return out
 
 
+def split_f16_e4m3(x: torch.Tensor, weight=False) -> BF2:
+    """Operand planes of a prec-6 GEMM (fp16 hi x hi pass + ONE e4m3 pass for both cross terms): hi = fp16(x) (rows, K),
+    lo = uint8 storage of the e4m3 planes (rows, 2K): activations [e4m3(h) | e4m3(2^10 (x - h))], weights [e4m3(2^14 (w - h)) | e4m3(2^4 h)]."""
+    x = x.contiguous().float()
+    K = x.shape[-1]
+    rows = x.numel() // K
+    h = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    p8 = torch.empty(x.shape[:-1] + (2 * K,), dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.load().hipie_split_f16_e4m3(_p(x), _p(h), _p(p8), rows, K, 1 if weight else 0, _stream()), "split_f16_e4m3")
+    return BF2(h, p8)
+
+
 def add_split(a, b=None, want_f32=False, want_split=True):
     a = a.contiguous()
     if b is not None:
@@ -144,7 +159,8 @@ def add_split(a, b=None, want_f32=False, want_split=True):
 def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, alpha=1.0, want_f32=True,
          want_split=False, out_f32=None, transposed=False, row_map=None, out_rows=None, bits_threshold=None,
          M=None, N=None, K=None, batch=1, lda=None, ldw=None, a_bstride=0, w_bstride=0, ldc=None, c_bstride=0,
-         ldr=None, r_bstride=0, prec=None, out_split=None, t_row_group=0, t_row_pad=0, out_fp16=False, relu_after_residual=False):
+         ldr=None, r_bstride=0, prec=None, out_split=None, t_row_group=0, t_row_pad=0, out_fp16=False, relu_after_residual=False,
+         out_e4m3=False):
     """C = act(alpha * A.W^T + bias) * colscale + residual.
 
     A: (.., M, K) planes, W: (N, K) planes.  Default: 2-D row-major operands.  Strided / batched views
@@ -155,7 +171,9 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
     prec = PREC if prec is None else prec
     if prec == 3 and (a.lo is None or w.lo is None):
         raise RuntimeError("gemm: prec=3 needs lo planes")
-    if prec in (2, 4) and not (a.hi.dtype == torch.float16 and w.hi.dtype == torch.float16):
+    if prec == 6 and not (a.lo is not None and w.lo is not None and a.lo.dtype == torch.uint8 and w.lo.dtype == torch.uint8):
+        raise RuntimeError("gemm: prec=6 takes fp16 + e4m3 planes (split_f16_e4m3 / layernorm(out_e4m3=True) / gemm(out_e4m3=True))")
+    if prec in (2, 4, 6) and not (a.hi.dtype == torch.float16 and w.hi.dtype == torch.float16):
         raise RuntimeError("gemm: prec=2 / 4 take fp16 planes (gemm(out_fp16=True) / layernorm(out_fp16=True) / row_softmax(out_fp16=True) / split_weight_f16)")
     if prec == 4 and (w.lo is None or w.lo.dtype != torch.float16):
         raise RuntimeError("gemm: prec=4 (A one fp16 plane, W fp16 hi + lo) needs the weight's fp16 lo plane (split_weight_f16)")
@@ -181,7 +199,13 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
     padded = transposed and batch == 1 and ldc is not None and ldc > rows_out
     ashape = (N, ldc) if padded else shape
     c_f32 = out_f32 if out_f32 is not None else (torch.empty(ashape, dtype=torch.float32, device=dev) if want_f32 else None)
-    if out_fp16:       # one IEEE fp16 plane (operand of the single-pass fp16 contractions); returned as BF2(hi=fp16 tensor, lo=None)
+    c8 = None
+    if out_e4m3:       # fp16 plane + e4m3 planes (rows, 2N): the A operand of a following prec-6 GEMM
+        assert not transposed and batch == 1 and out_split is None
+        c8 = torch.empty((rows_out, 2 * N), dtype=torch.uint8, device=dev)
+        c_split = BF2(torch.empty(ashape, dtype=torch.float16, device=dev), None)
+        out_fp16 = True
+    elif out_fp16:     # one IEEE fp16 plane (operand of the single-pass fp16 contractions); returned as BF2(hi=fp16 tensor, lo=None)
         c_split = out_split if out_split is not None else BF2(torch.empty(ashape, dtype=torch.float16, device=dev), None)
         assert c_split.lo is None
     else:
@@ -206,8 +230,11 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
         bits_threshold=float(bits_threshold) if bits_threshold is not None else 0.0,
         M=M, N=N, K=K, batch=batch, act=act, prec=prec, alpha=float(alpha), transposed=1 if transposed else 0,
         c_row_map=row_map.data_ptr() if row_map is not None else None, t_row_group=t_row_group, t_row_pad=t_row_pad,
-        relu_after_residual=1 if relu_after_residual else 0, c_fp16=1 if out_fp16 else 0)
-    tag = ("gemm_tc[f16x1]" if prec == 2 else ("gemm_tc[f16x2]" if prec == 4 else f"gemm_tc[p{prec}]")) + (":mask_embed" if c_bits is not None else "")
+        relu_after_residual=1 if relu_after_residual else 0, c_fp16=1 if out_fp16 else 0,
+        a8=a.lo.data_ptr() if prec == 6 else None, lda8=a.lo.stride(-2) if prec == 6 else 0,
+        w8=w.lo.data_ptr() if prec == 6 else None, ldw8=w.lo.stride(-2) if prec == 6 else 0,
+        c8=c8.data_ptr() if c8 is not None else None, ldc8=2 * N if c8 is not None else 0)
+    tag = {2: "gemm_tc[f16x1]", 4: "gemm_tc[f16x2]", 6: "gemm_tc[f16+e4m3]"}.get(prec, f"gemm_tc[p{prec}]") + (":mask_embed" if c_bits is not None else "")
     if profiler.enabled and profiler.shapes:
         tag += f" {M}x{N}x{K}" + (f"x{batch}" if batch > 1 else "") + ("T" if transposed else "")
     work = 2.0 * M * N * K * batch
@@ -215,6 +242,8 @@ def gemm(a: BF2, w: BF2, bias=None, act=ACT_NONE, colscale=None, residual=None, 
         work = float(batch) * ((M * K + N * K) * 2.0 * (2 if prec == 3 else 1) + M * N * 4.0 + M * N / 8.0)
     with _timed(tag, work):
         _lib.check(lib.hipie_gemm(ctypes.byref(args), _stream()), "gemm")
+    if c8 is not None:
+        c_split = BF2(c_split.hi, c8)
     if padded:
         if c_f32 is not None and out_f32 is None:
             c_f32 = c_f32[:, :rows_out]
@@ -237,8 +266,10 @@ def linear(x: BF2, w: BF2, bias=None, **kw):
 
 
 def layernorm(x, gamma, beta, eps, add=None, want_f32=False, want_split=True, want_sum=False, row_map=None,
-              out_rows=None, out_split: Optional[BF2] = None, out_fp16=False):
-    """out_fp16: the normalised rows leave as ONE IEEE fp16 plane (BF2(hi=fp16, lo=None)), the A operand of a prec-4 GEMM."""
+              out_rows=None, out_split: Optional[BF2] = None, out_fp16=False, out_e4m3=False):
+    """out_fp16: the normalised rows leave as ONE IEEE fp16 plane (BF2(hi=fp16, lo=None)), the A operand of a prec-4 GEMM;
+    out_e4m3: fp16 plane + e4m3 planes (rows, 2C) (BF2(hi=fp16, lo=uint8)), the A operand of a prec-6 GEMM."""
+    out_fp16 = out_fp16 or out_e4m3
     x = x.contiguous()
     C = x.shape[-1]
     rows = x.numel() // C
@@ -246,18 +277,21 @@ def layernorm(x, gamma, beta, eps, add=None, want_f32=False, want_split=True, wa
         add = add.contiguous()
     oshape = x.shape if out_rows is None else (out_rows, C)
     y = torch.empty(oshape, dtype=torch.float32, device=x.device) if want_f32 else None
-    if out_fp16:
+    if out_e4m3:
+        assert out_split is None and row_map is None
+        s = BF2(torch.empty(oshape, dtype=torch.float16, device=x.device), torch.empty(tuple(oshape[:-1]) + (2 * C,), dtype=torch.uint8, device=x.device))
+    elif out_fp16:
         s = out_split if out_split is not None else BF2(torch.empty(oshape, dtype=torch.float16, device=x.device), None)
         assert s.hi.dtype == torch.float16 and s.lo is None
     else:
         s = out_split if out_split is not None else (_empty_bf2(oshape, x.device) if want_split else None)
     ssum = torch.empty_like(x) if (want_sum and add is not None) else None
-    planes = 1 if (out_fp16 or PREC != 3) else 2
+    planes = 2 if (out_e4m3 or (PREC == 3 and not out_fp16)) else 1
     nbytes = x.numel() * 4.0 * (1 + (add is not None) + (ssum is not None) + (y is not None)) + (x.numel() * 2.0 * planes if s else 0.0)
     with _timed("layernorm", nbytes):
         if out_fp16:
             _lib.check(_lib.load().hipie_layernorm_f16(_p(x), _p(add), _p(gamma), _p(beta), float(eps), _p(ssum), _p(y), _p(s.hi),
-                                                       rows, C, _p(row_map), _stream()), "layernorm_f16")
+                                                       _p(s.lo) if out_e4m3 else None, rows, C, _p(row_map), _stream()), "layernorm_f16")
         else:
             _lib.check(_lib.load().hipie_layernorm(_p(x), _p(add), _p(gamma), _p(beta), float(eps), _p(ssum), _p(y),
                                                    _p(s.hi) if s else None, _p(s.lo) if (s and s.lo is not None) else None,

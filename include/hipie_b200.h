@@ -96,6 +96,10 @@ int hipie_msda_fused_forward(const void* value, const int64_t* spatial_shapes,
  *   prec == 2 : C = A.W, both ONE IEEE fp16 plane  (contractions normalised by a softmax)
  *   prec == 4 : C = A.Whi + A.Wlo, A ONE fp16 plane, W fp16 hi + lo (a_lo NULL): the weight exact to ~2^-22, the activation
  *               rounded to fp16 once -- the qkv linears, whose outputs the fp16 attention rounds to fp16 anyway
+ *   prec == 6 : C = Ah.Wh + 2^-14 (a8 . w8^T): the fp16 hi x hi product in one 16-bit pass, both cross terms Ah.Wl + Al.Wh in ONE
+ *               e4m3 pass over 2K (kind::f8f6f4 runs at twice the 16-bit rate): two pass-equivalents for ~2^-15.5 relative error
+ *               per product, the class of the three-pass bf16 split.  |A| must stay below 448 * 2 (e4m3 saturates),
+ *               |W| below 28; hipie_split_f16_e4m3 builds the planes.
  * Row strides (in elements) lda / ldw / ldc allow strided sub-matrices; K % 8 == 0,
  * all base pointers 16-byte aligned.  Outputs (any subset, NULL to skip):
  *   c_f32 (fp32), c_hi / c_lo (bf16 split of the fp32 result, for feeding the next GEMM),
@@ -127,6 +131,11 @@ typedef struct hipie_gemm_args {
     int relu_after_residual;  /* 1: ReLU applied AFTER the residual add (ResNet bottleneck: relu(conv3(x) + shortcut)); `act` is applied before */
     int c_fp16;               /* 1: c_hi receives IEEE fp16 values (one plane, c_lo must be NULL): operands of the single-pass fp16
                                  contractions (attention QK^T / PV); 0: bf16 hi (+ lo) planes */
+    /* prec 6 (fp16 + e4m3 split, see below): e4m3 planes of the operands, row strides in bytes */
+    const void* a8; int64_t lda8;   /* (M, 2K): [e4m3(Ah) | e4m3(2^10 (A - Ah))], Ah = fp16(A) = a_hi */
+    const void* w8; int64_t ldw8;   /* (N, 2K): [e4m3(2^14 (W - Wh)) | e4m3(2^4 Wh)], Wh = fp16(W) = w_hi */
+    void* c8; int64_t ldc8;         /* optional with c_fp16: the result's own e4m3 planes (M, 2N) in the a8 layout, so that the
+                                       output feeds the next prec-6 GEMM (fc1 -> fc2); needs N % 32 == 0 */
 } hipie_gemm_args;
 
 /* Encoder form of the fused MSDeformAttn op (Lq == S: the queries are the pixels of the four levels; 2-d reference points; fp32
@@ -144,6 +153,10 @@ int hipie_gemm(const hipie_gemm_args* args, void* stream);
 /* fp32 -> bf16 hi (+ lo = bf16(x - hi)) split of a contiguous array of n elements. */
 int hipie_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
 
+/* fp32 (rows, cols) -> the operand planes of a prec-6 hipie_gemm: h16 (rows, cols) fp16 and p8 (rows, 2 * cols) e4m3.
+ * weight == 0 (activation A): p8 = [e4m3(h) | e4m3(2^10 (x - h))];  weight == 1 (W): p8 = [e4m3(2^14 (x - h)) | e4m3(2^4 h)]. */
+int hipie_split_f16_e4m3(const float* x, void* h16, void* p8, int64_t rows, int cols, int weight, void* stream);
+
 /* LayerNorm over the last dim C of x[rows, C] (fp32 in).  Outputs: y_f32 and/or bf16 split
  * (y_hi, y_lo).  Optional `add` tensor is added to x before normalisation and the sum is
  * written to sum_out (residual stream), matching post-LN layers: y = LN(x + add). */
@@ -151,9 +164,10 @@ int hipie_layernorm(const float* x, const float* add, const float* gamma, const 
                     float eps, float* sum_out, float* y_f32, void* y_hi, void* y_lo,
                     int64_t rows, int C, const int32_t* out_row_map, void* stream);
 /* Same LayerNorm with the normalised rows written as ONE IEEE fp16 plane: the A operand of a prec-4 (two-pass fp16) hipie_gemm
- * -- the qkv linears of the ViT blocks (H:backbone/vit.py:67-70), whose outputs are rounded to fp16 for the attention anyway. */
+ * -- the qkv linears of the ViT blocks (H:backbone/vit.py:67-70), whose outputs are rounded to fp16 for the attention anyway.
+ * y_e4m3 (optional, rows x 2C): additionally the e4m3 planes [e4m3(h) | e4m3(2^10 (y - h))] of a prec-6 GEMM's A operand (norm2 -> fc1). */
 int hipie_layernorm_f16(const float* x, const float* add, const float* gamma, const float* beta,
-                        float eps, float* sum_out, float* y_f32, void* y_f16,
+                        float eps, float* sum_out, float* y_f32, void* y_f16, void* y_e4m3,
                         int64_t rows, int C, const int32_t* out_row_map, void* stream);
 
 /* GroupNorm(G) over NHWC fp32 (N, HW, C) with per-sample strides, optional fused ReLU and a

@@ -784,6 +784,76 @@ def test_gemm_transposed_fp16_vectorised_epilogue(ops, cuda):
                 assert (outs[1].view(N, -1, grp + pad)[:, :, grp:] == 7.0).all()
 
 
+def _e4m3(t):
+    return t.view(torch.float8_e4m3fn).float()
+
+
+def test_split_f16_e4m3_planes(ops, cuda):
+    """hipie_split_f16_e4m3 against torch's own fp16 / float8_e4m3fn conversions (round-to-nearest-even, saturating at 448)."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(300, 256, device=cuda, generator=g) * torch.logspace(-3, 1.5, 256, device=cuda)
+    f8 = lambda t: t.clamp(-448, 448).to(torch.float8_e4m3fn).float()
+    h = x.half()
+    a = ops.split_f16_e4m3(x)
+    assert a.hi.dtype == torch.float16 and a.lo.dtype == torch.uint8 and a.lo.shape == (300, 512)
+    assert torch.equal(a.hi, h)
+    assert torch.equal(_e4m3(a.lo[:, :256]), f8(h.float())) and torch.equal(_e4m3(a.lo[:, 256:]), f8((x - h.float()) * 1024.0))
+    assert (a.float() - x).abs().max() <= (x.abs() * 2.0 ** -15).max()      # hi + lo / 2^10 restores x to ~2^-16
+    w = ops.split_f16_e4m3(x * 0.01, weight=True)
+    hw = (x * 0.01).half()
+    assert torch.equal(w.hi, hw)
+    assert torch.equal(_e4m3(w.lo[:, :256]), f8((x * 0.01 - hw.float()) * 16384.0)) and torch.equal(_e4m3(w.lo[:, 256:]), f8(hw.float() * 16.0))
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (4096, 5120, 1280), (2048, 1280, 5120), (1000, 96, 320), (3000, 384, 200), (130, 40, 64)])
+def test_gemm_f16_e4m3_split(ops, cuda, M, N, K):
+    """prec 6: C = Ah.Wh (fp16 pass) + 2^-14 (A8 . W8^T) (ONE e4m3 pass over 2K, folded in by the scale-input-d of the first fp16 MMA).
+    (i) against fp64 on exactly the planes the kernel reads: only fp32 accumulation differs; (ii) against the unrounded fp32 product:
+    the split restores A.W to the accuracy class of the three-pass bf16 mode."""
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + K)
+    a = torch.randn(M, K, device=cuda, generator=g) * 1.5
+    w = torch.randn(N, K, device=cuda, generator=g) * 0.05
+    b = torch.randn(N, device=cuda, generator=g)
+    A, W = ops.split_f16_e4m3(a), ops.split_f16_e4m3(w, weight=True)
+    c, _, _ = ops.gemm(A, W, bias=b, prec=6)
+    planes = A.hi.double() @ W.hi.double().t() + (_e4m3(A.lo).double() @ _e4m3(W.lo).double().t()) * 2.0 ** -14 + b.double()
+    tol = 3e-5 * math.sqrt(K) * 1.5 * 0.05 * 4 + 1e-5
+    err = (c.double() - planes).abs().max().item()
+    assert err < tol, f"vs the planes: {err} (tol {tol})"
+    exact = a.double() @ w.double().t() + b.double()
+    c3, _, _ = ops.gemm(ops.split(a), ops.split_weight(w), bias=b, prec=3)
+    e6, e3 = (c.double() - exact).abs().max().item(), (c3.double() - exact).abs().max().item()
+    assert e6 < 4e-5 * math.sqrt(K) * 1.5 * 0.05 * 4 + 1e-5, f"vs exact: {e6} (three-pass bf16: {e3})"
+
+
+def test_gemm_f16_e4m3_output_planes(ops, cuda):
+    """fc1 -> fc2 hand-off: the GELU epilogue emits the fp16 plane and the e4m3 planes of its result (TMA-store path); they must be
+    exactly the split of the fp32 result."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 1024, 640, 256
+    a, w, b = torch.randn(M, K, device=cuda, generator=g), torch.randn(N, K, device=cuda, generator=g) * 0.1, torch.randn(N, device=cuda, generator=g)
+    A, W = ops.split_f16_e4m3(a), ops.split_f16_e4m3(w, weight=True)
+    c32, _, _ = ops.gemm(A, W, bias=b, act=ops.ACT_GELU, prec=6)
+    _, s, _ = ops.gemm(A, W, bias=b, act=ops.ACT_GELU, want_f32=False, out_e4m3=True, prec=6)
+    ref = ops.split_f16_e4m3(c32)
+    assert torch.equal(s.hi, ref.hi) and torch.equal(s.lo, ref.lo)
+    # and through the bf16x3 mainloop as well (the epilogue does not depend on the operand format)
+    _, s3, _ = ops.gemm(ops.split(a), ops.split_weight(w), bias=b, want_f32=False, out_e4m3=True, prec=3)
+    c3, _, _ = ops.gemm(ops.split(a), ops.split_weight(w), bias=b, prec=3)
+    r3 = ops.split_f16_e4m3(c3)
+    assert torch.equal(s3.hi, r3.hi) and torch.equal(s3.lo, r3.lo)
+
+
+def test_layernorm_e4m3_planes(ops, cuda):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for C in (1280, 200):
+        x = torch.randn(300, C, device=cuda, generator=g) * 2 + 0.3
+        gm, bt = torch.randn(C, device=cuda, generator=g), torch.randn(C, device=cuda, generator=g)
+        y32, s, _ = ops.layernorm(x, gm, bt, 1e-6, want_f32=True, out_e4m3=True)
+        ref = ops.split_f16_e4m3(y32)
+        assert torch.equal(s.hi, ref.hi) and torch.equal(s.lo, ref.lo)
+
+
 def test_layernorm_fp16_plane(ops, cuda):
     """hipie_layernorm_f16: the same statistics, the normalised rows rounded once to IEEE fp16 (with and without a row map)."""
     g = torch.Generator(device="cuda").manual_seed(8)

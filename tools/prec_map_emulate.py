@@ -44,6 +44,13 @@ def linear_forward(self, x):
     e = getattr(self, "_emu", None)
     if e is None:
         return _orig_forward(self, x)
+    if e[0] == "f16+e4m3":      # fp16 hi x hi pass + ONE fp8 pass for the two cross terms: Ah.Wh + 2^-14 [e4m3(Ah) | e4m3(2^10 Al)] . [e4m3(2^14 Wl) | e4m3(2^4 Wh)]
+        f8 = lambda t: t.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float()
+        w = self.weight
+        xh, wh = x.half().float(), w.half().float()
+        xl, wl = x - xh, w - wh
+        y = F.linear(xh, wh) + (F.linear(f8(xh), f8(wl * 2.0 ** 14)) + F.linear(f8(xl * 2.0 ** 10), f8(wh * 2.0 ** 4))) * 2.0 ** -14
+        return y if self.bias is None else y + self.bias
     return q(F.linear(q(x, e[0]), q(self.weight, e[1]), self.bias), e[2])
 
 
