@@ -349,7 +349,15 @@ def run_product(args, cfg):
     tot_prof = sum(v["ms"] for v in prof.values()) or 1.0
     top = max(prof.items(), key=lambda kv: kv[1]["ms"])
     kernels = {}
-    passes = 3 if args.precision == "bf16x3" else 1
+
+    def mma_passes(tag):
+        """bf16-rate pass-equivalents one algorithmic MAC costs in this kernel class: p3 = three bf16 passes; f16x2 = two fp16
+        passes; f16+e4m3 = one fp16 pass + ONE e4m3 pass over 2K at twice the 16-bit rate = two; f16x1 / p1 = one."""
+        if "[p3]" in tag:
+            return 3
+        if "[f16x2]" in tag or "[f16+e4m3]" in tag:
+            return 2
+        return 1
     for tag, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
         per = v["ms"] / v["launches"]
         entry = {"share_of_timed_kernels": v["ms"] / tot_prof, "launches_per_step": v["launches"] / prof_steps, "avg_ms": per}
@@ -358,19 +366,30 @@ def run_product(args, cfg):
             if tag.startswith(("msda", "condinst", "layernorm", "row_softmax", "seg_postprocess")) or "mask_embed" in tag:
                 entry.update(bound="hbm", achieved=rate / 1e9, unit="GB/s", frac=rate / 1e9 / pk["hbm"])
             else:
-                entry.update(bound="tensor", achieved=rate / 1e12, unit="TFLOP/s", frac=rate / 1e12 / pk["tf_sustained"])
+                entry.update(bound="tensor", achieved=rate / 1e12, unit="TFLOP/s", frac=rate / 1e12 / pk["tf_sustained"],
+                             mma_pass_equivalents=mma_passes(tag), executed_frac=rate / 1e12 * mma_passes(tag) / pk["tf_sustained"])
         kernels[tag] = entry
+    # all dense contractions of the step together (every gemm_tc class except the HBM-bound mask-embed)
+    gsel = [(t, v) for t, v in prof.items() if t.startswith("gemm_tc") and "mask_embed" not in t and v["work"] > 0]
+    g_ms = sum(v["ms"] for _, v in gsel) or 1.0
+    g_alg = sum(v["work"] for _, v in gsel) / (g_ms / 1000.0) / 1e12
+    g_exe = sum(v["work"] * mma_passes(t) for t, v in gsel) / (g_ms / 1000.0) / 1e12
+    gemm_all = {"share_of_timed_kernels": g_ms / tot_prof, "achieved": g_alg, "unit": "TFLOP/s", "frac": g_alg / pk["tf_sustained"],
+                "executed_tflops": g_exe, "executed_frac": g_exe / pk["tf_sustained"],
+                "classes": {t: round(v["ms"] / g_ms, 4) for t, v in sorted(gsel, key=lambda kv: -kv[1]["ms"])}}
     tk = kernels[top[0]]
     traffic, traffic_note = ncu_traffic(top[0])
     roofline = {"kernel": top[0], "bound": tk.get("bound", "tensor"), "achieved": tk.get("achieved"),
                 "peak": pk["hbm"] if tk.get("bound") == "hbm" else pk["tf_sustained"],
                 "unit": tk.get("unit"), "frac": tk.get("frac"), "traffic": traffic, "traffic_note": traffic_note,
-                "mma_passes": passes, "executed_tflops": (tk.get("achieved") or 0.0) * passes if tk.get("bound") == "tensor" else None,
-                "executed_frac": (tk.get("frac") or 0.0) * passes if tk.get("bound") == "tensor" else None,
-                "achieved_note": "algorithmic 2MNK flops of the fp32-class GEMMs / measured kernel time (CUDA events on the launching stream, "
-                                 "eager steps after the timed region); the bf16x3 parity mode issues 3 bf16 MMAs per algorithmic MAC "
-                                 "(executed_* = achieved x mma_passes against the same bf16 peak); attention QK^T / PV run single-pass fp16 "
-                                 "when the precision map allows (DESIGN.md 3)",
+                "mma_passes": mma_passes(top[0]), "executed_tflops": (tk.get("achieved") or 0.0) * mma_passes(top[0]) if tk.get("bound") == "tensor" else None,
+                "executed_frac": (tk.get("frac") or 0.0) * mma_passes(top[0]) if tk.get("bound") == "tensor" else None,
+                "achieved_note": "algorithmic 2MNK flops / measured kernel time (CUDA events on the launching stream, eager steps after the "
+                                 "timed region).  Every contraction is fp32-class: per algorithmic MAC the kernel issues mma_passes bf16-rate "
+                                 "pass-equivalents (p3: Ah.Wh + Ah.Wl + Al.Wh in bf16 = 3; f16x2: A.Wh + A.Wl in fp16 = 2; f16+e4m3: one fp16 pass + "
+                                 "ONE e4m3 pass over 2K at twice the rate = 2; f16x1 = 1), executed_* = achieved x mma_passes against the same "
+                                 "bf16 peak (DESIGN.md 3)",
+                "gemm_tc_all": gemm_all,
                 "peak_source": pk["src"] + " (sustained figure: kernel timed inside a long step)",
                 "vit_h_forward_tensor_frac": (cfg["vit_flops"] * B * world * args.steps / (ms_max / 1000.0)) / 1e12 / (pk["tf_sustained"] * world),
                 "north_star_hbm": {k: {"achieved_gbs": kernels[k]["achieved"], "frac": kernels[k]["frac"], "avg_ms": kernels[k]["avg_ms"]}

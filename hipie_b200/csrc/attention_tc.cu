@@ -73,8 +73,10 @@ struct FaParams {
     int kh;
     float* out_f32;
     __nv_bfloat16 *out_hi, *out_lo;
+    int out_e4m3;        // out_hi is ONE fp16 plane, out_lo the e4m3 planes (B*T rows of 2*o_ts bytes): the A operand of a prec-6 proj GEMM
     int64_t o_bs, o_ts;
     int B, H, T;
+    int T_rows;          // rows per batch item of the output (o_bs / o_ts)
     int q_col0, k_col0;           // column of head 0 inside the q / k rows
     float scale_log2e;
     long long* trace;             // debug: per-tile clock64 timestamps of CTA (0,0,0) or null
@@ -483,7 +485,19 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 for (int i = 0; i < 16; i += 4)
                     *reinterpret_cast<float4*>(p.out_f32 + obase + c + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
             }
-            if (row_ok && p.out_hi) {
+            if (row_ok && p.out_hi && p.out_e4m3) {
+                uint4 h0, h1, a8, b8;
+                uint2 t;
+                split4_f16_e4m3(make_float4(f[0], f[1], f[2], f[3]), t, a8.x, b8.x); h0.x = t.x; h0.y = t.y;
+                split4_f16_e4m3(make_float4(f[4], f[5], f[6], f[7]), t, a8.y, b8.y); h0.z = t.x; h0.w = t.y;
+                split4_f16_e4m3(make_float4(f[8], f[9], f[10], f[11]), t, a8.z, b8.z); h1.x = t.x; h1.y = t.y;
+                split4_f16_e4m3(make_float4(f[12], f[13], f[14], f[15]), t, a8.w, b8.w); h1.z = t.x; h1.w = t.y;
+                *reinterpret_cast<uint4*>(p.out_hi + obase + c) = h0;
+                *reinterpret_cast<uint4*>(p.out_hi + obase + c + 8) = h1;
+                uint8_t* o8 = reinterpret_cast<uint8_t*>(p.out_lo) + ((int64_t)b * p.T_rows + qrow) * 2 * p.o_ts + h * FA_HD + c;
+                *reinterpret_cast<uint4*>(o8) = a8;
+                *reinterpret_cast<uint4*>(o8 + p.o_ts) = b8;
+            } else if (row_ok && p.out_hi) {
                 uint4 h0, h1, l0, l1;
                 split2(f[0], f[1], h0.x, l0.x); split2(f[2], f[3], h0.y, l0.y);
                 split2(f[4], f[5], h0.z, l0.z); split2(f[6], f[7], h0.w, l0.w);
@@ -521,11 +535,13 @@ static int launch_fa(const FaMaps& maps, const FaParams& p, cudaStream_t st) {
 
 using namespace hipie;
 
-extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
-                                         const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
-                                         const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
-                                         int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
-                                         int H, int T, int hd, float scale, int prec, long long* trace, void* stream) {
+static int attention_tc_impl(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
+                             const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
+                             const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
+                             int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
+                             int H, int T, int hd, float scale, int prec, long long* trace, void* stream, int out_format) {
+    HIPIE_CHECK_ARG(out_format == 0 || (out_format == 1 && out_hi && out_lo && o_ts % 16 == 0 && o_bs % o_ts == 0 && o_ts == (int64_t)H * hd),
+                    "hipie_attention_tc: out_format 1 (fp16 + e4m3 planes) needs out_hi, out_lo and contiguous (B, rows, H*hd) outputs");
     HIPIE_CHECK_ARG(q_hi && k_hi && vt_hi, "hipie_attention_tc: q/k/vt hi planes required");
     HIPIE_CHECK_ARG(prec == 1 || prec == 2 || (prec == 3 && q_lo && k_lo && vt_lo), "hipie_attention_tc: prec/lo planes mismatch");
     const bool f16 = prec == 2;          // prec 2: q / k / v^T are single IEEE fp16 planes, one MMA pass
@@ -558,6 +574,8 @@ extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int
     p.q_hi = (const __nv_bfloat16*)q_hi; p.q_lo = (const __nv_bfloat16*)q_lo; p.q_bs = q_bs; p.q_ts = q_ts;
     p.rel_h = rel_h; p.rel_w = rel_w; p.kh = kh;
     p.out_f32 = out_f32; p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo;
+    p.out_e4m3 = out_format == 1 ? 1 : 0;
+    p.T_rows = (int)(o_bs / o_ts);
     p.o_bs = o_bs; p.o_ts = o_ts; p.B = B; p.H = H; p.T = T; p.q_col0 = q_col0; p.k_col0 = k_col0;
     p.scale_log2e = scale * 1.4426950408889634f;
     p.trace = trace;
@@ -566,6 +584,26 @@ extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int
     if (wide) return prec == 3 ? launch_fa<3, false, false, false, FA_GW2>(maps, p, st) : (f16 ? launch_fa<1, false, true, false, FA_GW2>(maps, p, st) : launch_fa<1, false, false, false, FA_GW2>(maps, p, st));
     if (win) return prec == 3 ? launch_fa<3, true, false>(maps, p, st) : (f16 ? launch_fa<1, true, true>(maps, p, st) : launch_fa<1, true, false>(maps, p, st));
     return prec == 3 ? launch_fa<3, false, false>(maps, p, st) : (f16 ? launch_fa<1, false, true>(maps, p, st) : launch_fa<1, false, false>(maps, p, st));
+}
+
+extern "C" int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
+                                         const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
+                                         const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
+                                         int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
+                                         int H, int T, int hd, float scale, int prec, long long* trace, void* stream) {
+    return attention_tc_impl(q_hi, q_lo, q_bs, q_ts, q_col0, q_width, k_hi, k_lo, k_bs, k_ts, k_col0, k_width, vt_hi, vt_lo, vt_ld, rel_h,
+                             rel_w, kh, kw, out_f32, out_hi, out_lo, o_bs, o_ts, B, H, T, hd, scale, prec, trace, stream, 0);
+}
+
+// Same attention with the output written as the operand planes of a prec-6 hipie_gemm (the proj linear): out_f16 (B, T, H*hd) one
+// fp16 plane, out_e4m3 (B*T, 2*H*hd) = [e4m3(h) | e4m3(2^10 (o - h))].
+extern "C" int hipie_attention_tc_planes(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
+                                         const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
+                                         const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
+                                         int kh, int kw, float* out_f32, void* out_f16, void* out_e4m3, int64_t o_bs, int64_t o_ts, int B,
+                                         int H, int T, int hd, float scale, int prec, void* stream) {
+    return attention_tc_impl(q_hi, q_lo, q_bs, q_ts, q_col0, q_width, k_hi, k_lo, k_bs, k_ts, k_col0, k_width, vt_hi, vt_lo, vt_ld, rel_h,
+                             rel_w, kh, kw, out_f32, out_f16, out_e4m3, o_bs, o_ts, B, H, T, hd, scale, prec, nullptr, stream, 1);
 }
 
 // Window mode (T == 196, kh == kw == 14): vt holds every window at a 200-column pitch, (H*80, B*200), pad columns zero.

@@ -275,16 +275,22 @@ class Engine:
                 Rw = W.cached(("relw", i, qw), lambda: ops.split_weight(_get_rel_pos_table(qw, qw, W[blk + ".attn.rel_pos_w"])))
                 rel_h = ops.relpos_bias_tc(q, st, Rh, 0, qh, qw, Bq, nh, hd)
                 rel_w = ops.relpos_bias_tc(q, st, Rw, 1, qh, qw, Bq, nh, hd)
+            proj6 = use_tc and f16 and self.mlp_f16e4m3      # attention output as fp16 + e4m3 planes, proj on gemm prec 6
             if use_tc:
                 _, ao = ops.attention_tc(q, k, vt, Bq, nh, Tq, hd, st[0], st[1], st[0], st[1], hd ** -0.5, rel_h=rel_h, rel_w=rel_w,
-                                         kh=qh, kw=qw, f16=f16)
+                                         kh=qh, kw=qw, f16=f16, out_e4m3=proj6)
             else:
                 _, ao = ops.attention(q, k, vv, Bq, nh, Tq, Tq, hd, st, st, st, hd ** -0.5, rel_h=rel_h, rel_w=rel_w, kh=qh, kw=qw)
-            ao = ao.view(Bq * Tq, E)
-            if windowed:
-                ops.gemm(ao, wproj, bias=bproj, residual=x, out_f32=x, row_map=win2tok, out_rows=B * T)
+            if proj6:
+                ao = BF2(ao.hi.view(Bq * Tq, E), ao.lo.view(Bq * Tq, 2 * E))
+                wproj = W.cached(("proj68", blk), lambda: ops.split_f16_e4m3(W[blk + ".attn.proj.weight"], weight=True))
             else:
-                ops.gemm(ao, wproj, bias=bproj, residual=x, out_f32=x)
+                ao = ao.view(Bq * Tq, E)
+            pprec = 6 if proj6 else None
+            if windowed:
+                ops.gemm(ao, wproj, bias=bproj, residual=x, out_f32=x, row_map=win2tok, out_rows=B * T, prec=pprec)
+            else:
+                ops.gemm(ao, wproj, bias=bproj, residual=x, out_f32=x, prec=pprec)
             if self.mlp_f16e4m3 and ops.PREC == 3 and E % 32 == 0:
                 # fc1 / fc2 in the fp16 + e4m3 split (gemm prec 6): the hi x hi product in ONE fp16 pass, both cross terms in ONE fp8
                 # pass -- two pass-equivalents instead of three for the same ~2^-15.5 operand accuracy.  norm2 and the GELU epilogue
@@ -423,6 +429,12 @@ class Engine:
     def ffn_postnorm(self, x, x_s, prefix, n1, n2, l1="linear1", l2="linear2"):
         """x = LN(x + linear2(relu(linear1(x))))"""
         W = self.W
+        if x_s.lo is not None and x_s.lo.dtype == torch.uint8:      # fp16 + e4m3 planes (encoder layers): both linears on gemm prec 6
+            w1, b1, w2, b2 = W.cached(("ffn68", prefix), lambda: (ops.split_f16_e4m3(W[f"{prefix}.{l1}.weight"], weight=True), W[f"{prefix}.{l1}.bias"],
+                                                                   ops.split_f16_e4m3(W[f"{prefix}.{l2}.weight"], weight=True), W[f"{prefix}.{l2}.bias"]))
+            _, h, _ = ops.gemm(x_s, w1, bias=b1, act=ops.ACT_RELU, want_f32=False, out_e4m3=True, prec=6)
+            y, _, _ = ops.gemm(h, w2, bias=b2, residual=x, prec=6)
+            return ops.layernorm(y, W[f"{prefix}.{n2}.weight"], W[f"{prefix}.{n2}.bias"], 1e-5, want_f32=True, want_split=True)[:2]
         w1, b1 = W.lin(f"{prefix}.{l1}")
         w2, b2 = W.lin(f"{prefix}.{l2}")
         _, h, _ = ops.gemm(x_s, w1, bias=b1, act=ops.ACT_RELU, want_f32=False, want_split=True)
@@ -437,7 +449,8 @@ class Engine:
                               shapes_host=shapes_host)
         wo, bo = W.lin(prefix + ".self_attn.output_proj")
         y, _, _ = ops.gemm(a_s.view(B * S, 256), wo, bias=bo, residual=src.view(B * S, 256))
-        x, x_s, _ = ops.layernorm(y, W[prefix + ".norm1.weight"], W[prefix + ".norm1.bias"], 1e-5, want_f32=True, want_split=True)
+        x, x_s, _ = ops.layernorm(y, W[prefix + ".norm1.weight"], W[prefix + ".norm1.bias"], 1e-5, want_f32=True, want_split=True,
+                                  out_e4m3=self.mlp_f16e4m3 and ops.PREC == 3)       # norm1 feeds linear1 only
         x, x_s = self.ffn_postnorm(x, x_s, prefix, "norm1", "norm2")
         return x.view(B, S, 256), x_s.view(B, S, 256)
 

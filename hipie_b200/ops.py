@@ -422,7 +422,7 @@ def attention(q: BF2, k: BF2, v: BF2, B, H, Tq, Tk, hd, q_strides, k_strides, v_
 
 
 def attention_tc(q: BF2, k: BF2, vt: BF2, B, H, T, hd, q_bs, q_ts, k_bs, k_ts, scale, rel_h=None, rel_w=None, kh=0, kw=0,
-                 want_f32=False, want_split=True, prec=None, f16=False):
+                 want_f32=False, want_split=True, prec=None, f16=False, out_e4m3=False):
     """tcgen05 flash attention.  q, k: plane views whose row (token) holds all heads contiguously (head h at columns
     [80h, 80h+80) of the view); vt: BF2 (H*hd, B*T) = V transposed.  Output (B, T, H*hd)."""
     prec = PREC if prec is None else prec
@@ -431,10 +431,14 @@ def attention_tc(q: BF2, k: BF2, vt: BF2, B, H, T, hd, q_bs, q_ts, k_bs, k_ts, s
         prec = 2
     dev = q.hi.device
     o = torch.empty((B, T, H * hd), dtype=torch.float32, device=dev) if want_f32 else None
-    s = _empty_bf2((B, T, H * hd), dev) if want_split else None
+    if out_e4m3:       # output as fp16 + e4m3 planes (the A operand of a prec-6 proj GEMM)
+        s = BF2(torch.empty((B, T, H * hd), dtype=torch.float16, device=dev), torch.empty((B, T, 2 * H * hd), dtype=torch.uint8, device=dev))
+    else:
+        s = _empty_bf2((B, T, H * hd), dev) if want_split else None
     lo = lambda t: _p(t.lo) if (t.lo is not None and prec == 3) else None
+    fn = _lib.load().hipie_attention_tc_planes if out_e4m3 else _lib.load().hipie_attention_tc
     with _timed("attention_tc[f16x1]" if f16 else f"attention_tc[p{prec}]", 4.0 * B * H * T * T * hd):
-        _lib.check(_lib.load().hipie_attention_tc(
+        _lib.check(fn(
             _p(q.hi), lo(q), q_bs, q_ts, 0, H * hd, _p(k.hi), lo(k), k_bs, k_ts, 0, H * hd, _p(vt.hi), lo(vt), vt.hi.stride(0),
             _p(rel_h), _p(rel_w), kh, kw, _p(o), _p(s.hi) if s else None, _p(s.lo) if (s and s.lo is not None) else None,
             T * H * hd, H * hd, B, H, T, hd, float(scale), prec, _stream()), "attention_tc")

@@ -253,6 +253,13 @@ int hipie_attention_tc_traced(const void* q_hi, const void* q_lo, int64_t q_bs, 
                               const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
                               int kh, int kw, float* out_f32, void* out_hi, void* out_lo, int64_t o_bs, int64_t o_ts, int B,
                               int H, int T, int hd, float scale, int prec, long long* trace, void* stream);
+/* Same attention, output written as the operand planes of a prec-6 hipie_gemm (the proj linear, H:backbone/vit.py:82): out_f16
+ * (B, T, H*hd) ONE fp16 plane and out_e4m3 (B*T, 2*H*hd) = [e4m3(h) | e4m3(2^10 (o - h))]; contiguous outputs (o_ts == H*hd). */
+int hipie_attention_tc_planes(const void* q_hi, const void* q_lo, int64_t q_bs, int64_t q_ts, int q_col0, int q_width,
+                              const void* k_hi, const void* k_lo, int64_t k_bs, int64_t k_ts, int k_col0, int k_width,
+                              const void* vt_hi, const void* vt_lo, int64_t vt_ld, const float* rel_h, const float* rel_w,
+                              int kh, int kw, float* out_f32, void* out_f16, void* out_e4m3, int64_t o_bs, int64_t o_ts, int B,
+                              int H, int T, int hd, float scale, int prec, void* stream);
 
 /* rel[b,h,q,j] = sum_c q[b,q,h,c] * table[idx(q,j), c] for the decomposed rel-pos bias.
  * axis 0: height (idx from q // qw), axis 1: width (q % qw).  table: (2*max(q,k)-1, hd) fp32,

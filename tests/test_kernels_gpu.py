@@ -907,6 +907,30 @@ def test_attention_tcgen05_fp16_single_pass(ops, cuda, win):
     assert (o.double() - ref32).abs().max().item() < 8e-3        # + fp16 rounding of q / k / v: ~8x tighter than the bf16 pass (3e-2)
 
 
+def test_attention_tcgen05_output_planes(ops, cuda):
+    """hipie_attention_tc_planes: the same attention, output as fp16 + e4m3 planes == the split of the fp32 output (global and window mode)."""
+    g = torch.Generator(device="cuda").manual_seed(43)
+    for win in (False, True):
+        B, H, hd, gh, gw = (5, 2, 80, 14, 14) if win else (2, 2, 80, 4, 64)
+        T, E = gh * gw, H * hd
+        qk16 = torch.randn(B * T, 2 * E, device=cuda, generator=g).half()
+        v = torch.randn(B * T, E, device=cuda, generator=g)
+        if win:
+            vpad = torch.zeros(E, B, 200, device=cuda)
+            vpad[:, :, :T] = v.t().reshape(E, B, T)
+            vt16 = vpad.view(E, B * 200).half()
+        else:
+            vt16 = v.t().contiguous().half()
+        q, k, vt = ops.BF2(qk16[:, :E], None), ops.BF2(qk16[:, E:], None), ops.BF2(vt16, None)
+        rel_h = torch.randn(B, H, T, gh, device=cuda, generator=g)
+        rel_w = torch.randn(B, H, T, gw, device=cuda, generator=g)
+        kw = dict(rel_h=rel_h, rel_w=rel_w, kh=gh, kw=gw, f16=True)
+        o32, _ = ops.attention_tc(q, k, vt, B, H, T, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, want_f32=True, want_split=False, **kw)
+        _, s = ops.attention_tc(q, k, vt, B, H, T, hd, T * 2 * E, 2 * E, T * 2 * E, 2 * E, hd ** -0.5, out_e4m3=True, **kw)
+        ref = ops.split_f16_e4m3(o32.view(B * T, E))
+        assert torch.equal(s.hi.view(B * T, E), ref.hi) and torch.equal(s.lo.view(B * T, 2 * E), ref.lo)
+
+
 def test_relpos_tc_fp16(ops, cuda):
     g = torch.Generator(device="cuda").manual_seed(12)
     B, H, hd, gh, gw = 1, 2, 80, 64, 64
