@@ -7,7 +7,9 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 SHAPES = [("vit fc1 gelu", 32768, 5120, 1280, dict(act=ops.ACT_GELU, want_f32=False), True),
           ("vit fc2 +res", 32768, 1280, 5120, dict(), False),
-          ("vit proj +res", 32768, 1280, 1280, dict(), False)]
+          ("vit proj +res", 32768, 1280, 1280, dict(), False),
+          ("enc ffn1 relu", 174080, 2048, 256, dict(act=ops.ACT_RELU, want_f32=False), True),
+          ("enc ffn2 +res", 174080, 256, 2048, dict(), False)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 

@@ -87,5 +87,23 @@ if which in ("proj256",):   # 174080 x 256 x 256 with f32 + split out
     A, W = ops.split(a), ops.split_weight(w)
     for _ in range(2):
         ops.gemm(A, W, want_f32=True, want_split=True)
+if which in ("gemm6",):      # ViT fc1 on the fp16 + e4m3 split (prec 6): fp16 sweep + ONE e4m3 sweep, planes out
+    a = torch.randn(32768, 1280, device=dev)
+    w = torch.randn(5120, 1280, device=dev) * 0.02
+    A, W = ops.split_f16_e4m3(a), ops.split_f16_e4m3(w, weight=True)
+    for _ in range(2):
+        ops.gemm(A, W, act=ops.ACT_GELU, want_f32=False, out_e4m3=True, prec=6)
+if which in ("qk4",):        # ViT qk linear on two fp16 passes (prec 4)
+    a = torch.randn(32768, 1280, device=dev)
+    w = torch.randn(2560, 1280, device=dev) * 0.02
+    A, W = ops.BF2(a.half(), None), ops.split_weight_f16(w)
+    for _ in range(2):
+        ops.gemm(A, W, want_f32=False, want_split=True, out_fp16=True, prec=4)
+if which in ("segpost",):    # semantic + panoptic post-processing of one 1024^2 image: 900 kept + 300 background queries, 80 classes
+    Q, C = 1200, 80
+    masks = torch.randn(Q, 256, 256, device=dev) * 3.0
+    cls = torch.softmax(torch.randn(Q, C, device=dev) * 3.0, -1)
+    for _ in range(2):
+        ops.seg_postprocess(masks, cls, 0.25, 1024, 1024)
 torch.cuda.synchronize()
 print("done", which)
