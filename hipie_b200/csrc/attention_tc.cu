@@ -494,9 +494,9 @@ attn_tc_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
                 split4_f16_e4m3(make_float4(f[12], f[13], f[14], f[15]), t, a8.w, b8.w); h1.z = t.x; h1.w = t.y;
                 *reinterpret_cast<uint4*>(p.out_hi + obase + c) = h0;
                 *reinterpret_cast<uint4*>(p.out_hi + obase + c + 8) = h1;
-                uint8_t* o8 = reinterpret_cast<uint8_t*>(p.out_lo) + ((int64_t)b * p.T_rows + qrow) * 2 * p.o_ts + h * FA_HD + c;
-                *reinterpret_cast<uint4*>(o8) = a8;
-                *reinterpret_cast<uint4*>(o8 + p.o_ts) = b8;
+                uint8_t* o8 = reinterpret_cast<uint8_t*>(p.out_lo) + ((int64_t)b * p.T_rows + qrow) * 2 * p.o_ts + e4m3_slot0(h * FA_HD + c);
+                *reinterpret_cast<uint4*>(o8) = a8;              // slot 0 / slot 1 of 16 columns inside one 32-column group (common.cuh)
+                *reinterpret_cast<uint4*>(o8 + 32) = b8;
             } else if (row_ok && p.out_hi) {
                 uint4 h0, h1, l0, l1;
                 split2(f[0], f[1], h0.x, l0.x); split2(f[2], f[3], h0.y, l0.y);

@@ -110,6 +110,12 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
     const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
     return lo | (hi << 16);
 }
+// Layout of an e4m3 operand plane (rows, 2K bytes): the two slots (hi-like / lo-like factor of the cross terms) are interleaved in
+// groups of 32 columns -- element k of slot 0 at byte (k / 32) * 64 + k % 32, of slot 1 at +32 -- so that a producer's 32-column
+// chunk is ONE 64-byte row segment (one TMA box with 64-byte rows in the GEMM epilogue).  The contraction over 2K is order-free as
+// long as A8 and W8 use the same order; K % 32 == 0.
+__host__ __device__ __forceinline__ int64_t e4m3_slot0(int64_t k) { return (k >> 5) * 64 + (k & 31); }
+
 __device__ __forceinline__ void split4_f16_e4m3(const float4& x, uint2& h16, uint32_t& hi8, uint32_t& lo8) {
     const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
     h16.x = *reinterpret_cast<const uint32_t*>(&h0);

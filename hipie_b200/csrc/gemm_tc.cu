@@ -28,7 +28,7 @@
 // The cross terms are 2^-11 of the product, so the 2^-4 relative rounding of their e4m3 factors lands at 2^-15..2^-16 -- the
 // class of the bf16x3 scheme (tools/prec_map_emulate.py: mask logits unchanged at 1.4e-4) -- and both of them are ONE fp8
 // contraction over 2K: operand planes A8 = [e4m3(Ah) | e4m3(2^10 Al)] (M x 2K) and W8 = [e4m3(2^14 Wl) | e4m3(2^4 Wh)]
-// (N x 2K).  Per tile the MMA warp first sweeps the fp8 planes (kind::f8f6f4, K = 32 per instruction: twice the rate of the
+// (N x 2K), the two slots interleaved in 32-column groups (common.cuh: e4m3_slot0) so that producers write 64-byte row segments.  Per tile the MMA warp first sweeps the fp8 planes (kind::f8f6f4, K = 32 per instruction: twice the rate of the
 // 16-bit kinds), accumulating 2^14 x the cross terms, then the fp16 planes, whose first MMA rescales the accumulator with the
 // instruction's scale-input-d immediate (D = A.B + D * 2^-14).  Two pass-equivalents instead of three, same operand bytes.
 #include "common.cuh"
@@ -383,10 +383,13 @@ __device__ __forceinline__ void epilogue_rows_tma(const GemmParams& p, const CUt
                 }
             }
             if (planes && p.c_e4m3) {
-                sts128(sbuf + 2048 + lane * 32, h8[0], h8[1], h8[2], h8[3]);
-                sts128(sbuf + 2048 + lane * 32 + 16, h8[4], h8[5], h8[6], h8[7]);
-                sts128(sbuf + 3072 + lane * 32, l8[0], l8[1], l8[2], l8[3]);
-                sts128(sbuf + 3072 + lane * 32 + 16, l8[4], l8[5], l8[6], l8[7]);
+                // ONE e4m3 box: 64-byte rows = [slot 0: 32 bytes | slot 1: 32 bytes] of this 32-column chunk (the planes interleave the slots in
+                // 32-column groups, common.cuh), 16-byte group c of row r at c ^ ((r >> 1) & 3)  (CU_TENSOR_MAP_SWIZZLE_64B)
+                const uint32_t rb = sbuf + 2048 + lane * 64, sw = (lane >> 1) & 3;
+                sts128(rb + ((0 ^ sw) << 4), h8[0], h8[1], h8[2], h8[3]);
+                sts128(rb + ((1 ^ sw) << 4), h8[4], h8[5], h8[6], h8[7]);
+                sts128(rb + ((2 ^ sw) << 4), l8[0], l8[1], l8[2], l8[3]);
+                sts128(rb + ((3 ^ sw) << 4), l8[4], l8[5], l8[6], l8[7]);
             }
             fence_proxy_async_smem();      // generic-proxy writes -> visible to the TMA (async proxy)
             __syncwarp();
@@ -395,10 +398,8 @@ __device__ __forceinline__ void epilogue_rows_tma(const GemmParams& p, const CUt
                     tma_store_3d(tm_f32, sbuf, nbase, m0, b);
                 } else {
                     tma_store_3d(tm_hi, sbuf, nbase, m0, b);
-                    if (p.c_e4m3) {
-                        tma_store_3d(tm_lo, sbuf + 2048, nbase, m0, b);             // e4m3(h)          -> columns [0, N)
-                        tma_store_3d(tm_lo, sbuf + 3072, p.N + nbase, m0, b);       // e4m3(2^10 (x-h)) -> columns [N, 2N)
-                    } else if (p.c_lo) tma_store_3d(tm_lo, sbuf + 2048, nbase, m0, b);
+                    if (p.c_e4m3) tma_store_3d(tm_lo, sbuf + 2048, 2 * nbase, m0, b);      // both slots of columns [nbase, nbase + 32): bytes [2 nbase, +64)
+                    else if (p.c_lo) tma_store_3d(tm_lo, sbuf + 2048, nbase, m0, b);
                 }
                 bulk_commit();
             }
@@ -863,7 +864,6 @@ int make_tmap(CUtensorMap* out, const void* ptr, int esize, int64_t rows, int64_
     cuuint32_t estr[3] = {1, 1, 1};
     CUtensorMapSwizzle swz = box_cols * esize == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                              : (box_cols * esize == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    if (esize == 1 && box_cols == 32) swz = CU_TENSOR_MAP_SWIZZLE_NONE;        // e4m3 output boxes: plain 32-byte rows
     const CUtensorMapDataType dt = esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
     CUresult r = enc(out, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -941,7 +941,7 @@ static int launch_gemm(const hipie_gemm_args* a, cudaStream_t st) {
         if (a->c_f32 && (rc = make_tmap(&tc_f32, a->c_f32, 4, a->M, a->N, a->ldc, a->batch, cbs, 32, 32))) return rc;
         if (a->c_hi && (rc = make_tmap(&tc_hi, a->c_hi, 2, a->M, a->N, a->ldc, a->batch, cbs, 32, 32))) return rc;
         if (a->c_lo && (rc = make_tmap(&tc_lo, a->c_lo, 2, a->M, a->N, a->ldc, a->batch, cbs, 32, 32))) return rc;
-        if (a->c8 && (rc = make_tmap(&tc_lo, a->c8, 1, a->M, 2 * (int64_t)a->N, a->ldc8, 1, 0, 32, 32))) return rc;
+        if (a->c8 && (rc = make_tmap(&tc_lo, a->c8, 1, a->M, 2 * (int64_t)a->N, a->ldc8, 1, 0, 32, 64))) return rc;
     }
     GemmParams p;
     p.tma_out = tma_out ? 1 : 0;
@@ -1001,6 +1001,7 @@ extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     HIPIE_CHECK_ARG(a != nullptr, "hipie_gemm: null args");
     HIPIE_CHECK_ARG(a->a_hi && a->w_hi, "hipie_gemm: a_hi / w_hi required");
     HIPIE_CHECK_ARG((a->prec >= 1 && a->prec <= 4) || a->prec == 6, "hipie_gemm: prec must be 1, 2, 3, 4 or 6 (got %d)", a->prec);
+    HIPIE_CHECK_ARG(a->prec != 6 || a->K % 32 == 0, "hipie_gemm: prec 6 needs K %% 32 == 0 (the e4m3 planes interleave 32-column groups)");
     HIPIE_CHECK_ARG(a->prec != 6 || (a->a8 && a->w8 && a->batch == 1 && a->lda8 % 16 == 0 && a->ldw8 % 16 == 0 && a->lda8 >= 2 * (int64_t)a->K &&
                                      a->ldw8 >= 2 * (int64_t)a->K),
                     "hipie_gemm: prec 6 needs the e4m3 planes a8 (M x 2K) / w8 (N x 2K) with 16-byte aligned row strides, batch 1");

@@ -515,7 +515,8 @@ static inline int grid_for(int64_t n, int threads = 256) {
 
 using namespace hipie;
 
-// fp32 (rows, cols) -> fp16 plane + e4m3 planes of a prec-6 GEMM operand (gemm_tc.cu); thread = 4 consecutive columns
+// fp32 (rows, cols) -> fp16 plane + e4m3 planes of a prec-6 GEMM operand (gemm_tc.cu); thread = 4 consecutive columns.
+// Activations: slot 0 = e4m3(h), slot 1 = e4m3(2^10 (x - h)); weights: slot 0 = e4m3(2^14 (w - h)), slot 1 = e4m3(2^4 h)
 __global__ void __launch_bounds__(256)
 split_f16_e4m3_kernel(const float* __restrict__ x, __half* __restrict__ h16, uint8_t* __restrict__ p8, int64_t rows, int cols, int weight) {
     const int c4 = cols >> 2;
@@ -538,14 +539,15 @@ split_f16_e4m3_kernel(const float* __restrict__ x, __half* __restrict__ h16, uin
             second = pack_e4m3x4((v.x - f0.x) * 1024.f, (v.y - f0.y) * 1024.f, (v.z - f1.x) * 1024.f, (v.w - f1.y) * 1024.f);
         }
         *reinterpret_cast<uint2*>(h16 + r * cols + c) = h;
-        *reinterpret_cast<uint32_t*>(p8 + r * 2 * cols + c) = first;
-        *reinterpret_cast<uint32_t*>(p8 + r * 2 * cols + cols + c) = second;
+        uint8_t* o8 = p8 + r * 2 * cols + e4m3_slot0(c);          // the two planes interleaved in 32-column groups (common.cuh)
+        *reinterpret_cast<uint32_t*>(o8) = first;
+        *reinterpret_cast<uint32_t*>(o8 + 32) = second;
     }
 }
 
 extern "C" int hipie_split_f16_e4m3(const float* x, void* h16, void* p8, int64_t rows, int cols, int weight, void* stream) {
     HIPIE_CHECK_ARG(x && h16 && p8, "hipie_split_f16_e4m3: null pointer");
-    HIPIE_CHECK_ARG(rows >= 0 && cols > 0 && cols % 4 == 0, "hipie_split_f16_e4m3: cols must be a positive multiple of 4");
+    HIPIE_CHECK_ARG(rows >= 0 && cols > 0 && cols % 32 == 0, "hipie_split_f16_e4m3: cols must be a positive multiple of 32");
     if (rows == 0) return HIPIE_OK;
     const int64_t total = rows * (cols / 4);
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);

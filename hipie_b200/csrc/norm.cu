@@ -61,8 +61,9 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, con
                 uint32_t a8, b8;
                 split4_f16_e4m3(o, h16, a8, b8);
                 *reinterpret_cast<uint2*>(y_hi + orow * C + c0) = h16;
-                *reinterpret_cast<uint32_t*>(y8 + orow * 2 * C + c0) = a8;
-                *reinterpret_cast<uint32_t*>(y8 + orow * 2 * C + C + c0) = b8;
+                uint8_t* o8 = y8 + orow * 2 * C + e4m3_slot0(c0);
+                *reinterpret_cast<uint32_t*>(o8) = a8;
+                *reinterpret_cast<uint32_t*>(o8 + 32) = b8;
             } else if (y_hi) {
                 uint2 hi, lo;
                 split2m(o.x, o.y, hi.x, lo.x, y_fp16);       // y_fp16: y_hi is ONE IEEE fp16 plane (y_lo NULL)
@@ -118,8 +119,8 @@ layernorm_generic_kernel(const float* __restrict__ x, const float* __restrict__ 
             const __half h = __float2half_rn(o);
             reinterpret_cast<__half*>(y_hi)[orow * C + c] = h;
             if (y8) {
-                y8[orow * 2 * C + c] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(h), __NV_SATFINITE, __NV_E4M3);
-                y8[orow * 2 * C + C + c] = (uint8_t)__nv_cvt_float_to_fp8((o - __half2float(h)) * 1024.f, __NV_SATFINITE, __NV_E4M3);
+                y8[orow * 2 * C + e4m3_slot0(c)] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(h), __NV_SATFINITE, __NV_E4M3);
+                y8[orow * 2 * C + e4m3_slot0(c) + 32] = (uint8_t)__nv_cvt_float_to_fp8((o - __half2float(h)) * 1024.f, __NV_SATFINITE, __NV_E4M3);
             }
         } else if (y_hi) {
             const __nv_bfloat16 h = __float2bfloat16_rn(o);
@@ -245,7 +246,7 @@ extern "C" int hipie_layernorm_f16(const float* x, const float* add, const float
                                    float* sum_out, float* y_f32, void* y_f16, void* y_e4m3, int64_t rows, int C,
                                    const int32_t* out_row_map, void* stream) {
     HIPIE_CHECK_ARG(y_f16 != nullptr, "hipie_layernorm_f16: y_f16 required");
-    HIPIE_CHECK_ARG(!y_e4m3 || C % 4 == 0, "hipie_layernorm_f16: the e4m3 planes need C %% 4 == 0");
+    HIPIE_CHECK_ARG(!y_e4m3 || C % 32 == 0, "hipie_layernorm_f16: the e4m3 planes need C %% 32 == 0");
     return layernorm_launch(x, add, gamma, beta, eps, sum_out, y_f32, y_f16, nullptr, 1, rows, C, out_row_map, stream, (uint8_t*)y_e4m3);
 }
 

@@ -105,7 +105,8 @@ class BF2:
         f = self.hi.float()
         if self.lo is not None and self.lo.dtype == torch.uint8:      # fp16 + e4m3 planes of an ACTIVATION (split_f16_e4m3): [e4m3(h) | e4m3(2^10 l)]
             K = self.hi.shape[-1]
-            return f + self.lo[..., K:].view(torch.float8_e4m3fn).float() / 1024.0
+            slot1 = self.lo.view(*self.lo.shape[:-1], K // 32, 2, 32)[..., 1, :].reshape(self.hi.shape)      # slots interleaved in 32-column groups
+            return f + slot1.view(torch.float8_e4m3fn).float() / 1024.0
         return f if self.lo is None else f + self.lo.float()
 
 

@@ -132,8 +132,10 @@ typedef struct hipie_gemm_args {
     int c_fp16;               /* 1: c_hi receives IEEE fp16 values (one plane, c_lo must be NULL): operands of the single-pass fp16
                                  contractions (attention QK^T / PV); 0: bf16 hi (+ lo) planes */
     /* prec 6 (fp16 + e4m3 split, see below): e4m3 planes of the operands, row strides in bytes */
-    const void* a8; int64_t lda8;   /* (M, 2K): [e4m3(Ah) | e4m3(2^10 (A - Ah))], Ah = fp16(A) = a_hi */
-    const void* w8; int64_t ldw8;   /* (N, 2K): [e4m3(2^14 (W - Wh)) | e4m3(2^4 Wh)], Wh = fp16(W) = w_hi */
+    /* The e4m3 planes hold two "slots" per element, interleaved in 32-column groups: byte (k / 32) * 64 + k % 32 = slot 0 of column k,
+       +32 = slot 1 (a producer's 32-column chunk is one 64-byte segment); K % 32 == 0. */
+    const void* a8; int64_t lda8;   /* (M, 2K): slot 0 = e4m3(Ah), slot 1 = e4m3(2^10 (A - Ah)), Ah = fp16(A) = a_hi */
+    const void* w8; int64_t ldw8;   /* (N, 2K): slot 0 = e4m3(2^14 (W - Wh)), slot 1 = e4m3(2^4 Wh), Wh = fp16(W) = w_hi */
     void* c8; int64_t ldc8;         /* optional with c_fp16: the result's own e4m3 planes (M, 2N) in the a8 layout, so that the
                                        output feeds the next prec-6 GEMM (fc1 -> fc2); needs N % 32 == 0 */
 } hipie_gemm_args;
@@ -154,7 +156,8 @@ int hipie_gemm(const hipie_gemm_args* args, void* stream);
 int hipie_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
 
 /* fp32 (rows, cols) -> the operand planes of a prec-6 hipie_gemm: h16 (rows, cols) fp16 and p8 (rows, 2 * cols) e4m3.
- * weight == 0 (activation A): p8 = [e4m3(h) | e4m3(2^10 (x - h))];  weight == 1 (W): p8 = [e4m3(2^14 (x - h)) | e4m3(2^4 h)]. */
+ * weight == 0 (activation A): slots e4m3(h), e4m3(2^10 (x - h));  weight == 1 (W): slots e4m3(2^14 (x - h)), e4m3(2^4 h); the slots are
+ * interleaved in 32-column groups (see hipie_gemm_args.a8); cols % 32 == 0. */
 int hipie_split_f16_e4m3(const float* x, void* h16, void* p8, int64_t rows, int cols, int weight, void* stream);
 
 /* LayerNorm over the last dim C of x[rows, C] (fp32 in).  Outputs: y_f32 and/or bf16 split

@@ -40,3 +40,18 @@ for name, M, N, K, kw, planes_out in SHAPES:
         t6 = timed(lambda: ops.gemm(A6, W6, residual=res, out_f32=out, prec=6, **kw))
     fl = 2.0 * M * N * K
     print(f"{name:14s} {M:6d}x{N:5d}x{K:5d}  bf16x3 {t3*1000:7.1f} us {fl/t3/1e9:6.1f} TF   f16+e4m3 {t6*1000:7.1f} us {fl/t6/1e9:6.1f} TF", flush=True)
+
+# which half costs FFN1 (K = 256, store heavy): mainloop format x output format
+M, N, K = 174080, 2048, 256
+a = torch.randn(M, K, device=dev)
+w = torch.randn(N, K, device=dev) * 0.05
+A3, W3 = ops.split(a), ops.split_weight(w)
+A6, W6 = ops.split_f16_e4m3(a), ops.split_f16_e4m3(w, weight=True)
+for name, fn in (("p3 -> bf16 hi/lo", lambda: ops.gemm(A3, W3, act=ops.ACT_RELU, want_f32=False, want_split=True, prec=3)),
+                 ("p3 -> fp16+e4m3", lambda: ops.gemm(A3, W3, act=ops.ACT_RELU, want_f32=False, out_e4m3=True, prec=3)),
+                 ("p3 -> fp16 only", lambda: ops.gemm(A3, W3, act=ops.ACT_RELU, want_f32=False, want_split=True, out_fp16=True, prec=3)),
+                 ("p6 -> bf16 hi/lo", lambda: ops.gemm(A6, W6, act=ops.ACT_RELU, want_f32=False, want_split=True, prec=6)),
+                 ("p6 -> fp16+e4m3", lambda: ops.gemm(A6, W6, act=ops.ACT_RELU, want_f32=False, out_e4m3=True, prec=6)),
+                 ("p6 -> fp16 only", lambda: ops.gemm(A6, W6, act=ops.ACT_RELU, want_f32=False, want_split=True, out_fp16=True, prec=6))):
+    t = timed(fn)
+    print(f"ffn1 {name:18s} {t*1000:7.1f} us", flush=True)
