@@ -399,22 +399,47 @@ condinst_kernel(const float* __restrict__ feats, const float* __restrict__ param
                 float* __restrict__ out, int B, int Q, int Hf, int Wf, int stride) {
     extern __shared__ float coarse[];  // Hf*Wf
     const int q = blockIdx.x, b = blockIdx.y;
-    __shared__ float prm[169];
+    // the 169 dynamic parameters, re-laid out for 16-byte broadcast loads: w0 rows padded 10 -> 12 (the MLP is shared-memory
+    // bound: one LDS per weight and 4 pixels was 169 wavefronts per iteration, now 47)
+    __shared__ __align__(16) float prm[8 * 12 + 64 + 8 + 8 + 8 + 4];
     __shared__ float ref[2];
-    for (int i = threadIdx.x; i < 169; i += blockDim.x) prm[i] = params[((int64_t)b * Q + q) * 169 + i];
+    float* w0 = prm;                // [8][12]
+    float* w1 = prm + 96;           // [8][8]
+    float* w2 = prm + 160;          // [8]
+    float* b0 = prm + 168;
+    float* b1 = prm + 176;
+    if (threadIdx.x < 169) {
+        const int i = threadIdx.x;
+        const float v = params[((int64_t)b * Q + q) * 169 + i];
+        if (i < 80) w0[(i / 10) * 12 + i % 10] = v;
+        else if (i < 144) w1[i - 80] = v;
+        else if (i < 152) w2[i - 144] = v;
+        else if (i < 160) b0[i - 152] = v;
+        else if (i < 168) b1[i - 160] = v;
+        else prm[184] = v;
+    }
+    if (threadIdx.x >= 192 && threadIdx.x < 208) w0[((threadIdx.x - 192) >> 1) * 12 + 10 + (threadIdx.x & 1)] = 0.f;
     if (threadIdx.x < 2) ref[threadIdx.x] = ref_px[((int64_t)b * Q + q) * 2 + threadIdx.x];
     __syncthreads();
-    const float* w0 = prm;          // [8][10]
-    const float* w1 = prm + 80;     // [8][8]
-    const float* w2 = prm + 144;    // [8]
-    const float* b0 = prm + 152;
-    const float* b1 = prm + 160;
-    const float b2 = prm[168];
+    const float b2 = prm[184];
     const int HW = Hf * Wf;
     const float* fb = feats + (int64_t)b * HW * 8;
     // 4 coarse pixels per thread and iteration: every (broadcast) weight read from shared memory feeds 4 FMAs, otherwise the
     // 152 LDS per pixel make the MLP shared-memory bound (measured 3.1 ms for 8 x 910 queries; this layout ~3x faster)
     constexpr int PX = 4;
+    // the 8 feature channels of the NEXT 4 pixels are fetched while the current ones go through the 152-MAC MLP: with one CTA per SM
+    // (the unrolled MLP keeps the weights in registers) nothing else would hide the L2 latency of these loads
+    float4 nf[PX][2];
+    auto fetch = [&](int i0n) {
+#pragma unroll
+        for (int u = 0; u < PX; ++u) {
+            const int i = i0n + u * blockDim.x;
+            const int ii = i < HW ? i : 0;
+            nf[u][0] = ldg_nc_f4(fb + (int64_t)ii * 8);
+            nf[u][1] = ldg_nc_f4(fb + (int64_t)ii * 8 + 4);
+        }
+    };
+    fetch(threadIdx.x);
     for (int i0 = threadIdx.x; i0 < HW; i0 += blockDim.x * PX) {
         float in[PX][10];
         bool ok[PX];
@@ -426,38 +451,43 @@ condinst_kernel(const float* __restrict__ feats, const float* __restrict__ param
             const int y = ii / Wf, x = ii - y * Wf;
             in[u][0] = ref[0] - (float)(x * stride + stride / 2);
             in[u][1] = ref[1] - (float)(y * stride + stride / 2);
-            const float4 f0 = *reinterpret_cast<const float4*>(fb + (int64_t)ii * 8);
-            const float4 f1 = *reinterpret_cast<const float4*>(fb + (int64_t)ii * 8 + 4);
+            const float4 f0 = nf[u][0], f1 = nf[u][1];
             in[u][2] = f0.x; in[u][3] = f0.y; in[u][4] = f0.z; in[u][5] = f0.w;
             in[u][6] = f1.x; in[u][7] = f1.y; in[u][8] = f1.z; in[u][9] = f1.w;
         }
+        if (i0 + blockDim.x * PX < HW) fetch(i0 + blockDim.x * PX);
         float h0[PX][8], h1[PX][8];
+        const float4 bb0a = *reinterpret_cast<const float4*>(b0), bb0b = *reinterpret_cast<const float4*>(b0 + 4);
+        const float bb0[8] = {bb0a.x, bb0a.y, bb0a.z, bb0a.w, bb0b.x, bb0b.y, bb0b.z, bb0b.w};
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
             float a[PX];
-            const float bb = b0[o];
 #pragma unroll
-            for (int u = 0; u < PX; ++u) a[u] = bb;
+            for (int u = 0; u < PX; ++u) a[u] = bb0[o];
+            const float4 wa = *reinterpret_cast<const float4*>(w0 + o * 12), wb = *reinterpret_cast<const float4*>(w0 + o * 12 + 4);
+            const float2 wc = *reinterpret_cast<const float2*>(w0 + o * 12 + 8);
+            const float wr[10] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y};
 #pragma unroll
-            for (int k = 0; k < 10; ++k) {
-                const float wv = w0[o * 10 + k];
+            for (int k = 0; k < 10; ++k) {          // same accumulation order as before: bias, then k = 0..9
 #pragma unroll
-                for (int u = 0; u < PX; ++u) a[u] += wv * in[u][k];
+                for (int u = 0; u < PX; ++u) a[u] += wr[k] * in[u][k];
             }
 #pragma unroll
             for (int u = 0; u < PX; ++u) h0[u][o] = fmaxf(a[u], 0.f);
         }
+        const float4 bb1a = *reinterpret_cast<const float4*>(b1), bb1b = *reinterpret_cast<const float4*>(b1 + 4);
+        const float bb1[8] = {bb1a.x, bb1a.y, bb1a.z, bb1a.w, bb1b.x, bb1b.y, bb1b.z, bb1b.w};
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
             float a[PX];
-            const float bb = b1[o];
 #pragma unroll
-            for (int u = 0; u < PX; ++u) a[u] = bb;
+            for (int u = 0; u < PX; ++u) a[u] = bb1[o];
+            const float4 wa = *reinterpret_cast<const float4*>(w1 + o * 8), wb = *reinterpret_cast<const float4*>(w1 + o * 8 + 4);
+            const float wr[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const float wv = w1[o * 8 + k];
 #pragma unroll
-                for (int u = 0; u < PX; ++u) a[u] += wv * h0[u][k];
+                for (int u = 0; u < PX; ++u) a[u] += wr[k] * h0[u][k];
             }
 #pragma unroll
             for (int u = 0; u < PX; ++u) h1[u][o] = fmaxf(a[u], 0.f);
@@ -465,11 +495,14 @@ condinst_kernel(const float* __restrict__ feats, const float* __restrict__ param
         float a[PX];
 #pragma unroll
         for (int u = 0; u < PX; ++u) a[u] = b2;
+        {
+            const float4 wa = *reinterpret_cast<const float4*>(w2), wb = *reinterpret_cast<const float4*>(w2 + 4);
+            const float wr[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float wv = w2[k];
+            for (int k = 0; k < 8; ++k) {
 #pragma unroll
-            for (int u = 0; u < PX; ++u) a[u] += wv * h1[u][k];
+                for (int u = 0; u < PX; ++u) a[u] += wr[k] * h1[u][k];
+            }
         }
 #pragma unroll
         for (int u = 0; u < PX; ++u)
@@ -495,7 +528,22 @@ condinst_kernel(const float* __restrict__ feats, const float* __restrict__ param
         const int n4 = Ho * Wo / 4;
         for (int i = threadIdx.x; i < n4; i += blockDim.x) {
             const int Y = (i * 4) / Wo, X = i * 4 - Y * Wo;
-            *reinterpret_cast<float4*>(ob + (int64_t)i * 4) = make_float4(px(Y, X), px(Y, X + 1), px(Y, X + 2), px(Y, X + 3));
+            if (X == 0) {       // left border: the generic expression (clamped source columns)
+                *reinterpret_cast<float4*>(ob + (int64_t)i * 4) = make_float4(px(Y, 0), px(Y, 1), px(Y, 2), px(Y, 3));
+                continue;
+            }
+            // X = 4k > 0: source columns ux = X-1 .. X+2 touch coarse columns c, c+1, c+2 with c = X/2 - 1 (odd ux: midpoint of two
+            // columns, even ux: one column) -- 6 shared-memory loads for 4 outputs instead of 16, the same arithmetic per output as px()
+            const int uy = max(Y - 1, 0), y0 = uy >> 1, c = (X >> 1) - 1;
+            const float fy = (uy & 1) ? 0.5f : 0.f;
+            const float t0 = at(y0, c), t1 = at(y0, c + 1), t2 = at(y0, c + 2);
+            const float u0 = at(y0 + 1, c), u1 = at(y0 + 1, c + 1), u2 = at(y0 + 1, c + 2);
+            const float top0 = t0 + (t1 - t0) * 0.5f, bot0 = u0 + (u1 - u0) * 0.5f;
+            const float top1 = t1, bot1 = u1;                            // even ux: v00 + (v01 - v00) * 0 == v00 for finite logits
+            const float top2 = t1 + (t2 - t1) * 0.5f, bot2 = u1 + (u2 - u1) * 0.5f;
+            const float top3 = t2, bot3 = u2;
+            *reinterpret_cast<float4*>(ob + (int64_t)i * 4) = make_float4(top0 + (bot0 - top0) * fy, top1 + (bot1 - top1) * fy,
+                                                                          top2 + (bot2 - top2) * fy, top3 + (bot3 - top3) * fy);
         }
     } else {
         for (int i = threadIdx.x; i < Ho * Wo; i += blockDim.x) {
