@@ -462,3 +462,23 @@ def test_predictor_and_registry_components(setup, cuda, tmp_path):
     out_md, _ = head(ref)
     assert _err(out_md["pred_masks"], ref_md["pred_masks"]) < 1e-3
     assert out_md["pred_masks"].shape == ref_md["pred_masks"].shape and out_md["pred_logits"].shape == ref_md["pred_logits"].shape
+
+
+def test_pinned_arena_results_to_host(cuda):
+    """hipie_b200.hostio.PinnedArena: async device->host copies into ONE persistent page-locked buffer (views valid after wait();
+    dtype / shape / alignment preserved; a step that outgrows the arena spills to fresh pinned tensors and the arena grows at reset)."""
+    from hipie_b200.hostio import PinnedArena
+    arena = PinnedArena(1 << 16)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    tensors = [torch.randn(100, 7, device=cuda, generator=g), torch.randint(0, 255, (33,), device=cuda, dtype=torch.uint8, generator=g),
+               torch.randint(0, 9, (5, 11), device=cuda, generator=g), torch.randn(64, 64, device=cuda, generator=g) > 0]
+    for step in range(3):
+        arena.reset()
+        host = [arena.to_host(t) for t in tensors]
+        big = arena.to_host(torch.ones(1 << 15, device=cuda)) if step == 0 else None      # 128 KB > the 64 KB arena: spill, then growth
+        arena.wait()
+        for h, t in zip(host, tensors):
+            assert h.is_pinned() and h.dtype == t.dtype and h.shape == t.shape and torch.equal(h, t.cpu())
+            assert h.data_ptr() % 256 == 0 or big is not None
+        if big is not None:
+            assert big.is_pinned() and float(big.sum()) == float(1 << 15)
