@@ -69,16 +69,28 @@ __global__ void msda_generic_kernel(const T* __restrict__ value, const int64_t* 
 // ------------------------------------------------------------------------------------------
 // fast path
 // ------------------------------------------------------------------------------------------
-template <bool BF16V>
+// value-map storage: 0 = fp32 (128-byte lines per tap and head), 1 = bf16, 2 = IEEE fp16 (64-byte lines: half the L2 -> L1 fill traffic
+// that bounds the encoder calls; the precision map of DESIGN.md 3 adopts fp16 for the encoders' value maps)
+template <int BF16V>
 struct ValLoad;
 template <>
-struct ValLoad<false> {
+struct ValLoad<0> {
     static __device__ __forceinline__ float4 ld(const void* base, int64_t elem_off) {
         return ldg_nc_f4(reinterpret_cast<const float*>(base) + elem_off);
     }
 };
 template <>
-struct ValLoad<true> {
+struct ValLoad<2> {
+    static __device__ __forceinline__ float4 ld(const void* base, int64_t elem_off) {
+        uint2 r;
+        const __half* p = reinterpret_cast<const __half*>(base) + elem_off;
+        asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+template <>
+struct ValLoad<1> {
     static __device__ __forceinline__ float4 ld(const void* base, int64_t elem_off) {
         uint2 r;
         const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + elem_off;
@@ -94,7 +106,7 @@ struct ValLoad<true> {
 
 // FUSED: offs_logits rows are [M*L*P*2 offsets | M*L*P logits]; REFDIM in {2,4}.
 // otherwise loc/attw are the reference operator's tensors.
-template <bool BF16V, bool FUSED, int REFDIM, bool SPLIT_OUT>
+template <int BF16V, bool FUSED, int REFDIM, bool SPLIT_OUT>
 __global__ void __launch_bounds__(256)
 msda_fast_kernel(const void* __restrict__ value, const int64_t* __restrict__ shapes,
                  const int64_t* __restrict__ lstart, const float* __restrict__ loc,
@@ -468,7 +480,7 @@ msda_win_kernel(const __grid_constant__ MsdaWinMaps maps, const MsdaWinParams p)
     }
 }
 
-template <bool BF16V, bool FUSED, int REFDIM, bool SPLIT>
+template <int BF16V, bool FUSED, int REFDIM, bool SPLIT>
 static int launch_fast(const void* value, const int64_t* shapes, const int64_t* lstart,
                        const float* loc, const float* attw, const float* refp, float* out,
                        void* out_hi, void* out_lo, int N, int S, int M, int Lq, cudaStream_t st) {
@@ -504,10 +516,10 @@ extern "C" int hipie_msda_forward(const void* value, const int64_t* spatial_shap
                       (((uintptr_t)value | (uintptr_t)sampling_loc | (uintptr_t)attn_weight | (uintptr_t)out) & 15) == 0;
     if (fast) {
         if (value_dtype == HIPIE_BF16)
-            return launch_fast<true, false, 2, false>(value, spatial_shapes, level_start_index,
+            return launch_fast<1, false, 2, false>(value, spatial_shapes, level_start_index,
                                                       (const float*)sampling_loc, (const float*)attn_weight,
                                                       nullptr, (float*)out, nullptr, nullptr, N, S, M, Lq, st);
-        return launch_fast<false, false, 2, false>(value, spatial_shapes, level_start_index,
+        return launch_fast<0, false, 2, false>(value, spatial_shapes, level_start_index,
                                                    (const float*)sampling_loc, (const float*)attn_weight,
                                                    nullptr, (float*)out, nullptr, nullptr, N, S, M, Lq, st);
     }
@@ -539,7 +551,7 @@ extern "C" int hipie_msda_fused_forward(const void* value, const int64_t* spatia
     HIPIE_CHECK_ARG(D == 32 && L == 4 && P == 4 && M > 0 && (M % 4) == 0,
                     "hipie_msda_fused_forward: only D=32, L=4, P=4, M%%4==0 (got D=%d L=%d P=%d M=%d)", D, L, P, M);
     HIPIE_CHECK_ARG(ref_dim == 2 || ref_dim == 4, "hipie_msda_fused_forward: ref_dim must be 2 or 4");
-    HIPIE_CHECK_ARG(value_dtype == HIPIE_F32 || value_dtype == HIPIE_BF16, "bad value_dtype");
+    HIPIE_CHECK_ARG(value_dtype == HIPIE_F32 || value_dtype == HIPIE_BF16 || value_dtype == HIPIE_F16, "bad value_dtype");
     cudaStream_t st = (cudaStream_t)stream;
     if ((int64_t)N * Lq == 0) return HIPIE_OK;
     float* of = out_split_bf16 ? nullptr : (float*)out;
@@ -547,13 +559,15 @@ extern "C" int hipie_msda_fused_forward(const void* value, const int64_t* spatia
 #define HIPIE_MSDA_GO(BV, RD, SP)                                                                   \
     return launch_fast<BV, true, RD, SP>(value, spatial_shapes, level_start_index, offs_logits,    \
                                          nullptr, reference_points, of, ohi, out_lo, N, S, M, Lq, st)
-    const bool bv = value_dtype == HIPIE_BF16;
-    if (bv) {
-        if (ref_dim == 2) { if (out_split_bf16) HIPIE_MSDA_GO(true, 2, true); else HIPIE_MSDA_GO(true, 2, false); }
-        else { if (out_split_bf16) HIPIE_MSDA_GO(true, 4, true); else HIPIE_MSDA_GO(true, 4, false); }
+    if (value_dtype == HIPIE_BF16) {
+        if (ref_dim == 2) { if (out_split_bf16) HIPIE_MSDA_GO(1, 2, true); else HIPIE_MSDA_GO(1, 2, false); }
+        else { if (out_split_bf16) HIPIE_MSDA_GO(1, 4, true); else HIPIE_MSDA_GO(1, 4, false); }
+    } else if (value_dtype == HIPIE_F16) {
+        if (ref_dim == 2) { if (out_split_bf16) HIPIE_MSDA_GO(2, 2, true); else HIPIE_MSDA_GO(2, 2, false); }
+        else { if (out_split_bf16) HIPIE_MSDA_GO(2, 4, true); else HIPIE_MSDA_GO(2, 4, false); }
     } else {
-        if (ref_dim == 2) { if (out_split_bf16) HIPIE_MSDA_GO(false, 2, true); else HIPIE_MSDA_GO(false, 2, false); }
-        else { if (out_split_bf16) HIPIE_MSDA_GO(false, 4, true); else HIPIE_MSDA_GO(false, 4, false); }
+        if (ref_dim == 2) { if (out_split_bf16) HIPIE_MSDA_GO(0, 2, true); else HIPIE_MSDA_GO(0, 2, false); }
+        else { if (out_split_bf16) HIPIE_MSDA_GO(0, 4, true); else HIPIE_MSDA_GO(0, 4, false); }
     }
 #undef HIPIE_MSDA_GO
 }

@@ -506,13 +506,13 @@ MSDA_WINDOWS = False     # True: encoder calls gather from TMA-staged shared-mem
 
 def msda_fused(value, spatial_shapes, level_start_index, offs_logits, reference_points, M=8, D=32, L=4, P=4,
                want_split=True, shapes_host=None):
-    """value (N,S,M*D) fp32|bf16; offs_logits (N,Lq,M*L*P*3) fp32; reference_points (N,Lq,L,2|4) fp32.
+    """value (N,S,M*D) fp32|bf16|fp16; offs_logits (N,Lq,M*L*P*3) fp32; reference_points (N,Lq,L,2|4) fp32.
     shapes_host: the level (H, W) list on the host -- with it, encoder calls (Lq == S, 2-d reference points, fp32 value map) run the
     shared-memory window kernel."""
     N, S = value.shape[0], value.shape[1]
     Lq = offs_logits.shape[1]
     ref_dim = reference_points.shape[-1]
-    vdt = 2 if value.dtype == torch.bfloat16 else 0
+    vdt = 2 if value.dtype == torch.bfloat16 else (3 if value.dtype == torch.float16 else 0)
     dev = value.device
     if want_split:
         s = _empty_bf2((N, Lq, M * D), dev)
@@ -520,7 +520,7 @@ def msda_fused(value, spatial_shapes, level_start_index, offs_logits, reference_
     else:
         s = None
         out, out_lo = torch.empty((N, Lq, M * D), dtype=torch.float32, device=dev), None
-    fv = 2 if vdt == 2 else 4
+    fv = 4      # algorithmic bytes are counted on the fp32 value map of the reference op whatever the storage format
     # algorithmic bytes: value map + offsets/logits (3 floats per sample) + output
     alg = float(N) * (S * M * D * fv + Lq * M * L * P * 3 * 4 + Lq * M * D * 4)
     offs_logits, reference_points = offs_logits.contiguous(), reference_points.contiguous()

@@ -45,6 +45,7 @@ extern "C" {
 #define HIPIE_F32 0
 #define HIPIE_F64 1
 #define HIPIE_BF16 2
+#define HIPIE_F16 3   /* IEEE fp16 value map of hipie_msda_fused_forward */
 
 /* epilogue activation codes for hipie_gemm */
 #define HIPIE_ACT_NONE 0

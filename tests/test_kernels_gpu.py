@@ -104,6 +104,13 @@ def test_msda_fused_front_half(ops, cuda, ref_dim):
     assert (out - ref).abs().max() < 2e-5
     s = ops.msda_fused(value.to(cuda), shapes_t.to(cuda), lsi.to(cuda), packed, refp.to(cuda), want_split=True)
     assert (s.float().cpu() - ref).abs().max() < 2e-4
+    # IEEE fp16 value map (the encoders' storage format): exact against the same op on the fp16-rounded values,
+    # and within the 2^-12 operand rounding of the fp32 result
+    v16 = value.half()
+    ref16 = ms_deform_attn_core(v16.float().view(N, S, M, 32).double(), shapes_t, loc.double(), w.double()).float()
+    out16 = ops.msda_fused(v16.to(cuda), shapes_t.to(cuda), lsi.to(cuda), packed, refp.to(cuda), want_split=False).cpu()
+    assert (out16 - ref16).abs().max() < 2e-5
+    assert (out16 - ref).abs().max() < 2.0 ** -11 * value.abs().max()
 
 
 # ------------------------------------------------------------------------------------------ GEMM
