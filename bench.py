@@ -424,7 +424,8 @@ def run_product(args, cfg):
     bert_rows = 1 if same_rows else B
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 (split-bf16 tensor-core operands, fp32 accumulate; fp32-class results)" if prec == 3 else "bf16",
+            "dtype": "fp32-class split precision on the tensor cores (operand planes per contraction: fp16 + e4m3 split, two fp16 passes, "
+                     "three bf16 passes, one fp16 pass for softmax-normalised products; fp32 accumulate; DESIGN.md 3)" if prec == 3 else "bf16",
             "data": "synthetic",
             "config": {"workload": f"{cfg['name']}: {cfg['desc']}",
                        "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world} (image sharding, one packed all-gather of logits / boxes)",

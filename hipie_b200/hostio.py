@@ -17,8 +17,7 @@ class PinnedArena:
     def reset(self):
         """Start a new step: every view handed out before is recycled (the caller has consumed or copied the previous results)."""
         if self._spill:        # the last step did not fit: grow once, outside the copies
-            need = self._off + sum(t.numel() * t.element_size() + 256 for t in self._spill)
-            self._buf = torch.empty(int(need * 1.25), dtype=torch.uint8, pin_memory=True)
+            self._buf = torch.empty(int(self._off * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)      # _off counted the spilled bytes too
             self._spill = []
         self._off = 0
 
