@@ -1042,11 +1042,14 @@ extern "C" int hipie_gemm(const hipie_gemm_args* a, void* stream) {
     return p3 ? launch_gemm<3, 256, 1>(a, st) : launch_gemm<1, 256, 1>(a, st);
 }
 
+extern int g_ln_grid_cap, g_ln_bulk;          // norm.cu (global scope)
 extern "C" int hipie_set_option(const char* name, int value) {
     HIPIE_CHECK_ARG(name != nullptr, "hipie_set_option: null name");
     if (strcmp(name, "gemm_cta_pairs") == 0) { g_gemm_cta_pairs = value ? 1 : 0; return HIPIE_OK; }
     if (strcmp(name, "gemm_tma_store") == 0) { g_gemm_tma_store = value ? 1 : 0; return HIPIE_OK; }
     if (strcmp(name, "gemm_fast_transposed") == 0) { g_gemm_fast_transposed = value ? 1 : 0; return HIPIE_OK; }
+    if (strcmp(name, "ln_grid_cap") == 0) { g_ln_grid_cap = value ? 1 : 0; return HIPIE_OK; }
+    if (strcmp(name, "ln_bulk") == 0) { g_ln_bulk = value ? 1 : 0; return HIPIE_OK; }
     set_error("hipie_set_option: unknown option '%s'", name);
     return HIPIE_EINVAL;
 }

@@ -4,6 +4,7 @@
 // DETR / MaskDINO post-LN eps 1e-5 (deformable_transformer_dino.py:385-450), GroupNorm(32) of the
 // input projections (deformable_detr.py:221-236, maskdino_encoder.py:253-306).
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace hipie {
 
@@ -15,10 +16,12 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, con
                  float* __restrict__ y_f32, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
                  int64_t rows, int C, const int* __restrict__ omap, int y_fp16, uint8_t* __restrict__ y8) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= rows) return;
-    const int64_t orow = omap ? omap[row] : row;
     const int nv = C >> 7;
+    // grid-stride over rows: the launcher caps the grid at the number of resident CTAs, so a 32768-row call is one full wave of
+    // long-lived CTAs instead of 3.5 waves of 8-row CTAs with a 46 % tail
+    const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += wstride) {
+    const int64_t orow = omap ? omap[row] : row;
     const float* xr = x + row * C;
     float4 v[MAXV];
     float s = 0.f;
@@ -70,6 +73,101 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, con
                 split2m(o.z, o.w, hi.y, lo.y, y_fp16);
                 *reinterpret_cast<uint2*>(y_hi + orow * C + c0) = hi;
                 if (y_lo) *reinterpret_cast<uint2*>(y_lo + orow * C + c0) = lo;
+            }
+        }
+    }
+    }
+}
+
+// Bulk-copy-staged variant for plain rows (no residual add): each warp keeps TWO rows in flight as 1-D cp.async.bulk copies into its own
+// shared-memory slots (completion on an mbarrier), so the next row streams in while the current one is reduced, normalised and
+// stored.  The register version above holds a row in 4 * MAXV registers per lane, which limits the SM to 32 warps and leaves
+// their loads exposed: 2.6 TB/s at 32768 x 1280 from a cold L2 (tools/ln_micro.py); the staged rows cost no registers.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_bulk_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      float* __restrict__ y_f32, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
+                      int64_t rows, int C, const int* __restrict__ omap, int y_fp16, uint8_t* __restrict__ y8) {
+    extern __shared__ __align__(128) uint8_t ln_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nv = C >> 7;
+    const uint32_t row_bytes = (uint32_t)C * 4u;
+    float* slots = reinterpret_cast<float*>(ln_smem) + (size_t)warp * 2 * C;              // [2][C] per warp
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)8 * 2 * C * 4) + warp * 2;
+    if (lane == 0) {
+        ptx::mbar_init(&bars[0], 1);
+        ptx::mbar_init(&bars[1], 1);
+        ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    auto issue = [&](int64_t r, int st) {
+        if (lane == 0) {
+            ptx::fence_proxy_async_smem();                 // the slot's previous generic-proxy reads are ordered before the async write
+            ptx::mbar_arrive_expect_tx(&bars[st], row_bytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             ptx::smem_u32(slots + (size_t)st * C)),
+                         "l"(x + r * C), "r"(row_bytes), "r"(ptx::smem_u32(&bars[st]))
+                         : "memory");
+        }
+    };
+    if (row < rows) issue(row, 0);
+    uint32_t ph[2] = {0u, 0u};
+    for (int it = 0; row < rows; row += wstride, ++it) {
+        const int st = it & 1;
+        if (row + wstride < rows) issue(row + wstride, st ^ 1);
+        ptx::mbar_wait(&bars[st], ph[st]);
+        ph[st] ^= 1u;
+        const float* xr = slots + (size_t)st * C;
+        const int64_t orow = omap ? omap[row] : row;
+        float4 v[MAXV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            if (i < nv) {
+                v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+        }
+        __syncwarp();                                      // every lane has read the slot: it may be refilled two iterations from now
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            if (i < nv) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            if (i < nv) {
+                const int c0 = (i * 32 + lane) * 4;
+                const float4 g = *reinterpret_cast<const float4*>(gamma + c0);
+                const float4 b = *reinterpret_cast<const float4*>(beta + c0);
+                float4 o;
+                o.x = (v[i].x - mean) * rstd * g.x + b.x;
+                o.y = (v[i].y - mean) * rstd * g.y + b.y;
+                o.z = (v[i].z - mean) * rstd * g.z + b.z;
+                o.w = (v[i].w - mean) * rstd * g.w + b.w;
+                if (y_f32) *reinterpret_cast<float4*>(y_f32 + orow * C + c0) = o;
+                if (y_hi && y8) {
+                    uint2 h16;
+                    uint32_t a8, b8;
+                    split4_f16_e4m3(o, h16, a8, b8);
+                    *reinterpret_cast<uint2*>(y_hi + orow * C + c0) = h16;
+                    uint8_t* o8 = y8 + orow * 2 * C + e4m3_slot0(c0);
+                    *reinterpret_cast<uint32_t*>(o8) = a8;
+                    *reinterpret_cast<uint32_t*>(o8 + 32) = b8;
+                } else if (y_hi) {
+                    uint2 hi, lo;
+                    split2m(o.x, o.y, hi.x, lo.x, y_fp16);
+                    split2m(o.z, o.w, hi.y, lo.y, y_fp16);
+                    *reinterpret_cast<uint2*>(y_hi + orow * C + c0) = hi;
+                    if (y_lo) *reinterpret_cast<uint2*>(y_lo + orow * C + c0) = lo;
+                }
             }
         }
     }
@@ -210,6 +308,21 @@ groupnorm_apply_kernel(const float* __restrict__ x, const double* __restrict__ s
 
 using namespace hipie;
 
+// resident CTAs of layernorm_kernel<MAXV> on this device (register-limited: 4 per SM at MAXV = 10), queried once per instantiation
+int g_ln_bulk = 1;            // hipie_set_option("ln_bulk", 0): register-resident rows only (A/B switch)
+int g_ln_grid_cap = 1;        // hipie_set_option("ln_grid_cap", 0): one 8-row CTA per 8 rows as in round 1 (A/B switch)
+template <int MAXV>
+static int ln_resident_ctas() {
+    if (!g_ln_grid_cap) return 0x7fffffff;
+    static int n = 0;
+    if (n == 0) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_kernel<MAXV>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        n = per_sm * num_sms();
+    }
+    return n;
+}
+
 static int layernorm_launch(const float* x, const float* add, const float* gamma, const float* beta, float eps,
                             float* sum_out, float* y_f32, void* y_hi, void* y_lo, int y_fp16, int64_t rows, int C,
                             const int32_t* out_row_map, void* stream, uint8_t* y8 = nullptr) {
@@ -219,16 +332,41 @@ static int layernorm_launch(const float* x, const float* add, const float* gamma
     if (rows == 0) return HIPIE_OK;
     cudaStream_t st = (cudaStream_t)stream;
     __nv_bfloat16 *hi = (__nv_bfloat16*)y_hi, *lo = (__nv_bfloat16*)y_lo;
-    if (C % 128 == 0 && C <= 128 * 16) {
-        const int64_t blocks = (rows + 7) / 8;
+    if (g_ln_bulk && !add && C % 128 == 0 && C <= 128 * 10 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && rows >= 4096) {
+        // rows staged by bulk copies: 2 slots of C floats per warp (80 KB per CTA at C = 1280)
+        const int smem = 8 * 2 * C * 4 + 8 * 2 * 8;
+        const int64_t want = (rows + 7) / 8;
+        uint8_t* y8p = y8;
+        if (C <= 128 * 2) {
+            HIPIE_ENSURE_SMEM(layernorm_bulk_kernel<2>, smem);
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_bulk_kernel<2>, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            layernorm_bulk_kernel<2><<<(unsigned)std::min<int64_t>(want, (int64_t)per_sm * num_sms()), 256, smem, st>>>(x, gamma, beta, eps, y_f32, hi, lo, rows, C,
+                                                                                                           out_row_map, y_fp16, y8p);
+        } else if (C <= 128 * 6) {
+            HIPIE_ENSURE_SMEM(layernorm_bulk_kernel<6>, smem);
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_bulk_kernel<6>, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            layernorm_bulk_kernel<6><<<(unsigned)std::min<int64_t>(want, (int64_t)per_sm * num_sms()), 256, smem, st>>>(x, gamma, beta, eps, y_f32, hi, lo, rows, C,
+                                                                                                           out_row_map, y_fp16, y8p);
+        } else {
+            HIPIE_ENSURE_SMEM(layernorm_bulk_kernel<10>, smem);
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_bulk_kernel<10>, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            layernorm_bulk_kernel<10><<<(unsigned)std::min<int64_t>(want, (int64_t)per_sm * num_sms()), 256, smem, st>>>(x, gamma, beta, eps, y_f32, hi, lo, rows, C,
+                                                                                                            out_row_map, y_fp16, y8p);
+        }
+    } else if (C % 128 == 0 && C <= 128 * 16) {
+        const int64_t want = (rows + 7) / 8;
+        int64_t blocks;
         if (C <= 128 * 2)
-            layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
+            layernorm_kernel<2><<<(unsigned)(blocks = std::min<int64_t>(want, ln_resident_ctas<2>())), 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
         else if (C <= 128 * 6)
-            layernorm_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
+            layernorm_kernel<6><<<(unsigned)(blocks = std::min<int64_t>(want, ln_resident_ctas<6>())), 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
         else if (C <= 128 * 10)
-            layernorm_kernel<10><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
+            layernorm_kernel<10><<<(unsigned)(blocks = std::min<int64_t>(want, ln_resident_ctas<10>())), 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
         else
-            layernorm_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
+            layernorm_kernel<16><<<(unsigned)(blocks = std::min<int64_t>(want, ln_resident_ctas<16>())), 256, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
     } else {
         layernorm_generic_kernel<<<(unsigned)rows, 128, 0, st>>>(x, add, gamma, beta, eps, sum_out, y_f32, hi, lo, rows, C, out_row_map, y_fp16, y8);
     }
