@@ -58,8 +58,10 @@ const char* hipie_last_error(void);
 int hipie_abi_version(void);
 /* Number of kernel launches issued through this library by the calling process. */
 int64_t hipie_launch_count(void);
-/* Process-wide tuning switches (tests / A-B measurements).  "gemm_cta_pairs" (default 1): large GEMMs run as CTA pairs
- * (tcgen05 cta_group::2, 256-row tiles); 0 forces single-CTA tiles.  Unknown names return HIPIE_EINVAL. */
+/* Process-wide tuning switches (tests / A-B measurements), all default 1.  "gemm_cta_pairs": large GEMMs run as CTA pairs
+ * (tcgen05 cta_group::2, 256-row tiles), 0 forces single-CTA tiles; "gemm_tma_store": row-major outputs leave through TMA stores;
+ * "gemm_fast_transposed": vectorised epilogue of the transposed fp16 plane (V^T); "ln_bulk": LayerNorm rows staged by bulk copies;
+ * "ln_grid_cap": LayerNorm grid capped at the resident CTAs (rows grid-strided).  Unknown names return HIPIE_EINVAL. */
 int hipie_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------

@@ -1,4 +1,4 @@
-"""Two-pass fp16 GEMM (prec 4) on the qkv shapes against the 3-pass bf16 mode: ms and algorithmic TFLOP/s; k-block variants."""
+"""Two-pass fp16 GEMM (prec 4) on the qkv shapes against the 3-pass bf16 and the one-pass fp16 modes: ms and algorithmic TFLOP/s."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -29,9 +29,7 @@ for name, M, N, K, kw in SHAPES:
     A4, W4 = ops.BF2(a.half(), None), ops.split_weight_f16(w)
     out = {}
     out["p3"] = timed(lambda: ops.gemm(A3, W3, want_f32=False, want_split=True, out_fp16=True, prec=3, **kw))
-    for bk32 in (0, 1):
-        _lib.set_option("gemm_p4_bk32", bk32)
-        out[f"p4 bk{32 if bk32 else 64}"] = timed(lambda: ops.gemm(A4, W4, want_f32=False, want_split=True, out_fp16=True, prec=4, **kw))
-    _lib.set_option("gemm_p4_bk32", 0)
+    # (the 32-element k-block variant of the CTA-pair kernel measured 4 % slower -- profiles/r02_gemm_p4_micro.txt -- and was removed)
+    out["p4"] = timed(lambda: ops.gemm(A4, W4, want_f32=False, want_split=True, out_fp16=True, prec=4, **kw))
     out["f16x1"] = timed(lambda: ops.gemm(A4, W4, want_f32=False, want_split=True, out_fp16=True, prec=2, **kw))
     print(f"{name:20s} {M:6d}x{N:5d}x{K:5d} " + "  ".join(f"{k} {v*1000:7.1f} us {2.0*M*N*K/v/1e9:6.1f} TF" for k, v in out.items()), flush=True)
