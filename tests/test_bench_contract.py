@@ -58,3 +58,31 @@ def test_config_workloads():
             assert len(pos_map) == cfg["classes"] and bool((ids[0] == ids[1]).all())
             assert max(max(v) for v in pos_map.values()) < int(am[0].sum())
     assert int(bench.batch_text(bench.CONFIGS[4], 1)[1].sum()) > 512             # ADE-847 prompt takes the BERT chunk path
+
+
+def test_committed_product_lines_follow_the_contract():
+    """The bench lines committed under profiles/ (final code of round 2) carry every key of the driver's contract plus the tier's
+    roofline / cpu_baseline objects, and their derived numbers are consistent with each other."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+            "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"}
+    for name, n in (("r02_bench_config1.json", 1), ("r02_bench_2gpu.json", 2), ("r02_bench_4gpu.json", 4), ("r02_bench_8gpu.json", 8)):
+        line = json.loads(open(os.path.join(root, "profiles", name)).read())
+        assert need <= set(line), need - set(line)
+        assert line["n_gpus"] == n and line["unit"] == "images/s" and line["scaling"] == "weak" and line["vs_baseline"] is None
+        B = line["config"]["per_gpu_batch"]
+        assert abs(line["value"] - n * B / (line["ms_per_step"] / 1000.0)) < 1e-6 * line["value"]      # whole-job aggregate over all ranks
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and line["e2e"]["value"] < line["value"]
+        assert line["gpu_launches"] > 500 * line["steps"]          # ~1000 library kernels per captured step
+        r = line["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernels", "gemm_tc_all", "vit_h_forward_alone"} <= set(r)
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.0 < r["frac"] < 1.0
+        top = r["kernels"][r["kernel"]]
+        assert top["share_of_timed_kernels"] == max(k["share_of_timed_kernels"] for k in r["kernels"].values())
+        assert r["mma_passes"] == top["mma_pass_equivalents"] and abs(r["executed_frac"] - r["frac"] * r["mma_passes"]) < 1e-9
+        assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    line = json.loads(open(os.path.join(root, "profiles", "r02_bench_config1.json")).read())
+    cpu = line["cpu_baseline"]
+    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] > 0 and "sample" in cpu
+    assert line["roofline"]["vit_h_forward_alone"]["frac"] > 0.40            # north-star: >= 40 % of the tensor peak on the ViT-H forward
